@@ -1,0 +1,177 @@
+/*
+ * minorseq_b200.h -- C ABI of the B200-native juliet/fuse hot path.
+ *
+ * The reference (PacificBiosciences/minorseq) documents no library, plugin or
+ * FFI interface: its only boundary is the process interface
+ *     juliet [--config|-c X] [--region b-e] [--mode-phasing] [--min-perc p]
+ *            [--max-perc p] [--drm-only] in.bam out.{json,html}
+ *                                        (/root/reference/doc/JULIET.md:61-66,
+ *                                         :121,:195,:270-271,:342-354,:370)
+ *     fuse in.bam out.fasta              (/root/reference/doc/FUSE.md:22-32)
+ * so this header IS the drop-in boundary a maintainer would bind: the juliet /
+ * fuse mains (minorseq_b200/host/), bench.py and the tests all sit on top of
+ * it.  Each entry point names the documented juliet/fuse behaviour it replaces.
+ *
+ * Conventions: plain C types only; every function returns MS_OK (0) or a
+ * negative ms_status; ms_last_error(h) holds the text; no exceptions cross the
+ * ABI; one handle per GPU (per rank); calls on one handle are serialised by the
+ * caller; all device work is enqueued on the handle's stream.  There is NO CPU
+ * fallback: ms_create fails when no sm_100 device is present.
+ *
+ * Packed read format ("planar 4-bit", L/2 bytes per read rounded up to 16 B):
+ *   a read is ceil(L/32) blocks; block b is four consecutive u32 bit-planes
+ *   P0,P1,P2,P3 (words 4b..4b+3); bit j of each plane is reference column
+ *   32b+j.  (P0,P1,P2) = state bits 0,1,2:
+ *       0=A 1=C 2=G 3=T 4='-' deletion 5='N' QV-filtered base 7=not spanned
+ *   P3 = an insertion follows this column in this read.  Columns >= L in the
+ *   last block are state 7.  Rows are contiguous: read r starts at word
+ *   r * ms_row_words(L).
+ */
+#ifndef MINORSEQ_B200_H
+#define MINORSEQ_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    MS_OK = 0,
+    MS_ERR_ARG = -1,        /* bad argument / call order */
+    MS_ERR_CUDA = -2,       /* CUDA runtime error, text in ms_last_error */
+    MS_ERR_NODEVICE = -3,   /* no usable sm_100 GPU: there is no CPU fallback */
+    MS_ERR_CAPACITY = -4,   /* caller buffer too small; required size reported */
+    MS_ERR_FORMAT = -5      /* malformed input (e.g. CIGAR 'M', doc/JULIET.md:53) */
+} ms_status;
+
+enum { MS_A = 0, MS_C = 1, MS_G = 2, MS_T = 3, MS_DEL = 4, MS_N = 5, MS_UNCOV = 7 };
+enum { MS_COL_INS = 6, MS_COL_COV = 7 };     /* col[j][6] insertion flags, col[j][7] = A+C+G+T+-+N */
+enum { MS_FLAG_GAP = 1, MS_FLAG_HET = 2, MS_FLAG_PARTIAL = 4 };
+
+typedef struct ms_handle ms_handle;
+
+/* ---- format helpers (host only, no GPU work) -------------------------------- */
+/* u32 words per packed read = 4*ceil(L/32). */
+int32_t ms_row_words(int32_t L);
+/* one byte per column (bits0-2 state, bit3 insertion-follows) -> planar rows. */
+int ms_pack_states(const uint8_t *states, int64_t R, int32_t L, uint32_t *packed);
+int ms_unpack_states(const uint32_t *packed, int64_t R, int32_t L, uint8_t *states);
+/* Replaces juliet/fuse's per-record CIGAR walk (doc/JULIET.md:49-58, doc/FUSE.md:13-15):
+ * expands one aligned record into one packed row.  cigar = BAM-encoded ops
+ * (len<<4|op); op 'M'(0) is rejected with MS_ERR_FORMAT ("cigar M is forbidden").
+ * seq = one base per byte (ACGTN), qv_mask[i]!=0 turns base i into 'N'
+ * (doc/JULIET.md:256-259), may be NULL.  Inserted strings are appended to the
+ * caller's event arrays (ins_col/ins_off/ins_len/ins_pool) when non-NULL.       */
+int ms_expand_cigar(const uint32_t *cigar, int32_t ncigar, int32_t pos,
+                    const char *seq, const uint8_t *qv_mask, int32_t lseq,
+                    int32_t L, uint32_t *row /* ms_row_words(L) */,
+                    int32_t *ins_col, int64_t *ins_off, int32_t *ins_len,
+                    int64_t ins_cap, int64_t *nins, char *ins_pool, int64_t pool_cap,
+                    int64_t *pool_used);
+
+/* ---- lifecycle --------------------------------------------------------------- */
+int ms_create(int device, ms_handle **out);
+void ms_destroy(ms_handle *h);
+const char *ms_last_error(const ms_handle *h);   /* h == NULL: error of the last failed ms_create */
+/* cudaStream_t to enqueue on (e.g. torch's current stream); NULL = the handle's own stream. */
+int ms_set_stream(ms_handle *h, void *cuda_stream);
+int ms_synchronize(ms_handle *h);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t ms_launch_count(const ms_handle *h);
+
+/* ---- K1: pileup (juliet "MSA counts", doc/JULIET.md:96-100; fuse doc/FUSE.md:17-20) -- */
+/* Reference length and the columns where a codon of some configured gene starts
+ * (bit j of word j/32; NULL = count no codons, i.e. fuse).  Zeroes the counts.  */
+int ms_set_layout(ms_handle *h, int32_t L, const uint32_t *start_mask);
+int ms_reset_counts(ms_handle *h);
+/* Accumulate R device-resident packed reads into the handle's count tensor.     */
+int ms_pileup_dev(ms_handle *h, const uint32_t *d_packed, int64_t R);
+/* Same from host memory (pinned recommended): chunked H2D copies overlapped with
+ * the kernel.  If keep_dev != NULL it receives a device pointer to the uploaded
+ * rows, owned by the handle and valid until the next ms_pileup_host / ms_destroy,
+ * so ms_phase_dev can run without a second upload.                               */
+int ms_pileup_host(ms_handle *h, const uint32_t *h_packed, int64_t R, const uint32_t **keep_dev);
+/* The count tensor [ col: L*8 u32 | codon: L*64 u32 ] in device memory, for the
+ * caller's cross-GPU sum (one NCCL all-reduce; integer sums are order independent). */
+int ms_counts_device(ms_handle *h, uint32_t **d_counts, int64_t *nwords);
+/* Copy counts to host: col[L][8] = A,C,G,T,-,N,ins,coverage ; codon[L][64] indexed by
+ * start column, codon = 16*b0+4*b1+b2, only reads whose codon is all A/C/G/T.    */
+int ms_get_counts(ms_handle *h, uint32_t *col, uint32_t *codon);
+/* selects the K1 implementation: 0 = bit-sliced carry-save kernel (default),
+ * 1 = shared-memory-atomic histogram kernel (kept only as the ncu A/B baseline). */
+int ms_set_pileup_variant(ms_handle *h, int variant);
+
+/* ---- K2: per-codon minor-variant test (doc/JULIET.md:38-42) --------------------- */
+typedef struct { int32_t begin, end; } ms_gene;   /* 1-based [begin,end), doc/JULIET.md:134-136 */
+typedef struct {
+    double substitution_rate, deletion_rate;   /* error model (restatement choice U1) */
+    double alpha;                              /* call iff p * ntests < alpha */
+    double min_perc, max_perc;                 /* --min-perc / --max-perc, < 0 = off */
+    int32_t region_begin, region_end;          /* --region, 1-based [b,e); 0,0 = off */
+} ms_call_params;
+typedef struct {
+    int32_t gene, codon_index, col, ref_codon, codon;
+    uint32_t count, coverage, expected, ntests;
+    double pvalue;                             /* uncorrected one-sided Fisher p (fp64) */
+} ms_variant;
+void ms_call_params_default(ms_call_params *p);
+/* Runs on the handle's (all-reduced) counts.  refseq NULL or shorter than L =>
+ * tested against the major codon (doc/JULIET.md:133-134).  Variants come back
+ * sorted by (gene, col, codon).  *n receives the number found (may exceed cap). */
+int ms_call(ms_handle *h, const ms_gene *genes, int32_t ngenes, const char *refseq,
+            const ms_call_params *prm, ms_variant *out, int64_t cap, int64_t *n);
+
+/* ---- K3: read-level phasing (--mode-phasing, doc/JULIET.md:192-211,:372-381) ----- */
+typedef struct { uint64_t reported, insufficient, damaged, gaps, heteroduplex, partial; } ms_phase_counters;
+/* Declare the pooled variant list (start column, codon) and the number of reads
+ * this handle will phase; allocates the bit matrix and the grouping table.       */
+int ms_phase_begin(ms_handle *h, const int32_t *var_col, const int32_t *var_codon, int32_t V,
+                   int64_t max_reads);
+/* Bit-vectors + damage flags for R more device-resident reads, appended.          */
+int ms_phase_dev(ms_handle *h, const uint32_t *d_packed, int64_t R);
+/* Distinct patterns of this handle's undamaged reads with their counts (sorted by
+ * ascending pattern words), and the damage marginals.  *H may exceed cap.         */
+int ms_phase_groups(ms_handle *h, uint32_t *patterns /* cap*ceil(V/32) */, uint64_t *counts,
+                    int64_t cap, int64_t *H, ms_phase_counters *ctr);
+/* Host: merge-sorted (pattern,count) lists from all ranks -> juliet's haplotype
+ * order (count desc, then ascending words) in place; *nreported = count>=min_reads;
+ * fills reported/insufficient of ctr.  Pure host logic.                           */
+int ms_haplotype_order(uint32_t *patterns, uint64_t *counts, int64_t H, int32_t V,
+                       int32_t min_reads, int64_t *Hmerged, int64_t *nreported,
+                       ms_phase_counters *ctr);
+void ms_haplotype_name(int64_t rank, char buf[3]);      /* [A-Z][a-z]? doc/JULIET.md:198 */
+/* hap_id (host, one per phased read, in upload order): rank in ordered_patterns,
+ * or -1 if damaged.                                                               */
+int ms_phase_assign(ms_handle *h, const uint32_t *ordered_patterns, int64_t H, int32_t *hap_id);
+/* Device pointers to the per-read results (R*ceil(V/32) words, R bytes).          */
+int ms_phase_device(ms_handle *h, uint32_t **d_bits, uint8_t **d_flags, int64_t *R);
+/* C[v][w] = #reads carrying both (V*V int32, device buffer owned by the handle). */
+int ms_cooccurrence(ms_handle *h, int32_t **d_C);
+
+/* ---- K4: fuse consensus (doc/FUSE.md:17-24) --------------------------------------- */
+typedef struct { int32_t min_coverage; double ins_fraction; int32_t ins_distance; } ms_fuse_params;
+void ms_fuse_params_default(ms_fuse_params *p);
+/* Consensus of the handle's (all-reduced) column counts plus the in-frame
+ * insertion rule over the caller's insertion events.  *len may exceed cap.        */
+int ms_fuse(ms_handle *h, const ms_fuse_params *prm,
+            const int32_t *ins_col, const int64_t *ins_off, const int32_t *ins_len,
+            int64_t nins, const char *ins_pool, int64_t pool_len,
+            char *seq, int64_t cap, int64_t *len);
+
+/* ---- synthetic amplicon generator (bench/tests) ------------------------- */
+typedef struct {
+    uint64_t seed;
+    int32_t L, nstrains;
+    uint32_t thr_N, thr_sub, thr_ins20, thr_trunc16;  /* integer thresholds, see synth.py */
+} ms_synth_params;
+/* strain_base: nstrains*L bytes (0..3); thr_del: L u32; strain_cum: nstrains u32 cumulative
+ * mixture thresholds.  Writes R packed rows for reads [read0, read0+R) on the device.  */
+int ms_synth_dev(ms_handle *h, const ms_synth_params *p, const uint8_t *strain_base,
+                 const uint32_t *thr_del, const uint32_t *strain_cum,
+                 int64_t read0, int64_t R, uint32_t *d_packed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,323 @@
+"""Host-side mirror of the juliet / fuse process interface over the C ABI.
+
+The reference exposes only two executables (`juliet [options] in.bam out.{json,html}`,
+/root/reference/doc/JULIET.md:61-66; `fuse in.bam out.fasta`, /root/reference/doc/FUSE.md:26-32).
+`Juliet` and `Fuse` below keep their option names (config genes, region, mode_phasing,
+min_perc, max_perc) and drive the CUDA kernels through libminorseq_b200.so.  PyTorch is
+used only for device memory, streams and torch.distributed; with more than one rank the
+reads are sharded and the count tensor is summed by ONE NCCL all-reduce.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import (CallParams, FuseParams, Gene, PhaseCounters, SynthParams, Variant, check)
+from .synth import start_mask_words
+
+CODONS = [a + b + c for a in "ACGT" for b in "ACGT" for c in "ACGT"]
+# standard genetic code (NCBI table 1, TCAG order), re-indexed to 16*b0+4*b1+b2 with A<C<G<T.
+# Stop codons are reported as amino acid "X" (screenshot juliet_hiv-hiv.png: CGA->TGA, R8X).
+_NCBI = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"
+_AA = "".join(_NCBI[16 * "TCAG".index(a) + 4 * "TCAG".index(b) + "TCAG".index(c)].replace("*", "X")
+              for a in "ACGT" for b in "ACGT" for c in "ACGT")
+
+
+def translate(codon_index: int) -> str:
+    return _AA[codon_index]
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))
+
+
+@dataclass
+class Haplotypes:
+    patterns: np.ndarray            # [H, ceil(V/32)] uint32, juliet order
+    counts: np.ndarray              # [H] uint64
+    nreported: int
+    names: list
+    counters: dict
+    hap_id: np.ndarray = None       # per local read, -1 = damaged
+
+
+@dataclass
+class JulietResult:
+    variants: list = field(default_factory=list)     # list of dict
+    haplotypes: Haplotypes = None
+    col_counts: np.ndarray = None
+    codon_counts: np.ndarray = None
+
+
+class Handle:
+    """Thin RAII wrapper of ms_handle (one per GPU / rank)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.ms_create(device, C.byref(h))
+        if rc != 0:
+            raise _lib.MsError(f"ms_create failed ({rc}): {self.lib.ms_last_error(None).decode()}")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ms_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def use_torch_stream(self):
+        import torch
+        check(self.lib.ms_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), self.h)
+
+    @property
+    def launches(self):
+        return int(self.lib.ms_launch_count(self.h))
+
+
+class Juliet:
+    """juliet's pileup -> codon test -> phasing pass for one rank's shard of the reads."""
+
+    def __init__(self, L, genes, refseq=None, device=0, region=None, mode_phasing=False, min_perc=None,
+                 max_perc=None, substitution_rate=5e-4, deletion_rate=3e-3, alpha=0.01, min_hap_reads=10,
+                 handle=None):
+        self.hd = handle or Handle(device)
+        self.lib = self.hd.lib
+        self.L = int(L)
+        self.genes = [(int(b), int(e)) for (b, e) in genes]
+        self.refseq = refseq
+        self.region = region
+        self.mode_phasing = mode_phasing
+        self.min_hap_reads = min_hap_reads
+        p = CallParams()
+        self.lib.ms_call_params_default(C.byref(p))
+        p.substitution_rate, p.deletion_rate, p.alpha = substitution_rate, deletion_rate, alpha
+        p.min_perc = -1.0 if min_perc is None else float(min_perc)
+        p.max_perc = -1.0 if max_perc is None else float(max_perc)
+        if region:
+            p.region_begin, p.region_end = int(region[0]), int(region[1])
+        self.params = p
+        self.start_mask = start_mask_words(self.L, self.genes, region)
+        check(self.lib.ms_set_layout(self.hd.h, self.L, _ptr(self.start_mask)), self.hd.h)
+
+    @property
+    def row_words(self):
+        return int(self.lib.ms_row_words(self.L))
+
+    def reset(self):
+        check(self.lib.ms_reset_counts(self.hd.h), self.hd.h)
+
+    # -- K1
+    def pileup_device(self, d_packed_ptr: int, nreads: int):
+        check(self.lib.ms_pileup_dev(self.hd.h, C.c_void_p(d_packed_ptr), nreads), self.hd.h)
+
+    def pileup_host(self, packed: np.ndarray) -> int:
+        """packed: [R, row_words] uint32 host array (pinned recommended). Returns device ptr of the upload."""
+        keep = C.c_void_p()
+        check(self.lib.ms_pileup_host(self.hd.h, _ptr(packed), packed.shape[0], C.byref(keep)), self.hd.h)
+        return keep.value
+
+    def counts_tensor(self):
+        """torch view of the device count tensor [L*72] (int32 reinterpretation for NCCL)."""
+        import torch
+        p, n = C.c_void_p(), C.c_int64()
+        check(self.lib.ms_counts_device(self.hd.h, C.byref(p), C.byref(n)), self.hd.h)
+        return _as_tensor(p.value, (n.value,), torch.int32, self.hd.device)
+
+    def allreduce_counts(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.counts_tensor(), op=dist.ReduceOp.SUM)
+
+    def get_counts(self):
+        col = np.empty((self.L, 8), dtype=np.uint32)
+        codon = np.empty((self.L, 64), dtype=np.uint32)
+        check(self.lib.ms_get_counts(self.hd.h, _ptr(col), _ptr(codon)), self.hd.h)
+        return col, codon
+
+    # -- K2
+    def call(self, cap=1 << 16):
+        genes = (Gene * len(self.genes))(*[Gene(b, e) for (b, e) in self.genes])
+        out = (Variant * cap)()
+        n = C.c_int64()
+        ref = self.refseq.encode() if self.refseq else None
+        check(self.lib.ms_call(self.hd.h, genes, len(self.genes), ref, C.byref(self.params), out, cap, C.byref(n)), self.hd.h)
+        if n.value > cap:
+            return self.call(cap=int(n.value))
+        return [out[i] for i in range(n.value)]
+
+    # -- K3
+    def phase_device(self, variants, d_packed_ptr: int, nreads: int, want_hap_id=True) -> Haplotypes:
+        import torch.distributed as dist
+        keys = sorted({(v.col, v.codon) for v in variants})
+        V = len(keys)
+        vc = np.array([k[0] for k in keys], dtype=np.int32)
+        vd = np.array([k[1] for k in keys], dtype=np.int32)
+        nw = max(1, (V + 31) // 32)
+        self._V = V
+        check(self.lib.ms_phase_begin(self.hd.h, _ptr(vc), _ptr(vd), V, nreads), self.hd.h)
+        check(self.lib.ms_phase_dev(self.hd.h, C.c_void_p(d_packed_ptr), nreads), self.hd.h)
+        cap = 4096
+        while True:
+            pat = np.zeros((cap, nw), dtype=np.uint32)
+            cnt = np.zeros(cap, dtype=np.uint64)
+            H, ctr = C.c_int64(), PhaseCounters()
+            check(self.lib.ms_phase_groups(self.hd.h, _ptr(pat), _ptr(cnt), cap, C.byref(H), C.byref(ctr)), self.hd.h)
+            if H.value <= cap:
+                break
+            cap = int(H.value)
+        pat, cnt = pat[:H.value], cnt[:H.value]
+        marg = np.array([ctr.damaged, ctr.gaps, ctr.heteroduplex, ctr.partial], dtype=np.int64)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            pat, cnt, marg = _gather_groups(pat, cnt, marg, self.hd.device)
+        pat = np.ascontiguousarray(pat)
+        cnt = np.ascontiguousarray(cnt)
+        Hm, nrep, c2 = C.c_int64(), C.c_int64(), PhaseCounters()
+        check(self.lib.ms_haplotype_order(_ptr(pat), _ptr(cnt), len(cnt), V, self.min_hap_reads, C.byref(Hm),
+                                          C.byref(nrep), C.byref(c2)))
+        pat, cnt = pat[:Hm.value], cnt[:Hm.value]
+        names = []
+        buf = C.create_string_buffer(3)
+        for i in range(nrep.value):
+            self.lib.ms_haplotype_name(i, buf)
+            names.append(buf.value.decode())
+        counters = dict(reported=int(c2.reported), insufficient=int(c2.insufficient), damaged=int(marg[0]),
+                        gaps=int(marg[1]), heteroduplex=int(marg[2]), partial=int(marg[3]))
+        hap = None
+        if want_hap_id:
+            hap = np.empty(nreads, dtype=np.int32)
+            check(self.lib.ms_phase_assign(self.hd.h, _ptr(pat), len(cnt), _ptr(hap)), self.hd.h)
+        return Haplotypes(patterns=pat, counts=cnt, nreported=int(nrep.value), names=names, counters=counters, hap_id=hap), keys
+
+    def cooccurrence(self):
+        """[V, V] int32 torch tensor (device memory owned by the handle), summed over ranks."""
+        import torch
+        import torch.distributed as dist
+        p = C.c_void_p()
+        check(self.lib.ms_cooccurrence(self.hd.h, C.byref(p)), self.hd.h)
+        t = _as_tensor(p.value, (max(1, self._V * self._V),), torch.int32, self.hd.device)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t[: self._V * self._V].view(self._V, self._V)
+
+    # -- the whole pass on device-resident reads (what bench.py times)
+    def run_device(self, d_packed_ptr: int, nreads: int, want_hap_id=False) -> JulietResult:
+        self.reset()
+        self.pileup_device(d_packed_ptr, nreads)
+        self.allreduce_counts()
+        res = JulietResult(variants=self.call())
+        if self.mode_phasing:
+            res.haplotypes, res.keys = self.phase_device(res.variants, d_packed_ptr, nreads, want_hap_id)
+        return res
+
+    def run_host(self, packed: np.ndarray, want_hap_id=False) -> JulietResult:
+        """Reference-facing call with HOST buffers: H2D + kernels + D2H of the results."""
+        self.reset()
+        dptr = self.pileup_host(packed)
+        self.allreduce_counts()
+        res = JulietResult(variants=self.call())
+        if self.mode_phasing:
+            res.haplotypes, res.keys = self.phase_device(res.variants, dptr, packed.shape[0], want_hap_id)
+        return res
+
+    def variant_dicts(self, variants):
+        out = []
+        for v in variants:
+            out.append(dict(gene=v.gene, aa_pos=v.codon_index + 1, col=v.col, ref_codon=CODONS[v.ref_codon],
+                            ref_aa=translate(v.ref_codon), codon=CODONS[v.codon], aa=translate(v.codon),
+                            count=int(v.count), coverage=int(v.coverage), frequency=v.count / v.coverage,
+                            expected=int(v.expected), ntests=int(v.ntests), pvalue=float(v.pvalue)))
+        return out
+
+
+class Fuse:
+    """fuse's consensus for one rank's shard (doc/FUSE.md:17-24)."""
+
+    def __init__(self, L, device=0, min_coverage=50, ins_fraction=0.5, ins_distance=20, handle=None):
+        self.hd = handle or Handle(device)
+        self.lib = self.hd.lib
+        self.L = int(L)
+        self.params = FuseParams(min_coverage, ins_fraction, ins_distance)
+        check(self.lib.ms_set_layout(self.hd.h, self.L, None), self.hd.h)
+
+    def pileup_device(self, d_packed_ptr: int, nreads: int):
+        check(self.lib.ms_pileup_dev(self.hd.h, C.c_void_p(d_packed_ptr), nreads), self.hd.h)
+
+    def pileup_host(self, packed: np.ndarray) -> int:
+        keep = C.c_void_p()
+        check(self.lib.ms_pileup_host(self.hd.h, _ptr(packed), packed.shape[0], C.byref(keep)), self.hd.h)
+        return keep.value
+
+    allreduce_counts = Juliet.allreduce_counts
+    counts_tensor = Juliet.counts_tensor
+
+    def reset(self):
+        check(self.lib.ms_reset_counts(self.hd.h), self.hd.h)
+
+    def consensus(self, ins_col=None, ins_off=None, ins_len=None, ins_pool=b"") -> str:
+        nins = 0 if ins_col is None else len(ins_col)
+        ic = np.ascontiguousarray(ins_col, dtype=np.int32) if nins else None
+        io = np.ascontiguousarray(ins_off, dtype=np.int64) if nins else None
+        il = np.ascontiguousarray(ins_len, dtype=np.int32) if nins else None
+        pool = np.frombuffer(ins_pool, dtype=np.uint8) if nins else None
+        cap = self.L + (int(il.sum()) if nins else 0) + 16
+        seq = np.empty(cap, dtype=np.uint8)
+        n = C.c_int64()
+        check(self.lib.ms_fuse(self.hd.h, C.byref(self.params), _ptr(ic), _ptr(io), _ptr(il), nins, _ptr(pool),
+                               len(ins_pool), _ptr(seq), cap, C.byref(n)), self.hd.h)
+        return seq[: n.value].tobytes().decode()
+
+
+def _as_tensor(ptr, shape, dtype, device):
+    """Zero-copy torch tensor over raw device memory owned by the handle."""
+    import torch
+
+    class _Holder:
+        pass
+
+    itemsize = torch.empty((), dtype=dtype).element_size()
+    hold = _Holder()
+    hold.__cuda_array_interface__ = {
+        "shape": tuple(shape), "typestr": {4: "<i4", 8: "<i8", 1: "|u1"}[itemsize], "data": (int(ptr), False),
+        "version": 2, "strides": None,
+    }
+    return torch.as_tensor(hold, device=f"cuda:{device}")
+
+
+def _gather_groups(pat, cnt, marg, device):
+    """all-gather the ranks' (pattern, count) lists and sum the damage marginals."""
+    import torch
+    import torch.distributed as dist
+    ws = dist.get_world_size()
+    dev = f"cuda:{device}" if dist.get_backend() == "nccl" else "cpu"
+    n = torch.tensor([len(cnt)], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n) for _ in range(ws)]
+    dist.all_gather(sizes, n)
+    mx = max(1, int(max(s.item() for s in sizes)))
+    nw = pat.shape[1]
+    buf = torch.zeros((mx, nw + 2), dtype=torch.int64, device=dev)
+    if len(cnt):
+        buf[: len(cnt), :nw] = torch.from_numpy(pat.astype(np.int64)).to(dev)
+        buf[: len(cnt), nw] = torch.from_numpy(cnt.astype(np.int64)).to(dev)
+    bufs = [torch.zeros_like(buf) for _ in range(ws)]
+    dist.all_gather(bufs, buf)
+    m = torch.from_numpy(marg).to(dev)
+    dist.all_reduce(m, op=dist.ReduceOp.SUM)
+    pats, cnts = [], []
+    for s, b in zip(sizes, bufs):
+        k = int(s.item())
+        b = b[:k].cpu().numpy()
+        pats.append(b[:, :nw].astype(np.uint32))
+        cnts.append(b[:, nw].astype(np.uint64))
+    return np.concatenate(pats, axis=0), np.concatenate(cnts), m.cpu().numpy()

@@ -1,0 +1,237 @@
+// abi_core.cu -- lifecycle, layout and the K1 launchers of the C ABI (include/minorseq_b200.h).
+#include <algorithm>
+#include <cstring>
+#include "handle.h"
+#include "pileup.cuh"
+
+static std::string g_create_error;
+
+extern "C" {
+
+int ms_create(int device, ms_handle** out) {
+    if (!out) return MS_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        g_create_error = std::string("no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "index out of range") +
+                         "); minorseq_b200 has no CPU fallback";
+        return MS_ERR_NODEVICE;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        return MS_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        g_create_error = "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                         ", this library is built for sm_100a only";
+        return MS_ERR_NODEVICE;
+    }
+    ms_handle* h = new ms_handle();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    h->max_smem = static_cast<int>(prop.sharedMemPerBlockOptin);
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(cudaGetLastError());
+        delete h;
+        return MS_ERR_CUDA;
+    }
+    h->stream = h->own_stream;
+    cudaFuncSetAttribute(ms::pileup_csa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+    *out = h;
+    return MS_OK;
+}
+
+static void free_layout(ms_handle* h) {
+    cudaFree(h->d_counts); cudaFree(h->d_start); cudaFree(h->d_pivot); cudaFree(h->d_pivot_state);
+    cudaFree(h->d_part_col); cudaFree(h->d_part_piv);
+    h->d_counts = nullptr; h->d_start = nullptr; h->d_pivot = nullptr; h->d_pivot_state = nullptr;
+    h->d_part_col = h->d_part_piv = nullptr;
+}
+
+void ms_phase_free_internal(ms_handle* h);
+
+void ms_destroy(ms_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    free_layout(h);
+    ms_phase_free_internal(h);
+    cudaFree(h->d_upload); cudaFree(h->d_call_buf); cudaFree(h->d_seq);
+    cudaEventDestroy(h->ev_copy[0]); cudaEventDestroy(h->ev_copy[1]);
+    cudaStreamDestroy(h->own_stream); cudaStreamDestroy(h->copy_stream);
+    delete h;
+}
+
+const char* ms_last_error(const ms_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ms_set_stream(ms_handle* h, void* s) {
+    if (!h) return MS_ERR_ARG;
+    h->stream = s ? static_cast<cudaStream_t>(s) : h->own_stream;
+    return MS_OK;
+}
+
+int ms_synchronize(ms_handle* h) {
+    if (!h) return MS_ERR_ARG;
+    MS_CUDA(h, cudaSetDevice(h->device));
+    MS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return MS_OK;
+}
+
+int64_t ms_launch_count(const ms_handle* h) { return h ? h->launches : 0; }
+
+int ms_set_pileup_variant(ms_handle* h, int variant) {
+    if (!h || variant < 0 || variant > 1) return MS_ERR_ARG;
+    h->variant = variant;
+    return MS_OK;
+}
+
+int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
+    if (!h || L < 3) return MS_ERR_ARG;
+    MS_CUDA(h, cudaSetDevice(h->device));
+    const int32_t nblk = (L + 31) / 32;
+    const int32_t W = (nblk + 31) / 32;
+    if (W > 10) MS_FAIL(h, MS_ERR_ARG, "reference longer than 10240 columns is not supported by this build");
+    MS_CUDA(h, cudaStreamSynchronize(h->stream));
+    free_layout(h);
+    h->L = L; h->nblk = nblk; h->count_codons = start_mask != nullptr; h->have_pivot = false;
+    // CTA shape: G row-groups of W warps, ~9 consumer warps + 1 producer
+    h->wpg = W;
+    h->groups = std::max(1, 9 / W);
+    h->blocks8 = 1;
+    const int row_bytes = nblk * 16;
+    h->stage_bytes = h->groups * h->blocks8 * 8 * row_bytes;
+    const int budget = h->max_smem - 128 - 16;
+    h->stages = std::max(2, std::min(8, budget / h->stage_bytes));
+    h->smem_bytes = 128 + h->stages * h->stage_bytes + 16;
+    if (h->smem_bytes > h->max_smem) MS_FAIL(h, MS_ERR_ARG, "row too long for the shared-memory ring");
+    const size_t ncounts = static_cast<size_t>(L) * 72;
+    MS_CUDA(h, cudaMalloc(&h->d_counts, ncounts * 4));
+    MS_CUDA(h, cudaMemsetAsync(h->d_counts, 0, ncounts * 4, h->stream));
+    MS_CUDA(h, cudaMalloc(&h->d_start, nblk * 4));
+    MS_CUDA(h, cudaMalloc(&h->d_pivot, (nblk + 1) * sizeof(uint2)));
+    MS_CUDA(h, cudaMalloc(&h->d_pivot_state, nblk * 32 + 4));
+    MS_CUDA(h, cudaMemsetAsync(h->d_pivot, 0, (nblk + 1) * sizeof(uint2), h->stream));
+    MS_CUDA(h, cudaMemsetAsync(h->d_pivot_state, 0, nblk * 32 + 4, h->stream));
+    h->h_start.assign(nblk, 0u);
+    if (start_mask) {
+        for (int32_t b = 0; b < nblk; ++b) h->h_start[b] = start_mask[b];
+        // a codon must fit inside the reference
+        for (int32_t j = std::max(0, L - 2); j < nblk * 32; ++j) h->h_start[j >> 5] &= ~(1u << (j & 31));
+    }
+    MS_CUDA(h, cudaMemcpyAsync(h->d_start, h->h_start.data(), nblk * 4, cudaMemcpyHostToDevice, h->stream));
+    const size_t slices = static_cast<size_t>(h->num_sms) * h->groups;
+    MS_CUDA(h, cudaMalloc(&h->d_part_col, slices * nblk * 256 * 4));
+    MS_CUDA(h, cudaMalloc(&h->d_part_piv, slices * nblk * 32 * 4));
+    MS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return MS_OK;
+}
+
+int ms_reset_counts(ms_handle* h) {
+    if (!h || !h->d_counts) return MS_ERR_ARG;
+    MS_CUDA(h, cudaSetDevice(h->device));
+    MS_CUDA(h, cudaMemsetAsync(h->d_counts, 0, static_cast<size_t>(h->L) * 72 * 4, h->stream));
+    h->have_pivot = false;
+    return MS_OK;
+}
+
+int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
+    if (!h || !h->d_counts || R < 0 || (R > 0 && !d_packed)) return MS_ERR_ARG;
+    if (R == 0) return MS_OK;
+    MS_CUDA(h, cudaSetDevice(h->device));
+    uint32_t* col = h->d_counts;
+    uint32_t* codon = h->d_counts + static_cast<size_t>(h->L) * 8;
+    if (h->variant == 1) {
+        dim3 grid(std::max(1, std::min<int>(static_cast<int>((R + 255) / 256), 4 * h->num_sms / std::max(1, h->nblk / 8 + 1) + 1)),
+                  h->nblk);
+        ms::pileup_atomic_kernel<<<grid, 256, 256 * 4, h->stream>>>(d_packed, R, h->L, h->nblk, h->d_start, col, codon,
+                                                                   h->count_codons ? 1 : 0);
+        ms::coverage_kernel<<<(h->L + 255) / 256, 256, 0, h->stream>>>(col, h->L);
+        h->launches += 2;
+        MS_CUDA(h, cudaGetLastError());
+        return MS_OK;
+    }
+    if (h->count_codons && !h->have_pivot) {
+        ms::pivot_sample_kernel<<<h->nblk, 256, 0, h->stream>>>(d_packed, R, h->nblk, h->L, h->d_pivot, h->d_pivot_state);
+        h->launches++;
+        h->have_pivot = true;
+    }
+    ms::PileupArgs a;
+    a.packed = d_packed; a.R = R; a.L = h->L; a.nblk = h->nblk;
+    a.warps_per_group = h->wpg; a.groups = h->groups; a.blocks8 = h->blocks8;
+    a.stages = h->stages; a.stage_bytes = h->stage_bytes;
+    a.pivot = h->d_pivot; a.start_mask = h->d_start; a.codon = codon;
+    a.part_col = h->d_part_col; a.part_piv = h->d_part_piv;
+    a.count_codons = h->count_codons ? 1 : 0;
+    const int64_t T = static_cast<int64_t>(h->groups) * h->blocks8 * 8;
+    const int64_t ntiles = (R + T - 1) / T;
+    const int grid = static_cast<int>(std::min<int64_t>(h->num_sms, ntiles));
+    const int threads = (h->wpg * h->groups + 1) * 32;
+    ms::pileup_csa_kernel<<<grid, threads, h->smem_bytes, h->stream>>>(a);
+    const int64_t nfin = static_cast<int64_t>(h->L) * 9;
+    ms::pileup_finalize_kernel<<<static_cast<int>((nfin + 255) / 256), 256, 0, h->stream>>>(
+        h->d_part_col, h->d_part_piv, grid * h->groups, h->nblk, h->L, h->d_pivot_state, h->d_start, col, codon,
+        h->count_codons ? 1 : 0);
+    h->launches += 2;
+    MS_CUDA(h, cudaGetLastError());
+    return MS_OK;
+}
+
+int ms_pileup_host(ms_handle* h, const uint32_t* h_packed, int64_t R, const uint32_t** keep_dev) {
+    if (!h || !h->d_counts || R < 0 || (R > 0 && !h_packed)) return MS_ERR_ARG;
+    MS_CUDA(h, cudaSetDevice(h->device));
+    const size_t row_bytes = static_cast<size_t>(h->nblk) * 16;
+    const size_t need = std::max<size_t>(16, static_cast<size_t>(R) * row_bytes);
+    if (need > h->upload_cap) {
+        MS_CUDA(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_upload);
+        h->d_upload = nullptr; h->upload_cap = 0;
+        MS_CUDA(h, cudaMalloc(&h->d_upload, need));
+        h->upload_cap = need;
+    }
+    // chunked upload on the copy stream, kernels on the main stream behind an event per chunk
+    const int64_t chunk_rows = std::max<int64_t>(1024, (static_cast<int64_t>(64) << 20) / static_cast<int64_t>(row_bytes));
+    // the copy stream must not start overwriting d_upload before earlier work on the main stream is done
+    MS_CUDA(h, cudaEventRecord(h->ev_copy[1], h->stream));
+    MS_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_copy[1], 0));
+    std::vector<cudaEvent_t> evs;
+    for (int64_t r0 = 0; r0 < R; r0 += chunk_rows) {
+        const int64_t nr = std::min(chunk_rows, R - r0);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(h->d_upload) + static_cast<size_t>(r0) * row_bytes;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(h_packed) + static_cast<size_t>(r0) * row_bytes;
+        MS_CUDA(h, cudaMemcpyAsync(dst, src, static_cast<size_t>(nr) * row_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        cudaEvent_t ev;
+        MS_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        evs.push_back(ev);
+        MS_CUDA(h, cudaEventRecord(ev, h->copy_stream));
+        MS_CUDA(h, cudaStreamWaitEvent(h->stream, ev, 0));
+        int rc = ms_pileup_dev(h, reinterpret_cast<const uint32_t*>(dst), nr);
+        if (rc != MS_OK) return rc;
+    }
+    for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
+    if (keep_dev) *keep_dev = h->d_upload;
+    return MS_OK;
+}
+
+int ms_counts_device(ms_handle* h, uint32_t** d_counts, int64_t* nwords) {
+    if (!h || !h->d_counts) return MS_ERR_ARG;
+    if (d_counts) *d_counts = h->d_counts;
+    if (nwords) *nwords = static_cast<int64_t>(h->L) * 72;
+    return MS_OK;
+}
+
+int ms_get_counts(ms_handle* h, uint32_t* col, uint32_t* codon) {
+    if (!h || !h->d_counts) return MS_ERR_ARG;
+    MS_CUDA(h, cudaSetDevice(h->device));
+    const size_t L = h->L;
+    if (col) MS_CUDA(h, cudaMemcpyAsync(col, h->d_counts, L * 8 * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (codon) MS_CUDA(h, cudaMemcpyAsync(codon, h->d_counts + L * 8, L * 64 * 4, cudaMemcpyDeviceToHost, h->stream));
+    MS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return MS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,422 @@
+/*
+ * ms_oracle.c -- CPU RESTATEMENT (test oracle) of juliet's pileup / codon test /
+ * phasing and fuse's consensus.  See ms_oracle.h: test infrastructure only,
+ * PARITY UNPINNED (the reference ships documentation only).
+ *
+ * Every function cites the reference text it restates (path:line under
+ * /root/reference) and, where the docs are silent, the SURVEY.md App. B
+ * "restatement choice" it implements.  Written to be obviously correct, not
+ * fast: one byte per column, plain loops, long-double log-gamma for Fisher.
+ */
+#define _GNU_SOURCE
+#include "ms_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ---- format bridge -------------------------------------------------------
+ * The product stores a read as ceil(L/32) blocks of four u32 bit-planes
+ * (include/minorseq_b200.h): plane p of block b is word 4*b+p, bit j is column
+ * 32*b+j; planes 0..2 are the state bits, plane 3 the insertion flag.        */
+void mso_unpack_planar(const uint32_t *packed, int64_t R, int32_t L, uint8_t *states)
+{
+    int32_t nblk = (L + 31) / 32;
+    for (int64_t r = 0; r < R; ++r) {
+        const uint32_t *row = packed + (size_t)r * 4 * nblk;
+        uint8_t *out = states + (size_t)r * L;
+        for (int32_t j = 0; j < L; ++j) {
+            const uint32_t *w = row + 4 * (j >> 5);
+            int sh = j & 31;
+            out[j] = (uint8_t)(((w[0] >> sh) & 1) | (((w[1] >> sh) & 1) << 1) |
+                               (((w[2] >> sh) & 1) << 2) | (((w[3] >> sh) & 1) << 3));
+        }
+    }
+}
+
+/* ---- a4 + a5: per-column and per-codon histograms --------------------------
+ * doc/JULIET.md:99-100 ("counts of the multiple-sequence alignment"), screenshot
+ * juliet_hiv-context.png: columns A C G T - N; every row sums to the number of
+ * reads spanning the column (SURVEY C-1).  A QV-filtered base is 'N' and "does
+ * not count towards the coverage" (doc/JULIET.md:256-259): codon coverage is the
+ * number of reads whose three states are all A/C/G/T.         */
+static void pileup_range(const uint8_t *states, int64_t r0, int64_t r1, int32_t L,
+                         const uint8_t *start_mask, uint32_t *col, uint32_t *codon)
+{
+    for (int64_t r = r0; r < r1; ++r) {
+        const uint8_t *s = states + (size_t)r * L;
+        for (int32_t j = 0; j < L; ++j) {
+            int st = s[j] & 7;
+            if (st <= MSO_N) {
+                col[(size_t)j * 8 + st]++;
+                col[(size_t)j * 8 + MSO_COL_COV]++;
+                if (s[j] & 8) col[(size_t)j * 8 + MSO_COL_INS]++;
+            }
+        }
+        if (!codon) continue;
+        for (int32_t j = 0; j + 2 < L; ++j) {
+            if (start_mask && !start_mask[j]) continue;
+            int a = s[j] & 7, b = s[j + 1] & 7, c = s[j + 2] & 7;
+            if (a > 3 || b > 3 || c > 3) continue;
+            codon[(size_t)j * 64 + 16 * a + 4 * b + c]++;
+        }
+    }
+}
+
+void mso_pileup(const uint8_t *states, int64_t R, int32_t L, const uint8_t *start_mask,
+                uint32_t *col, uint32_t *codon, int nthreads)
+{
+    memset(col, 0, (size_t)L * 8 * sizeof(uint32_t));
+    if (codon) memset(codon, 0, (size_t)L * 64 * sizeof(uint32_t));
+#ifdef _OPENMP
+    if (nthreads > 1) {
+#pragma omp parallel num_threads(nthreads)
+        {
+            int t = omp_get_thread_num(), nt = omp_get_num_threads();
+            uint32_t *c1 = calloc((size_t)L * 8, sizeof(uint32_t));
+            uint32_t *c2 = codon ? calloc((size_t)L * 64, sizeof(uint32_t)) : NULL;
+            pileup_range(states, R * t / nt, R * (t + 1) / nt, L, start_mask, c1, c2);
+#pragma omp critical
+            {
+                for (size_t i = 0; i < (size_t)L * 8; ++i) col[i] += c1[i];
+                if (codon) for (size_t i = 0; i < (size_t)L * 64; ++i) codon[i] += c2[i];
+            }
+            free(c1); free(c2);
+        }
+        return;
+    }
+#endif
+    (void)nthreads;
+    pileup_range(states, 0, R, L, start_mask, col, codon);
+}
+
+/* ---- a8: Fisher's exact test ---------------------------------------------
+ * doc/JULIET.md:42 "Bonferroni-corrected Fisher's Exact test".  Sidedness and
+ * table are restatement choice U2: one-sided "greater" on [[a,b],[c,d]].
+ * P(X >= a), X ~ Hypergeometric(white = a+c, black = b+d, draws = a+b).
+ * Long-double log-gamma keeps the relative error near 1e-11 at n = 1e6.      */
+static long double lchoose_ld(long double n, long double k)
+{
+    return lgammal(n + 1.0L) - lgammal(k + 1.0L) - lgammal(n - k + 1.0L);
+}
+
+double mso_fisher_greater(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    long double white = (long double)a + c, black = (long double)b + d, draws = (long double)a + b;
+    long double xmax = white < draws ? white : draws;
+    long double x = a;
+    long double lp = lchoose_ld(white, x) + lchoose_ld(black, draws - x) - lchoose_ld(white + black, draws);
+    long double term = expl(lp), sum = term;
+    while (x < xmax && term > 0.0L) {
+        /* pmf(x+1)/pmf(x) */
+        term *= (white - x) * (draws - x) / ((x + 1.0L) * (black - draws + x + 1.0L));
+        sum += term;
+        x += 1.0L;
+    }
+    if (sum > 1.0L) sum = 1.0L;
+    return (double)sum;
+}
+
+/* ---- a7: error-model expectation -------------------------------------------
+ * doc/JULIET.md:40-41 "number of expected mutations at a given position"; the
+ * constants are not documented (doc/JULIET.md:221-225 only says chemistry-
+ * dependent with a permissive fallback).  Restatement choice U1: independent
+ * per-base errors, P = prod(match if equal else substitution/3),
+ * match = 1 - substitution - deletion.                                         */
+double mso_codon_error_prob(int ref_codon, int codon, double sub_rate, double del_rate)
+{
+    double match = 1.0 - sub_rate - del_rate, mis = sub_rate / 3.0;
+    int nm = 0;
+    for (int i = 0; i < 3; ++i)
+        if (((ref_codon >> (2 * i)) & 3) != ((codon >> (2 * i)) & 3)) nm++;
+    /* fixed evaluation order so every implementation can reproduce the double exactly */
+    double p = 1.0;
+    for (int i = 0; i < 3 - nm; ++i) p *= match;
+    for (int i = 0; i < nm; ++i) p *= mis;
+    return p;
+}
+
+static int base_code(char ch)
+{
+    switch (ch) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    default: return -1;
+    }
+}
+
+/* ---- a6-a9: per-gene, per-codon minor-variant test ---------------------------
+ * doc/JULIET.md:38-42 (model), :133-136 (reference sequence vs major codon;
+ * 1-based [begin,end) in alignment space), :261-264 (each gene separately,
+ * overlaps allowed), :270-271 (--region), :342-354 (--min-perc/--max-perc).
+ * Restatement choices: U2 table [[k,n-k],[e,n-e]] with e = ceil(n*P) clipped
+ * to n; U3 Bonferroni factor = codon positions tested in this gene; U6 lowest
+ * code wins majority ties.  Synonymous codons are reported (screenshot
+ * juliet_hiv-own.png); all 64 codons translate (stop = X, F19).    */
+static int cmp_variant(const void *pa, const void *pb)
+{
+    const mso_variant *a = pa, *b = pb;
+    if (a->gene != b->gene) return a->gene < b->gene ? -1 : 1;
+    if (a->col != b->col) return a->col < b->col ? -1 : 1;
+    return (a->codon > b->codon) - (a->codon < b->codon);
+}
+
+int64_t mso_call(const uint32_t *codon, int32_t L, const mso_gene *genes, int32_t ngenes,
+                 const char *refseq, const mso_call_params *prm, mso_variant *out, int64_t cap)
+{
+    int64_t nout = 0;
+    int32_t lo = 0, hi = L;
+    if (prm->region_end > prm->region_begin) {
+        lo = prm->region_begin - 1; hi = prm->region_end - 1;
+        if (lo < 0) lo = 0;
+        if (hi > L) hi = L;
+    }
+    for (int32_t g = 0; g < ngenes; ++g) {
+        int32_t gb = genes[g].begin - 1, ge = genes[g].end - 1; /* 0-based [gb,ge) */
+        if (ge > L) ge = L;
+        /* count tested positions first: Bonferroni factor (U3) */
+        uint32_t ntests = 0;
+        for (int32_t s = gb; s + 3 <= ge; s += 3)
+            if (s >= lo && s + 3 <= hi && s >= 0) ntests++;
+        for (int32_t s = gb, ci = 0; s + 3 <= ge; s += 3, ++ci) {
+            if (!(s >= lo && s + 3 <= hi && s >= 0)) continue;
+            const uint32_t *h = codon + (size_t)s * 64;
+            uint64_t n = 0;
+            for (int c = 0; c < 64; ++c) n += h[c];
+            if (n == 0) continue;
+            int ref = -1;
+            if (refseq) {
+                int b0 = base_code(refseq[s]), b1 = base_code(refseq[s + 1]), b2 = base_code(refseq[s + 2]);
+                if (b0 >= 0 && b1 >= 0 && b2 >= 0) ref = 16 * b0 + 4 * b1 + b2;
+            }
+            if (ref < 0) { /* doc/JULIET.md:133-134 "otherwise it will be tested against the major codon" */
+                ref = 0;
+                for (int c = 1; c < 64; ++c) if (h[c] > h[ref]) ref = c;
+            }
+            for (int c = 0; c < 64; ++c) {
+                uint32_t k = h[c];
+                if (c == ref || k == 0) continue;
+                double P = mso_codon_error_prob(ref, c, prm->substitution_rate, prm->deletion_rate);
+                double ex = ceil((double)n * P);
+                uint32_t e = ex >= (double)n ? (uint32_t)n : (uint32_t)ex;
+                double p = mso_fisher_greater(k, (uint32_t)(n - k), e, (uint32_t)(n - e));
+                if (!(p * (double)ntests < prm->alpha)) continue;
+                double perc = 100.0 * (double)k / (double)n;
+                if (prm->min_perc >= 0 && !(perc > prm->min_perc)) continue;
+                if (prm->max_perc >= 0 && !(perc < prm->max_perc)) continue;
+                if (nout < cap) {
+                    mso_variant *v = &out[nout];
+                    v->gene = g; v->codon_index = ci; v->col = s; v->ref_codon = ref; v->codon = c;
+                    v->count = k; v->coverage = (uint32_t)n; v->expected = e; v->ntests = ntests;
+                    v->pvalue = p;
+                }
+                nout++;
+            }
+        }
+    }
+    qsort(out, (size_t)(nout < cap ? nout : cap), sizeof(mso_variant), cmp_variant);
+    return nout;
+}
+
+/* ---- a11: per-read variant presence and damage flags -------------------------
+ * doc/JULIET.md:194-203 (which variants co-occur on a read), :278-288 (a read
+ * with a deletion in any identified variant codon cannot be assigned), :372-381
+ * and screenshot juliet_haplotype-tooltip.png (marginals: gaps, heteroduplexes
+ * = 'N' codons, partial = read does not span every variant codon). */
+void mso_phase_bits(const uint8_t *states, int64_t R, int32_t L,
+                    const int32_t *var_col, const int32_t *var_codon, int32_t V,
+                    uint32_t *bits, uint8_t *flags)
+{
+    int32_t nw = (V + 31) / 32;
+    for (int64_t r = 0; r < R; ++r) {
+        const uint8_t *s = states + (size_t)r * L;
+        uint32_t *bw = bits + (size_t)r * nw;
+        uint8_t f = 0;
+        for (int32_t w = 0; w < nw; ++w) bw[w] = 0;
+        for (int32_t v = 0; v < V; ++v) {
+            int32_t j = var_col[v];
+            int st[3];
+            for (int i = 0; i < 3; ++i) st[i] = (j + i < L) ? (s[j + i] & 7) : MSO_UNCOV;
+            int clean = 1;
+            for (int i = 0; i < 3; ++i) {
+                if (st[i] == MSO_DEL) { f |= MSO_FLAG_GAP; clean = 0; }
+                else if (st[i] == MSO_N) { f |= MSO_FLAG_HET; clean = 0; }
+                else if (st[i] > 3) { f |= MSO_FLAG_PARTIAL; clean = 0; }
+            }
+            if (clean && 16 * st[0] + 4 * st[1] + st[2] == var_codon[v]) bw[v >> 5] |= 1u << (v & 31);
+        }
+        flags[r] = f;
+    }
+}
+
+/* ---- a12: haplotype grouping --------------------------------------------------
+ * doc/JULIET.md:198-211, :253-254 (>= 10 reads to report), :372-381 (reported /
+ * insufficient / unsuitable partition the reads).  Order: descending count
+ * (screenshot juliet_hiv-phasing.png 92.5, 1.2, 1.2, 1 ...), ties by ascending
+ * pattern words, word 0 first (restatement choice U12).                        */
+typedef struct { const uint32_t *bits; int32_t nw; } sort_ctx;
+static int cmp_read_pattern(const void *pa, const void *pb, void *vctx)
+{
+    const sort_ctx *ctx = vctx;
+    const uint32_t *a = ctx->bits + (size_t)(*(const int64_t *)pa) * ctx->nw;
+    const uint32_t *b = ctx->bits + (size_t)(*(const int64_t *)pb) * ctx->nw;
+    for (int32_t w = 0; w < ctx->nw; ++w)
+        if (a[w] != b[w]) return a[w] < b[w] ? -1 : 1;
+    return 0;
+}
+typedef struct { int64_t first, count; } grp;
+static int cmp_grp(const void *pa, const void *pb, void *vctx)
+{
+    const grp *a = pa, *b = pb;
+    if (a->count != b->count) return a->count > b->count ? -1 : 1;
+    return cmp_read_pattern(&a->first, &b->first, vctx);
+}
+
+int64_t mso_phase_group(const uint32_t *bits, const uint8_t *flags, int64_t R, int32_t V,
+                        int32_t min_reads, int32_t *hap_id, uint32_t *patterns, uint64_t *counts,
+                        int64_t cap, int64_t *nreported, mso_phase_counters *ctr)
+{
+    int32_t nw = (V + 31) / 32;
+    sort_ctx ctx = { bits, nw };
+    mso_phase_counters c = { 0, 0, 0, 0, 0, 0 };
+    int64_t *idx = malloc(sizeof(int64_t) * (size_t)(R > 0 ? R : 1));
+    int64_t n = 0;
+    for (int64_t r = 0; r < R; ++r) {
+        hap_id[r] = -1;
+        if (flags[r]) {
+            c.damaged++;
+            if (flags[r] & MSO_FLAG_GAP) c.gaps++;
+            if (flags[r] & MSO_FLAG_HET) c.heteroduplex++;
+            if (flags[r] & MSO_FLAG_PARTIAL) c.partial++;
+        } else idx[n++] = r;
+    }
+    qsort_r(idx, (size_t)n, sizeof(int64_t), cmp_read_pattern, &ctx);
+    grp *g = malloc(sizeof(grp) * (size_t)(n > 0 ? n : 1));
+    int64_t H = 0;
+    for (int64_t i = 0; i < n;) {
+        int64_t j = i + 1;
+        while (j < n && cmp_read_pattern(&idx[i], &idx[j], &ctx) == 0) ++j;
+        g[H].first = idx[i]; g[H].count = j - i; ++H;
+        i = j;
+    }
+    qsort_r(g, (size_t)H, sizeof(grp), cmp_grp, &ctx);
+    /* rank lookup: walk the sorted reads again */
+    int64_t nrep = 0;
+    for (int64_t h = 0; h < H; ++h) {
+        if (g[h].count >= min_reads) { nrep++; c.reported += (uint64_t)g[h].count; }
+        else c.insufficient += (uint64_t)g[h].count;
+        if (h < cap) {
+            memcpy(patterns + (size_t)h * nw, bits + (size_t)g[h].first * nw, sizeof(uint32_t) * (size_t)nw);
+            counts[h] = (uint64_t)g[h].count;
+        }
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        /* linear probe over groups is O(n*H); fine for an oracle, but use bsearch-free two-pointer:
+           groups are re-ordered, so map by comparing against each group's first read lazily */
+        hap_id[idx[i]] = -2;
+    }
+    for (int64_t h = 0; h < H; ++h) {
+        /* locate the group's run in idx via binary search on the pattern */
+        int64_t lo = 0, hi = n;
+        while (lo < hi) {
+            int64_t mid = (lo + hi) / 2;
+            if (cmp_read_pattern(&idx[mid], &g[h].first, &ctx) < 0) lo = mid + 1; else hi = mid;
+        }
+        for (int64_t i = lo; i < lo + g[h].count; ++i) hap_id[idx[i]] = (int32_t)h;
+    }
+    free(idx); free(g);
+    if (nreported) *nreported = nrep;
+    if (ctr) *ctr = c;
+    return H;
+}
+
+void mso_haplotype_name(int64_t i, char *buf)
+{
+    /* doc/JULIET.md:198 "[A-Z]{1}[a-z]?" */
+    if (i < 26) { buf[0] = (char)('A' + i); buf[1] = 0; return; }
+    i -= 26;
+    buf[0] = (char)('A' + (i / 26) % 26); buf[1] = (char)('a' + i % 26); buf[2] = 0;
+}
+
+/* ---- a13: co-occurrence (north_star addition; doc/JULIET.md:201 "variants that co-occur") */
+void mso_cooccurrence(const uint32_t *bits, int64_t R, int32_t V, int32_t *C)
+{
+    int32_t nw = (V + 31) / 32;
+    memset(C, 0, sizeof(int32_t) * (size_t)V * V);
+    int32_t *set = malloc(sizeof(int32_t) * (size_t)(V > 0 ? V : 1));
+    for (int64_t r = 0; r < R; ++r) {
+        const uint32_t *bw = bits + (size_t)r * nw;
+        int32_t ns = 0;
+        for (int32_t v = 0; v < V; ++v) if ((bw[v >> 5] >> (v & 31)) & 1) set[ns++] = v;
+        for (int32_t i = 0; i < ns; ++i)
+            for (int32_t j = 0; j < ns; ++j) C[(size_t)set[i] * V + set[j]]++;
+    }
+    free(set);
+}
+
+/* ---- a14 + a15: fuse consensus --------------------------------------------------
+ * doc/FUSE.md:17-20: "creation of a high-quality consensus sequence", "includes
+ * in-frame insertions with a certain distance to each other", "Major deletions
+ * are being removed".  Restatement choices: U6 majority over A,C,G,T,- with the
+ * lowest code winning ties and 'N' not voting; U8 columns with fewer than
+ * min_coverage voting reads emit nothing; U7 an inserted string after column j
+ * is accepted iff its length is a multiple of 3, its support exceeds
+ * ins_fraction * voting reads at j, and it is >= ins_distance columns past the
+ * previously accepted insertion (greedy, left to right).                       */
+typedef struct { int32_t col; int32_t len; const char *s; } ins_ev;
+static int cmp_ins(const void *pa, const void *pb)
+{
+    const ins_ev *a = pa, *b = pb;
+    if (a->col != b->col) return a->col < b->col ? -1 : 1;
+    if (a->len != b->len) return a->len < b->len ? -1 : 1;
+    int c = memcmp(a->s, b->s, (size_t)a->len);
+    return c < 0 ? -1 : (c > 0);
+}
+
+int64_t mso_fuse(const uint32_t *col, int32_t L, const int32_t *ins_col, const int64_t *ins_off,
+                 const int32_t *ins_len, int64_t nins, const char *ins_pool,
+                 const mso_fuse_params *prm, char *seq, int64_t cap)
+{
+    static const char base[4] = { 'A', 'C', 'G', 'T' };
+    ins_ev *ev = malloc(sizeof(ins_ev) * (size_t)(nins > 0 ? nins : 1));
+    for (int64_t i = 0; i < nins; ++i) {
+        ev[i].col = ins_col[i]; ev[i].len = ins_len[i]; ev[i].s = ins_pool + ins_off[i];
+    }
+    qsort(ev, (size_t)nins, sizeof(ins_ev), cmp_ins);
+    /* accepted insertion per column: index into ev or -1 */
+    int64_t *acc = malloc(sizeof(int64_t) * (size_t)L);
+    for (int32_t j = 0; j < L; ++j) acc[j] = -1;
+    int32_t last = -1;
+    for (int64_t i = 0; i < nins;) {
+        int64_t j = i + 1;
+        while (j < nins && cmp_ins(&ev[i], &ev[j]) == 0) ++j;
+        int32_t c = ev[i].col;
+        if (c >= 0 && c < L && acc[c] < 0 && ev[i].len > 0 && ev[i].len % 3 == 0) {
+            const uint32_t *h = col + (size_t)c * 8;
+            uint64_t votes = (uint64_t)h[0] + h[1] + h[2] + h[3] + h[4];
+            if ((double)(j - i) > prm->ins_fraction * (double)votes &&
+                (last < 0 || c - last >= prm->ins_distance)) {
+                acc[c] = i; last = c;
+            }
+        }
+        i = j;
+    }
+    int64_t n = 0;
+    for (int32_t j = 0; j < L; ++j) {
+        const uint32_t *h = col + (size_t)j * 8;
+        uint64_t votes = (uint64_t)h[0] + h[1] + h[2] + h[3] + h[4];
+        if (votes >= (uint64_t)prm->min_coverage && votes > 0) {
+            int best = 0;
+            for (int s = 1; s < 5; ++s) if (h[s] > h[best]) best = s;
+            if (best < 4) { if (n < cap) seq[n] = base[best]; n++; }
+        }
+        if (acc[j] >= 0)
+            for (int32_t k = 0; k < ev[acc[j]].len; ++k) { if (n < cap) seq[n] = ev[acc[j]].s[k]; n++; }
+    }
+    free(ev); free(acc);
+    return n;
+}
