@@ -79,6 +79,11 @@ int ms_set_stream(ms_handle *h, void *cuda_stream);
 int ms_synchronize(ms_handle *h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t ms_launch_count(const ms_handle *h);
+/* on: record CUDA events around each K1 launch on the handle's stream; ms_pileup_kernel_ms
+ * then returns the device time of the most recent K1 kernel and the reads it processed
+ * (bench.py's roofline.achieved).                                                     */
+int ms_set_timing(ms_handle *h, int on);
+int ms_pileup_kernel_ms(ms_handle *h, double *ms, int64_t *reads);
 
 /* ---- K1: pileup (juliet "MSA counts", doc/JULIET.md:96-100; fuse doc/FUSE.md:17-20) -- */
 /* Reference length and the columns where a codon of some configured gene starts

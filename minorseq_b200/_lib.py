@@ -54,6 +54,8 @@ _SIGNATURES = {
     "ms_set_stream": (C.c_int, [_P, _P]),
     "ms_synchronize": (C.c_int, [_P]),
     "ms_launch_count": (C.c_int64, [_P]),
+    "ms_set_timing": (C.c_int, [_P, C.c_int]),
+    "ms_pileup_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ms_set_layout": (C.c_int, [_P, C.c_int32, _P]),
     "ms_reset_counts": (C.c_int, [_P]),
     "ms_pileup_dev": (C.c_int, [_P, _P, C.c_int64]),

@@ -35,7 +35,8 @@ int ms_create(int device, ms_handle** out) {
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreate(&h->ev_k1[0]) != cudaSuccess || cudaEventCreate(&h->ev_k1[1]) != cudaSuccess) {
         g_create_error = cudaGetErrorString(cudaGetLastError());
         delete h;
         return MS_ERR_CUDA;
@@ -63,6 +64,7 @@ void ms_destroy(ms_handle* h) {
     ms_phase_free_internal(h);
     cudaFree(h->d_upload); cudaFree(h->d_call_buf); cudaFree(h->d_seq);
     cudaEventDestroy(h->ev_copy[0]); cudaEventDestroy(h->ev_copy[1]);
+    cudaEventDestroy(h->ev_k1[0]); cudaEventDestroy(h->ev_k1[1]);
     cudaStreamDestroy(h->own_stream); cudaStreamDestroy(h->copy_stream);
     delete h;
 }
@@ -83,6 +85,23 @@ int ms_synchronize(ms_handle* h) {
 }
 
 int64_t ms_launch_count(const ms_handle* h) { return h ? h->launches : 0; }
+
+int ms_set_timing(ms_handle* h, int on) {
+    if (!h) return MS_ERR_ARG;
+    h->timing = on != 0;
+    return MS_OK;
+}
+
+int ms_pileup_kernel_ms(ms_handle* h, double* ms, int64_t* reads) {
+    if (!h || !ms || !h->timing) return MS_ERR_ARG;
+    MS_CUDA(h, cudaSetDevice(h->device));
+    MS_CUDA(h, cudaEventSynchronize(h->ev_k1[1]));
+    float f = 0.f;
+    MS_CUDA(h, cudaEventElapsedTime(&f, h->ev_k1[0], h->ev_k1[1]));
+    *ms = f;
+    if (reads) *reads = h->k1_reads;
+    return MS_OK;
+}
 
 int ms_set_pileup_variant(ms_handle* h, int variant) {
     if (!h || variant < 0 || variant > 1) return MS_ERR_ARG;
@@ -171,7 +190,9 @@ int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     const int64_t ntiles = (R + T - 1) / T;
     const int grid = static_cast<int>(std::min<int64_t>(h->num_sms, ntiles));
     const int threads = (h->wpg * h->groups + 1) * 32;
+    if (h->timing) MS_CUDA(h, cudaEventRecord(h->ev_k1[0], h->stream));
     ms::pileup_csa_kernel<<<grid, threads, h->smem_bytes, h->stream>>>(a);
+    if (h->timing) { MS_CUDA(h, cudaEventRecord(h->ev_k1[1], h->stream)); h->k1_reads = R; }
     const int64_t nfin = static_cast<int64_t>(h->L) * 9;
     ms::pileup_finalize_kernel<<<static_cast<int>((nfin + 255) / 256), 256, 0, h->stream>>>(
         h->d_part_col, h->d_part_piv, grid * h->groups, h->nblk, h->L, h->d_pivot_state, h->d_start, col, codon,

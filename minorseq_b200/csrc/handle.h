@@ -12,6 +12,9 @@ struct ms_handle {
     int max_smem = 0;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr, stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    cudaEvent_t ev_k1[2] = {nullptr, nullptr};  // around the last K1 launch when timing is on
+    bool timing = false;
+    int64_t k1_reads = 0;
     std::string err;
     int64_t launches = 0;
 
