@@ -87,8 +87,11 @@ int ms_pileup_kernel_ms(ms_handle *h, double *ms, int64_t *reads);
 
 /* ---- K1: pileup (juliet "MSA counts", doc/JULIET.md:96-100; fuse doc/FUSE.md:17-20) -- */
 /* Reference length and the columns where a codon of some configured gene starts
- * (bit j of word j/32; NULL = count no codons, i.e. fuse).  Zeroes the counts.  */
+ * (bit j of word j/32; NULL = count no codons, i.e. fuse).  Zeroes the counts.
+ * With a start mask the insertion flags are not tallied (col[j][6] stays 0: juliet
+ * ignores insertions, doc/JULIET.md:26-27) unless ms_set_count_insertions(h, 1).  */
 int ms_set_layout(ms_handle *h, int32_t L, const uint32_t *start_mask);
+int ms_set_count_insertions(ms_handle *h, int on);
 int ms_reset_counts(ms_handle *h);
 /* Accumulate R device-resident packed reads into the handle's count tensor.     */
 int ms_pileup_dev(ms_handle *h, const uint32_t *d_packed, int64_t R);

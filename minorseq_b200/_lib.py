@@ -57,6 +57,7 @@ _SIGNATURES = {
     "ms_set_timing": (C.c_int, [_P, C.c_int]),
     "ms_pileup_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ms_set_layout": (C.c_int, [_P, C.c_int32, _P]),
+    "ms_set_count_insertions": (C.c_int, [_P, C.c_int]),
     "ms_reset_counts": (C.c_int, [_P]),
     "ms_pileup_dev": (C.c_int, [_P, _P, C.c_int64]),
     "ms_pileup_host": (C.c_int, [_P, _P, C.c_int64, C.POINTER(_P)]),

@@ -118,6 +118,10 @@ class Juliet:
     def reset(self):
         check(self.lib.ms_reset_counts(self.hd.h), self.hd.h)
 
+    def set_count_insertions(self, on: bool):
+        """juliet ignores insertions (doc/JULIET.md:26-27); turn the tally on to get col[:, 6] as well."""
+        check(self.lib.ms_set_count_insertions(self.hd.h, 1 if on else 0), self.hd.h)
+
     # -- K1
     def pileup_device(self, d_packed_ptr: int, nreads: int):
         check(self.lib.ms_pileup_dev(self.hd.h, C.c_void_p(d_packed_ptr), nreads), self.hd.h)
@@ -147,7 +151,7 @@ class Juliet:
         return col, codon
 
     # -- K2
-    def call(self, cap=1 << 16):
+    def call(self, cap=4096):
         genes = (Gene * len(self.genes))(*[Gene(b, e) for (b, e) in self.genes])
         out = (Variant * cap)()
         n = C.c_int64()

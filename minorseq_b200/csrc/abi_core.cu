@@ -42,7 +42,7 @@ int ms_create(int device, ms_handle** out) {
         return MS_ERR_CUDA;
     }
     h->stream = h->own_stream;
-    cudaFuncSetAttribute(ms::pileup_csa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+    ms::pileup_set_smem_attr(h->max_smem);
     *out = h;
     return MS_OK;
 }
@@ -63,6 +63,7 @@ void ms_destroy(ms_handle* h) {
     free_layout(h);
     ms_phase_free_internal(h);
     cudaFree(h->d_upload); cudaFree(h->d_call_buf); cudaFree(h->d_seq);
+    if (h->call_stage) cudaFreeHost(h->call_stage);
     cudaEventDestroy(h->ev_copy[0]); cudaEventDestroy(h->ev_copy[1]);
     cudaEventDestroy(h->ev_k1[0]); cudaEventDestroy(h->ev_k1[1]);
     cudaStreamDestroy(h->own_stream); cudaStreamDestroy(h->copy_stream);
@@ -103,6 +104,12 @@ int ms_pileup_kernel_ms(ms_handle* h, double* ms, int64_t* reads) {
     return MS_OK;
 }
 
+int ms_set_count_insertions(ms_handle* h, int on) {
+    if (!h) return MS_ERR_ARG;
+    h->count_ins = on != 0;
+    return MS_OK;
+}
+
 int ms_set_pileup_variant(ms_handle* h, int variant) {
     if (!h || variant < 0 || variant > 1) return MS_ERR_ARG;
     h->variant = variant;
@@ -118,15 +125,17 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
     MS_CUDA(h, cudaStreamSynchronize(h->stream));
     free_layout(h);
     h->L = L; h->nblk = nblk; h->count_codons = start_mask != nullptr; h->have_pivot = false;
-    // CTA shape: G row-groups of W warps, ~9 consumer warps + 1 producer
+    // CTA shape: G row-groups of W warps; W*G is a multiple of 4 where possible so that every
+    // SM sub-partition hosts the same number of consumer warps, plus 1 producer warp
+    static const int kGroups[11] = {0, 12, 6, 4, 3, 2, 2, 1, 1, 1, 1};
     h->wpg = W;
-    h->groups = std::max(1, 9 / W);
-    h->blocks8 = 1;
+    h->groups = kGroups[W];
     const int row_bytes = nblk * 16;
-    h->stage_bytes = h->groups * h->blocks8 * 8 * row_bytes;
+    h->stage_bytes = h->groups * 8 * row_bytes;
     const int budget = h->max_smem - 128 - 16;
-    h->stages = std::max(2, std::min(8, budget / h->stage_bytes));
-    h->smem_bytes = 128 + h->stages * h->stage_bytes + 16;
+    h->stages = std::max(3, std::min(8, budget / h->stage_bytes));
+    const int merge_bytes = (h->groups - 1) * 8 * ms::kPlanes * W * 32 * 4 + 64;  // end-of-kernel group merge reuses the ring
+    h->smem_bytes = 128 + std::max(h->stages * h->stage_bytes + 16, merge_bytes);
     if (h->smem_bytes > h->max_smem) MS_FAIL(h, MS_ERR_ARG, "row too long for the shared-memory ring");
     const size_t ncounts = static_cast<size_t>(L) * 72;
     MS_CUDA(h, cudaMalloc(&h->d_counts, ncounts * 4));
@@ -143,7 +152,7 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
         for (int32_t j = std::max(0, L - 2); j < nblk * 32; ++j) h->h_start[j >> 5] &= ~(1u << (j & 31));
     }
     MS_CUDA(h, cudaMemcpyAsync(h->d_start, h->h_start.data(), nblk * 4, cudaMemcpyHostToDevice, h->stream));
-    const size_t slices = static_cast<size_t>(h->num_sms) * h->groups;
+    const size_t slices = static_cast<size_t>(h->num_sms);
     MS_CUDA(h, cudaMalloc(&h->d_part_col, slices * nblk * 256 * 4));
     MS_CUDA(h, cudaMalloc(&h->d_part_piv, slices * nblk * 32 * 4));
     MS_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -181,21 +190,21 @@ int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     }
     ms::PileupArgs a;
     a.packed = d_packed; a.R = R; a.L = h->L; a.nblk = h->nblk;
-    a.warps_per_group = h->wpg; a.groups = h->groups; a.blocks8 = h->blocks8;
+    a.warps_per_group = h->wpg; a.groups = h->groups;
     a.stages = h->stages; a.stage_bytes = h->stage_bytes;
     a.pivot = h->d_pivot; a.start_mask = h->d_start; a.codon = codon;
     a.part_col = h->d_part_col; a.part_piv = h->d_part_piv;
-    a.count_codons = h->count_codons ? 1 : 0;
-    const int64_t T = static_cast<int64_t>(h->groups) * h->blocks8 * 8;
+    const int mode = !h->count_codons ? ms::kModeFuse : (h->count_ins ? ms::kModeBoth : ms::kModeJuliet);
+    const int64_t T = static_cast<int64_t>(h->groups) * 8;
     const int64_t ntiles = (R + T - 1) / T;
     const int grid = static_cast<int>(std::min<int64_t>(h->num_sms, ntiles));
-    const int threads = (h->wpg * h->groups + 1) * 32;
+    const int threads = h->wpg * h->groups * 32;
     if (h->timing) MS_CUDA(h, cudaEventRecord(h->ev_k1[0], h->stream));
-    ms::pileup_csa_kernel<<<grid, threads, h->smem_bytes, h->stream>>>(a);
+    ms::pileup_launch(mode, grid, threads, h->smem_bytes, h->stream, a);
     if (h->timing) { MS_CUDA(h, cudaEventRecord(h->ev_k1[1], h->stream)); h->k1_reads = R; }
-    const int64_t nfin = static_cast<int64_t>(h->L) * 9;
+    const int64_t nfin = static_cast<int64_t>(h->L) * 9 * 4;
     ms::pileup_finalize_kernel<<<static_cast<int>((nfin + 255) / 256), 256, 0, h->stream>>>(
-        h->d_part_col, h->d_part_piv, grid * h->groups, h->nblk, h->L, h->d_pivot_state, h->d_start, col, codon,
+        h->d_part_col, h->d_part_piv, grid, h->nblk, h->L, h->d_pivot_state, h->d_start, col, codon,
         h->count_codons ? 1 : 0);
     h->launches += 2;
     MS_CUDA(h, cudaGetLastError());

@@ -7,6 +7,7 @@
 // treated separately, overlaps allowed (:261-264); --region (:270-271);
 // --min-perc / --max-perc (:342-354).  SURVEY.md rows a6-a9; unpinned choices U1-U3, U6.
 #include <algorithm>
+#include <cstring>
 #include <vector>
 #include "fisher_core.h"
 #include "handle.h"
@@ -128,20 +129,37 @@ int ms_call(ms_handle* h, const ms_gene* genes, int32_t ngenes, const char* refs
     if (pos.empty()) return MS_OK;
     const size_t npos = pos.size();
     const size_t dev_cap = npos * 63;
-    const size_t need = npos * sizeof(ms::CallPos) + dev_cap * sizeof(ms_variant) + 64;
+    const size_t need = 64 + dev_cap * sizeof(ms_variant) + npos * sizeof(ms::CallPos);
     if (need > h->call_cap) {
         MS_CUDA(h, cudaStreamSynchronize(h->stream));
         cudaFree(h->d_call_buf);
         h->d_call_buf = nullptr; h->call_cap = 0;
         MS_CUDA(h, cudaMalloc(&h->d_call_buf, need));
         h->call_cap = need;
+        h->call_pos_cache.clear();
     }
     uint8_t* base = static_cast<uint8_t*>(h->d_call_buf);
     unsigned long long* d_n = reinterpret_cast<unsigned long long*>(base);
     ms_variant* d_out = reinterpret_cast<ms_variant*>(base + 64);
     ms::CallPos* d_pos = reinterpret_cast<ms::CallPos*>(base + 64 + dev_cap * sizeof(ms_variant));
+    // small pinned stage: position table up, [count | first variants] down, one copy each way
+    constexpr size_t kQuick = 1024;
+    const size_t stage_need = std::max(npos * sizeof(ms::CallPos), 64 + kQuick * sizeof(ms_variant));
+    if (stage_need > h->call_stage_cap) {
+        if (h->call_stage) cudaFreeHost(h->call_stage);
+        h->call_stage = nullptr; h->call_stage_cap = 0;
+        MS_CUDA(h, cudaMallocHost(&h->call_stage, stage_need + 4096));
+        h->call_stage_cap = stage_need + 4096;
+    }
+    const size_t pos_bytes = npos * sizeof(ms::CallPos);
+    const bool same_pos = h->call_pos_cache.size() == pos_bytes && memcmp(h->call_pos_cache.data(), pos.data(), pos_bytes) == 0;
     MS_CUDA(h, cudaMemsetAsync(d_n, 0, 8, h->stream));
-    MS_CUDA(h, cudaMemcpyAsync(d_pos, pos.data(), npos * sizeof(ms::CallPos), cudaMemcpyHostToDevice, h->stream));
+    if (!same_pos) {
+        memcpy(h->call_stage, pos.data(), pos_bytes);
+        MS_CUDA(h, cudaMemcpyAsync(d_pos, h->call_stage, pos_bytes, cudaMemcpyHostToDevice, h->stream));
+        MS_CUDA(h, cudaStreamSynchronize(h->stream));  // the stage is reused for the download below
+        h->call_pos_cache.assign(reinterpret_cast<const uint8_t*>(pos.data()), reinterpret_cast<const uint8_t*>(pos.data()) + pos_bytes);
+    }
     ms::CallConst cc;
     ms::codon_error_table(prm->substitution_rate, prm->deletion_rate, cc.P);
     cc.alpha = prm->alpha; cc.min_perc = prm->min_perc; cc.max_perc = prm->max_perc;
@@ -151,11 +169,15 @@ int ms_call(ms_handle* h, const ms_gene* genes, int32_t ngenes, const char* refs
                                                        static_cast<int32_t>(npos), cc, d_out, d_n, dev_cap);
     h->launches++;
     MS_CUDA(h, cudaGetLastError());
-    unsigned long long cnt = 0;
-    MS_CUDA(h, cudaMemcpyAsync(&cnt, d_n, 8, cudaMemcpyDeviceToHost, h->stream));
+    const size_t quick = std::min(kQuick, dev_cap);
+    MS_CUDA(h, cudaMemcpyAsync(h->call_stage, base, 64 + quick * sizeof(ms_variant), cudaMemcpyDeviceToHost, h->stream));
     MS_CUDA(h, cudaStreamSynchronize(h->stream));
+    unsigned long long cnt = 0;
+    memcpy(&cnt, h->call_stage, 8);
     std::vector<ms_variant> v(cnt);
-    if (cnt) {
+    if (cnt <= quick) {
+        if (cnt) memcpy(v.data(), static_cast<uint8_t*>(h->call_stage) + 64, cnt * sizeof(ms_variant));
+    } else {
         MS_CUDA(h, cudaMemcpyAsync(v.data(), d_out, cnt * sizeof(ms_variant), cudaMemcpyDeviceToHost, h->stream));
         MS_CUDA(h, cudaStreamSynchronize(h->stream));
     }

@@ -6,6 +6,22 @@
 #include <vector>
 #include "../../include/minorseq_b200.h"
 
+// grow-only device buffer: the hot path never pays cudaMalloc/cudaFree twice for the same size
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap && p) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        const size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
 struct ms_handle {
     int device = 0;
     int num_sms = 0;
@@ -21,13 +37,14 @@ struct ms_handle {
     // layout
     int32_t L = 0, nblk = 0;
     bool count_codons = false;
+    bool count_ins = false;  // with a codon layout, also tally insertion flags (kModeBoth)
     int variant = 0;
     uint32_t* d_counts = nullptr;  // [L*8 | L*64]
     uint32_t* d_start = nullptr;   // [nblk]
     uint2* d_pivot = nullptr;      // [nblk+1]
     uint8_t* d_pivot_state = nullptr;  // [nblk*32 + 2]
     uint32_t *d_part_col = nullptr, *d_part_piv = nullptr;
-    int32_t groups = 1, wpg = 1, blocks8 = 1, stages = 2, stage_bytes = 0, smem_bytes = 0;
+    int32_t groups = 1, wpg = 1, stages = 2, stage_bytes = 0, smem_bytes = 0;
     bool have_pivot = false;
     std::vector<uint32_t> h_start;
 
@@ -38,24 +55,21 @@ struct ms_handle {
     // call
     void* d_call_buf = nullptr;
     size_t call_cap = 0;
+    void* call_stage = nullptr;   // pinned
+    size_t call_stage_cap = 0;
+    std::vector<uint8_t> call_pos_cache;
 
-    // phasing
+    // phasing (all buffers grow-only, reused across ms_phase_begin calls)
     int32_t V = 0, vwords = 0;
     int64_t phase_cap = 0, phase_n = 0;
-    int32_t* d_var = nullptr;       // [V] {col, codon, ...} packed
-    int32_t* d_blocklist = nullptr; // distinct blocks touched by the variants
     int32_t nblocklist = 0;
-    uint32_t* d_bits = nullptr;
-    uint8_t* d_flags = nullptr;
-    uint64_t* d_hash = nullptr;     // per read
-    int32_t* d_slot = nullptr;      // per read -> table slot
-    uint64_t* d_tab_key = nullptr;  // open-addressing table
-    uint32_t* d_tab_cnt = nullptr;
-    int64_t* d_tab_rep = nullptr;
     int64_t tab_size = 0;
-    uint64_t* d_ctr = nullptr;      // damage counters + collision flag
-    int32_t* d_cooc = nullptr;
-    uint32_t* d_bits_t = nullptr;
+    bool table_valid = false;
+    int table_attempt = 0;
+    DevBuf b_var, b_blocklist, b_bits, b_flags, b_slot, b_tab_key, b_tab_cnt, b_tab_rep, b_ctr, b_groups, b_rank, b_hap,
+        b_pat, b_cooc, b_bits_t;
+    void* h_stage = nullptr;      // pinned host staging for small D2H reads
+    size_t h_stage_cap = 0;
 
     // fuse
     char* d_seq = nullptr;

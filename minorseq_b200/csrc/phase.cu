@@ -92,27 +92,124 @@ __global__ void __launch_bounds__(kPhaseWarps * 32) phase_bits_kernel(
     }
 }
 
+// V <= 32: no staging.  LPR lanes per read (power of two >= V), 32/LPR reads per warp pass; each
+// lane gathers the 16-byte block(s) of its own variant straight from global memory, four passes
+// in flight.  Lanes of one read that hit the same block coalesce into one sector.
+template <int LPR>
+__global__ void __launch_bounds__(256) phase_bits_sparse_kernel(const uint4* __restrict__ packed, int64_t R, int32_t nblk,
+                                                                const VarDev* __restrict__ vars, const int32_t* __restrict__ blocklist,
+                                                                int32_t V, uint32_t* __restrict__ bits, uint8_t* __restrict__ flags,
+                                                                unsigned long long* __restrict__ ctr) {
+    constexpr int RPW = 32 / LPR;   // reads per warp pass
+    constexpr int UNR = 4;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPR, vl = lane % LPR;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const bool has = vl < V;
+    VarDev vd = {0, 0, 0, -1};
+    int32_t blkA = 0, blkB = 0;
+    if (has) {
+        vd = vars[vl];
+        if (vd.codon >= 0) { blkA = blocklist[vd.slotA]; blkB = blocklist[vd.slotB]; }
+    }
+    const uint32_t submask = (LPR == 32 ? 0xffffffffu : ((1u << LPR) - 1u)) << (sub * LPR);
+    unsigned long long c_dam = 0, c_gap = 0, c_het = 0, c_par = 0;
+    for (int64_t base = warp * RPW * UNR; base < R; base += nwarps * RPW * UNR) {
+        uint4 a[UNR], b[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t r = base + u * RPW + sub;
+            a[u] = make_uint4(0, 0, 0, 0);
+            b[u] = a[u];
+            if (has && vd.codon >= 0 && r < R) {
+                const uint4* row = packed + static_cast<size_t>(r) * nblk;
+                a[u] = row[blkA];
+                b[u] = blkB == blkA ? a[u] : row[blkB];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t r = base + u * RPW + sub;
+            bool bit = false, gap = false, het = false, par = false;
+            if (has && r < R) {
+                if (vd.codon < 0) par = true;
+                else {
+                    const uint32_t b0 = __funnelshift_r(a[u].x, b[u].x, vd.shift) & 7u;
+                    const uint32_t b1 = __funnelshift_r(a[u].y, b[u].y, vd.shift) & 7u;
+                    const uint32_t z = __funnelshift_r(a[u].z, b[u].z, vd.shift) & 7u;
+                    gap = (z & ~b0 & ~b1) != 0;
+                    het = (z & b0 & ~b1) != 0;
+                    par = (z & b1) != 0;
+                    const uint32_t cod = ((b0 & 1u) << 4) | ((b1 & 1u) << 5) | ((b0 & 2u) << 1) | ((b1 & 2u) << 2) |
+                                         ((b0 & 4u) >> 2) | ((b1 & 4u) >> 1);
+                    bit = (z == 0u) && (cod == static_cast<uint32_t>(vd.codon));
+                }
+            }
+            const uint32_t wb = __ballot_sync(0xffffffffu, bit), wg = __ballot_sync(0xffffffffu, gap);
+            const uint32_t wh = __ballot_sync(0xffffffffu, het), wp = __ballot_sync(0xffffffffu, par);
+            if (vl == 0 && r < R) {
+                const uint32_t f = ((wg & submask) ? MS_FLAG_GAP : 0) | ((wh & submask) ? MS_FLAG_HET : 0) |
+                                   ((wp & submask) ? MS_FLAG_PARTIAL : 0);
+                bits[r] = (wb & submask) >> (sub * LPR);
+                flags[r] = static_cast<uint8_t>(f);
+                if (f) {
+                    ++c_dam;
+                    if (f & MS_FLAG_GAP) ++c_gap;
+                    if (f & MS_FLAG_HET) ++c_het;
+                    if (f & MS_FLAG_PARTIAL) ++c_par;
+                }
+            }
+        }
+    }
+    // warp totals -> one atomic per counter per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c_dam += __shfl_xor_sync(0xffffffffu, c_dam, o);
+        c_gap += __shfl_xor_sync(0xffffffffu, c_gap, o);
+        c_het += __shfl_xor_sync(0xffffffffu, c_het, o);
+        c_par += __shfl_xor_sync(0xffffffffu, c_par, o);
+    }
+    if (lane == 0 && c_dam) {
+        atomicAdd(ctr + 0, c_dam);
+        atomicAdd(ctr + 1, c_gap);
+        atomicAdd(ctr + 2, c_het);
+        atomicAdd(ctr + 3, c_par);
+    }
+}
+
 __device__ __forceinline__ uint64_t pattern_hash(const uint32_t* w, int32_t vwords, uint64_t seed) {
     uint64_t hsh = seed;
     for (int32_t i = 0; i < vwords; ++i) hsh = mix64d(hsh ^ (static_cast<uint64_t>(w[i]) + 0x9E3779B97F4A7C15ULL * (i + 1)));
     return hsh ? hsh : 1ULL;
 }
 
+// One thread per read; lanes of a warp that carry the same pattern elect a leader (lowest lane =
+// lowest read index) which alone touches the table: one CAS probe, one count add, one rep min.
 __global__ void phase_insert_kernel(const uint32_t* __restrict__ bits, const uint8_t* __restrict__ flags, int64_t R,
                                     int32_t vwords, uint64_t seed, unsigned long long* tab_key, uint32_t* tab_cnt,
                                     long long* tab_rep, int64_t mask, int32_t* __restrict__ slot) {
     const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    if (flags[r]) { slot[r] = -1; return; }
+    const int lane = threadIdx.x & 31;
+    const bool valid = r < R && flags[r] == 0;
+    if (r < R && !valid) slot[r] = -1;
+    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
     const uint64_t key = pattern_hash(bits + static_cast<size_t>(r) * vwords, vwords, seed);
-    int64_t idx = static_cast<int64_t>(key) & mask;
-    for (;;) {
-        const unsigned long long prev = atomicCAS(tab_key + idx, 0ULL, static_cast<unsigned long long>(key));
-        if (prev == 0ULL || prev == key) break;
-        idx = (idx + 1) & mask;
+    const uint32_t peers = __match_any_sync(vmask, static_cast<unsigned long long>(key));
+    const int leader = __ffs(peers) - 1;
+    int64_t idx = 0;
+    if (lane == leader) {
+        idx = static_cast<int64_t>(key) & mask;
+        for (;;) {
+            const unsigned long long prev = atomicCAS(tab_key + idx, 0ULL, static_cast<unsigned long long>(key));
+            if (prev == 0ULL || prev == key) break;
+            idx = (idx + 1) & mask;
+        }
+        atomicAdd(tab_cnt + idx, static_cast<uint32_t>(__popc(peers)));
+        atomicMin(tab_rep + idx, static_cast<long long>(r));
     }
-    atomicAdd(tab_cnt + idx, 1u);
-    atomicMin(tab_rep + idx, static_cast<long long>(r));
+    idx = __shfl_sync(peers, idx, leader);
     slot[r] = static_cast<int32_t>(idx);
 }
 
@@ -129,23 +226,19 @@ __global__ void phase_verify_kernel(const uint32_t* __restrict__ bits, int64_t R
         if (a[i] != b[i]) { atomicAdd(collision, 1ULL); return; }
 }
 
+// Distinct patterns out of the table: count + the representative's bit-vector, compacted.
 __global__ void phase_compact_kernel(const uint32_t* __restrict__ tab_cnt, const long long* __restrict__ tab_rep,
-                                     int64_t tab_size, unsigned long long* ngroups, int32_t* __restrict__ g_slot,
-                                     uint32_t* __restrict__ g_cnt, long long* __restrict__ g_rep, int64_t cap) {
+                                     int64_t tab_size, const uint32_t* __restrict__ bits, int32_t vwords,
+                                     unsigned long long* ngroups, uint32_t* __restrict__ g_cnt,
+                                     uint32_t* __restrict__ g_pat, int64_t cap) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= tab_size || tab_cnt[i] == 0) return;
     const unsigned long long k = atomicAdd(ngroups, 1ULL);
     if (static_cast<int64_t>(k) < cap) {
-        g_slot[k] = static_cast<int32_t>(i); g_cnt[k] = tab_cnt[i]; g_rep[k] = tab_rep[i];
+        g_cnt[k] = tab_cnt[i];
+        const uint32_t* src = bits + static_cast<size_t>(tab_rep[i]) * vwords;
+        for (int32_t w = 0; w < vwords; ++w) g_pat[k * vwords + w] = src[w];
     }
-}
-
-__global__ void phase_gather_kernel(const uint32_t* __restrict__ bits, const long long* __restrict__ g_rep, int64_t H,
-                                    int32_t vwords, uint32_t* __restrict__ out) {
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= H * vwords) return;
-    const int64_t g = i / vwords;
-    out[i] = bits[static_cast<size_t>(g_rep[g]) * vwords + (i - g * vwords)];
 }
 
 // rank lookup for ms_phase_assign: ordered pattern -> its slot in this rank's table
@@ -238,26 +331,66 @@ static inline bool pattern_less(const uint32_t* a, const uint32_t* b, int32_t nw
 
 }  // namespace ms
 
+namespace {
+
+constexpr int64_t kGroupCapInit = 4096;
+
+int ensure_stage(ms_handle* h, size_t bytes) {
+    if (bytes <= h->h_stage_cap) return MS_OK;
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    h->h_stage = nullptr; h->h_stage_cap = 0;
+    MS_CUDA(h, cudaMallocHost(&h->h_stage, bytes + bytes / 4 + 4096));
+    h->h_stage_cap = bytes + bytes / 4 + 4096;
+    return MS_OK;
+}
+
+uint64_t phase_seed(int attempt) { return 0x6d696e6f72736571ULL + 0x9E3779B97F4A7C15ULL * static_cast<uint64_t>(attempt); }
+
+// ctr layout (u64): [0] damaged [1] gaps [2] heteroduplex [3] partial [4] hash collisions [5] ngroups [6..7] spare
+unsigned long long* ctr_ptr(ms_handle* h) { return h->b_ctr.as<unsigned long long>(); }
+
+int build_table(ms_handle* h, int attempt) {
+    const int64_t R = h->phase_n;
+    MS_CUDA(h, cudaMemsetAsync(h->b_tab_key.p, 0, static_cast<size_t>(h->tab_size) * 8, h->stream));
+    MS_CUDA(h, cudaMemsetAsync(h->b_tab_cnt.p, 0, static_cast<size_t>(h->tab_size) * 4, h->stream));
+    MS_CUDA(h, cudaMemsetAsync(h->b_tab_rep.p, 0x7f, static_cast<size_t>(h->tab_size) * 8, h->stream));
+    MS_CUDA(h, cudaMemsetAsync(ctr_ptr(h) + 4, 0, 8, h->stream));
+    if (R > 0) {
+        const int grid = static_cast<int>((R + 255) / 256);
+        ms::phase_insert_kernel<<<grid, 256, 0, h->stream>>>(h->b_bits.as<uint32_t>(), h->b_flags.as<uint8_t>(), R, h->vwords,
+                                                             phase_seed(attempt), h->b_tab_key.as<unsigned long long>(),
+                                                             h->b_tab_cnt.as<uint32_t>(), h->b_tab_rep.as<long long>(),
+                                                             h->tab_size - 1, h->b_slot.as<int32_t>());
+        ms::phase_verify_kernel<<<grid, 256, 0, h->stream>>>(h->b_bits.as<uint32_t>(), R, h->vwords, h->b_tab_rep.as<long long>(),
+                                                             h->b_slot.as<int32_t>(), ctr_ptr(h) + 4);
+        h->launches += 2;
+    }
+    h->table_attempt = attempt;
+    MS_CUDA(h, cudaGetLastError());
+    return MS_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 void ms_phase_free_internal(ms_handle* h) {
-    cudaFree(h->d_var); cudaFree(h->d_blocklist); cudaFree(h->d_bits); cudaFree(h->d_flags); cudaFree(h->d_hash);
-    cudaFree(h->d_slot); cudaFree(h->d_tab_key); cudaFree(h->d_tab_cnt); cudaFree(h->d_tab_rep); cudaFree(h->d_ctr);
-    cudaFree(h->d_cooc); cudaFree(h->d_bits_t);
-    h->d_var = nullptr; h->d_blocklist = nullptr; h->d_bits = nullptr; h->d_flags = nullptr; h->d_hash = nullptr;
-    h->d_slot = nullptr; h->d_tab_key = nullptr; h->d_tab_cnt = nullptr; h->d_tab_rep = nullptr; h->d_ctr = nullptr;
-    h->d_cooc = nullptr; h->d_bits_t = nullptr;
-    h->phase_cap = h->phase_n = 0; h->V = 0; h->vwords = 0;
+    DevBuf* all[] = {&h->b_var, &h->b_blocklist, &h->b_bits, &h->b_flags, &h->b_slot, &h->b_tab_key, &h->b_tab_cnt, &h->b_tab_rep,
+                     &h->b_ctr, &h->b_groups, &h->b_rank, &h->b_hap, &h->b_pat, &h->b_cooc, &h->b_bits_t};
+    for (DevBuf* b : all) b->release();
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    h->h_stage = nullptr; h->h_stage_cap = 0;
+    h->phase_cap = h->phase_n = 0; h->V = 0; h->vwords = 0; h->table_valid = false;
 }
 
 int ms_phase_begin(ms_handle* h, const int32_t* var_col, const int32_t* var_codon, int32_t V, int64_t max_reads) {
     if (!h || h->L <= 0 || V < 0 || max_reads < 0 || (V > 0 && (!var_col || !var_codon))) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
-    MS_CUDA(h, cudaStreamSynchronize(h->stream));
-    ms_phase_free_internal(h);
     h->V = V;
     h->vwords = std::max(1, (V + 31) / 32);
     h->phase_cap = std::max<int64_t>(1, max_reads);
+    h->phase_n = 0;
+    h->table_valid = false;
     // distinct 32-column blocks the variants touch
     std::vector<int32_t> blocks;
     for (int32_t v = 0; v < V; ++v) {
@@ -278,113 +411,134 @@ int ms_phase_begin(ms_handle* h, const int32_t* var_col, const int32_t* var_codo
         } else { d.slotA = d.slotB = 0; d.shift = 0; d.codon = -1; }
         vd[v] = d;
     }
-    MS_CUDA(h, cudaMalloc(&h->d_var, vd.size() * sizeof(ms::VarDev)));
-    MS_CUDA(h, cudaMalloc(&h->d_blocklist, blocks.size() * 4));
-    MS_CUDA(h, cudaMemcpyAsync(h->d_var, vd.data(), vd.size() * sizeof(ms::VarDev), cudaMemcpyHostToDevice, h->stream));
-    MS_CUDA(h, cudaMemcpyAsync(h->d_blocklist, blocks.data(), blocks.size() * 4, cudaMemcpyHostToDevice, h->stream));
-    MS_CUDA(h, cudaMalloc(&h->d_bits, static_cast<size_t>(h->phase_cap) * h->vwords * 4));
-    MS_CUDA(h, cudaMalloc(&h->d_flags, static_cast<size_t>(h->phase_cap)));
-    MS_CUDA(h, cudaMalloc(&h->d_slot, static_cast<size_t>(h->phase_cap) * 4));
     int64_t ts = 1024;
     while (ts < 2 * h->phase_cap) ts <<= 1;
     h->tab_size = ts;
-    MS_CUDA(h, cudaMalloc(&h->d_tab_key, static_cast<size_t>(ts) * 8));
-    MS_CUDA(h, cudaMalloc(&h->d_tab_cnt, static_cast<size_t>(ts) * 4));
-    MS_CUDA(h, cudaMalloc(&h->d_tab_rep, static_cast<size_t>(ts) * 8));
-    MS_CUDA(h, cudaMalloc(&h->d_ctr, 8 * 8));
-    MS_CUDA(h, cudaMemsetAsync(h->d_ctr, 0, 8 * 8, h->stream));
-    MS_CUDA(h, cudaStreamSynchronize(h->stream));
+    // the previous pass may still be reading these buffers on the stream if they have to move
+    const bool grow = vd.size() * sizeof(ms::VarDev) > h->b_var.cap || blocks.size() * 4 > h->b_blocklist.cap ||
+                      static_cast<size_t>(h->phase_cap) * h->vwords * 4 > h->b_bits.cap || static_cast<size_t>(h->phase_cap) > h->b_flags.cap ||
+                      static_cast<size_t>(ts) * 8 > h->b_tab_key.cap || !h->b_ctr.p;
+    if (grow) MS_CUDA(h, cudaStreamSynchronize(h->stream));
+    MS_CUDA(h, h->b_var.ensure(vd.size() * sizeof(ms::VarDev)));
+    MS_CUDA(h, h->b_blocklist.ensure(blocks.size() * 4));
+    MS_CUDA(h, h->b_bits.ensure(static_cast<size_t>(h->phase_cap) * h->vwords * 4));
+    MS_CUDA(h, h->b_flags.ensure(static_cast<size_t>(h->phase_cap)));
+    MS_CUDA(h, h->b_slot.ensure(static_cast<size_t>(h->phase_cap) * 4));
+    MS_CUDA(h, h->b_tab_key.ensure(static_cast<size_t>(ts) * 8));
+    MS_CUDA(h, h->b_tab_cnt.ensure(static_cast<size_t>(ts) * 4));
+    MS_CUDA(h, h->b_tab_rep.ensure(static_cast<size_t>(ts) * 8));
+    MS_CUDA(h, h->b_ctr.ensure(64));
+    int rc = ensure_stage(h, 1 << 20);
+    if (rc != MS_OK) return rc;
+    // pageable -> device copies of the small tables go through the pinned stage to stay asynchronous
+    uint8_t* st = static_cast<uint8_t*>(h->h_stage);
+    MS_CUDA(h, cudaStreamSynchronize(h->stream));  // the stage may still be in flight from the previous pass
+    const size_t nb_var = vd.size() * sizeof(ms::VarDev), nb_blk = blocks.size() * 4;
+    if (nb_var + nb_blk <= h->h_stage_cap) {
+        memcpy(st, vd.data(), nb_var);
+        memcpy(st + nb_var, blocks.data(), nb_blk);
+        MS_CUDA(h, cudaMemcpyAsync(h->b_var.p, st, nb_var, cudaMemcpyHostToDevice, h->stream));
+        MS_CUDA(h, cudaMemcpyAsync(h->b_blocklist.p, st + nb_var, nb_blk, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        MS_CUDA(h, cudaMemcpy(h->b_var.p, vd.data(), nb_var, cudaMemcpyHostToDevice));
+        MS_CUDA(h, cudaMemcpy(h->b_blocklist.p, blocks.data(), nb_blk, cudaMemcpyHostToDevice));
+    }
+    MS_CUDA(h, cudaMemsetAsync(h->b_ctr.p, 0, 64, h->stream));
     return MS_OK;
 }
 
 int ms_phase_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
-    if (!h || !h->d_bits || R < 0 || (R > 0 && !d_packed)) return MS_ERR_ARG;
+    if (!h || !h->b_bits.p || R < 0 || (R > 0 && !d_packed)) return MS_ERR_ARG;
     if (h->phase_n + R > h->phase_cap) MS_FAIL(h, MS_ERR_CAPACITY, "more reads than ms_phase_begin(max_reads)");
     if (R == 0) return MS_OK;
     MS_CUDA(h, cudaSetDevice(h->device));
-    const size_t smem = static_cast<size_t>(ms::kPhaseWarps) * h->nblocklist * sizeof(uint4);
-    if (smem > 48 * 1024)
-        MS_CUDA(h, cudaFuncSetAttribute(ms::phase_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    const int64_t want = (R + ms::kPhaseWarps - 1) / ms::kPhaseWarps;
-    const int grid = static_cast<int>(std::min<int64_t>(want, static_cast<int64_t>(h->num_sms) * 8));
-    ms::phase_bits_kernel<<<grid, ms::kPhaseWarps * 32, smem, h->stream>>>(
-        reinterpret_cast<const uint4*>(d_packed), R, h->nblk, h->d_blocklist, h->nblocklist,
-        reinterpret_cast<const ms::VarDev*>(h->d_var), h->V, h->vwords,
-        h->d_bits + static_cast<size_t>(h->phase_n) * h->vwords, h->d_flags + h->phase_n,
-        reinterpret_cast<unsigned long long*>(h->d_ctr));
+    h->table_valid = false;
+    uint32_t* bits = h->b_bits.as<uint32_t>() + static_cast<size_t>(h->phase_n) * h->vwords;
+    uint8_t* flags = h->b_flags.as<uint8_t>() + h->phase_n;
+    const uint4* pk = reinterpret_cast<const uint4*>(d_packed);
+    const ms::VarDev* vars = h->b_var.as<ms::VarDev>();
+    unsigned long long* ctr = ctr_ptr(h);
+    if (h->V <= 32) {
+        int lpr = 1;
+        while (lpr < h->V) lpr <<= 1;
+        const int rpw = 32 / lpr;
+        const int64_t warps_needed = (R + rpw * 4 - 1) / (rpw * 4);
+        const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((warps_needed + 7) / 8, static_cast<int64_t>(h->num_sms) * 8)));
+#define MS_SPARSE(N) ms::phase_bits_sparse_kernel<N><<<grid, 256, 0, h->stream>>>(pk, R, h->nblk, vars, h->b_blocklist.as<int32_t>(), h->V, bits, flags, ctr)
+        switch (lpr) {
+        case 1: MS_SPARSE(1); break;
+        case 2: MS_SPARSE(2); break;
+        case 4: MS_SPARSE(4); break;
+        case 8: MS_SPARSE(8); break;
+        case 16: MS_SPARSE(16); break;
+        default: MS_SPARSE(32); break;
+        }
+#undef MS_SPARSE
+    } else {
+        const size_t smem = static_cast<size_t>(ms::kPhaseWarps) * h->nblocklist * sizeof(uint4);
+        if (smem > 48 * 1024)
+            MS_CUDA(h, cudaFuncSetAttribute(ms::phase_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        const int64_t want = (R + ms::kPhaseWarps - 1) / ms::kPhaseWarps;
+        const int grid = static_cast<int>(std::min<int64_t>(want, static_cast<int64_t>(h->num_sms) * 8));
+        ms::phase_bits_kernel<<<grid, ms::kPhaseWarps * 32, smem, h->stream>>>(pk, R, h->nblk, h->b_blocklist.as<int32_t>(), h->nblocklist,
+                                                                              vars, h->V, h->vwords, bits, flags, ctr);
+    }
     h->launches++;
     MS_CUDA(h, cudaGetLastError());
     h->phase_n += R;
     return MS_OK;
 }
 
-static uint64_t phase_seed(int attempt) { return 0x6d696e6f72736571ULL + 0x9E3779B97F4A7C15ULL * static_cast<uint64_t>(attempt); }
-
-// builds the table (re-hashing on a 64-bit collision); leaves h->d_tab_* valid
-static int phase_build_table(ms_handle* h, int* attempt_out) {
-    const int64_t R = h->phase_n;
-    unsigned long long* d_coll = reinterpret_cast<unsigned long long*>(h->d_ctr) + 4;
-    for (int attempt = 0; attempt < 4; ++attempt) {
-        MS_CUDA(h, cudaMemsetAsync(h->d_tab_key, 0, static_cast<size_t>(h->tab_size) * 8, h->stream));
-        MS_CUDA(h, cudaMemsetAsync(h->d_tab_cnt, 0, static_cast<size_t>(h->tab_size) * 4, h->stream));
-        MS_CUDA(h, cudaMemsetAsync(h->d_tab_rep, 0x7f, static_cast<size_t>(h->tab_size) * 8, h->stream));
-        MS_CUDA(h, cudaMemsetAsync(d_coll, 0, 8, h->stream));
-        if (R > 0) {
-            const int grid = static_cast<int>((R + 255) / 256);
-            ms::phase_insert_kernel<<<grid, 256, 0, h->stream>>>(h->d_bits, h->d_flags, R, h->vwords, phase_seed(attempt),
-                                                                 reinterpret_cast<unsigned long long*>(h->d_tab_key), h->d_tab_cnt,
-                                                                 reinterpret_cast<long long*>(h->d_tab_rep), h->tab_size - 1, h->d_slot);
-            ms::phase_verify_kernel<<<grid, 256, 0, h->stream>>>(h->d_bits, R, h->vwords, reinterpret_cast<long long*>(h->d_tab_rep),
-                                                                 h->d_slot, d_coll);
-            h->launches += 2;
-        }
-        unsigned long long coll = 0;
-        MS_CUDA(h, cudaMemcpyAsync(&coll, d_coll, 8, cudaMemcpyDeviceToHost, h->stream));
-        MS_CUDA(h, cudaStreamSynchronize(h->stream));
-        if (coll == 0) { *attempt_out = attempt; return MS_OK; }
-    }
-    MS_FAIL(h, MS_ERR_CUDA, "haplotype hash collided under four seeds");
-}
-
 int ms_phase_groups(ms_handle* h, uint32_t* patterns, uint64_t* counts, int64_t cap, int64_t* H, ms_phase_counters* ctr) {
-    if (!h || !h->d_bits || !H) return MS_ERR_ARG;
+    if (!h || !h->b_bits.p || !H) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
-    int attempt = 0;
-    int rc = phase_build_table(h, &attempt);
-    if (rc != MS_OK) return rc;
-    // compact
-    const int64_t maxg = std::max<int64_t>(1, h->phase_n);
-    int32_t* g_slot = nullptr; uint32_t* g_cnt = nullptr; long long* g_rep = nullptr; uint32_t* g_pat = nullptr;
-    unsigned long long* d_ng = reinterpret_cast<unsigned long long*>(h->d_ctr) + 5;
-    MS_CUDA(h, cudaMalloc(&g_slot, maxg * 4)); MS_CUDA(h, cudaMalloc(&g_cnt, maxg * 4)); MS_CUDA(h, cudaMalloc(&g_rep, maxg * 8));
-    MS_CUDA(h, cudaMemsetAsync(d_ng, 0, 8, h->stream));
-    ms::phase_compact_kernel<<<static_cast<int>((h->tab_size + 255) / 256), 256, 0, h->stream>>>(
-        h->d_tab_cnt, reinterpret_cast<long long*>(h->d_tab_rep), h->tab_size, d_ng, g_slot, g_cnt, g_rep, maxg);
-    h->launches++;
-    unsigned long long ng = 0;
-    uint64_t hc[4];
-    MS_CUDA(h, cudaMemcpyAsync(&ng, d_ng, 8, cudaMemcpyDeviceToHost, h->stream));
-    MS_CUDA(h, cudaMemcpyAsync(hc, h->d_ctr, 32, cudaMemcpyDeviceToHost, h->stream));
-    MS_CUDA(h, cudaStreamSynchronize(h->stream));
     const int32_t nw = h->vwords;
-    std::vector<uint32_t> pat(static_cast<size_t>(ng) * nw), cnt(ng);
-    if (ng) {
-        MS_CUDA(h, cudaMalloc(&g_pat, static_cast<size_t>(ng) * nw * 4));
-        const int64_t tot = static_cast<int64_t>(ng) * nw;
-        ms::phase_gather_kernel<<<static_cast<int>((tot + 255) / 256), 256, 0, h->stream>>>(h->d_bits, g_rep, static_cast<int64_t>(ng), nw, g_pat);
+    int64_t gcap = kGroupCapInit;
+    int attempt = h->table_valid ? h->table_attempt : 0;
+    std::vector<uint8_t> host;
+    unsigned long long ng = 0;
+    uint64_t hc[8];
+    for (;;) {
+        if (!h->table_valid) {
+            int rc = build_table(h, attempt);
+            if (rc != MS_OK) return rc;
+        }
+        const size_t payload = static_cast<size_t>(gcap) * 4 * (1 + nw);
+        MS_CUDA(h, h->b_groups.ensure(payload));
+        int rc = ensure_stage(h, 64 + payload);
+        if (rc != MS_OK) return rc;
+        uint32_t* g_cnt = h->b_groups.as<uint32_t>();
+        uint32_t* g_pat = g_cnt + gcap;
+        MS_CUDA(h, cudaMemsetAsync(ctr_ptr(h) + 5, 0, 8, h->stream));
+        ms::phase_compact_kernel<<<static_cast<int>((h->tab_size + 255) / 256), 256, 0, h->stream>>>(
+            h->b_tab_cnt.as<uint32_t>(), h->b_tab_rep.as<long long>(), h->tab_size, h->b_bits.as<uint32_t>(), nw, ctr_ptr(h) + 5,
+            g_cnt, g_pat, gcap);
         h->launches++;
-        MS_CUDA(h, cudaMemcpyAsync(pat.data(), g_pat, pat.size() * 4, cudaMemcpyDeviceToHost, h->stream));
-        MS_CUDA(h, cudaMemcpyAsync(cnt.data(), g_cnt, cnt.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+        uint8_t* st = static_cast<uint8_t*>(h->h_stage);
+        MS_CUDA(h, cudaMemcpyAsync(st, h->b_ctr.p, 64, cudaMemcpyDeviceToHost, h->stream));
+        MS_CUDA(h, cudaMemcpyAsync(st + 64, h->b_groups.p, payload, cudaMemcpyDeviceToHost, h->stream));
         MS_CUDA(h, cudaStreamSynchronize(h->stream));
+        memcpy(hc, st, 64);
+        if (hc[4] != 0) {  // 64-bit hash collision between different patterns: re-hash with another seed
+            if (++attempt >= 4) MS_FAIL(h, MS_ERR_CUDA, "haplotype hash collided under four seeds");
+            h->table_valid = false;
+            continue;
+        }
+        h->table_valid = true;
+        ng = hc[5];
+        if (static_cast<int64_t>(ng) > gcap) { gcap = static_cast<int64_t>(ng); continue; }
+        host.assign(st + 64, st + 64 + payload);
+        break;
     }
-    cudaFree(g_slot); cudaFree(g_cnt); cudaFree(g_rep); cudaFree(g_pat);
+    const uint32_t* cnt = reinterpret_cast<const uint32_t*>(host.data());
+    const uint32_t* pat = cnt + gcap;
     std::vector<int64_t> order(ng);
     std::iota(order.begin(), order.end(), 0);
     std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
-        return ms::pattern_less(pat.data() + static_cast<size_t>(a) * nw, pat.data() + static_cast<size_t>(b) * nw, nw);
+        return ms::pattern_less(pat + static_cast<size_t>(a) * nw, pat + static_cast<size_t>(b) * nw, nw);
     });
     for (int64_t i = 0; i < std::min<int64_t>(cap, static_cast<int64_t>(ng)); ++i) {
-        if (patterns) memcpy(patterns + static_cast<size_t>(i) * nw, pat.data() + static_cast<size_t>(order[i]) * nw, static_cast<size_t>(nw) * 4);
+        if (patterns) memcpy(patterns + static_cast<size_t>(i) * nw, pat + static_cast<size_t>(order[i]) * nw, static_cast<size_t>(nw) * 4);
         if (counts) counts[i] = cnt[order[i]];
     }
     *H = static_cast<int64_t>(ng);
@@ -433,63 +587,64 @@ void ms_haplotype_name(int64_t rank, char buf[3]) {
 }
 
 int ms_phase_assign(ms_handle* h, const uint32_t* ordered_patterns, int64_t H, int32_t* hap_id) {
-    if (!h || !h->d_bits || H < 0 || (H > 0 && !ordered_patterns) || !hap_id) return MS_ERR_ARG;
+    if (!h || !h->b_bits.p || H < 0 || (H > 0 && !ordered_patterns) || !hap_id) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
-    int attempt = 0;
-    int rc = phase_build_table(h, &attempt);
-    if (rc != MS_OK) return rc;
+    if (!h->table_valid) {
+        int64_t dummy = 0;
+        int rc = ms_phase_groups(h, nullptr, nullptr, 0, &dummy, nullptr);
+        if (rc != MS_OK) return rc;
+    }
     const int64_t R = h->phase_n;
     const int32_t nw = h->vwords;
-    int32_t *d_rank = nullptr, *d_hap = nullptr; uint32_t* d_pat = nullptr;
-    MS_CUDA(h, cudaMalloc(&d_rank, static_cast<size_t>(h->tab_size) * 4));
-    MS_CUDA(h, cudaMalloc(&d_hap, static_cast<size_t>(std::max<int64_t>(1, R)) * 4));
-    MS_CUDA(h, cudaMalloc(&d_pat, static_cast<size_t>(std::max<int64_t>(1, H)) * nw * 4));
-    MS_CUDA(h, cudaMemsetAsync(d_rank, 0xff, static_cast<size_t>(h->tab_size) * 4, h->stream));
+    MS_CUDA(h, h->b_rank.ensure(static_cast<size_t>(h->tab_size) * 4));
+    MS_CUDA(h, h->b_hap.ensure(static_cast<size_t>(std::max<int64_t>(1, R)) * 4));
+    MS_CUDA(h, h->b_pat.ensure(static_cast<size_t>(std::max<int64_t>(1, H)) * nw * 4));
+    MS_CUDA(h, cudaMemsetAsync(h->b_rank.p, 0xff, static_cast<size_t>(h->tab_size) * 4, h->stream));
     if (H > 0) {
-        MS_CUDA(h, cudaMemcpyAsync(d_pat, ordered_patterns, static_cast<size_t>(H) * nw * 4, cudaMemcpyHostToDevice, h->stream));
+        MS_CUDA(h, cudaMemcpyAsync(h->b_pat.p, ordered_patterns, static_cast<size_t>(H) * nw * 4, cudaMemcpyHostToDevice, h->stream));
         ms::phase_rank_kernel<<<static_cast<int>((H + 127) / 128), 128, 0, h->stream>>>(
-            d_pat, H, nw, phase_seed(attempt), reinterpret_cast<unsigned long long*>(h->d_tab_key),
-            reinterpret_cast<long long*>(h->d_tab_rep), h->tab_size - 1, h->d_bits, d_rank);
+            h->b_pat.as<uint32_t>(), H, nw, phase_seed(h->table_attempt), h->b_tab_key.as<unsigned long long>(),
+            h->b_tab_rep.as<long long>(), h->tab_size - 1, h->b_bits.as<uint32_t>(), h->b_rank.as<int32_t>());
         h->launches++;
     }
     if (R > 0) {
-        ms::phase_assign_kernel<<<static_cast<int>((R + 255) / 256), 256, 0, h->stream>>>(h->d_slot, d_rank, R, d_hap);
+        ms::phase_assign_kernel<<<static_cast<int>((R + 255) / 256), 256, 0, h->stream>>>(h->b_slot.as<int32_t>(), h->b_rank.as<int32_t>(), R,
+                                                                                         h->b_hap.as<int32_t>());
         h->launches++;
-        MS_CUDA(h, cudaMemcpyAsync(hap_id, d_hap, static_cast<size_t>(R) * 4, cudaMemcpyDeviceToHost, h->stream));
+        MS_CUDA(h, cudaMemcpyAsync(hap_id, h->b_hap.p, static_cast<size_t>(R) * 4, cudaMemcpyDeviceToHost, h->stream));
     }
     MS_CUDA(h, cudaStreamSynchronize(h->stream));
-    cudaFree(d_rank); cudaFree(d_hap); cudaFree(d_pat);
     MS_CUDA(h, cudaGetLastError());
     return MS_OK;
 }
 
 int ms_phase_device(ms_handle* h, uint32_t** d_bits, uint8_t** d_flags, int64_t* R) {
-    if (!h || !h->d_bits) return MS_ERR_ARG;
-    if (d_bits) *d_bits = h->d_bits;
-    if (d_flags) *d_flags = h->d_flags;
+    if (!h || !h->b_bits.p) return MS_ERR_ARG;
+    if (d_bits) *d_bits = h->b_bits.as<uint32_t>();
+    if (d_flags) *d_flags = h->b_flags.as<uint8_t>();
     if (R) *R = h->phase_n;
     return MS_OK;
 }
 
 int ms_cooccurrence(ms_handle* h, int32_t** d_C) {
-    if (!h || !h->d_bits || !d_C) return MS_ERR_ARG;
+    if (!h || !h->b_bits.p || !d_C) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
     const int32_t V = h->V, nw = h->vwords;
     const int64_t R = h->phase_n, rwords = std::max<int64_t>(1, (R + 31) / 32);
-    cudaFree(h->d_cooc); cudaFree(h->d_bits_t);
-    h->d_cooc = nullptr; h->d_bits_t = nullptr;
-    MS_CUDA(h, cudaMalloc(&h->d_cooc, std::max<size_t>(4, static_cast<size_t>(V) * V * 4)));
-    MS_CUDA(h, cudaMalloc(&h->d_bits_t, static_cast<size_t>(nw) * 32 * rwords * 4));
-    MS_CUDA(h, cudaMemsetAsync(h->d_cooc, 0, std::max<size_t>(4, static_cast<size_t>(V) * V * 4), h->stream));
+    const size_t cbytes = std::max<size_t>(4, static_cast<size_t>(V) * V * 4);
+    MS_CUDA(h, h->b_cooc.ensure(cbytes));
+    MS_CUDA(h, h->b_bits_t.ensure(static_cast<size_t>(nw) * 32 * rwords * 4));
+    MS_CUDA(h, cudaMemsetAsync(h->b_cooc.p, 0, cbytes, h->stream));
     if (V > 0) {
         const int64_t nwarps = rwords * nw;
-        ms::bits_transpose_kernel<<<static_cast<unsigned>((nwarps * 32 + 255) / 256), 256, 0, h->stream>>>(h->d_bits, R, nw, rwords, h->d_bits_t);
+        ms::bits_transpose_kernel<<<static_cast<unsigned>((nwarps * 32 + 255) / 256), 256, 0, h->stream>>>(h->b_bits.as<uint32_t>(), R, nw, rwords,
+                                                                                                         h->b_bits_t.as<uint32_t>());
         dim3 grid((V + ms::kCoTile - 1) / ms::kCoTile, (V + ms::kCoTile - 1) / ms::kCoTile);
-        ms::cooccurrence_kernel<<<grid, 256, 0, h->stream>>>(h->d_bits_t, V, rwords, h->d_cooc);
+        ms::cooccurrence_kernel<<<grid, 256, 0, h->stream>>>(h->b_bits_t.as<uint32_t>(), V, rwords, h->b_cooc.as<int32_t>());
         h->launches += 2;
     }
     MS_CUDA(h, cudaGetLastError());
-    *d_C = h->d_cooc;
+    *d_C = h->b_cooc.as<int32_t>();
     return MS_OK;
 }
 

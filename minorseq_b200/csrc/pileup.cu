@@ -16,17 +16,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
 }
 // bulk global->shared copy completing on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -40,19 +44,39 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void consumer_barrier(int nthreads) {
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
 
 // carry-save adder: (h,l) = a + b + c per bit position.  Two LOP3.
 __device__ __forceinline__ void csa(uint32_t& h, uint32_t& l, uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t u = a ^ b;
+    const uint32_t u = a ^ b;
     h = (a & b) | (u & c);
     l = u ^ c;
 }
+
+template <int MODE>
+struct Traits {
+    static constexpr int NM = MODE == kModeBoth ? 8 : 7;
+    static constexpr bool CODON = MODE != kModeFuse;
+    static constexpr bool INS = MODE != kModeJuliet;
+    static constexpr int iINS = 6;
+    static constexpr int iNP = MODE == kModeBoth ? 7 : 6;  // "not the pivot codon"
+};
 
 // ---------------------------------------------------------------- per-thread state
 template <int NM>
 struct Vert {
     uint32_t c[NM][kPlanes];  // vertical counters, plane k has weight 2^k
-    uint32_t p3[NM], p4[NM], p5[NM];  // pending carry-save inputs of weight 8, 16, 32
+    uint32_t p3[NM], p4[NM];  // pending carry-save inputs of weight 8 and 16
 };
 
 template <int NM>
@@ -60,7 +84,7 @@ __device__ __forceinline__ void ripple(Vert<NM>& v, int i, int level, uint32_t x
 #pragma unroll
     for (int k = 0; k < kPlanes; ++k) {
         if (k >= level) {
-            uint32_t t = v.c[i][k] & x;
+            const uint32_t t = v.c[i][k] & x;
             v.c[i][k] ^= x;
             x = t;
         }
@@ -75,11 +99,20 @@ struct CodonCtx {
     int32_t colbase;            // 32*blk
 };
 
-// Build the NM one-bit masks of one read for this thread's 32 columns.
-// m[0..2] raw state planes, m[3..5] pair ANDs, m[6] insertion flag,
-// m[7] = "codon starting here is not the clean pivot codon".
-template <bool CODON>
-__device__ __forceinline__ void read_masks(uint32_t addr, const CodonCtx& cx, uint32_t (&m)[kMasks]) {
+// "codon starting at column j is not the clean pivot codon" for all 32 j, and the clean ones among them
+__device__ __forceinline__ void codon_masks(const uint4& q, const uint4& n, const CodonCtx& cx, uint32_t& np, uint32_t& e) {
+    const uint32_t X = ((q.x ^ cx.r0) | q.z) | (q.y ^ cx.r1);  // column is not the clean pivot base
+    const uint32_t Xn = ((n.x ^ cx.r0n) | n.z) | (n.y ^ cx.r1n);
+    np = X | __funnelshift_r(X, Xn, 1) | __funnelshift_r(X, Xn, 2);
+    const uint32_t dirty = q.z | __funnelshift_r(q.z, n.z, 1) | __funnelshift_r(q.z, n.z, 2);
+    e = ~dirty & np & cx.start;  // clean codon that is not the pivot codon: rare
+}
+
+// Build the one-bit masks of one read for this thread's 32 columns.
+template <int MODE>
+__device__ __forceinline__ void read_masks(uint32_t addr, const CodonCtx& cx, uint32_t (&m)[Traits<MODE>::NM], uint32_t& pm,
+                                           uint32_t rdbit) {
+    using T = Traits<MODE>;
     const uint4 q = lds128(addr);
     m[0] = q.x;
     m[1] = q.y;
@@ -87,15 +120,26 @@ __device__ __forceinline__ void read_masks(uint32_t addr, const CodonCtx& cx, ui
     m[3] = q.x & q.y;
     m[4] = q.x & q.z;
     m[5] = q.y & q.z;
-    m[6] = q.w;
-    if (CODON) {
+    if (T::INS) m[T::iINS] = q.w;
+    if (T::CODON) {
         const uint4 n = lds128(addr + 16);  // look-ahead block (garbage past the row end is masked by `start`)
-        const uint32_t X = ((q.x ^ cx.r0) | q.z) | (q.y ^ cx.r1);     // column is not the clean pivot base
-        const uint32_t Xn = ((n.x ^ cx.r0n) | n.z) | (n.y ^ cx.r1n);
-        const uint32_t nm = X | __funnelshift_r(X, Xn, 1) | __funnelshift_r(X, Xn, 2);
-        m[7] = nm;
-        const uint32_t dirty = q.z | __funnelshift_r(q.z, n.z, 1) | __funnelshift_r(q.z, n.z, 2);
-        uint32_t e = ~dirty & nm & cx.start;  // clean codon that is not the pivot codon: rare
+        uint32_t np, e;
+        codon_masks(q, n, cx, np, e);
+        m[T::iNP] = np;
+        if (e) pm |= rdbit;
+    }
+}
+
+// Rare path: the reads flagged in pm carry clean non-pivot codons; re-read them from the stage
+// (still owned by this CTA) and add each codon to the global 64-bin histogram.
+__device__ __forceinline__ void codon_exceptions(uint32_t addr, uint32_t row_bytes, uint32_t pm, const CodonCtx& cx) {
+    while (pm) {
+        const int rd = __ffs(pm) - 1;
+        pm &= pm - 1;
+        const uint32_t a = addr + static_cast<uint32_t>(rd) * row_bytes;
+        const uint4 q = lds128(a), n = lds128(a + 16);
+        uint32_t np, e;
+        codon_masks(q, n, cx, np, e);
         while (e) {
             const int j = __ffs(e) - 1;
             e &= e - 1;
@@ -105,62 +149,49 @@ __device__ __forceinline__ void read_masks(uint32_t addr, const CodonCtx& cx, ui
                                  ((b0 & 4u) >> 2) | ((b1 & 4u) >> 1);
             atomicAdd(cx.codon + (static_cast<size_t>(cx.colbase + j) * 64 + cod), 1u);
         }
-    } else {
-        m[7] = 0;
     }
 }
 
-template <bool CODON>
+template <int MODE>
 __device__ __forceinline__ void block8(uint32_t addr, uint32_t row_bytes, const CodonCtx& cx,
-                                       Vert<kMasks>& v, uint32_t bi) {
-    constexpr int NM = CODON ? kMasks : kMasks - 1;
-    uint32_t m0[kMasks], m1[kMasks], twosA[kMasks], twosB[kMasks], foursA[kMasks], foursB[kMasks];
+                                       Vert<Traits<MODE>::NM>& v, uint32_t bi) {
+    constexpr int NM = Traits<MODE>::NM;
+    uint32_t m0[NM], m1[NM], twosA[NM], twosB[NM], foursA[NM], foursB[NM];
+    uint32_t pm = 0;
     // reads 0..3
-    read_masks<CODON>(addr, cx, m0);
-    read_masks<CODON>(addr + row_bytes, cx, m1);
+    read_masks<MODE>(addr, cx, m0, pm, 1u);
+    read_masks<MODE>(addr + row_bytes, cx, m1, pm, 2u);
 #pragma unroll
     for (int i = 0; i < NM; ++i) csa(twosA[i], v.c[i][0], v.c[i][0], m0[i], m1[i]);
-    read_masks<CODON>(addr + 2 * row_bytes, cx, m0);
-    read_masks<CODON>(addr + 3 * row_bytes, cx, m1);
+    read_masks<MODE>(addr + 2 * row_bytes, cx, m0, pm, 4u);
+    read_masks<MODE>(addr + 3 * row_bytes, cx, m1, pm, 8u);
 #pragma unroll
     for (int i = 0; i < NM; ++i) {
         csa(twosB[i], v.c[i][0], v.c[i][0], m0[i], m1[i]);
         csa(foursA[i], v.c[i][1], v.c[i][1], twosA[i], twosB[i]);
     }
     // reads 4..7
-    read_masks<CODON>(addr + 4 * row_bytes, cx, m0);
-    read_masks<CODON>(addr + 5 * row_bytes, cx, m1);
+    read_masks<MODE>(addr + 4 * row_bytes, cx, m0, pm, 16u);
+    read_masks<MODE>(addr + 5 * row_bytes, cx, m1, pm, 32u);
 #pragma unroll
     for (int i = 0; i < NM; ++i) csa(twosA[i], v.c[i][0], v.c[i][0], m0[i], m1[i]);
-    read_masks<CODON>(addr + 6 * row_bytes, cx, m0);
-    read_masks<CODON>(addr + 7 * row_bytes, cx, m1);
+    read_masks<MODE>(addr + 6 * row_bytes, cx, m0, pm, 64u);
+    read_masks<MODE>(addr + 7 * row_bytes, cx, m1, pm, 128u);
 #pragma unroll
     for (int i = 0; i < NM; ++i) {
         csa(twosB[i], v.c[i][0], v.c[i][0], m0[i], m1[i]);
         csa(foursB[i], v.c[i][1], v.c[i][1], twosA[i], twosB[i]);
-        uint32_t e8;
-        csa(e8, v.c[i][2], v.c[i][2], foursA[i], foursB[i]);
-        twosA[i] = e8;  // weight-8 carry out of this block
+        csa(twosA[i], v.c[i][2], v.c[i][2], foursA[i], foursB[i]);  // twosA now holds the weight-8 carry
     }
     // second level: combine the weight-8 words of successive blocks lazily (branches are CTA-uniform)
     if (bi & 1u) {
         if (bi & 2u) {
-            if (bi & 4u) {
 #pragma unroll
-                for (int i = 0; i < NM; ++i) {
-                    uint32_t x16, x32, x64;
-                    csa(x16, v.c[i][3], v.c[i][3], v.p3[i], twosA[i]);
-                    csa(x32, v.c[i][4], v.c[i][4], v.p4[i], x16);
-                    csa(x64, v.c[i][5], v.c[i][5], v.p5[i], x32);
-                    ripple(v, i, 6, x64);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < NM; ++i) {
-                    uint32_t x16;
-                    csa(x16, v.c[i][3], v.c[i][3], v.p3[i], twosA[i]);
-                    csa(v.p5[i], v.c[i][4], v.c[i][4], v.p4[i], x16);
-                }
+            for (int i = 0; i < NM; ++i) {
+                uint32_t x16, x32;
+                csa(x16, v.c[i][3], v.c[i][3], v.p3[i], twosA[i]);
+                csa(x32, v.c[i][4], v.c[i][4], v.p4[i], x16);
+                ripple(v, i, 5, x32);
             }
         } else {
 #pragma unroll
@@ -170,73 +201,128 @@ __device__ __forceinline__ void block8(uint32_t addr, uint32_t row_bytes, const 
 #pragma unroll
         for (int i = 0; i < NM; ++i) v.p3[i] = twosA[i];
     }
+    if (Traits<MODE>::CODON) {
+        if (pm) codon_exceptions(addr, row_bytes, pm, cx);
+    }
 }
 
-// Fold pendings, extract per-column counts, write (or add to) this thread's private slice.
-template <bool CODON>
-__device__ __forceinline__ void flush(Vert<kMasks>& v, uint32_t bi, uint32_t n, uint32_t start, uint32_t* pc,
-                                   uint32_t* pp, bool first) {
-    constexpr int NM = CODON ? kMasks : kMasks - 1;
+// ---------------------------------------------------------------- flush (cold path)
+// 16 words x 32 bits holding two 16x16 bit matrices side by side: after the call, word j has
+// bit k (low half) = old word k bit j, and bit 16+k (high half) = old word k bit 16+j.
+__device__ __forceinline__ void transpose16x2(uint32_t (&a)[16]) {
+#pragma unroll
+    for (int s = 8; s >= 1; s >>= 1) {
+        const uint32_t m = s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (k & s) continue;
+            const uint32_t t = ((a[k] >> s) ^ a[k + s]) & m;
+            a[k + s] ^= t;
+            a[k] ^= t << s;
+        }
+    }
+}
+
+// planes: this thread's counters (pendings already folded), [NM][kPlanes] in local memory.
+// Adds the other groups' planes from shared memory (bit-sliced ripple-carry), transposes to
+// per-column integers and stores / adds them into the CTA's slice.
+template <int MODE>
+__device__ __noinline__ void emit_slice(const uint32_t* planes, uint32_t merge_base, int other_groups, uint32_t group_stride,
+                                        uint32_t thread_stride, uint32_t n, uint32_t start, uint32_t* pc, uint32_t* pp,
+                                        bool add) {
+    using T = Traits<MODE>;
+    constexpr int NM = T::NM;
+    uint32_t tr[NM][16];
+#pragma unroll
+    for (int i = 0; i < NM; ++i) {
+        uint32_t acc[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[k] = k < kPlanes ? planes[i * kPlanes + k] : 0u;
+        for (int g = 0; g < other_groups; ++g) {
+            uint32_t carry = 0;
+            const uint32_t base = merge_base + static_cast<uint32_t>(g) * group_stride + static_cast<uint32_t>(i * kPlanes) * thread_stride;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t b = k < kPlanes ? lds32(base + static_cast<uint32_t>(k) * thread_stride) : 0u;
+                const uint32_t u = acc[k] ^ b;
+                const uint32_t nc = (acc[k] & b) | (u & carry);
+                acc[k] = u ^ carry;
+                carry = nc;
+            }
+        }
+        transpose16x2(acc);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) tr[i][k] = acc[k];
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int colj = j + 16 * half;
+            uint32_t s[NM];
+#pragma unroll
+            for (int i = 0; i < NM; ++i) s[i] = half ? (tr[i][j] >> 16) : (tr[i][j] & 0xffffu);
+            // states: A=000 C=001 G=010 T=011 -=100 N=101 U=111 ; s0=sum p0, s1=sum p1, s2=sum p2,
+            // s3=sum p0&p1, s4=sum p0&p2, s5=sum p1&p2
+            const uint32_t nU = s[5];
+            const uint32_t nN = s[4] - nU;
+            const uint32_t nT = s[3] - nU;
+            const uint32_t nD = s[2] - nN - nU;
+            const uint32_t nG = s[1] - nT - nU;
+            const uint32_t nC = s[0] - nT - nN - nU;
+            const uint32_t cov = n - nU;
+            const uint32_t nA = cov - (nC + nG + nT + nD + nN);
+            uint4 lo = make_uint4(nA, nC, nG, nT);
+            uint4 hi = make_uint4(nD, nN, T::INS ? s[T::iINS] : 0u, cov);
+            uint4* dst = reinterpret_cast<uint4*>(pc + colj * 8);
+            if (add) {
+                const uint4 x = dst[0], y = dst[1];
+                lo.x += x.x; lo.y += x.y; lo.z += x.z; lo.w += x.w;
+                hi.x += y.x; hi.y += y.y; hi.z += y.z; hi.w += y.w;
+            }
+            dst[0] = lo;
+            dst[1] = hi;
+            if (T::CODON) {
+                uint32_t piv = ((start >> colj) & 1u) ? n - s[T::iNP] : 0u;
+                if (add) piv += pp[colj];
+                pp[colj] = piv;
+            }
+        }
+    }
+}
+
+template <int NM>
+__device__ __forceinline__ void fold_pendings(Vert<NM>& v, uint32_t bi) {
 #pragma unroll
     for (int i = 0; i < NM; ++i) {
         if (bi & 1u) ripple(v, i, 3, v.p3[i]);
         if (bi & 2u) ripple(v, i, 4, v.p4[i]);
-        if (bi & 4u) ripple(v, i, 5, v.p5[i]);
-    }
-    for (int j = 0; j < 32; ++j) {
-        uint32_t s[kMasks];
-#pragma unroll
-        for (int i = 0; i < NM; ++i) {
-            uint32_t acc = 0;
-#pragma unroll
-            for (int k = 0; k < kPlanes; ++k) acc |= ((v.c[i][k] >> j) & 1u) << k;
-            s[i] = acc;
-        }
-        // states: A=000 C=001 G=010 T=011 -=100 N=101 U=111 ; s0=sum p0, s1=sum p1, s2=sum p2,
-        // s3=sum p0&p1, s4=sum p0&p2, s5=sum p1&p2
-        const uint32_t nU = s[5];
-        const uint32_t nN = s[4] - nU;
-        const uint32_t nT = s[3] - nU;
-        const uint32_t nD = s[2] - nN - nU;
-        const uint32_t nG = s[1] - nT - nU;
-        const uint32_t nC = s[0] - nT - nN - nU;
-        const uint32_t cov = n - nU;
-        const uint32_t nA = cov - (nC + nG + nT + nD + nN);
-        uint4 lo = make_uint4(nA, nC, nG, nT);
-        uint4 hi = make_uint4(nD, nN, s[6], cov);
-        uint4* dst = reinterpret_cast<uint4*>(pc + j * 8);
-        if (!first) {
-            const uint4 a = dst[0], b = dst[1];
-            lo.x += a.x; lo.y += a.y; lo.z += a.z; lo.w += a.w;
-            hi.x += b.x; hi.y += b.y; hi.z += b.z; hi.w += b.w;
-        }
-        dst[0] = lo;
-        dst[1] = hi;
-        if (CODON) {
-            uint32_t piv = ((start >> j) & 1u) ? n - s[7] : 0u;
-            if (!first) piv += pp[j];
-            pp[j] = piv;
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < kMasks; ++i) {
-#pragma unroll
-        for (int k = 0; k < kPlanes; ++k) v.c[i][k] = 0;
-        v.p3[i] = v.p4[i] = v.p5[i] = 0;
     }
 }
 
-template <bool CODON>
+template <int NM>
+__device__ __forceinline__ void clear(Vert<NM>& v) {
+#pragma unroll
+    for (int i = 0; i < NM; ++i) {
+#pragma unroll
+        for (int k = 0; k < kPlanes; ++k) v.c[i][k] = 0;
+        v.p3[i] = v.p4[i] = 0;
+    }
+}
+
+template <int MODE>
 __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
+    using T = Traits<MODE>;
+    constexpr int NM = T::NM;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int W = a.warps_per_group, G = a.groups, U = a.blocks8, S = a.stages;
-    const int ncw = W * G;
+    const int W = a.warps_per_group, G = a.groups, S = a.stages;
+    const int ncw = W * G;  // all warps are consumers; lane 0 of warp 0 also produces
     const uint32_t row_bytes = static_cast<uint32_t>(a.nblk) * 16u;
     const uint32_t bar0 = smem_u32(smem);          // full[s] at bar0+8s, empty[s] at bar0+8(S+s)
     const uint32_t data0 = bar0 + 128;             // stage s at data0 + s*stage_bytes
-    const int64_t T = static_cast<int64_t>(G) * U * 8;
-    const int64_t ntiles = (a.R + T - 1) / T;
+    const int64_t Tr = static_cast<int64_t>(G) * 8;  // reads per tile
+    const int64_t ntiles = (a.R + Tr - 1) / Tr;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -248,32 +334,10 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     }
     __syncthreads();
 
-    if (warp == ncw) {
-        // ---------------- producer: one lane streams tiles into the ring
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-                mbar_wait(bar0 + 8 * (S + stage), phase ^ 1u);
-                const int64_t r0 = t * T;
-                const int64_t valid = (a.R - r0 < T) ? (a.R - r0) : T;
-                const uint32_t full = bar0 + 8 * stage;
-                mbar_expect_tx(full, static_cast<uint32_t>(valid) * row_bytes);
-                const uint8_t* src = reinterpret_cast<const uint8_t*>(a.packed) + static_cast<size_t>(r0) * row_bytes;
-                const uint32_t dst = data0 + stage * static_cast<uint32_t>(a.stage_bytes);
-                for (int64_t off = 0; off < valid; off += 8) {
-                    const uint32_t nr = static_cast<uint32_t>((valid - off < 8) ? (valid - off) : 8);
-                    bulk_g2s(dst + static_cast<uint32_t>(off) * row_bytes, src + static_cast<size_t>(off) * row_bytes,
-                             nr * row_bytes, full);
-                }
-                if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1u; }
-            }
-        }
-        return;
-    }
-
-    // ---------------- consumers: group g of W warps walks its reads of every tile
+    // ---------------- consumers: group g of W warps walks its 8 reads of every tile
     const int group = warp / W;
-    int blk = (warp - group * W) * 32 + lane;
+    const int tig = (warp - group * W) * 32 + lane;  // thread in group
+    int blk = tig;
     const bool active = blk < a.nblk;
     if (!active) blk = 0;
 
@@ -282,66 +346,138 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     cx.colbase = blk * 32;
     cx.r0 = cx.r1 = cx.r0n = cx.r1n = 0;
     cx.start = 0;
-    if (CODON) {
+    if (T::CODON) {
         const uint2 p = a.pivot[blk], pn = a.pivot[blk + 1];
         cx.r0 = p.x; cx.r1 = p.y; cx.r0n = pn.x; cx.r1n = pn.y;
         cx.start = active ? a.start_mask[blk] : 0u;
     }
 
-    Vert<kMasks> v;
-#pragma unroll
-    for (int i = 0; i < kMasks; ++i) {
-#pragma unroll
-        for (int k = 0; k < kPlanes; ++k) v.c[i][k] = 0;
-        v.p3[i] = v.p4[i] = v.p5[i] = 0;
-    }
-    uint32_t bi = 0, n = 0;
-    bool first = true;
-    const size_t slice = static_cast<size_t>(blockIdx.x) * G + group;
-    uint32_t* pc = a.part_col + (slice * a.nblk + blk) * 256;
-    uint32_t* pp = a.part_piv + (slice * a.nblk + blk) * 32;
+    Vert<NM> v;
+    clear(v);
+    uint32_t bi = 0, n = 0, tiles_since_flush = 0;
+    bool mid = false;
+    uint32_t* pc = a.part_col + (static_cast<size_t>(blockIdx.x) * a.nblk + blk) * 256;
+    uint32_t* pp = a.part_piv + (static_cast<size_t>(blockIdx.x) * a.nblk + blk) * 32;
+    const int nct = ncw * 32;
+
+    // Tile producer: lane 0 of warp 0 keeps S-2 tiles in flight ahead of the one being consumed.
+    // Refilling the stage of tile k-2 (not k-1) means the wait on its "empty" barrier is almost
+    // always already satisfied, so the producing lane does not stall its own warp.
+    const bool producer = threadIdx.x == 0;
+    auto issue_tile = [&](int64_t k) {  // k = index among this CTA's tiles
+        const int64_t t = static_cast<int64_t>(blockIdx.x) + k * gridDim.x;
+        if (t >= ntiles) return;
+        const uint32_t st = static_cast<uint32_t>(k % S);
+        if (k >= S) {
+            const uint32_t ph = static_cast<uint32_t>((k / S) & 1);
+            while (!mbar_try_wait(bar0 + 8 * (S + st), ph ^ 1u)) {}
+        }
+        const int64_t r0 = t * Tr;
+        const int64_t valid = (a.R - r0 < Tr) ? (a.R - r0) : Tr;
+        const uint32_t full = bar0 + 8 * st;
+        mbar_expect_tx(full, static_cast<uint32_t>(valid) * row_bytes);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.packed) + static_cast<size_t>(r0) * row_bytes;
+        const uint32_t dst = data0 + st * static_cast<uint32_t>(a.stage_bytes);
+        for (int64_t off = 0; off < valid; off += 8) {
+            const uint32_t nr = static_cast<uint32_t>((valid - off < 8) ? (valid - off) : 8);
+            bulk_g2s(dst + static_cast<uint32_t>(off) * row_bytes, src + static_cast<size_t>(off) * row_bytes, nr * row_bytes, full);
+        }
+    };
+    if (producer)
+        for (int k = 0; k < S - 2; ++k) issue_tile(k);
 
     uint32_t stage = 0, phase = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        mbar_wait(bar0 + 8 * stage, phase);
-        const int64_t r0 = t * T;
-        const int valid = static_cast<int>((a.R - r0 < T) ? (a.R - r0) : T);
-        for (int ub = 0; ub < U; ++ub) {
-            const int first_read = (group * U + ub) * 8;
-            int nv = valid - first_read;
-            nv = nv < 0 ? 0 : (nv > 8 ? 8 : nv);
-            const uint32_t addr = data0 + stage * static_cast<uint32_t>(a.stage_bytes) +
-                                  static_cast<uint32_t>(first_read) * row_bytes + static_cast<uint32_t>(blk) * 16u;
-            if (nv == 8) {
-                block8<CODON>(addr, row_bytes, cx, v, bi);
-                ++bi;
-                n += 8;
-            } else {
-                for (int i = 0; i < nv; ++i) {
-                    uint32_t m[kMasks];
-                    read_masks<CODON>(addr + i * row_bytes, cx, m);
+    int64_t kt = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++kt) {
+        if (producer) issue_tile(kt + S - 2);
+        if (8u * (tiles_since_flush + 1u) > static_cast<uint32_t>(kMaxReadsPerFlush)) {
+            // counters would overflow: every group adds its integers into the slice, one group at a time
+            fold_pendings(v, bi);
+            uint32_t planes[NM * kPlanes];
 #pragma unroll
-                    for (int q = 0; q < kMasks; ++q) ripple(v, q, 0, m[q]);
-                    ++n;
-                }
+            for (int i = 0; i < NM; ++i)
+#pragma unroll
+                for (int k = 0; k < kPlanes; ++k) planes[i * kPlanes + k] = v.c[i][k];
+            for (int g = 0; g < G; ++g) {
+                if (g == group && active) emit_slice<MODE>(planes, 0u, 0, 0u, 0u, n, cx.start, pc, pp, mid || g > 0);
+                consumer_barrier(nct);
             }
-            if (n > static_cast<uint32_t>(kMaxReadsPerFlush - 8)) {
-                if (active) flush<CODON>(v, bi, n, cx.start, pc, pp, first);
-                first = false;
-                bi = 0;
-                n = 0;
+            clear(v);
+            bi = 0; n = 0; tiles_since_flush = 0; mid = true;
+        }
+        mbar_wait(bar0 + 8 * stage, phase);
+        const int64_t r0 = t * Tr;
+        const int valid = static_cast<int>((a.R - r0 < Tr) ? (a.R - r0) : Tr);
+        int nv = valid - group * 8;
+        nv = nv < 0 ? 0 : (nv > 8 ? 8 : nv);
+        const uint32_t addr = data0 + stage * static_cast<uint32_t>(a.stage_bytes) +
+                              static_cast<uint32_t>(group * 8) * row_bytes + static_cast<uint32_t>(blk) * 16u;
+        if (nv == 8) {
+            block8<MODE>(addr, row_bytes, cx, v, bi);
+            ++bi;
+            n += 8;
+        } else {
+            for (int i = 0; i < nv; ++i) {
+                uint32_t m[NM];
+                uint32_t pm = 0;
+                read_masks<MODE>(addr + i * row_bytes, cx, m, pm, 1u);
+#pragma unroll
+                for (int q = 0; q < NM; ++q) ripple(v, q, 0, m[q]);
+                if (T::CODON && pm) codon_exceptions(addr + i * row_bytes, row_bytes, 1u, cx);
+                ++n;
             }
         }
+        ++tiles_since_flush;
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + 8 * (S + stage));
         if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1u; }
     }
-    if (active) flush<CODON>(v, bi, n, cx.start, pc, pp, first);
+
+    // ---------------- final merge: groups 1..G-1 hand their planes to group 0 through shared memory
+    fold_pendings(v, bi);
+    // all tiles are consumed and every bulk copy has landed, so the stage ring is free to reuse
+    consumer_barrier(nct);
+    const uint32_t tg = static_cast<uint32_t>(W) * 32u;           // threads per group
+    const uint32_t thread_stride = tg * 4u;                       // bytes between planes
+    const uint32_t group_stride = static_cast<uint32_t>(NM * kPlanes) * thread_stride;
+    const uint32_t ncount0 = data0 + static_cast<uint32_t>(G - 1) * group_stride;  // n of groups 1..G-1
+    if (group > 0) {
+        const uint32_t base = data0 + static_cast<uint32_t>(group - 1) * group_stride + static_cast<uint32_t>(tig) * 4u;
+#pragma unroll
+        for (int i = 0; i < NM; ++i)
+#pragma unroll
+            for (int k = 0; k < kPlanes; ++k) sts32(base + static_cast<uint32_t>(i * kPlanes + k) * thread_stride, v.c[i][k]);
+        if (tig == 0) sts32(ncount0 + static_cast<uint32_t>(group - 1) * 4u, n);
+    }
+    consumer_barrier(nct);
+    if (group == 0 && active) {
+        uint32_t ntot = n;
+        for (int g = 1; g < G; ++g) ntot += lds32(ncount0 + static_cast<uint32_t>(g - 1) * 4u);
+        uint32_t planes[NM * kPlanes];
+#pragma unroll
+        for (int i = 0; i < NM; ++i)
+#pragma unroll
+            for (int k = 0; k < kPlanes; ++k) planes[i * kPlanes + k] = v.c[i][k];
+        emit_slice<MODE>(planes, data0 + static_cast<uint32_t>(tig) * 4u, G - 1, group_stride, thread_stride, ntot, cx.start,
+                         pc, pp, mid);
+    }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kPileupMaxThreads, 1) pileup_csa_kernel(PileupArgs a) {
-    if (a.count_codons) pileup_body<true>(a);
-    else pileup_body<false>(a);
+    pileup_body<MODE>(a);
+}
+
+void pileup_set_smem_attr(int max_smem) {
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeJuliet>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeFuse>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeBoth>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+}
+
+void pileup_launch(int mode, int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a) {
+    if (mode == kModeJuliet) pileup_csa_kernel<kModeJuliet><<<grid, threads, smem, s>>>(a);
+    else if (mode == kModeFuse) pileup_csa_kernel<kModeFuse><<<grid, threads, smem, s>>>(a);
+    else pileup_csa_kernel<kModeBoth><<<grid, threads, smem, s>>>(a);
 }
 
 // ---------------------------------------------------------------- pivot sampling
@@ -383,23 +519,33 @@ __global__ void pivot_sample_kernel(const uint32_t* packed, int64_t R, int32_t n
 }
 
 // ---------------------------------------------------------------- finalize
-// counts += sum over slices; pivot-codon bin of every start column += its bit-sliced count.
+// counts += sum over the CTAs' slices; pivot-codon bin of every start column += its bit-sliced count.
+// Four lanes share one output element and split the slices between them.
 __global__ void pileup_finalize_kernel(const uint32_t* part_col, const uint32_t* part_piv, int32_t slices,
                                        int32_t nblk, int32_t L, const uint8_t* pivot_state,
                                        const uint32_t* start_mask, uint32_t* col, uint32_t* codon,
                                        int32_t count_codons) {
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t gt = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t i = gt >> 2;
+    const int part = static_cast<int>(gt & 3);
     const int64_t ncol = static_cast<int64_t>(L) * 8;
     const size_t cstride = static_cast<size_t>(nblk) * 256, pstride = static_cast<size_t>(nblk) * 32;
-    if (i < ncol) {
-        uint32_t s = 0;
-        for (int k = 0; k < slices; ++k) s += part_col[k * cstride + i];
-        col[i] += s;
+    uint32_t s = 0;
+    bool is_col = i < ncol, is_piv = false;
+    int64_t j = 0;
+    if (is_col) {
+        for (int k = part; k < slices; k += 4) s += part_col[k * cstride + i];
     } else if (count_codons && i < ncol + L) {
-        const int64_t j = i - ncol;
-        if (j + 2 < L && ((start_mask[j >> 5] >> (j & 31)) & 1u)) {
-            uint32_t s = 0;
-            for (int k = 0; k < slices; ++k) s += part_piv[k * pstride + j];
+        j = i - ncol;
+        is_piv = j + 2 < L && ((start_mask[j >> 5] >> (j & 31)) & 1u);
+        if (is_piv)
+            for (int k = part; k < slices; k += 4) s += part_piv[k * pstride + j];
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (part == 0) {
+        if (is_col) col[i] += s;
+        else if (is_piv) {
             const uint32_t cod = 16u * pivot_state[j] + 4u * pivot_state[j + 1] + pivot_state[j + 2];
             codon[j * 64 + cod] += s;
         }
@@ -413,7 +559,7 @@ __global__ void pileup_finalize_kernel(const uint32_t* part_col, const uint32_t*
 __global__ void pileup_atomic_kernel(const uint32_t* packed, int64_t R, int32_t L, int32_t nblk,
                                      const uint32_t* start_mask, uint32_t* col, uint32_t* codon,
                                      int32_t count_codons) {
-    extern __shared__ uint32_t bins[];  // [32 columns][8] per warp-block... one block column per CTA.y
+    extern __shared__ uint32_t bins[];  // [32 columns][8] of this CTA's column block
     const int blk = blockIdx.y;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) bins[i] = 0;
     __syncthreads();

@@ -55,15 +55,20 @@ def c1():
     return t, st, pack_states(st)
 
 
-def check_pileup(oracle, hd, st, L, genes, variant=0):
+def check_pileup(oracle, hd, st, L, genes, variant=0, count_ins=False):
     packed = pack_states(st) if st.shape[0] else np.zeros((0, 4 * ((L + 31) // 32)), dtype=np.uint32)
     j = Juliet(L, genes, handle=hd)
+    j.set_count_insertions(count_ins)
     _lib.check(j.lib.ms_set_pileup_variant(hd.h, variant), hd.h)
     d = to_dev(packed) if st.shape[0] else None
     j.pileup_device(d.data_ptr() if d is not None else 0, st.shape[0])
     col, codon = j.get_counts()
     _lib.check(j.lib.ms_set_pileup_variant(hd.h, 0), hd.h)
     ocol, ocodon = oracle.pileup(st, mask_bytes(j.start_mask, L)) if st.shape[0] else (np.zeros((L, 8), np.uint32), np.zeros((L, 64), np.uint32))
+    if not count_ins and variant == 0:
+        ocol = ocol.copy()
+        ocol[:, 6] = 0          # juliet mode does not tally insertion flags (doc/JULIET.md:26-27)
+    j.set_count_insertions(False)
     assert np.array_equal(col, ocol), f"column counts differ at {np.argwhere(col != ocol)[:5]}"
     assert np.array_equal(codon, ocodon), f"codon counts differ at {np.argwhere(codon != ocodon)[:5]}"
     return j, d, col, codon
@@ -72,6 +77,11 @@ def check_pileup(oracle, hd, st, L, genes, variant=0):
 def test_pileup_c1(oracle, hd, c1):
     t, st, _ = c1
     check_pileup(oracle, hd, st, 3000, [(1, 3001)])
+
+
+def test_pileup_c1_with_insertion_tally(oracle, hd, c1):
+    t, st, _ = c1
+    check_pileup(oracle, hd, st, 3000, [(1, 3001), (2, 3001)], count_ins=True)
 
 
 def test_pileup_c1_atomic_variant(oracle, hd, c1):
@@ -125,6 +135,7 @@ def test_pileup_accumulates_batches_and_host_path(oracle, hd, c1):
     j.pileup_device(d.data_ptr() + 2000 * row * 4, 3000)
     col, codon = j.get_counts()
     ocol, ocodon = oracle.pileup(st, mask_bytes(j.start_mask, L))
+    ocol[:, 6] = 0
     assert np.array_equal(col, ocol) and np.array_equal(codon, ocodon)
     j.reset()
     pinned = torch.from_numpy(packed.view(np.int32)).pin_memory()
@@ -142,16 +153,17 @@ def test_synth_gpu_equals_numpy(hd):
 
 
 def test_pileup_counter_overflow_flush(oracle, hd):
-    """More than 4088 reads per row-group forces the mid-kernel flush of the 12-plane counters."""
+    """More than 2040 reads per row-group forces the mid-kernel flush of the 11-plane counters."""
     cfg = SynthConfig(L=96, seed=31, variants_per_minor=(1, 1), minor_fracs=(0.05,))
     t = make_tables(cfg)
-    R = 148 * 9 * 4088 + 12345
+    R = 148 * 12 * 2040 + 12345
     d = gpu_synth(hd, t, 0, R)
     j = Juliet(96, [(1, 97), (2, 97)], handle=hd)
     j.pileup_device(d.data_ptr(), R)
     col, codon = j.get_counts()
     st = oracle.unpack(d.cpu().numpy().view(np.uint32), 96)
     ocol, ocodon = oracle.pileup(st, mask_bytes(j.start_mask, 96), nthreads=8)
+    ocol[:, 6] = 0
     assert np.array_equal(col, ocol) and np.array_equal(codon, ocodon)
 
 
