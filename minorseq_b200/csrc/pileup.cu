@@ -76,7 +76,7 @@ struct Traits {
 template <int NM>
 struct Vert {
     uint32_t c[NM][kPlanes];  // vertical counters, plane k has weight 2^k
-    uint32_t p3[NM], p4[NM];  // pending carry-save inputs of weight 8 and 16
+    uint32_t p3[NM], p4[NM], p5[NM];  // pending carry-save inputs of weight 8, 16 and 32
 };
 
 template <int NM>
@@ -183,15 +183,25 @@ __device__ __forceinline__ void block8(uint32_t addr, uint32_t row_bytes, const 
         csa(foursB[i], v.c[i][1], v.c[i][1], twosA[i], twosB[i]);
         csa(twosA[i], v.c[i][2], v.c[i][2], foursA[i], foursB[i]);  // twosA now holds the weight-8 carry
     }
-    // second level: combine the weight-8 words of successive blocks lazily (branches are CTA-uniform)
+    // upper levels: combine the weight-8 words of successive blocks lazily (branches are CTA-uniform)
     if (bi & 1u) {
         if (bi & 2u) {
+            if (bi & 4u) {
 #pragma unroll
-            for (int i = 0; i < NM; ++i) {
-                uint32_t x16, x32;
-                csa(x16, v.c[i][3], v.c[i][3], v.p3[i], twosA[i]);
-                csa(x32, v.c[i][4], v.c[i][4], v.p4[i], x16);
-                ripple(v, i, 5, x32);
+                for (int i = 0; i < NM; ++i) {
+                    uint32_t x16, x32, x64;
+                    csa(x16, v.c[i][3], v.c[i][3], v.p3[i], twosA[i]);
+                    csa(x32, v.c[i][4], v.c[i][4], v.p4[i], x16);
+                    csa(x64, v.c[i][5], v.c[i][5], v.p5[i], x32);
+                    ripple(v, i, 6, x64);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NM; ++i) {
+                    uint32_t x16;
+                    csa(x16, v.c[i][3], v.c[i][3], v.p3[i], twosA[i]);
+                    csa(v.p5[i], v.c[i][4], v.c[i][4], v.p4[i], x16);
+                }
             }
         } else {
 #pragma unroll
@@ -297,6 +307,7 @@ __device__ __forceinline__ void fold_pendings(Vert<NM>& v, uint32_t bi) {
     for (int i = 0; i < NM; ++i) {
         if (bi & 1u) ripple(v, i, 3, v.p3[i]);
         if (bi & 2u) ripple(v, i, 4, v.p4[i]);
+        if (bi & 4u) ripple(v, i, 5, v.p5[i]);
     }
 }
 
@@ -306,7 +317,7 @@ __device__ __forceinline__ void clear(Vert<NM>& v) {
     for (int i = 0; i < NM; ++i) {
 #pragma unroll
         for (int k = 0; k < kPlanes; ++k) v.c[i][k] = 0;
-        v.p3[i] = v.p4[i] = 0;
+        v.p3[i] = v.p4[i] = v.p5[i] = 0;
     }
 }
 
@@ -319,7 +330,7 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     const int W = a.warps_per_group, G = a.groups, S = a.stages;
     const int ncw = W * G;  // all warps are consumers; lane 0 of warp 0 also produces
     const uint32_t row_bytes = static_cast<uint32_t>(a.nblk) * 16u;
-    const uint32_t bar0 = smem_u32(smem);          // full[s] at bar0+8s, empty[s] at bar0+8(S+s)
+    const uint32_t bar0 = smem_u32(smem);          // full[s] at bar0+8s, release counter of stage s at bar0+8S+4s
     const uint32_t data0 = bar0 + 128;             // stage s at data0 + s*stage_bytes
     const int64_t Tr = static_cast<int64_t>(G) * 8;  // reads per tile
     const int64_t ntiles = (a.R + Tr - 1) / Tr;
@@ -327,7 +338,7 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(bar0 + 8 * s, 1);
-            mbar_init(bar0 + 8 * (S + s), ncw);
+            sts32(bar0 + 8 * S + 4 * s, 0u);  // release counter of stage s
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -360,21 +371,17 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     uint32_t* pp = a.part_piv + (static_cast<size_t>(blockIdx.x) * a.nblk + blk) * 32;
     const int nct = ncw * 32;
 
-    // Tile producer: lane 0 of warp 0 keeps S-2 tiles in flight ahead of the one being consumed.
-    // Refilling the stage of tile k-2 (not k-1) means the wait on its "empty" barrier is almost
-    // always already satisfied, so the producing lane does not stall its own warp.
-    const bool producer = threadIdx.x == 0;
+    // Tile ring without a producer warp: the warp that arrives LAST at a stage's release counter
+    // knows the stage is free and refills it at once, so S-1 tiles stay in flight and nobody
+    // ever blocks on an "empty" barrier.
     auto issue_tile = [&](int64_t k) {  // k = index among this CTA's tiles
         const int64_t t = static_cast<int64_t>(blockIdx.x) + k * gridDim.x;
         if (t >= ntiles) return;
         const uint32_t st = static_cast<uint32_t>(k % S);
-        if (k >= S) {
-            const uint32_t ph = static_cast<uint32_t>((k / S) & 1);
-            while (!mbar_try_wait(bar0 + 8 * (S + st), ph ^ 1u)) {}
-        }
         const int64_t r0 = t * Tr;
         const int64_t valid = (a.R - r0 < Tr) ? (a.R - r0) : Tr;
         const uint32_t full = bar0 + 8 * st;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads of the stage before the async write
         mbar_expect_tx(full, static_cast<uint32_t>(valid) * row_bytes);
         const uint8_t* src = reinterpret_cast<const uint8_t*>(a.packed) + static_cast<size_t>(r0) * row_bytes;
         const uint32_t dst = data0 + st * static_cast<uint32_t>(a.stage_bytes);
@@ -383,13 +390,12 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
             bulk_g2s(dst + static_cast<uint32_t>(off) * row_bytes, src + static_cast<size_t>(off) * row_bytes, nr * row_bytes, full);
         }
     };
-    if (producer)
-        for (int k = 0; k < S - 2; ++k) issue_tile(k);
+    if (threadIdx.x == 0)
+        for (int k = 0; k < S; ++k) issue_tile(k);
 
     uint32_t stage = 0, phase = 0;
     int64_t kt = 0;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++kt) {
-        if (producer) issue_tile(kt + S - 2);
         if (8u * (tiles_since_flush + 1u) > static_cast<uint32_t>(kMaxReadsPerFlush)) {
             // counters would overflow: every group adds its integers into the slice, one group at a time
             fold_pendings(v, bi);
@@ -429,7 +435,17 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         }
         ++tiles_since_flush;
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar0 + 8 * (S + stage));
+        if (lane == 0) {
+            __threadfence_block();
+            const uint32_t cnt_addr = bar0 + 8 * S + 4 * stage;
+            uint32_t old;
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt_addr) : "memory");
+            if (old == static_cast<uint32_t>(ncw - 1)) {  // last warp out refills the stage
+                __threadfence_block();
+                sts32(cnt_addr, 0u);
+                issue_tile(kt + S);
+            }
+        }
         if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1u; }
     }
 
