@@ -44,6 +44,7 @@ class SynthParams(C.Structure):
 _P = C.c_void_p
 _SIGNATURES = {
     "ms_row_words": (C.c_int32, [C.c_int32]),
+    "ms_read_admitted": (C.c_int, [C.c_uint32]),
     "ms_pack_states": (C.c_int, [_P, C.c_int64, C.c_int32, _P]),
     "ms_unpack_states": (C.c_int, [_P, C.c_int64, C.c_int32, _P]),
     "ms_expand_cigar": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_char_p, _P, C.c_int32, C.c_int32, _P, _P, _P, _P,

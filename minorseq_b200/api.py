@@ -150,6 +150,16 @@ class Juliet:
         check(self.lib.ms_get_counts(self.hd.h, _ptr(col), _ptr(codon)), self.hd.h)
         return col, codon
 
+    def context(self, col_counts: np.ndarray, col: int):
+        """The 9-row MSA context juliet shows under a variant (rows -3..+5 around the codon's first
+        column; doc/JULIET.md:99-100, screenshot juliet_hiv-context.png): list of (rel, A, C, G, T, -, N)."""
+        rows = []
+        for rel in range(-3, 6):
+            j = col + rel
+            if 0 <= j < self.L:
+                rows.append((rel,) + tuple(int(x) for x in col_counts[j, :6]))
+        return rows
+
     # -- K2
     def call(self, cap=4096):
         genes = (Gene * len(self.genes))(*[Gene(b, e) for (b, e) in self.genes])

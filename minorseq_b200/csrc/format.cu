@@ -10,6 +10,10 @@ extern "C" {
 
 int32_t ms_row_words(int32_t L) { return L > 0 ? 4 * ((L + 31) / 32) : 0; }
 
+// "Reads that are not primary or supplementary alignments, get ignored" (doc/JULIET.md:58):
+// drop unmapped (0x4) and secondary (0x100) records; supplementary (0x800) stays.
+int ms_read_admitted(uint32_t bam_flag) { return (bam_flag & (0x4u | 0x100u)) == 0 ? 1 : 0; }
+
 int ms_pack_states(const uint8_t* states, int64_t R, int32_t L, uint32_t* packed) {
     if (!states || !packed || R < 0 || L <= 0) return MS_ERR_ARG;
     const int32_t nblk = (L + 31) / 32;

@@ -21,9 +21,13 @@
  * The product stores a read as ceil(L/32) blocks of four u32 bit-planes
  * (include/minorseq_b200.h): plane p of block b is word 4*b+p, bit j is column
  * 32*b+j; planes 0..2 are the state bits, plane 3 the insertion flag.        */
-void mso_unpack_planar(const uint32_t *packed, int64_t R, int32_t L, uint8_t *states)
+void mso_unpack_planar_mt(const uint32_t *packed, int64_t R, int32_t L, uint8_t *states, int nthreads)
 {
     int32_t nblk = (L + 31) / 32;
+    (void)nthreads;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads > 1 ? nthreads : 1) schedule(static)
+#endif
     for (int64_t r = 0; r < R; ++r) {
         const uint32_t *row = packed + (size_t)r * 4 * nblk;
         uint8_t *out = states + (size_t)r * L;
@@ -34,6 +38,11 @@ void mso_unpack_planar(const uint32_t *packed, int64_t R, int32_t L, uint8_t *st
                                (((w[2] >> sh) & 1) << 2) | (((w[3] >> sh) & 1) << 3));
         }
     }
+}
+
+void mso_unpack_planar(const uint32_t *packed, int64_t R, int32_t L, uint8_t *states)
+{
+    mso_unpack_planar_mt(packed, R, L, states, 1);
 }
 
 /* ---- a4 + a5: per-column and per-codon histograms --------------------------
@@ -231,7 +240,18 @@ void mso_phase_bits(const uint8_t *states, int64_t R, int32_t L,
                     const int32_t *var_col, const int32_t *var_codon, int32_t V,
                     uint32_t *bits, uint8_t *flags)
 {
+    mso_phase_bits_mt(states, R, L, var_col, var_codon, V, bits, flags, 1);
+}
+
+void mso_phase_bits_mt(const uint8_t *states, int64_t R, int32_t L,
+                       const int32_t *var_col, const int32_t *var_codon, int32_t V,
+                       uint32_t *bits, uint8_t *flags, int nthreads)
+{
     int32_t nw = (V + 31) / 32;
+    (void)nthreads;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads > 1 ? nthreads : 1) schedule(static)
+#endif
     for (int64_t r = 0; r < R; ++r) {
         const uint8_t *s = states + (size_t)r * L;
         uint32_t *bw = bits + (size_t)r * nw;

@@ -69,6 +69,7 @@ typedef struct {
 
 /* unpack the product's planar 4-bit rows (include/minorseq_b200.h) into one byte per column */
 void mso_unpack_planar(const uint32_t *packed, int64_t R, int32_t L, uint8_t *states);
+void mso_unpack_planar_mt(const uint32_t *packed, int64_t R, int32_t L, uint8_t *states, int nthreads);
 
 /* a4 + a5 of SURVEY section 8a.  start_mask[j]!=0 marks columns where a codon of some gene begins. */
 void mso_pileup(const uint8_t *states, int64_t R, int32_t L, const uint8_t *start_mask,
@@ -89,6 +90,9 @@ int64_t mso_call(const uint32_t *codon /* L*64 */, int32_t L,
 void mso_phase_bits(const uint8_t *states, int64_t R, int32_t L,
                     const int32_t *var_col, const int32_t *var_codon, int32_t V,
                     uint32_t *bits /* R*ceil(V/32) */, uint8_t *flags /* R */);
+void mso_phase_bits_mt(const uint8_t *states, int64_t R, int32_t L,
+                       const int32_t *var_col, const int32_t *var_codon, int32_t V,
+                       uint32_t *bits, uint8_t *flags, int nthreads);
 
 /* a12: groups undamaged reads by identical bit-vector.  hap_id[r] = rank of the read's
  * haplotype in the output order (count desc, then ascending words) or -1 damaged.

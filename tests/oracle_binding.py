@@ -60,8 +60,8 @@ class Oracle:
         L.mso_call.argtypes = [_P, C.c_int32, C.POINTER(Gene), C.c_int32, C.c_char_p, C.POINTER(CallParams),
                                C.POINTER(Variant), C.c_int64]
         L.mso_pileup.argtypes = [_P, C.c_int64, C.c_int32, _P, _P, _P, C.c_int]
-        L.mso_unpack_planar.argtypes = [_P, C.c_int64, C.c_int32, _P]
-        L.mso_phase_bits.argtypes = [_P, C.c_int64, C.c_int32, _P, _P, C.c_int32, _P, _P]
+        L.mso_unpack_planar_mt.argtypes = [_P, C.c_int64, C.c_int32, _P, C.c_int]
+        L.mso_phase_bits_mt.argtypes = [_P, C.c_int64, C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int]
         L.mso_phase_group.restype = C.c_int64
         L.mso_phase_group.argtypes = [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64,
                                       C.POINTER(C.c_int64), C.POINTER(PhaseCounters)]
@@ -70,10 +70,10 @@ class Oracle:
         L.mso_fuse.restype = C.c_int64
         L.mso_fuse.argtypes = [_P, C.c_int32, _P, _P, _P, C.c_int64, _P, C.POINTER(FuseParams), _P, C.c_int64]
 
-    def unpack(self, packed, L):
+    def unpack(self, packed, L, nthreads=1):
         R = packed.shape[0]
         out = np.empty((R, L), dtype=np.uint8)
-        self.lib.mso_unpack_planar(_p(np.ascontiguousarray(packed)), R, L, _p(out))
+        self.lib.mso_unpack_planar_mt(_p(np.ascontiguousarray(packed)), R, L, _p(out), nthreads)
         return out
 
     def pileup(self, states, start_mask_bytes=None, codons=True, nthreads=1):
@@ -98,7 +98,7 @@ class Oracle:
         assert n <= cap
         return [out[i] for i in range(n)]
 
-    def phase_bits(self, states, var_col, var_codon):
+    def phase_bits(self, states, var_col, var_codon, nthreads=1):
         R, L = states.shape
         V = len(var_col)
         nw = max(1, (V + 31) // 32)
@@ -108,7 +108,7 @@ class Oracle:
         vd = np.ascontiguousarray(var_codon, dtype=np.int32)
         if V == 0:
             bits[:] = 0
-        self.lib.mso_phase_bits(_p(np.ascontiguousarray(states)), R, L, _p(vc), _p(vd), V, _p(bits), _p(flags))
+        self.lib.mso_phase_bits_mt(_p(np.ascontiguousarray(states)), R, L, _p(vc), _p(vd), V, _p(bits), _p(flags), nthreads)
         if V == 0:
             bits = np.zeros((R, 1), dtype=np.uint32)
         return bits, flags

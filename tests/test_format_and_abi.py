@@ -55,6 +55,14 @@ def test_pack_roundtrip(mslib, oracle, L):
         assert ((last[:, 0] & hi) == hi).all() and ((last[:, 2] & hi) == hi).all() and ((last[:, 3] & hi) == 0).all()
 
 
+def test_read_admission_filter(mslib):
+    """doc/JULIET.md:58: only primary and supplementary alignments are used."""
+    assert mslib.ms_read_admitted(0) == 1 and mslib.ms_read_admitted(16) == 1      # primary fwd / rev
+    assert mslib.ms_read_admitted(0x800) == 1 and mslib.ms_read_admitted(0x810) == 1  # supplementary
+    assert mslib.ms_read_admitted(0x100) == 0 and mslib.ms_read_admitted(0x4) == 0    # secondary, unmapped
+    assert mslib.ms_read_admitted(0x904) == 0
+
+
 def test_pack_rejects_reserved_state(mslib):
     st = np.array([[6, 0, 1]], dtype=np.uint8)
     packed = np.zeros((1, 4), dtype=np.uint32)
