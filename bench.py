@@ -32,6 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "aligned CCS reads/sec pileup+call+phase"
+MIN_PERC = 0.5   # juliet --min-perc (doc/JULIET.md:342-344): keeps the called set (V = 13) independent of the total read count
 UNIT = "reads/s"
 
 
@@ -52,42 +53,46 @@ def parse():
 
 def workload_config(args):
     return {"workload": f"juliet --mode-phasing, synthetic HIV-like amplicon: {args.reads_per_gpu} CCS reads x {args.L} columns per GPU, "
-                        "4 strains (major + 10/5/1 % minors), one gene in frame 0, reference-guided calling",
-            "reads_per_gpu": args.reads_per_gpu, "L": args.L, "strains": 4, "seed": args.seed,
+                        "4 strains (major + 10/5/1 % minors), one gene in frame 0, reference-guided calling, --min-perc 0.5",
+            "reads_per_gpu": args.reads_per_gpu, "L": args.L, "strains": 4, "seed": args.seed, "min_perc": MIN_PERC,
             "l2_policy": "packed input per GPU (%.2f GB) is larger than the 126 MB L2" % (args.reads_per_gpu * ((args.L + 31) // 32) * 16 / 1e9),
             "parallelism": f"read-sharded x{args.gpus}, one NCCL all-reduce of the count tensor"}
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks + throttle reasons (B200_PROFILING.md).  The subprocess is started BEFORE CUDA / NCCL
+    are initialised (forking a process that already holds NCCL state can wedge later collectives) and keeps
+    sampling every 20 ms; finish(t0, t1) reports the samples that fall inside the timed window."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.rows = []
-        self.stop_flag = False
         self.proc = None
-
-    def run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def run(self):
+        if not self.proc:
+            return
+        try:
             for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
-                if self.stop_flag:
-                    break
+                self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
         except Exception:
             pass
 
-    def finish(self):
-        self.stop_flag = True
+    def finish(self, t0, t1):
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
+        inside = [r for (ts, r) in self.rows if t0 - 0.02 <= ts <= t1 + 0.02]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -97,7 +102,8 @@ class ClockSampler(threading.Thread):
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "window": "timed steps + e2e steps"}
 
 
 def measured_peak():
@@ -118,7 +124,7 @@ def cpu_pass(oracle, packed, L, genes, refseq, nthreads):
     t0 = time.perf_counter()
     st = oracle.unpack(packed, L, nthreads=nthreads)
     col, codon = oracle.pileup(st, mask, nthreads=nthreads)
-    v = oracle.call(codon, genes, refseq=refseq)
+    v = oracle.call(codon, genes, refseq=refseq, min_perc=MIN_PERC)
     keys = sorted({(x.col, x.codon) for x in v})
     bits, flags = oracle.phase_bits(st, [k[0] for k in keys], [k[1] for k in keys], nthreads=nthreads)
     oracle.phase_group(bits, flags, len(keys))
@@ -157,6 +163,9 @@ def run_reference(args, rank):
 
 def main():
     args = parse()
+    if os.environ.get("BENCH_WATCHDOG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG"]), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -164,6 +173,8 @@ def main():
         run_reference(args, rank)
         return
 
+    sampler = ClockSampler(local_rank)   # before CUDA / NCCL come up
+    sampler.start()
     import torch
     import torch.distributed as dist
     from minorseq_b200 import Juliet, _lib
@@ -179,9 +190,8 @@ def main():
     cfg = SynthConfig(L=L, seed=args.seed)
     t = make_tables(cfg)
     genes = [(1, L - L % 3 + 1)]
-    j = Juliet(L, genes, refseq=t.refseq, device=local_rank, mode_phasing=True)
+    j = Juliet(L, genes, refseq=t.refseq, device=local_rank, mode_phasing=True, min_perc=MIN_PERC)
     lib = j.lib
-    j.hd.use_torch_stream()
     nw = j.row_words
     d_packed = torch.empty((Rg, nw), dtype=torch.int32, device=f"cuda:{local_rank}")
     sp = SynthParams(t.cfg.seed, L, t.nstrains, t.thr_N, t.thr_sub, t.thr_ins20, t.thr_trunc16)
@@ -202,23 +212,20 @@ def main():
     for _ in range(max(3, args.warmup)):
         res = step()
     # ---- timed region: device-resident inputs
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
     k1_ms, launches0 = [], j.hd.launches
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    t_window0 = time.time()
+    _lib.check(lib.ms_timer_start(j.hd.h), j.hd.h)      # CUDA events on the stream the kernels are launched on
     for _ in range(args.steps):
         res = step()
         ms, rd = C.c_double(), C.c_int64()
         _lib.check(lib.ms_pileup_kernel_ms(j.hd.h, C.byref(ms), C.byref(rd)), j.hd.h)
         k1_ms.append(ms.value)
-    e1.record()
+    el = C.c_double()
+    _lib.check(lib.ms_timer_stop(j.hd.h, C.byref(el)), j.hd.h)
     barrier()
-    elapsed_ms = e0.elapsed_time(e1)
+    elapsed_ms = el.value
     launches = j.hd.launches - launches0
-    clocks = sampler.finish()
     tm = torch.tensor([elapsed_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -249,6 +256,8 @@ def main():
         e2e = {"value": world * Rg / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(world * Rg * nw * 4),
                "d2h_bytes_per_step": int(world * d2h), "ms_per_step": float(dt.item()) * 1e3, "steps": esteps}
         del host
+
+    clocks = sampler.finish(t_window0, time.time())
 
     # ---- roofline of the dominant kernel (K1)
     peak, peak_src = measured_peak()

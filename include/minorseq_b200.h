@@ -86,6 +86,10 @@ int64_t ms_launch_count(const ms_handle *h);
  * then returns the device time of the most recent K1 kernel and the reads it processed
  * (bench.py's roofline.achieved).                                                     */
 int ms_set_timing(ms_handle *h, int on);
+/* CUDA-event stopwatch on the handle's stream: start records an event, stop records a second one,
+ * waits for it and returns the device time between them in milliseconds.              */
+int ms_timer_start(ms_handle *h);
+int ms_timer_stop(ms_handle *h, double *ms);
 int ms_pileup_kernel_ms(ms_handle *h, double *ms, int64_t *reads);
 
 /* ---- K1: pileup (juliet "MSA counts", doc/JULIET.md:96-100; fuse doc/FUSE.md:17-20) -- */

@@ -56,6 +56,8 @@ _SIGNATURES = {
     "ms_synchronize": (C.c_int, [_P]),
     "ms_launch_count": (C.c_int64, [_P]),
     "ms_set_timing": (C.c_int, [_P, C.c_int]),
+    "ms_timer_start": (C.c_int, [_P]),
+    "ms_timer_stop": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "ms_pileup_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ms_set_layout": (C.c_int, [_P, C.c_int32, _P]),
     "ms_set_count_insertions": (C.c_int, [_P, C.c_int]),

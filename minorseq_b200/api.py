@@ -140,9 +140,17 @@ class Juliet:
         return _as_tensor(p.value, (n.value,), torch.int32, self.hd.device)
 
     def allreduce_counts(self):
+        """The path's one data-path collective: integer sum of the count tensor over the ranks.
+        The handle works on its own non-blocking stream, NCCL on torch's: the hand-over is two host
+        synchronisations (tens of microseconds), which keeps the legacy default stream and NCCL's
+        internal streams out of each other's way."""
+        import torch
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            check(self.lib.ms_synchronize(self.hd.h), self.hd.h)
             dist.all_reduce(self.counts_tensor(), op=dist.ReduceOp.SUM)
+            if dist.get_backend() == "nccl":
+                torch.cuda.current_stream(self.hd.device).synchronize()
 
     def get_counts(self):
         col = np.empty((self.L, 8), dtype=np.uint32)
@@ -221,8 +229,10 @@ class Juliet:
         p = C.c_void_p()
         check(self.lib.ms_cooccurrence(self.hd.h, C.byref(p)), self.hd.h)
         t = _as_tensor(p.value, (max(1, self._V * self._V),), torch.int32, self.hd.device)
+        check(self.lib.ms_synchronize(self.hd.h), self.hd.h)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            torch.cuda.current_stream(self.hd.device).synchronize()
         return t[: self._V * self._V].view(self._V, self._V)
 
     # -- the whole pass on device-resident reads (what bench.py times)
@@ -309,29 +319,42 @@ def _as_tensor(ptr, shape, dtype, device):
     return torch.as_tensor(hold, device=f"cuda:{device}")
 
 
+_GATHER_ROWS = 2048
+
+
 def _gather_groups(pat, cnt, marg, device):
-    """all-gather the ranks' (pattern, count) lists and sum the damage marginals."""
+    """all-gather the ranks' (pattern, count) lists in ONE collective: every rank contributes a fixed
+    block of _GATHER_ROWS rows whose row 0 is [n, damaged, gaps, heteroduplex, partial].  A rank with
+    more than _GATHER_ROWS distinct patterns (the dense phasing stress case) triggers a second,
+    exactly-sized exchange on all ranks.  The marginals are summed on the host."""
     import torch
     import torch.distributed as dist
     ws = dist.get_world_size()
     dev = f"cuda:{device}" if dist.get_backend() == "nccl" else "cpu"
-    n = torch.tensor([len(cnt)], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros_like(n) for _ in range(ws)]
-    dist.all_gather(sizes, n)
-    mx = max(1, int(max(s.item() for s in sizes)))
     nw = pat.shape[1]
-    buf = torch.zeros((mx, nw + 2), dtype=torch.int64, device=dev)
-    if len(cnt):
-        buf[: len(cnt), :nw] = torch.from_numpy(pat.astype(np.int64)).to(dev)
-        buf[: len(cnt), nw] = torch.from_numpy(cnt.astype(np.int64)).to(dev)
-    bufs = [torch.zeros_like(buf) for _ in range(ws)]
-    dist.all_gather(bufs, buf)
-    m = torch.from_numpy(marg).to(dev)
-    dist.all_reduce(m, op=dist.ReduceOp.SUM)
-    pats, cnts = [], []
-    for s, b in zip(sizes, bufs):
-        k = int(s.item())
-        b = b[:k].cpu().numpy()
-        pats.append(b[:, :nw].astype(np.uint32))
-        cnts.append(b[:, nw].astype(np.uint64))
-    return np.concatenate(pats, axis=0), np.concatenate(cnts), m.cpu().numpy()
+    cols = max(nw + 1, 5)
+
+    def exchange(rows):
+        host = np.zeros((rows + 1, cols), dtype=np.int64)
+        host[0, 0] = len(cnt)
+        host[0, 1:5] = marg
+        k = min(len(cnt), rows)
+        if k:
+            host[1: 1 + k, :nw] = pat[:k]
+            host[1: 1 + k, nw] = cnt[:k].astype(np.int64)
+        buf = torch.from_numpy(host).to(dev)
+        out = torch.empty((ws,) + tuple(buf.shape), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out, buf) if dev != "cpu" else dist.all_gather(list(out.unbind(0)), buf)
+        return out.cpu().numpy()
+
+    blocks = exchange(_GATHER_ROWS)
+    need = int(blocks[:, 0, 0].max())
+    if need > _GATHER_ROWS:
+        blocks = exchange(need)
+    pats, cnts, m = [], [], np.zeros(4, dtype=np.int64)
+    for b in blocks:
+        k = int(b[0, 0])
+        m += b[0, 1:5]
+        pats.append(b[1: 1 + k, :nw].astype(np.uint32))
+        cnts.append(b[1: 1 + k, nw].astype(np.uint64))
+    return np.concatenate(pats, axis=0), np.concatenate(cnts), m

@@ -36,7 +36,8 @@ int ms_create(int device, ms_handle** out) {
         cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreate(&h->ev_k1[0]) != cudaSuccess || cudaEventCreate(&h->ev_k1[1]) != cudaSuccess) {
+        cudaEventCreate(&h->ev_k1[0]) != cudaSuccess || cudaEventCreate(&h->ev_k1[1]) != cudaSuccess ||
+        cudaEventCreate(&h->ev_timer[0]) != cudaSuccess || cudaEventCreate(&h->ev_timer[1]) != cudaSuccess) {
         g_create_error = cudaGetErrorString(cudaGetLastError());
         delete h;
         return MS_ERR_CUDA;
@@ -66,6 +67,7 @@ void ms_destroy(ms_handle* h) {
     if (h->call_stage) cudaFreeHost(h->call_stage);
     cudaEventDestroy(h->ev_copy[0]); cudaEventDestroy(h->ev_copy[1]);
     cudaEventDestroy(h->ev_k1[0]); cudaEventDestroy(h->ev_k1[1]);
+    cudaEventDestroy(h->ev_timer[0]); cudaEventDestroy(h->ev_timer[1]);
     cudaStreamDestroy(h->own_stream); cudaStreamDestroy(h->copy_stream);
     delete h;
 }
@@ -86,6 +88,24 @@ int ms_synchronize(ms_handle* h) {
 }
 
 int64_t ms_launch_count(const ms_handle* h) { return h ? h->launches : 0; }
+
+int ms_timer_start(ms_handle* h) {
+    if (!h) return MS_ERR_ARG;
+    MS_CUDA(h, cudaSetDevice(h->device));
+    MS_CUDA(h, cudaEventRecord(h->ev_timer[0], h->stream));
+    return MS_OK;
+}
+
+int ms_timer_stop(ms_handle* h, double* ms) {
+    if (!h || !ms) return MS_ERR_ARG;
+    MS_CUDA(h, cudaSetDevice(h->device));
+    MS_CUDA(h, cudaEventRecord(h->ev_timer[1], h->stream));
+    MS_CUDA(h, cudaEventSynchronize(h->ev_timer[1]));
+    float f = 0.f;
+    MS_CUDA(h, cudaEventElapsedTime(&f, h->ev_timer[0], h->ev_timer[1]));
+    *ms = f;
+    return MS_OK;
+}
 
 int ms_set_timing(ms_handle* h, int on) {
     if (!h) return MS_ERR_ARG;

@@ -59,6 +59,9 @@ __global__ void call_kernel(const uint32_t* __restrict__ codon, const CallPos* _
         for (int i = 0; i < 3; ++i) nm += (((ref >> (2 * i)) & 3) != ((c >> (2 * i)) & 3)) ? 1 : 0;
         const double ex = ceil(static_cast<double>(n) * cc.P[nm]);
         const uint32_t e = ex >= static_cast<double>(n) ? n : static_cast<uint32_t>(ex);
+        // Both rows of [[k,n-k],[e,n-e]] sum to n, so X is symmetric about (k+e)/2 and k <= e implies
+        // p >= 1/2: such a codon can never be called when alpha <= ntests/2, skip the exact tail.
+        if (k <= e && 0.5 * static_cast<double>(ps.ntests) >= cc.alpha) continue;
         const double p = fisher_greater(k, n - k, e, n - e);
         if (!(p * static_cast<double>(ps.ntests) < cc.alpha)) continue;
         const double perc = 100.0 * static_cast<double>(k) / static_cast<double>(n);

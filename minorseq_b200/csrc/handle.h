@@ -29,6 +29,7 @@ struct ms_handle {
     cudaStream_t own_stream = nullptr, copy_stream = nullptr, stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     cudaEvent_t ev_k1[2] = {nullptr, nullptr};  // around the last K1 launch when timing is on
+    cudaEvent_t ev_timer[2] = {nullptr, nullptr};  // ms_timer_start / ms_timer_stop
     bool timing = false;
     int64_t k1_reads = 0;
     std::string err;

@@ -1,0 +1,75 @@
+"""Read-sharded 2-GPU run (NCCL) must reproduce the 1-GPU result bit for bit.
+Skipped on boxes with fewer than 2 GPUs; run with `gpurun --gpus 2`."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+L, R = 3000, 60000
+
+
+def _pass(device, read0, nreads, world_rank=None):
+    sys.path.insert(0, ROOT)
+    import ctypes as C
+    from minorseq_b200 import Juliet, _lib
+    from minorseq_b200._lib import SynthParams
+    from minorseq_b200.synth import SynthConfig, make_tables
+    t = make_tables(SynthConfig(L=L, seed=20240003, n_rate=2e-3))
+    j = Juliet(L, [(1, 3001), (2, 3000)], refseq=t.refseq, device=device, mode_phasing=True)
+    d = torch.empty((nreads, j.row_words), dtype=torch.int32, device=f"cuda:{device}")
+    sp = SynthParams(t.cfg.seed, L, t.nstrains, t.thr_N, t.thr_sub, t.thr_ins20, t.thr_trunc16)
+    _lib.check(j.lib.ms_synth_dev(j.hd.h, C.byref(sp), t.strain_base.ctypes.data_as(C.c_void_p), t.thr_del.ctypes.data_as(C.c_void_p),
+                                  t.strain_cum.ctypes.data_as(C.c_void_p), read0, nreads, C.c_void_p(d.data_ptr())), j.hd.h)
+    res = j.run_device(d.data_ptr(), nreads, want_hap_id=True)
+    col, codon = j.get_counts()
+    v = [(x.gene, x.col, x.codon, x.count, x.coverage, x.expected, x.ntests, x.pvalue) for x in res.variants]
+    h = res.haplotypes
+    return dict(col=col, codon=codon, variants=v, patterns=h.patterns, counts=h.counts, nreported=h.nreported,
+                counters=h.counters, hap_id=h.hap_id)
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        per = R // world
+        q.put((rank, _pass(rank, rank * per, per)))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_gpus_equal_one_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = dict(q.get(timeout=500) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    one = _pass(0, 0, R)
+    for r in range(world):
+        m = out[r]
+        assert np.array_equal(m["col"], one["col"]) and np.array_equal(m["codon"], one["codon"])   # all-reduced counts
+        assert m["variants"] == one["variants"]                                                   # replicated K2, bit-identical p
+        assert np.array_equal(m["patterns"], one["patterns"]) and np.array_equal(m["counts"], one["counts"])
+        assert m["nreported"] == one["nreported"] and m["counters"] == one["counters"]
+    hap = np.concatenate([out[r]["hap_id"] for r in range(world)])
+    assert np.array_equal(hap, one["hap_id"])
