@@ -192,6 +192,8 @@ def main():
     genes = [(1, L - L % 3 + 1)]
     j = Juliet(L, genes, refseq=t.refseq, device=local_rank, mode_phasing=True, min_perc=MIN_PERC)
     lib = j.lib
+    if world > 1:
+        j.hd.attach_comm()     # native ncclAllReduce / ncclAllGather on the handle's stream
     nw = j.row_words
     d_packed = torch.empty((Rg, nw), dtype=torch.int32, device=f"cuda:{local_rank}")
     sp = SynthParams(t.cfg.seed, L, t.nstrains, t.thr_N, t.thr_sub, t.thr_ins20, t.thr_trunc16)

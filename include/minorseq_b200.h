@@ -117,6 +117,18 @@ int ms_get_counts(ms_handle *h, uint32_t *col, uint32_t *codon);
  * 1 = shared-memory-atomic histogram kernel (kept only as the ncu A/B baseline). */
 int ms_set_pileup_variant(ms_handle *h, int variant);
 
+/* ---- cross-GPU exchange (one process per GPU) ---------------------------------
+ * Rank 0 creates the 128-byte NCCL unique id, the caller hands it to every rank over its own
+ * control channel, every rank attaches its handle.  world == 1 is a no-op.              */
+int ms_comm_unique_id(char id[128]);
+int ms_comm_init(ms_handle *h, const char id[128], int rank, int world);
+int ms_comm_size(const ms_handle *h);
+/* The path's one data-path collective: in-place integer sum of the count tensor over all
+ * ranks (ncclAllReduce, uint32, sum), enqueued on the handle's stream between K1 and K2.
+ * With a communicator attached, ms_phase_groups also all-gathers the ranks' compact
+ * (pattern, count) lists and returns the concatenation and the summed marginals.        */
+int ms_allreduce_counts(ms_handle *h);
+
 /* ---- K2: per-codon minor-variant test (doc/JULIET.md:38-42) --------------------- */
 typedef struct { int32_t begin, end; } ms_gene;   /* 1-based [begin,end), doc/JULIET.md:134-136 */
 typedef struct {

@@ -67,6 +67,10 @@ _SIGNATURES = {
     "ms_counts_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "ms_get_counts": (C.c_int, [_P, _P, _P]),
     "ms_set_pileup_variant": (C.c_int, [_P, C.c_int]),
+    "ms_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "ms_comm_init": (C.c_int, [_P, C.c_char_p, C.c_int, C.c_int]),
+    "ms_comm_size": (C.c_int, [_P]),
+    "ms_allreduce_counts": (C.c_int, [_P]),
     "ms_call_params_default": (None, [C.POINTER(CallParams)]),
     "ms_call": (C.c_int, [_P, C.POINTER(Gene), C.c_int32, C.c_char_p, C.POINTER(CallParams), C.POINTER(Variant),
                           C.c_int64, C.POINTER(C.c_int64)]),

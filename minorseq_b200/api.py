@@ -65,6 +65,7 @@ class Handle:
             raise _lib.MsError(f"ms_create failed ({rc}): {self.lib.ms_last_error(None).decode()}")
         self.h = h
         self.device = device
+        self.native_comm = False
 
     def close(self):
         if getattr(self, "h", None):
@@ -76,6 +77,27 @@ class Handle:
             self.close()
         except Exception:
             pass
+
+    def attach_comm(self):
+        """Give the handle its own NCCL communicator over the ranks of the initialised torch.distributed
+        group (torch only carries the 128-byte unique id).  After this the count all-reduce and the
+        haplotype-list all-gather run inside the library on the handle's stream."""
+        import torch
+        import torch.distributed as dist
+        self.native_comm = False
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1 or dist.get_backend() != "nccl":
+            return False
+        ident = C.create_string_buffer(128)
+        if dist.get_rank() == 0:
+            rc = self.lib.ms_comm_unique_id(ident)
+            if rc != 0:
+                raise _lib.MsError(f"ms_comm_unique_id failed ({rc})")
+        t = torch.frombuffer(bytearray(ident.raw), dtype=torch.uint8).to(f"cuda:{self.device}")
+        dist.broadcast(t, src=0)
+        ident = C.create_string_buffer(bytes(t.cpu().numpy().tobytes()), 128)
+        check(self.lib.ms_comm_init(self.h, ident, dist.get_rank(), dist.get_world_size()), self.h)
+        self.native_comm = True
+        return True
 
     def use_torch_stream(self):
         import torch
@@ -146,6 +168,9 @@ class Juliet:
         internal streams out of each other's way."""
         import torch
         import torch.distributed as dist
+        if getattr(self.hd, "native_comm", False):
+            check(self.lib.ms_allreduce_counts(self.hd.h), self.hd.h)   # ncclAllReduce on the handle's stream
+            return
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             check(self.lib.ms_synchronize(self.hd.h), self.hd.h)
             dist.all_reduce(self.counts_tensor(), op=dist.ReduceOp.SUM)
@@ -201,8 +226,8 @@ class Juliet:
             cap = int(H.value)
         pat, cnt = pat[:H.value], cnt[:H.value]
         marg = np.array([ctr.damaged, ctr.gaps, ctr.heteroduplex, ctr.partial], dtype=np.int64)
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            pat, cnt, marg = _gather_groups(pat, cnt, marg, self.hd.device)
+        if not getattr(self.hd, "native_comm", False) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            pat, cnt, marg = _gather_groups(pat, cnt, marg, self.hd.device)   # torch.distributed fallback (e.g. gloo)
         pat = np.ascontiguousarray(pat)
         cnt = np.ascontiguousarray(cnt)
         Hm, nrep, c2 = C.c_int64(), C.c_int64(), PhaseCounters()

@@ -56,11 +56,13 @@ static void free_layout(ms_handle* h) {
 }
 
 void ms_phase_free_internal(ms_handle* h);
+void ms_comm_free_internal(ms_handle* h);
 
 void ms_destroy(ms_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    ms_comm_free_internal(h);
     free_layout(h);
     ms_phase_free_internal(h);
     cudaFree(h->d_upload); cudaFree(h->d_call_buf); cudaFree(h->d_seq);

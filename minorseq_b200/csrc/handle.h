@@ -67,10 +67,14 @@ struct ms_handle {
     int64_t tab_size = 0;
     bool table_valid = false;
     int table_attempt = 0;
-    DevBuf b_var, b_blocklist, b_bits, b_flags, b_slot, b_tab_key, b_tab_cnt, b_tab_rep, b_ctr, b_groups, b_rank, b_hap,
+    DevBuf b_var, b_blocklist, b_bits, b_flags, b_slot, b_tab_key, b_tab_cnt, b_tab_rep, b_ctr, b_groups, b_gather, b_rank, b_hap,
         b_pat, b_cooc, b_bits_t;
     void* h_stage = nullptr;      // pinned host staging for small D2H reads
     size_t h_stage_cap = 0;
+
+    // cross-GPU exchange (comm.cu): ncclComm_t, NULL = single rank
+    void* comm = nullptr;
+    int world = 1, rank = 0;
 
     // fuse
     char* d_seq = nullptr;

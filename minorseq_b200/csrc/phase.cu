@@ -331,6 +331,8 @@ static inline bool pattern_less(const uint32_t* a, const uint32_t* b, int32_t nw
 
 }  // namespace ms
 
+int ms_comm_allgather_bytes(ms_handle* h, const void* d_send, void* d_recv, size_t bytes_per_rank);
+
 namespace {
 
 constexpr int64_t kGroupCapInit = 4096;
@@ -376,7 +378,7 @@ extern "C" {
 
 void ms_phase_free_internal(ms_handle* h) {
     DevBuf* all[] = {&h->b_var, &h->b_blocklist, &h->b_bits, &h->b_flags, &h->b_slot, &h->b_tab_key, &h->b_tab_cnt, &h->b_tab_rep,
-                     &h->b_ctr, &h->b_groups, &h->b_rank, &h->b_hap, &h->b_pat, &h->b_cooc, &h->b_bits_t};
+                     &h->b_ctr, &h->b_groups, &h->b_gather, &h->b_rank, &h->b_hap, &h->b_pat, &h->b_cooc, &h->b_bits_t};
     for (DevBuf* b : all) b->release();
     if (h->h_stage) cudaFreeHost(h->h_stage);
     h->h_stage = nullptr; h->h_stage_cap = 0;
@@ -493,58 +495,88 @@ int ms_phase_groups(ms_handle* h, uint32_t* patterns, uint64_t* counts, int64_t 
     if (!h || !h->b_bits.p || !H) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
     const int32_t nw = h->vwords;
+    const int world = h->comm ? h->world : 1;
     int64_t gcap = kGroupCapInit;
     int attempt = h->table_valid ? h->table_attempt : 0;
-    std::vector<uint8_t> host;
-    unsigned long long ng = 0;
-    uint64_t hc[8];
+    std::vector<uint32_t> all_cnt, all_pat;   // concatenation over ranks
+    uint64_t marg[4] = {0, 0, 0, 0};
     for (;;) {
         if (!h->table_valid) {
             int rc = build_table(h, attempt);
             if (rc != MS_OK) return rc;
         }
-        const size_t payload = static_cast<size_t>(gcap) * 4 * (1 + nw);
-        MS_CUDA(h, h->b_groups.ensure(payload));
-        int rc = ensure_stage(h, 64 + payload);
+        // block = [64-byte header (the 8 counters) | cnt u32[gcap] | pat u32[gcap*nw]]
+        const size_t block = 64 + static_cast<size_t>(gcap) * 4 * (1 + nw);
+        MS_CUDA(h, h->b_groups.ensure(block));
+        if (world > 1) MS_CUDA(h, h->b_gather.ensure(block * world));
+        int rc = ensure_stage(h, block * world);
         if (rc != MS_OK) return rc;
-        uint32_t* g_cnt = h->b_groups.as<uint32_t>();
+        uint8_t* blk = h->b_groups.as<uint8_t>();
+        uint32_t* g_cnt = reinterpret_cast<uint32_t*>(blk + 64);
         uint32_t* g_pat = g_cnt + gcap;
         MS_CUDA(h, cudaMemsetAsync(ctr_ptr(h) + 5, 0, 8, h->stream));
         ms::phase_compact_kernel<<<static_cast<int>((h->tab_size + 255) / 256), 256, 0, h->stream>>>(
             h->b_tab_cnt.as<uint32_t>(), h->b_tab_rep.as<long long>(), h->tab_size, h->b_bits.as<uint32_t>(), nw, ctr_ptr(h) + 5,
             g_cnt, g_pat, gcap);
         h->launches++;
+        MS_CUDA(h, cudaMemcpyAsync(blk, h->b_ctr.p, 64, cudaMemcpyDeviceToDevice, h->stream));
         uint8_t* st = static_cast<uint8_t*>(h->h_stage);
-        MS_CUDA(h, cudaMemcpyAsync(st, h->b_ctr.p, 64, cudaMemcpyDeviceToHost, h->stream));
-        MS_CUDA(h, cudaMemcpyAsync(st + 64, h->b_groups.p, payload, cudaMemcpyDeviceToHost, h->stream));
-        MS_CUDA(h, cudaStreamSynchronize(h->stream));
-        memcpy(hc, st, 64);
-        if (hc[4] != 0) {  // 64-bit hash collision between different patterns: re-hash with another seed
-            if (++attempt >= 4) MS_FAIL(h, MS_ERR_CUDA, "haplotype hash collided under four seeds");
-            h->table_valid = false;
-            continue;
+        if (world > 1) {
+            // the only exchange of the phasing step: every rank's compact (pattern, count) list and marginals
+            rc = ms_comm_allgather_bytes(h, blk, h->b_gather.p, block);
+            if (rc != MS_OK) return rc;
+            MS_CUDA(h, cudaMemcpyAsync(st, h->b_gather.p, block * world, cudaMemcpyDeviceToHost, h->stream));
+        } else {
+            MS_CUDA(h, cudaMemcpyAsync(st, blk, block, cudaMemcpyDeviceToHost, h->stream));
         }
-        h->table_valid = true;
-        ng = hc[5];
-        if (static_cast<int64_t>(ng) > gcap) { gcap = static_cast<int64_t>(ng); continue; }
-        host.assign(st + 64, st + 64 + payload);
+        MS_CUDA(h, cudaStreamSynchronize(h->stream));
+        // every rank sees every header, so all ranks take the same branch below
+        bool any_collision = false;
+        int64_t max_ng = 0;
+        const int me = h->comm ? h->rank : 0;
+        for (int r = 0; r < world; ++r) {
+            uint64_t hc[8];
+            memcpy(hc, st + static_cast<size_t>(r) * block, 64);
+            if (hc[4] != 0) {
+                any_collision = true;
+                if (r == me) {  // a 64-bit hash collision between different patterns here: re-hash with another seed
+                    if (++attempt >= 4) MS_FAIL(h, MS_ERR_CUDA, "haplotype hash collided under four seeds");
+                    h->table_valid = false;
+                }
+            } else if (r == me) {
+                h->table_valid = true;
+            }
+            max_ng = std::max<int64_t>(max_ng, static_cast<int64_t>(hc[5]));
+        }
+        if (any_collision) continue;
+        if (max_ng > gcap) { gcap = max_ng; continue; }
+        all_cnt.clear(); all_pat.clear();
+        for (int r = 0; r < world; ++r) {
+            const uint8_t* base = st + static_cast<size_t>(r) * block;
+            uint64_t hc[8];
+            memcpy(hc, base, 64);
+            for (int i = 0; i < 4; ++i) marg[i] += hc[i];
+            const uint32_t* c = reinterpret_cast<const uint32_t*>(base + 64);
+            const uint32_t* p = c + gcap;
+            all_cnt.insert(all_cnt.end(), c, c + hc[5]);
+            all_pat.insert(all_pat.end(), p, p + hc[5] * nw);
+        }
         break;
     }
-    const uint32_t* cnt = reinterpret_cast<const uint32_t*>(host.data());
-    const uint32_t* pat = cnt + gcap;
+    const int64_t ng = static_cast<int64_t>(all_cnt.size());
     std::vector<int64_t> order(ng);
     std::iota(order.begin(), order.end(), 0);
     std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
-        return ms::pattern_less(pat + static_cast<size_t>(a) * nw, pat + static_cast<size_t>(b) * nw, nw);
+        return ms::pattern_less(all_pat.data() + static_cast<size_t>(a) * nw, all_pat.data() + static_cast<size_t>(b) * nw, nw);
     });
-    for (int64_t i = 0; i < std::min<int64_t>(cap, static_cast<int64_t>(ng)); ++i) {
-        if (patterns) memcpy(patterns + static_cast<size_t>(i) * nw, pat + static_cast<size_t>(order[i]) * nw, static_cast<size_t>(nw) * 4);
-        if (counts) counts[i] = cnt[order[i]];
+    for (int64_t i = 0; i < std::min<int64_t>(cap, ng); ++i) {
+        if (patterns) memcpy(patterns + static_cast<size_t>(i) * nw, all_pat.data() + static_cast<size_t>(order[i]) * nw, static_cast<size_t>(nw) * 4);
+        if (counts) counts[i] = all_cnt[order[i]];
     }
-    *H = static_cast<int64_t>(ng);
+    *H = ng;
     if (ctr) {
         ctr->reported = 0; ctr->insufficient = 0;
-        ctr->damaged = hc[0]; ctr->gaps = hc[1]; ctr->heteroduplex = hc[2]; ctr->partial = hc[3];
+        ctr->damaged = marg[0]; ctr->gaps = marg[1]; ctr->heteroduplex = marg[2]; ctr->partial = marg[3];
     }
     return MS_OK;
 }

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 L, R = 3000, 60000
 
 
-def _pass(device, read0, nreads, world_rank=None):
+def _pass(device, read0, nreads, native=False):
     sys.path.insert(0, ROOT)
     import ctypes as C
     from minorseq_b200 import Juliet, _lib
@@ -24,6 +24,8 @@ def _pass(device, read0, nreads, world_rank=None):
     from minorseq_b200.synth import SynthConfig, make_tables
     t = make_tables(SynthConfig(L=L, seed=20240003, n_rate=2e-3))
     j = Juliet(L, [(1, 3001), (2, 3000)], refseq=t.refseq, device=device, mode_phasing=True)
+    if native:
+        assert j.hd.attach_comm()
     d = torch.empty((nreads, j.row_words), dtype=torch.int32, device=f"cuda:{device}")
     sp = SynthParams(t.cfg.seed, L, t.nstrains, t.thr_N, t.thr_sub, t.thr_ins20, t.thr_trunc16)
     _lib.check(j.lib.ms_synth_dev(j.hd.h, C.byref(sp), t.strain_base.ctypes.data_as(C.c_void_p), t.thr_del.ctypes.data_as(C.c_void_p),
@@ -36,28 +38,29 @@ def _pass(device, read0, nreads, world_rank=None):
                 counters=h.counters, hap_id=h.hap_id)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, native):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
     try:
         per = R // world
-        q.put((rank, _pass(rank, rank * per, per)))
+        q.put((rank, _pass(rank, rank * per, per, native)))
     finally:
         dist.barrier()
         dist.destroy_process_group()
 
 
 @pytest.mark.timeout(600)
-def test_two_gpus_equal_one_gpu():
+@pytest.mark.parametrize("native", [True, False], ids=["library-nccl", "torch-distributed"])
+def test_two_gpus_equal_one_gpu(native):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     world = 2
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, native)) for r in range(world)]
     for p in procs:
         p.start()
     out = dict(q.get(timeout=500) for _ in range(world))
