@@ -154,10 +154,10 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
     h->groups = kGroups[W];
     const int row_bytes = nblk * 16;
     h->stage_bytes = h->groups * 8 * row_bytes;
-    const int budget = h->max_smem - 128 - 16;
+    const int budget = h->max_smem - ms::kPileupSmemHeader - 16;
     h->stages = std::max(3, std::min(8, budget / h->stage_bytes));
     const int merge_bytes = (h->groups - 1) * 8 * ms::kPlanes * W * 32 * 4 + 64;  // end-of-kernel group merge reuses the ring
-    h->smem_bytes = 128 + std::max(h->stages * h->stage_bytes + 16, merge_bytes);
+    h->smem_bytes = ms::kPileupSmemHeader + std::max(h->stages * h->stage_bytes + 16, merge_bytes);
     if (h->smem_bytes > h->max_smem) MS_FAIL(h, MS_ERR_ARG, "row too long for the shared-memory ring");
     const size_t ncounts = static_cast<size_t>(L) * 72;
     MS_CUDA(h, cudaMalloc(&h->d_counts, ncounts * 4));

@@ -330,15 +330,17 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     const int W = a.warps_per_group, G = a.groups, S = a.stages;
     const int ncw = W * G;  // all warps are consumers; lane 0 of warp 0 also produces
     const uint32_t row_bytes = static_cast<uint32_t>(a.nblk) * 16u;
-    const uint32_t bar0 = smem_u32(smem);          // full[s] at bar0+8s, release counter of stage s at bar0+8S+4s
-    const uint32_t data0 = bar0 + 128;             // stage s at data0 + s*stage_bytes
-    const int64_t Tr = static_cast<int64_t>(G) * 8;  // reads per tile
+    const uint32_t bar0 = smem_u32(smem);          // full barrier of slot (g,s) at bar0 + 8*(g*S+s)
+    const uint32_t cnt0 = bar0 + 1024;             // release counter of slot (g,s) at cnt0 + 4*(g*S+s)
+    const uint32_t data0 = bar0 + kPileupSmemHeader;  // slot (g,s) at data0 + (g*S+s)*chunk_bytes
+    const uint32_t chunk_bytes = 8u * row_bytes;
+    const int64_t Tr = static_cast<int64_t>(G) * 8;  // reads per tile (one 8-read chunk per row-group)
     const int64_t ntiles = (a.R + Tr - 1) / Tr;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) {
+        for (int s = 0; s < S * G; ++s) {
             mbar_init(bar0 + 8 * s, 1);
-            sts32(bar0 + 8 * S + 4 * s, 0u);  // release counter of stage s
+            sts32(cnt0 + 4 * s, 0u);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -371,27 +373,25 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     uint32_t* pp = a.part_piv + (static_cast<size_t>(blockIdx.x) * a.nblk + blk) * 32;
     const int nct = ncw * 32;
 
-    // Tile ring without a producer warp: the warp that arrives LAST at a stage's release counter
-    // knows the stage is free and refills it at once, so S-1 tiles stay in flight and nobody
-    // ever blocks on an "empty" barrier.
-    auto issue_tile = [&](int64_t k) {  // k = index among this CTA's tiles
+    // Chunk rings without a producer warp.  Every row-group owns S slots of 8 reads; the warp of the
+    // group that arrives LAST at a slot's release counter knows the slot is free and refills it at
+    // once (one cp.async.bulk), so S-1 chunks per group stay in flight, nobody blocks on an "empty"
+    // barrier, and a slow group never holds back the others.
+    auto issue_chunk = [&](int64_t k) {  // k = index among this CTA's tiles
         const int64_t t = static_cast<int64_t>(blockIdx.x) + k * gridDim.x;
         if (t >= ntiles) return;
-        const uint32_t st = static_cast<uint32_t>(k % S);
-        const int64_t r0 = t * Tr;
-        const int64_t valid = (a.R - r0 < Tr) ? (a.R - r0) : Tr;
-        const uint32_t full = bar0 + 8 * st;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads of the stage before the async write
-        mbar_expect_tx(full, static_cast<uint32_t>(valid) * row_bytes);
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.packed) + static_cast<size_t>(r0) * row_bytes;
-        const uint32_t dst = data0 + st * static_cast<uint32_t>(a.stage_bytes);
-        for (int64_t off = 0; off < valid; off += 8) {
-            const uint32_t nr = static_cast<uint32_t>((valid - off < 8) ? (valid - off) : 8);
-            bulk_g2s(dst + static_cast<uint32_t>(off) * row_bytes, src + static_cast<size_t>(off) * row_bytes, nr * row_bytes, full);
-        }
+        const int64_t r0 = t * Tr + group * 8;
+        if (r0 >= a.R) return;
+        const uint32_t valid = static_cast<uint32_t>((a.R - r0 < 8) ? (a.R - r0) : 8);
+        const uint32_t slot = static_cast<uint32_t>(group * S + static_cast<int>(k % S));
+        const uint32_t full = bar0 + 8 * slot;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads of the slot before the async write
+        mbar_expect_tx(full, valid * row_bytes);
+        bulk_g2s(data0 + slot * chunk_bytes, reinterpret_cast<const uint8_t*>(a.packed) + static_cast<size_t>(r0) * row_bytes,
+                 valid * row_bytes, full);
     };
-    if (threadIdx.x == 0)
-        for (int k = 0; k < S; ++k) issue_tile(k);
+    if (tig == 0)
+        for (int k = 0; k < S; ++k) issue_chunk(k);
 
     uint32_t stage = 0, phase = 0;
     int64_t kt = 0;
@@ -411,13 +411,12 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
             clear(v);
             bi = 0; n = 0; tiles_since_flush = 0; mid = true;
         }
-        mbar_wait(bar0 + 8 * stage, phase);
-        const int64_t r0 = t * Tr;
-        const int valid = static_cast<int>((a.R - r0 < Tr) ? (a.R - r0) : Tr);
-        int nv = valid - group * 8;
-        nv = nv < 0 ? 0 : (nv > 8 ? 8 : nv);
-        const uint32_t addr = data0 + stage * static_cast<uint32_t>(a.stage_bytes) +
-                              static_cast<uint32_t>(group * 8) * row_bytes + static_cast<uint32_t>(blk) * 16u;
+        const int64_t r0 = t * Tr + group * 8;
+        const int64_t left = a.R - r0;
+        const int nv = left <= 0 ? 0 : (left > 8 ? 8 : static_cast<int>(left));
+        const uint32_t slot = static_cast<uint32_t>(group * S) + stage;
+        if (nv > 0) mbar_wait(bar0 + 8 * slot, phase);
+        const uint32_t addr = data0 + slot * chunk_bytes + static_cast<uint32_t>(blk) * 16u;
         if (nv == 8) {
             block8<MODE>(addr, row_bytes, cx, v, bi);
             ++bi;
@@ -435,15 +434,15 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         }
         ++tiles_since_flush;
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && nv > 0) {
             __threadfence_block();
-            const uint32_t cnt_addr = bar0 + 8 * S + 4 * stage;
+            const uint32_t cnt_addr = cnt0 + 4 * slot;
             uint32_t old;
             asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(cnt_addr) : "memory");
-            if (old == static_cast<uint32_t>(ncw - 1)) {  // last warp out refills the stage
+            if (old == static_cast<uint32_t>(W - 1)) {  // last warp of the group out refills the slot
                 __threadfence_block();
                 sts32(cnt_addr, 0u);
-                issue_tile(kt + S);
+                issue_chunk(kt + S);
             }
         }
         if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1u; }

@@ -26,6 +26,7 @@ namespace ms {
 
 constexpr int kPlanes = 11;             // vertical counter depth: up to 2047 reads between flushes
 constexpr int kMaxReadsPerFlush = 2047;
+constexpr int kPileupSmemHeader = 2048;  // mbarriers + release counters in front of the chunk slots
 constexpr int kPileupMaxThreads = 384;  // 12 warps = 3 per SM sub-partition -> 168 registers per thread
 
 // which one-bit masks are counted
