@@ -80,6 +80,9 @@ const char *ms_last_error(const ms_handle *h);   /* h == NULL: error of the last
 /* cudaStream_t to enqueue on (e.g. torch's current stream); NULL = the handle's own stream. */
 int ms_set_stream(ms_handle *h, void *cuda_stream);
 int ms_synchronize(ms_handle *h);
+/* page-locked host memory for the packed rows handed to ms_pileup_host (NULL on failure) */
+void *ms_alloc_pinned(size_t bytes);
+void ms_free_pinned(void *p);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t ms_launch_count(const ms_handle *h);
 /* on: record CUDA events around each K1 launch on the handle's stream; ms_pileup_kernel_ms

@@ -54,6 +54,8 @@ _SIGNATURES = {
     "ms_last_error": (C.c_char_p, [_P]),
     "ms_set_stream": (C.c_int, [_P, _P]),
     "ms_synchronize": (C.c_int, [_P]),
+    "ms_alloc_pinned": (_P, [C.c_size_t]),
+    "ms_free_pinned": (None, [_P]),
     "ms_launch_count": (C.c_int64, [_P]),
     "ms_set_timing": (C.c_int, [_P, C.c_int]),
     "ms_timer_start": (C.c_int, [_P]),

@@ -39,5 +39,29 @@ def build_library(force=False, verbose=False):
     return LIB
 
 
+HOST = os.path.join(HERE, "host")
+BIN = os.path.join(HERE, "bin")
+HOST_PROGRAMS = {"juliet": "juliet_main.cpp", "fuse": "fuse_main.cpp", "host_selftest": "host_selftest.cpp"}
+
+
+def build_host(force=False):
+    """The C++ host layer above the C ABI: juliet / fuse mains and the CPU-only self test (g++, zlib)."""
+    os.makedirs(BIN, exist_ok=True)
+    hdrs = [os.path.join(HOST, f) for f in os.listdir(HOST)] + [os.path.join(HERE, "..", "include", "minorseq_b200.h"), LIB]
+    for name, src in HOST_PROGRAMS.items():
+        out = os.path.join(BIN, name)
+        if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in hdrs if os.path.exists(d)):
+            continue
+        cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-o", out, os.path.join(HOST, src), "-lz"]
+        if name != "host_selftest":
+            cmd += ["-L" + HERE, "-lminorseq_b200", "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath," + HERE]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError(f"g++ failed building {name}")
+    return BIN
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose="-v" in sys.argv))
+    print(build_host(force=True))

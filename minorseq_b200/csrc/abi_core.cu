@@ -91,6 +91,15 @@ int ms_synchronize(ms_handle* h) {
 
 int64_t ms_launch_count(const ms_handle* h) { return h ? h->launches : 0; }
 
+void* ms_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr;
+}
+
+void ms_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 int ms_timer_start(ms_handle* h) {
     if (!h) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));

@@ -1,0 +1,361 @@
+// bgzf_bam.hpp -- minimal BGZF + BAM reader/writer on zlib (host side of the hot path).
+//
+// juliet and fuse "operate on (aligned) CCS records in the BAM format" (/root/reference/doc/JULIET.md:49-58,
+// /root/reference/doc/FUSE.md:13-15).  north_star names pbbam/htslib for this; neither exists in the image
+// (SURVEY App. E), so this is a from-scratch reader of the public SAM/BAM specification: BGZF blocks
+// (RFC 1952 members with a 'BC' extra field), the BAM header, alignment records, and typed aux tags.
+// Real PacBio BAM compatibility is unverified here (no fixture is available offline); the tests round-trip
+// files written by BamWriter below.
+#pragma once
+#include <zlib.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace msbam {
+
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+
+struct RefSeq { std::string name; int32_t length = 0; };
+
+struct Record {
+    int32_t ref_id = -1, pos = -1;
+    uint8_t mapq = 0;
+    uint16_t flag = 0;
+    std::string name;
+    std::vector<uint32_t> cigar;   // BAM encoding: len << 4 | op  (MIDNSHP=X)
+    std::string seq;               // one base per byte
+    std::vector<uint8_t> qual;     // phred, 0xff when absent
+    std::vector<uint8_t> aux;      // raw aux block
+
+    // find a tag; returns pointer to the type byte or nullptr
+    const uint8_t* find_tag(const char tag[2]) const;
+    // Z/H string tag
+    bool tag_string(const char tag[2], std::string& out) const;
+    // per-base QV track: 'Z' (phred+33 text) or 'B' array of c/C/s/S; empty when absent
+    std::vector<int> tag_per_base(const char tag[2]) const;
+    // numeric scalar (c C s S i I f)
+    bool tag_number(const char tag[2], double& out) const;
+};
+
+namespace detail {
+inline uint16_t u16(const uint8_t* p) { return static_cast<uint16_t>(p[0] | (p[1] << 8)); }
+inline uint32_t u32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | (static_cast<uint32_t>(p[3]) << 24); }
+inline int32_t i32(const uint8_t* p) { return static_cast<int32_t>(u32(p)); }
+inline void put16(std::vector<uint8_t>& v, uint16_t x) { v.push_back(x & 0xff); v.push_back(x >> 8); }
+inline void put32(std::vector<uint8_t>& v, uint32_t x) { for (int i = 0; i < 4; ++i) v.push_back((x >> (8 * i)) & 0xff); }
+
+// size in bytes of the value of an aux field starting at its type byte; 0 on malformed
+inline size_t aux_value_size(const uint8_t* t, const uint8_t* end) {
+    if (t >= end) return 0;
+    switch (*t) {
+    case 'A': case 'c': case 'C': return 1 + 1;
+    case 's': case 'S': return 1 + 2;
+    case 'i': case 'I': case 'f': return 1 + 4;
+    case 'Z': case 'H': {
+        const uint8_t* p = t + 1;
+        while (p < end && *p) ++p;
+        return p < end ? static_cast<size_t>(p - t) + 1 : 0;
+    }
+    case 'B': {
+        if (t + 6 > end) return 0;
+        const uint32_t n = u32(t + 2);
+        size_t w = 0;
+        switch (t[1]) { case 'c': case 'C': w = 1; break; case 's': case 'S': w = 2; break; case 'i': case 'I': case 'f': w = 4; break; default: return 0; }
+        return 1 + 1 + 4 + static_cast<size_t>(n) * w;
+    }
+    default: return 0;
+    }
+}
+}  // namespace detail
+
+inline const uint8_t* Record::find_tag(const char tag[2]) const {
+    const uint8_t* p = aux.data();
+    const uint8_t* end = p + aux.size();
+    while (p + 3 <= end) {
+        const size_t vs = detail::aux_value_size(p + 2, end);
+        if (vs == 0) return nullptr;
+        if (p[0] == static_cast<uint8_t>(tag[0]) && p[1] == static_cast<uint8_t>(tag[1])) return p + 2;
+        p += 2 + vs;
+    }
+    return nullptr;
+}
+
+inline bool Record::tag_string(const char tag[2], std::string& out) const {
+    const uint8_t* t = find_tag(tag);
+    if (!t || (*t != 'Z' && *t != 'H')) return false;
+    out.assign(reinterpret_cast<const char*>(t + 1));
+    return true;
+}
+
+inline bool Record::tag_number(const char tag[2], double& out) const {
+    const uint8_t* t = find_tag(tag);
+    if (!t) return false;
+    switch (*t) {
+    case 'c': out = static_cast<int8_t>(t[1]); return true;
+    case 'C': out = t[1]; return true;
+    case 's': out = static_cast<int16_t>(detail::u16(t + 1)); return true;
+    case 'S': out = detail::u16(t + 1); return true;
+    case 'i': out = detail::i32(t + 1); return true;
+    case 'I': out = detail::u32(t + 1); return true;
+    case 'f': { float f; memcpy(&f, t + 1, 4); out = f; return true; }
+    default: return false;
+    }
+}
+
+inline std::vector<int> Record::tag_per_base(const char tag[2]) const {
+    std::vector<int> v;
+    const uint8_t* t = find_tag(tag);
+    if (!t) return v;
+    if (*t == 'Z') {
+        for (const uint8_t* p = t + 1; *p; ++p) v.push_back(static_cast<int>(*p) - 33);
+    } else if (*t == 'B') {
+        const uint32_t n = detail::u32(t + 2);
+        const uint8_t* p = t + 6;
+        for (uint32_t i = 0; i < n; ++i) {
+            switch (t[1]) {
+            case 'c': v.push_back(static_cast<int8_t>(p[i])); break;
+            case 'C': v.push_back(p[i]); break;
+            case 's': v.push_back(static_cast<int16_t>(detail::u16(p + 2 * i))); break;
+            case 'S': v.push_back(detail::u16(p + 2 * i)); break;
+            default: return std::vector<int>();
+            }
+        }
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------ BGZF reader
+class BgzfReader {
+public:
+    explicit BgzfReader(const std::string& path) : f_(fopen(path.c_str(), "rb")) {
+        if (!f_) throw Error("cannot open " + path);
+    }
+    ~BgzfReader() { if (f_) fclose(f_); }
+    BgzfReader(const BgzfReader&) = delete;
+    // read exactly n bytes of the uncompressed stream; returns false on clean EOF at a boundary
+    bool read(void* dst, size_t n) {
+        uint8_t* out = static_cast<uint8_t*>(dst);
+        size_t got = 0;
+        while (got < n) {
+            if (off_ == buf_.size() && !next_block()) {
+                if (got == 0) return false;
+                throw Error("truncated BAM stream");
+            }
+            const size_t k = std::min(n - got, buf_.size() - off_);
+            memcpy(out + got, buf_.data() + off_, k);
+            off_ += k; got += k;
+        }
+        return true;
+    }
+private:
+    bool next_block() {
+        for (;;) {
+            uint8_t hd[18];
+            const size_t r = fread(hd, 1, 18, f_);
+            if (r == 0) return false;
+            if (r != 18 || hd[0] != 31 || hd[1] != 139 || hd[2] != 8 || !(hd[3] & 4)) throw Error("not a BGZF block");
+            const uint16_t xlen = detail::u16(hd + 10);
+            std::vector<uint8_t> extra(xlen);
+            memcpy(extra.data(), hd + 12, std::min<size_t>(6, xlen));
+            if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, f_) != static_cast<size_t>(xlen - 6)) throw Error("truncated BGZF header");
+            int bsize = -1;
+            for (size_t i = 0; i + 4 <= extra.size();) {
+                const uint16_t slen = detail::u16(extra.data() + i + 2);
+                if (extra[i] == 66 && extra[i + 1] == 67 && slen == 2) bsize = detail::u16(extra.data() + i + 4);
+                i += 4 + slen;
+            }
+            if (bsize < 0) throw Error("BGZF block without BC field");
+            const long cdata = static_cast<long>(bsize) + 1 - 12 - xlen - 8;
+            if (cdata < 0) throw Error("bad BGZF block size");
+            std::vector<uint8_t> comp(static_cast<size_t>(cdata) + 8);
+            if (fread(comp.data(), 1, comp.size(), f_) != comp.size()) throw Error("truncated BGZF block");
+            const uint32_t crc = detail::u32(comp.data() + cdata), isize = detail::u32(comp.data() + cdata + 4);
+            buf_.resize(isize);
+            off_ = 0;
+            if (isize == 0) continue;  // empty block (EOF marker)
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, -15) != Z_OK) throw Error("inflateInit2 failed");
+            zs.next_in = comp.data(); zs.avail_in = static_cast<uInt>(cdata);
+            zs.next_out = buf_.data(); zs.avail_out = isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            if (rc != Z_STREAM_END || zs.avail_out != 0) throw Error("BGZF inflate failed");
+            if (crc32(crc32(0L, Z_NULL, 0), buf_.data(), isize) != crc) throw Error("BGZF CRC mismatch");
+            return true;
+        }
+    }
+    FILE* f_;
+    std::vector<uint8_t> buf_;
+    size_t off_ = 0;
+};
+
+// ------------------------------------------------------------------ BAM reader
+class BamReader {
+public:
+    explicit BamReader(const std::string& path) : z_(path) {
+        uint8_t magic[4];
+        if (!z_.read(magic, 4) || memcmp(magic, "BAM\1", 4) != 0) throw Error(path + ": not a BAM file");
+        uint8_t b4[4];
+        z_.read(b4, 4);
+        text_.resize(detail::u32(b4));
+        if (!text_.empty()) z_.read(&text_[0], text_.size());
+        z_.read(b4, 4);
+        const uint32_t nref = detail::u32(b4);
+        for (uint32_t i = 0; i < nref; ++i) {
+            z_.read(b4, 4);
+            std::string nm(detail::u32(b4), '\0');
+            z_.read(&nm[0], nm.size());
+            if (!nm.empty() && nm.back() == '\0') nm.pop_back();
+            z_.read(b4, 4);
+            refs_.push_back({nm, detail::i32(b4)});
+        }
+    }
+    const std::string& header_text() const { return text_; }
+    const std::vector<RefSeq>& refs() const { return refs_; }
+    bool next(Record& r) {
+        uint8_t b4[4];
+        if (!z_.read(b4, 4)) return false;
+        const uint32_t bs = detail::u32(b4);
+        if (bs < 32) throw Error("BAM record too small");
+        raw_.resize(bs);
+        z_.read(raw_.data(), bs);
+        const uint8_t* p = raw_.data();
+        r.ref_id = detail::i32(p); r.pos = detail::i32(p + 4);
+        const uint8_t l_name = p[8];
+        r.mapq = p[9];
+        const uint16_t ncig = detail::u16(p + 12);
+        r.flag = detail::u16(p + 14);
+        const uint32_t lseq = detail::u32(p + 16);
+        size_t o = 32;
+        if (o + l_name + 4ull * ncig + (lseq + 1) / 2 + lseq > bs) throw Error("corrupt BAM record");
+        r.name.assign(reinterpret_cast<const char*>(p + o), l_name ? l_name - 1 : 0);
+        o += l_name;
+        r.cigar.resize(ncig);
+        for (uint16_t i = 0; i < ncig; ++i) r.cigar[i] = detail::u32(p + o + 4 * i);
+        o += 4ull * ncig;
+        static const char dec[] = "=ACMGRSVTWYHKDBN";
+        r.seq.resize(lseq);
+        for (uint32_t i = 0; i < lseq; ++i) r.seq[i] = dec[(p[o + i / 2] >> (i & 1 ? 0 : 4)) & 15];
+        o += (lseq + 1) / 2;
+        r.qual.assign(p + o, p + o + lseq);
+        o += lseq;
+        r.aux.assign(p + o, p + bs);
+        return true;
+    }
+private:
+    BgzfReader z_;
+    std::string text_;
+    std::vector<RefSeq> refs_;
+    std::vector<uint8_t> raw_;
+};
+
+// ------------------------------------------------------------------ BAM writer (fixtures, mixdata)
+class BamWriter {
+public:
+    BamWriter(const std::string& path, const std::string& header_text, const std::vector<RefSeq>& refs) : f_(fopen(path.c_str(), "wb")) {
+        if (!f_) throw Error("cannot create " + path);
+        std::vector<uint8_t> h;
+        h.insert(h.end(), {'B', 'A', 'M', 1});
+        detail::put32(h, static_cast<uint32_t>(header_text.size()));
+        h.insert(h.end(), header_text.begin(), header_text.end());
+        detail::put32(h, static_cast<uint32_t>(refs.size()));
+        for (const RefSeq& r : refs) {
+            detail::put32(h, static_cast<uint32_t>(r.name.size() + 1));
+            h.insert(h.end(), r.name.begin(), r.name.end());
+            h.push_back(0);
+            detail::put32(h, static_cast<uint32_t>(r.length));
+        }
+        append(h.data(), h.size());
+    }
+    ~BamWriter() { close(); }
+    void write(const Record& r) {
+        std::vector<uint8_t> b;
+        const uint32_t lseq = static_cast<uint32_t>(r.seq.size());
+        detail::put32(b, 0);  // block size, patched below
+        detail::put32(b, static_cast<uint32_t>(r.ref_id));
+        detail::put32(b, static_cast<uint32_t>(r.pos));
+        b.push_back(static_cast<uint8_t>(r.name.size() + 1));
+        b.push_back(r.mapq);
+        detail::put16(b, 4680);  // bin: unused by this reader
+        detail::put16(b, static_cast<uint16_t>(r.cigar.size()));
+        detail::put16(b, r.flag);
+        detail::put32(b, lseq);
+        detail::put32(b, static_cast<uint32_t>(-1));
+        detail::put32(b, static_cast<uint32_t>(-1));
+        detail::put32(b, 0);
+        b.insert(b.end(), r.name.begin(), r.name.end());
+        b.push_back(0);
+        for (uint32_t c : r.cigar) detail::put32(b, c);
+        static const char dec[] = "=ACMGRSVTWYHKDBN";
+        for (uint32_t i = 0; i < lseq; i += 2) {
+            auto code = [&](char ch) { const char* q = strchr(dec, ch >= 'a' ? ch - 32 : ch); return static_cast<uint8_t>(q && *q ? q - dec : 15); };
+            const uint8_t hi = code(r.seq[i]), lo = i + 1 < lseq ? code(r.seq[i + 1]) : 0;
+            b.push_back(static_cast<uint8_t>((hi << 4) | lo));
+        }
+        if (r.qual.size() == lseq) b.insert(b.end(), r.qual.begin(), r.qual.end());
+        else b.insert(b.end(), lseq, 0xff);
+        b.insert(b.end(), r.aux.begin(), r.aux.end());
+        const uint32_t bs = static_cast<uint32_t>(b.size() - 4);
+        for (int i = 0; i < 4; ++i) b[i] = (bs >> (8 * i)) & 0xff;
+        append(b.data(), b.size());
+    }
+    void close() {
+        if (!f_) return;
+        flush_block();
+        static const uint8_t eof[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        fwrite(eof, 1, 28, f_);
+        fclose(f_);
+        f_ = nullptr;
+    }
+    static void aux_string(std::vector<uint8_t>& aux, const char tag[2], const std::string& s) {
+        aux.push_back(tag[0]); aux.push_back(tag[1]); aux.push_back('Z');
+        aux.insert(aux.end(), s.begin(), s.end());
+        aux.push_back(0);
+    }
+    static void aux_float(std::vector<uint8_t>& aux, const char tag[2], float f) {
+        aux.push_back(tag[0]); aux.push_back(tag[1]); aux.push_back('f');
+        uint8_t b[4]; memcpy(b, &f, 4);
+        aux.insert(aux.end(), b, b + 4);
+    }
+private:
+    void append(const uint8_t* p, size_t n) {
+        while (n) {
+            const size_t k = std::min(n, static_cast<size_t>(0xff00) - pend_.size());
+            pend_.insert(pend_.end(), p, p + k);
+            p += k; n -= k;
+            if (pend_.size() >= 0xff00) flush_block();
+        }
+    }
+    void flush_block() {
+        if (pend_.empty()) return;
+        std::vector<uint8_t> out(compressBound(static_cast<uLong>(pend_.size())) + 64);
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw Error("deflateInit2 failed");
+        zs.next_in = pend_.data(); zs.avail_in = static_cast<uInt>(pend_.size());
+        zs.next_out = out.data(); zs.avail_out = static_cast<uInt>(out.size());
+        if (deflate(&zs, Z_FINISH) != Z_STREAM_END) throw Error("deflate failed");
+        const size_t clen = zs.total_out;
+        deflateEnd(&zs);
+        const size_t total = 18 + clen + 8;
+        if (total - 1 > 0xffff) throw Error("BGZF block too large");
+        uint8_t hd[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 0, 0};
+        hd[16] = static_cast<uint8_t>((total - 1) & 0xff); hd[17] = static_cast<uint8_t>((total - 1) >> 8);
+        fwrite(hd, 1, 18, f_);
+        fwrite(out.data(), 1, clen, f_);
+        std::vector<uint8_t> tail;
+        detail::put32(tail, static_cast<uint32_t>(crc32(crc32(0L, Z_NULL, 0), pend_.data(), static_cast<uInt>(pend_.size()))));
+        detail::put32(tail, static_cast<uint32_t>(pend_.size()));
+        fwrite(tail.data(), 1, 8, f_);
+        pend_.clear();
+    }
+    FILE* f_;
+    std::vector<uint8_t> pend_;
+};
+
+}  // namespace msbam

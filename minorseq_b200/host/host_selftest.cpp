@@ -1,0 +1,99 @@
+// host_selftest.cpp -- CPU-only checks of the C++ host layer (no GPU calls): BAM write/read round trip,
+// aux tags, target-config JSON + DRM grammar, report JSON -> HTML.  Exit code 0 = all good.
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include "bgzf_bam.hpp"
+#include "json.hpp"
+#include "report.hpp"
+#include "target_config.hpp"
+
+#define REQUIRE(c)                                                          \
+    do {                                                                    \
+        if (!(c)) { fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } \
+    } while (0)
+
+int main(int argc, char** argv) {
+    const std::string tmp = argc > 1 ? argv[1] : "/tmp/ms_selftest.bam";
+    {   // ---- BAM round trip over several BGZF blocks
+        msbam::BamWriter w(tmp, "@HD\tVN:1.5\tSO:coordinate\n@SQ\tSN:ref\tLN:1000\n", {{"ref", 1000}});
+        for (int i = 0; i < 3000; ++i) {
+            msbam::Record r;
+            r.ref_id = 0; r.pos = i % 50; r.flag = (i % 7 == 0) ? 0x100 : (i % 5 == 0 ? 0x10 : 0); r.mapq = 60;
+            r.name = "m/" + std::to_string(i) + "/ccs";
+            r.cigar = {(10u << 4) | 7u, (2u << 4) | 1u, (1u << 4) | 8u, (3u << 4) | 2u, (20u << 4) | 7u};
+            r.seq = "ACGTACGTACGGTACGTACGTACGTACGTACGT";
+            r.qual.assign(r.seq.size(), 40);
+            msbam::BamWriter::aux_string(r.aux, "sq", std::string(r.seq.size(), i % 3 ? 'I' : '+'));
+            msbam::BamWriter::aux_float(r.aux, "rq", 0.999f);
+            w.write(r);
+        }
+        w.close();
+        msbam::BamReader rd(tmp);
+        REQUIRE(rd.refs().size() == 1 && rd.refs()[0].name == "ref" && rd.refs()[0].length == 1000);
+        REQUIRE(rd.header_text().find("SN:ref") != std::string::npos);
+        msbam::Record r;
+        int n = 0;
+        while (rd.next(r)) {
+            REQUIRE(r.name == "m/" + std::to_string(n) + "/ccs");
+            REQUIRE(r.pos == n % 50 && r.cigar.size() == 5 && (r.cigar[1] & 15u) == 1u && (r.cigar[1] >> 4) == 2u);
+            REQUIRE(r.seq == "ACGTACGTACGGTACGTACGTACGTACGTACGT" && r.qual.size() == r.seq.size() && r.qual[0] == 40);
+            std::vector<int> sq = r.tag_per_base("sq");
+            REQUIRE(sq.size() == r.seq.size() && sq[0] == (n % 3 ? 'I' - 33 : '+' - 33));
+            double rq = 0;
+            REQUIRE(r.tag_number("rq", rq) && rq > 0.998 && rq < 1.0);
+            REQUIRE(r.tag_per_base("zz").empty());
+            ++n;
+        }
+        REQUIRE(n == 3000);
+    }
+    {   // ---- target config: the example of doc/JULIET.md:138-157 and the DRM grammar of :167-176
+        const std::string text = R"({"genes":[{"begin":2550,"drms":[{"name":"fancy drug","positions":["M41L"]},
+            {"name":"ATV/r","positions":["V32I","L33","46IL","I54VTALM","V82ATFS","84"]}],"end":2700,"name":"Reverse Transcriptase"}],
+            "referenceName":"my seq","referenceSequence":"TGGAAGGGCT","version":"v","databaseVersion":"DrugDB"})";
+        mscfg::TargetConfig c = mscfg::from_json(msjson::Parser(text).parse());
+        REQUIRE(c.genes.size() == 1 && c.genes[0].begin == 2550 && c.genes[0].end == 2700 && c.genes[0].drms.size() == 2);
+        const auto& atv = c.genes[0].drms[1].positions;
+        REQUIRE(atv.size() == 6);
+        REQUIRE(mscfg::drm_matches(atv[0], 32, 'V', 'I') && !mscfg::drm_matches(atv[0], 32, 'V', 'L') && !mscfg::drm_matches(atv[0], 32, 'A', 'I'));
+        REQUIRE(mscfg::drm_matches(atv[1], 33, 'L', 'F') && mscfg::drm_matches(atv[1], 33, 'L', 'X'));          // "L33": any mutant
+        REQUIRE(mscfg::drm_matches(atv[2], 46, 'M', 'I') && mscfg::drm_matches(atv[2], 46, 'Q', 'L') && !mscfg::drm_matches(atv[2], 46, 'M', 'V'));
+        REQUIRE(mscfg::drm_matches(atv[3], 54, 'I', 'M') && !mscfg::drm_matches(atv[3], 54, 'I', 'K'));
+        REQUIRE(mscfg::drm_matches(atv[5], 84, 'I', 'V') && mscfg::drm_matches(atv[5], 84, 'Z', 'Q') && !mscfg::drm_matches(atv[5], 85, 'I', 'V'));
+        const mscfg::DrmPosition p1 = mscfg::parse_drm_position("103"), p2 = mscfg::parse_drm_position("M130"), p3 = mscfg::parse_drm_position("103LG");
+        REQUIRE(p1.ref_aa == '*' && p1.pos == 103 && p1.mut_aas.empty());
+        REQUIRE(p2.ref_aa == 'M' && p2.pos == 130 && p2.mut_aas.empty());
+        REQUIRE(p3.ref_aa == '*' && p3.pos == 103 && p3.mut_aas == "LG");
+        REQUIRE(mscfg::load("HIV").genes.size() == 8 && mscfg::load("HIV").genes[7].drms.size() == 7);
+        REQUIRE(mscfg::load("ABL1").genes[0].drms.size() == 4);
+        REQUIRE(mscfg::translate(0) == 'K' && mscfg::translate(63) == 'F' && mscfg::translate(16 * 3 + 4 * 2 + 0) == 'X');   // AAA, TTT, TGA
+        REQUIRE(mscfg::translate(16 * 0 + 4 * 3 + 2) == 'M' && mscfg::translate(16 * 0 + 4 * 2 + 0) == 'R');                   // ATG, AGA
+    }
+    {   // ---- report: formatting rules read off the screenshots, JSON -> HTML
+        REQUIRE(msreport::perc2(1.107) == "1.1" && msreport::perc2(0.912) == "0.91" && msreport::perc2(98.4) == "98" && msreport::perc2(100.0) == "100");
+        REQUIRE(msreport::perc1(92.52) == "92.5" && msreport::perc1(1.0) == "1" && msreport::perc1(0.74) == "0.7");
+        mscfg::TargetConfig cfg = mscfg::load("HIV");
+        std::vector<msreport::VariantRow> rows(1);
+        rows[0].gene = 7; rows[0].aa_pos = 46; rows[0].col = 2252 + 45 * 3; rows[0].ref_codon = 14; rows[0].codon = 12;  // ATG -> ATA (M46I)
+        rows[0].count = 28; rows[0].coverage = 2529; rows[0].expected = 1; rows[0].ntests = 99; rows[0].pvalue = 5.2e-8;
+        rows[0].drugs = {"ATV/r", "NFV"};
+        rows[0].haplotype_hit = {false, true};
+        std::vector<unsigned> col(9719 * 8, 7);
+        std::vector<msreport::HaplotypeRow> haps(2);
+        haps[0].name = "A"; haps[0].reads = 900; haps[0].frequency = 0.9; haps[0].codons = {""}; haps[0].read_names = {"r1", "r2"};
+        haps[1].name = "B"; haps[1].reads = 100; haps[1].frequency = 0.1; haps[1].codons = {"ATA"}; haps[1].read_names = {"r3"};
+        const unsigned long long ctr[6] = {1000, 5, 20, 3, 15, 4};
+        const msjson::Value rep = msreport::build("2017-05-16T11:00:12.187Z", "in.bam", "juliet in.bam out.json", "test", cfg, 9719, cfg.genes, rows, col, 9719, true, haps, ctr);
+        const std::string js = msjson::dump(rep);
+        const msjson::Value back = msjson::Parser(js).parse();
+        REQUIRE(msjson::dump(back) == js);                                                   // writer/parser round trip
+        REQUIRE(js.find("\"haplotype_hit\": [false, true]") != std::string::npos);
+        REQUIRE(js.find("\"percentage\": \"1.1\"") != std::string::npos && js.find("\"known_drm\": \"ATV/r + NFV\"") != std::string::npos);
+        REQUIRE(js.find("\"rel_pos\": -3") != std::string::npos && js.find("\"rel_pos\": 5") != std::string::npos);
+        const std::string html = msreport::to_html(back);
+        for (const char* needle : {"Input data", "Target config", "Variant Discovery", "Drug Summaries", "Haplotypes %", "ATV/r + NFV", "2017-05-16T11:00:12.187Z", "M46I"})
+            REQUIRE(html.find(needle) != std::string::npos);
+    }
+    puts("host selftest ok");
+    return 0;
+}

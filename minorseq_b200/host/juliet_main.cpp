@@ -1,0 +1,239 @@
+// juliet_main.cpp -- `juliet [options] in.bam out.json|out.html ...` on top of the C ABI.
+//
+// Keeps the reference's process interface (/root/reference/doc/JULIET.md): outputs chosen by file
+// extension, either or both (:61-66); --config/-c <HIV|ABL1|file.json> (:118-162); --region b-e (:270-271);
+// --mode-phasing (:192-211); --min-perc / --max-perc (:342-354); --drm-only (:370).  The unpinned model
+// constants are options with the restatement's defaults.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
+#include <fstream>
+#include <map>
+#include <string>
+#include <vector>
+#include "host_common.hpp"
+#include "report.hpp"
+#include "target_config.hpp"
+
+#define MS_VERSION "minorseq_b200 juliet 0.1.0 (B200-native restatement; not PacBio juliet)"
+
+static void usage() {
+    puts("Usage: juliet [options] <in.bam> <out.json|out.html> [<out.html|out.json>]\n"
+         "  -c, --config <HIV|ABL1|file.json>  target configuration (genes, DRMs, referenceSequence)\n"
+         "      --region <begin-end>           1-based window to subset the target config\n"
+         "      --mode-phasing                 phase variants into haplotypes\n"
+         "      --min-perc <p>                 only variants with abundance > p %\n"
+         "      --max-perc <p>                 only variants with abundance < p %\n"
+         "      --drm-only                     only known drug-resistance mutations\n"
+         "      --substitution-rate <r>        error model (default 5e-4)\n"
+         "      --deletion-rate <r>            error model (default 3e-3)\n"
+         "      --alpha <a>                    significance after Bonferroni (default 0.01)\n"
+         "      --min-haplotype-reads <n>      reads needed to report a haplotype (default 10)\n"
+         "      --qv-threshold <q>             rich-QV base filter, 0 = off (default 20 on dq,iq,sq when present)\n"
+         "      --device <n>                   CUDA device (default 0)\n"
+         "  -h, --help / --version");
+}
+
+static bool ends_with(const std::string& s, const std::string& e) { return s.size() >= e.size() && s.compare(s.size() - e.size(), e.size(), e) == 0; }
+
+#define CK(h, call)                                                                            \
+    do {                                                                                       \
+        int rc_ = (call);                                                                      \
+        if (rc_ != MS_OK) mshost::die(std::string(#call) + " failed: " + ms_last_error(h));     \
+    } while (0)
+
+int main(int argc, char** argv) {
+    std::string config, region, cmdline;
+    bool phasing = false, drm_only = false;
+    double min_perc = -1, max_perc = -1, sub = 5e-4, del = 3e-3, alpha = 0.01;
+    int min_hap = 10, device = 0;
+    mshost::QvFilter qv;
+    std::vector<std::string> pos;
+    for (int i = 0; i < argc; ++i) cmdline += (i ? " " : "") + std::string(argv[i]);
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto need = [&](const char* name) -> std::string {
+            if (i + 1 >= argc) mshost::die(std::string("option ") + name + " needs a value");
+            return argv[++i];
+        };
+        if (a == "-h" || a == "--help") { usage(); return 0; }
+        else if (a == "--version") { puts(MS_VERSION); return 0; }
+        else if (a == "-c" || a == "--config") config = need("--config");
+        else if (a == "--region") region = need("--region");
+        else if (a == "--mode-phasing") phasing = true;
+        else if (a == "--drm-only") drm_only = true;
+        else if (a == "--min-perc") min_perc = atof(need("--min-perc").c_str());
+        else if (a == "--max-perc") max_perc = atof(need("--max-perc").c_str());
+        else if (a == "--substitution-rate") sub = atof(need("--substitution-rate").c_str());
+        else if (a == "--deletion-rate") del = atof(need("--deletion-rate").c_str());
+        else if (a == "--alpha") alpha = atof(need("--alpha").c_str());
+        else if (a == "--min-haplotype-reads") min_hap = atoi(need("--min-haplotype-reads").c_str());
+        else if (a == "--qv-threshold") qv.threshold = atoi(need("--qv-threshold").c_str());
+        else if (a == "--device") device = atoi(need("--device").c_str());
+        else if (!a.empty() && a[0] == '-') mshost::die("unknown option " + a);
+        else pos.push_back(a);
+    }
+    if (pos.size() < 2) { usage(); return 1; }
+    std::string out_json, out_html;
+    for (size_t i = 1; i < pos.size(); ++i) {
+        if (ends_with(pos[i], ".json")) out_json = pos[i];
+        else if (ends_with(pos[i], ".html")) out_html = pos[i];
+        else mshost::die("output must end in .json or .html: " + pos[i]);
+    }
+    int rb = 0, re = 0;
+    if (!region.empty()) {
+        if (sscanf(region.c_str(), "%d-%d", &rb, &re) != 2 || rb < 1 || re <= rb) mshost::die("--region expects <begin-end>");
+    }
+
+    try {
+        mscfg::TargetConfig cfg;
+        if (!config.empty()) cfg = mscfg::load(config);
+
+        ms_handle* h = nullptr;
+        if (ms_create(device, &h) != MS_OK) mshost::die(ms_last_error(nullptr));   // fail before any work: there is no CPU path
+
+        mshost::Alignments aln;
+        mshost::load_alignments(pos[0], qv, phasing, false, aln);
+        if (aln.nreads == 0) mshost::die("no primary or supplementary alignments in " + pos[0]);
+        const int32_t L = aln.L;
+
+        // genes: from the config, or one ORF labelled "unknown" (doc/JULIET.md:182-188)
+        std::vector<mscfg::Gene> genes = cfg.genes;
+        if (genes.empty()) {
+            mscfg::Gene g;
+            g.name = "unknown";
+            g.begin = rb > 0 ? rb : 1;
+            g.end = re > 0 ? re : L + 1;
+            genes.push_back(g);
+        }
+        if (cfg.reference_name.empty()) cfg.reference_name = config.empty() ? "" : aln.ref_name;
+        std::vector<uint32_t> start((L + 31) / 32, 0u);
+        std::vector<ms_gene> mg;
+        const int lo = rb > 0 ? rb - 1 : 0, hi = re > 0 ? std::min(L, re - 1) : L;
+        for (const mscfg::Gene& g : genes) {
+            mg.push_back({g.begin, g.end});
+            for (int s = g.begin - 1; s + 3 <= std::min(g.end - 1, L); s += 3)
+                if (s >= lo && s + 3 <= hi && s >= 0) start[s >> 5] |= 1u << (s & 31);
+        }
+
+        CK(h, ms_set_layout(h, L, start.data()));
+        const uint32_t* d_rows = nullptr;
+        CK(h, ms_pileup_host(h, aln.rows, aln.nreads, &d_rows));
+
+        ms_call_params prm;
+        ms_call_params_default(&prm);
+        prm.substitution_rate = sub; prm.deletion_rate = del; prm.alpha = alpha;
+        prm.min_perc = min_perc; prm.max_perc = max_perc; prm.region_begin = rb; prm.region_end = re;
+        std::vector<ms_variant> mv(4096);
+        int64_t nv = 0;
+        const char* ref = cfg.reference_sequence.size() >= static_cast<size_t>(L) ? cfg.reference_sequence.c_str() : nullptr;
+        CK(h, ms_call(h, mg.data(), static_cast<int32_t>(mg.size()), ref, &prm, mv.data(), static_cast<int64_t>(mv.size()), &nv));
+        if (nv > static_cast<int64_t>(mv.size())) {
+            mv.resize(nv);
+            CK(h, ms_call(h, mg.data(), static_cast<int32_t>(mg.size()), ref, &prm, mv.data(), static_cast<int64_t>(mv.size()), &nv));
+        }
+        mv.resize(nv);
+
+        // DRM annotation and --drm-only (doc/JULIET.md:104-107,:370)
+        std::vector<msreport::VariantRow> rows;
+        for (const ms_variant& v : mv) {
+            msreport::VariantRow r;
+            r.gene = v.gene; r.aa_pos = v.codon_index + 1; r.col = v.col; r.ref_codon = v.ref_codon; r.codon = v.codon;
+            r.count = v.count; r.coverage = v.coverage; r.expected = v.expected; r.ntests = v.ntests; r.pvalue = v.pvalue;
+            const char ra = mscfg::translate(v.ref_codon), va = mscfg::translate(v.codon);
+            for (const mscfg::Drm& d : genes[v.gene].drms)
+                for (const mscfg::DrmPosition& p : d.positions)
+                    if (mscfg::drm_matches(p, r.aa_pos, ra, va)) { r.drugs.push_back(d.name); break; }
+            if (drm_only && r.drugs.empty()) continue;
+            rows.push_back(r);
+        }
+
+        std::vector<uint32_t> col(static_cast<size_t>(L) * 8);
+        CK(h, ms_get_counts(h, col.data(), nullptr));
+
+        std::vector<msreport::HaplotypeRow> haps;
+        unsigned long long counters[6] = {0, 0, 0, 0, 0, 0};
+        if (phasing) {
+            // one global variant list over all genes (screenshot juliet_hiv-phasing.png: same columns in every table)
+            std::vector<std::pair<int, int>> keys;
+            for (const msreport::VariantRow& r : rows) keys.emplace_back(r.col, r.codon);
+            std::sort(keys.begin(), keys.end());
+            keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+            const int32_t V = static_cast<int32_t>(keys.size());
+            const int32_t nw = std::max(1, (V + 31) / 32);
+            std::vector<int32_t> vc(V), vk(V);
+            for (int32_t i = 0; i < V; ++i) { vc[i] = keys[i].first; vk[i] = keys[i].second; }
+            CK(h, ms_phase_begin(h, vc.data(), vk.data(), V, aln.nreads));
+            CK(h, ms_phase_dev(h, d_rows, aln.nreads));
+            int64_t H = 0, cap = 4096;
+            std::vector<uint32_t> pat;
+            std::vector<uint64_t> cnt;
+            ms_phase_counters ctr;
+            for (;;) {
+                pat.assign(static_cast<size_t>(cap) * nw, 0u);
+                cnt.assign(cap, 0);
+                CK(h, ms_phase_groups(h, pat.data(), cnt.data(), cap, &H, &ctr));
+                if (H <= cap) break;
+                cap = H;
+            }
+            int64_t Hm = 0, nrep = 0;
+            ms_phase_counters c2;
+            if (ms_haplotype_order(pat.data(), cnt.data(), H, V, min_hap, &Hm, &nrep, &c2) != MS_OK) mshost::die("ms_haplotype_order failed");
+            std::vector<int32_t> hap(aln.nreads);
+            CK(h, ms_phase_assign(h, pat.data(), Hm, hap.data()));
+            counters[0] = c2.reported; counters[1] = c2.insufficient; counters[2] = ctr.damaged;
+            counters[3] = ctr.gaps; counters[4] = ctr.heteroduplex; counters[5] = ctr.partial;
+            haps.resize(nrep);
+            for (int64_t k = 0; k < nrep; ++k) {
+                char nb[3];
+                ms_haplotype_name(k, nb);
+                haps[k].name = nb;
+                haps[k].reads = cnt[k];
+                haps[k].frequency = c2.reported ? static_cast<double>(cnt[k]) / static_cast<double>(c2.reported) : 0.0;
+                for (int32_t v = 0; v < V; ++v) {
+                    char cb[4];
+                    const bool on = (pat[static_cast<size_t>(k) * nw + (v >> 5)] >> (v & 31)) & 1u;
+                    haps[k].codons.push_back(on ? mscfg::codon_string(vk[v], cb) : "");
+                }
+            }
+            for (int64_t r = 0; r < aln.nreads; ++r)
+                if (hap[r] >= 0 && hap[r] < nrep) haps[hap[r]].read_names.push_back(aln.names[r]);
+            for (msreport::VariantRow& r : rows) {
+                const int32_t v = static_cast<int32_t>(std::lower_bound(keys.begin(), keys.end(), std::make_pair(r.col, r.codon)) - keys.begin());
+                r.haplotype_hit.resize(nrep);
+                for (int64_t k = 0; k < nrep; ++k) r.haplotype_hit[k] = (pat[static_cast<size_t>(k) * nw + (v >> 5)] >> (v & 31)) & 1u;
+            }
+        }
+
+        char ts[40];
+        const auto now = std::chrono::system_clock::now();
+        const std::time_t tt = std::chrono::system_clock::to_time_t(now);
+        const long ms = static_cast<long>(std::chrono::duration_cast<std::chrono::milliseconds>(now.time_since_epoch()).count() % 1000);
+        std::tm tmv;
+        gmtime_r(&tt, &tmv);
+        char base[32];
+        strftime(base, sizeof base, "%Y-%m-%dT%H:%M:%S", &tmv);
+        snprintf(ts, sizeof ts, "%s.%03ldZ", base, ms);
+        if (getenv("MS_FIXED_TIMESTAMP")) snprintf(ts, sizeof ts, "%s", getenv("MS_FIXED_TIMESTAMP"));
+
+        const msjson::Value report = msreport::build(ts, pos[0], cmdline, MS_VERSION, cfg, L, genes, rows, col, L, phasing, haps, counters);
+        if (!out_json.empty()) {
+            std::ofstream f(out_json);
+            if (!f) mshost::die("cannot write " + out_json);
+            f << msjson::dump(report);
+        }
+        if (!out_html.empty()) {
+            std::ofstream f(out_html);
+            if (!f) mshost::die("cannot write " + out_html);
+            f << msreport::to_html(report);
+        }
+        fprintf(stderr, "juliet: %lld reads (%lld skipped), %zu variants%s\n", static_cast<long long>(aln.nreads),
+                static_cast<long long>(aln.nskipped), rows.size(), phasing ? (", " + std::to_string(haps.size()) + " haplotypes").c_str() : "");
+        ms_destroy(h);
+    } catch (const std::exception& e) {
+        mshost::die(e.what());
+    }
+    return 0;
+}

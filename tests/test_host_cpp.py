@@ -1,0 +1,165 @@
+"""C++ host layer (minorseq_b200/host): CPU-only self test, and -- on a GPU -- the juliet / fuse binaries
+run end to end on BAM files written by an independent Python BAM writer, checked against the oracle."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import bam_util
+from minorseq_b200 import build as msbuild
+from minorseq_b200.synth import SynthConfig, make_tables, synth_states
+
+BIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "minorseq_b200", "bin")
+
+
+@pytest.fixture(scope="module")
+def binaries():
+    msbuild.build_library()
+    msbuild.build_host()
+    return BIN
+
+
+def test_host_selftest(binaries, tmp_path):
+    out = subprocess.run([os.path.join(binaries, "host_selftest"), str(tmp_path / "t.bam")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "host selftest ok" in out.stdout
+
+
+def test_cli_fails_loudly_without_gpu(binaries, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    out = subprocess.run([os.path.join(binaries, "juliet"), "x.bam", str(tmp_path / "o.json")], capture_output=True, text=True)
+    assert out.returncode != 0 and "no CPU fallback" in out.stderr
+    assert subprocess.run([os.path.join(binaries, "juliet"), "--help"], capture_output=True).returncode == 0
+
+
+def _make_bam(path, t, st, insertions=None, n_via_qv=False):
+    recs = []
+    ref = t.strain_base[0]
+    for r in range(st.shape[0]):
+        flag = 0x10 if r % 5 == 0 else 0
+        rec = bam_util.states_to_record(f"m/{r}/ccs", st[r], ref, insertions.get(r) if insertions else None, flag, n_via_qv)
+        if rec is not None:
+            recs.append(rec)
+    # records juliet must ignore: secondary and unmapped (doc/JULIET.md:58)
+    recs.append(bam_util.record("secondary", 0x100, 0, [(30, "=")], "A" * 30))
+    recs.append(bam_util.record("unmapped", 0x4, 0, [], "ACGT", ref_id=-1))
+    bam_util.write_bam(path, "synthetic_ref", t.cfg.L, recs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_via_qv", [False, True], ids=["N-in-seq", "N-by-richQV"])
+def test_juliet_cli_matches_oracle(binaries, oracle, tmp_path, n_via_qv):
+    cfg = SynthConfig(L=600, seed=77, n_rate=2e-3, trunc=0.05, ins=0.0)
+    t = make_tables(cfg)
+    st = synth_states(t, 0, 6000)
+    bam = str(tmp_path / "in.bam")
+    _make_bam(bam, t, st, n_via_qv=n_via_qv)
+    conf = {"genes": [{"name": "geneA", "begin": 1, "end": 301, "drms": [{"name": "drugX", "positions": [str(p) for p in range(1, 101)]}]},
+                      {"name": "geneB", "begin": 302, "end": 599}],
+            "referenceName": "synthetic_ref", "referenceSequence": t.refseq, "version": "test"}
+    cpath = tmp_path / "cfg.json"
+    cpath.write_text(json.dumps(conf))
+    oj, oh = str(tmp_path / "out.json"), str(tmp_path / "out.html")
+    res = subprocess.run([os.path.join(binaries, "juliet"), "--config", str(cpath), "--mode-phasing", bam, oj, oh], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    rep = json.load(open(oj))
+    genes = [(1, 301), (302, 599)]
+    keep = (st & 7 != 7).any(axis=1)
+    sto = st[keep]
+    mask = np.zeros(600, dtype=np.uint8)
+    for (b, e) in genes:
+        mask[b - 1: e - 3: 3] = 1
+    col, codon = oracle.pileup(sto, mask)
+    ov = oracle.call(codon, genes, refseq=t.refseq)
+    got = []
+    for gi, g in enumerate(rep["genes"]):
+        for vp in g["variant_positions"]:
+            for va in vp["variant_amino_acids"]:
+                for vc in va["variant_codons"]:
+                    got.append((gi, vp["ref_position"], vc["codon"], vc["count"], vp["coverage"], vc["pValue"]))
+    want = [(v.gene, v.codon_index + 1, "".join("ACGT"[(v.codon >> s) & 3] for s in (4, 2, 0)), v.count, v.coverage, v.pvalue) for v in ov]
+    assert sorted(x[:5] for x in got) == sorted(x[:5] for x in want)
+    for a, b in zip(sorted(got), sorted(want)):
+        assert abs(a[5] - b[5]) <= 1e-9 * b[5]
+    # MSA context rows come from the column counts
+    vp = rep["genes"][0]["variant_positions"][0]
+    c0 = 3 * (vp["ref_position"] - 1)
+    for row in vp["msa"]:
+        j = c0 + row["rel_pos"]
+        assert [row[k] for k in "ACGT-N"] == [int(x) for x in col[j, :6]]
+    # haplotypes: counts, order, categories and read names against the oracle
+    keys = sorted({(v.col, v.codon) for v in ov})
+    bits, flags = oracle.phase_bits(sto, [k[0] for k in keys], [k[1] for k in keys])
+    g = oracle.phase_group(bits, flags, len(keys))
+    assert [h["reads"] for h in rep["haplotypes"]] == [int(x) for x in g["counts"][: g["nreported"]]]
+    assert [h["name"] for h in rep["haplotypes"]] == [oracle.hap_name(i) for i in range(g["nreported"])]
+    cats = rep["haplotype_read_categories"]
+    assert (cats["reported"], cats["insufficient_coverage"], cats["unsuitable"]) == (g["counters"]["reported"], g["counters"]["insufficient"], g["counters"]["damaged"])
+    names = np.array([f"m/{r}/ccs" for r in range(st.shape[0])])[keep]
+    for k, h in enumerate(rep["haplotypes"]):
+        assert h["read_names"] == list(names[g["hap_id"] == k])
+    # DRM annotation: every geneA variant at AA positions 1..100 is labelled drugX
+    for vp in rep["genes"][0]["variant_positions"]:
+        for va in vp["variant_amino_acids"]:
+            for vc in va["variant_codons"]:
+                assert (vc["known_drm"] == "drugX") == (vp["ref_position"] <= 100)
+    html = open(oh).read()
+    assert "Variant Discovery" in html and "Haplotypes %" in html and "geneA" in html
+    # --drm-only, --region, --min-perc
+    res = subprocess.run([os.path.join(binaries, "juliet"), "-c", str(cpath), "--drm-only", "--region", "1-200", "--min-perc", "2", bam, oj], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    rep2 = json.load(open(oj))
+    ov2 = oracle.call(codon, genes, refseq=t.refseq, region=(1, 200), min_perc=2.0)
+    got2 = sorted((gi, vp["ref_position"], vc["codon"]) for gi, g2 in enumerate(rep2["genes"]) for vp in g2["variant_positions"]
+                  for va in vp["variant_amino_acids"] for vc in va["variant_codons"])
+    want2 = sorted((v.gene, v.codon_index + 1, "".join("ACGT"[(v.codon >> s) & 3] for s in (4, 2, 0))) for v in ov2 if v.gene == 0 and v.codon_index < 100)
+    assert got2 == want2
+
+
+@pytest.mark.gpu
+def test_juliet_cli_rejects_cigar_m(binaries, tmp_path):
+    bam = str(tmp_path / "m.bam")
+    bam_util.write_bam(bam, "r", 100, [bam_util.record("bad", 0, 0, [(50, "M")], "A" * 50)])
+    res = subprocess.run([os.path.join(binaries, "juliet"), bam, str(tmp_path / "o.json")], capture_output=True, text=True)
+    assert res.returncode != 0 and "cigar M is forbidden" in res.stderr
+
+
+@pytest.mark.gpu
+def test_fuse_cli_matches_oracle(binaries, oracle, tmp_path):
+    cfg = SynthConfig(L=900, seed=5, ins=0.0, trunc=0.02)
+    t = make_tables(cfg)
+    st = synth_states(t, 0, 2000)
+    st[:, 300:303] = np.where(np.arange(2000)[:, None] % 4 != 0, np.uint8(4), st[:, 300:303])     # major deletion
+    ins = {}
+    for r in range(2000):
+        d = {}
+        if r % 10 < 8 and (st[r, 450] & 7) != 7:
+            d[450] = "GGC"
+        if r % 10 < 7 and (st[r, 460] & 7) != 7:
+            d[460] = "TTT"           # too close to the accepted one
+        if r % 10 < 9 and (st[r, 600] & 7) != 7:
+            d[600] = "AC"            # not in frame
+        for c in d:
+            st[r, c] |= 8
+        ins[r] = d
+    bam = str(tmp_path / "f.bam")
+    _make_bam(bam, t, st, insertions=ins)
+    fa = str(tmp_path / "out.fasta")
+    res = subprocess.run([os.path.join(binaries, "fuse"), bam, fa], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    lines = open(fa).read().split("\n")
+    assert lines[0].startswith(">f.bam|fuse|synthetic_ref")
+    got = "".join(lines[1:])
+    keep = (st & 7 != 7).any(axis=1)
+    ocol, _ = oracle.pileup(st[keep], None, codons=False)
+    ev = [(c, s) for r in range(2000) if keep[r] for c, s in sorted(ins[r].items())]
+    pool = "".join(s for _, s in ev).encode()
+    il = [len(s) for _, s in ev]
+    io = np.concatenate([[0], np.cumsum(il)[:-1]]) if ev else []
+    want = oracle.fuse(ocol, [c for c, _ in ev], io, il, pool)
+    assert got == want
+    assert "GGC" in got and len(got) == 900 - 3 + 3
