@@ -160,13 +160,15 @@ int ms_phase_begin(ms_handle *h, const int32_t *var_col, const int32_t *var_codo
                    int64_t max_reads);
 /* Bit-vectors + damage flags for R more device-resident reads, appended.          */
 int ms_phase_dev(ms_handle *h, const uint32_t *d_packed, int64_t R);
-/* Distinct patterns of this handle's undamaged reads with their counts (sorted by
- * ascending pattern words), and the damage marginals.  *H may exceed cap.         */
+/* Distinct patterns of this handle's undamaged reads with their counts (in no particular
+ * order; with a communicator attached, the concatenation over all ranks), and the damage
+ * marginals.  *H may exceed cap: call again with a larger buffer (the pass is cached).  */
 int ms_phase_groups(ms_handle *h, uint32_t *patterns /* cap*ceil(V/32) */, uint64_t *counts,
                     int64_t cap, int64_t *H, ms_phase_counters *ctr);
-/* Host: merge-sorted (pattern,count) lists from all ranks -> juliet's haplotype
- * order (count desc, then ascending words) in place; *nreported = count>=min_reads;
- * fills reported/insufficient of ctr.  Pure host logic.                           */
+/* Host: (pattern,count) lists from all ranks -> equal patterns merged, then juliet's
+ * haplotype order (count desc, then ascending words) in place; entries [0,*nreported)
+ * have count >= min_reads; the unreported rest follows in the same order (left unsorted
+ * when it exceeds 65536 entries); fills reported/insufficient of ctr.  Pure host logic. */
 int ms_haplotype_order(uint32_t *patterns, uint64_t *counts, int64_t H, int32_t V,
                        int32_t min_reads, int64_t *Hmerged, int64_t *nreported,
                        ms_phase_counters *ctr);

@@ -69,6 +69,9 @@ struct ms_handle {
     int table_attempt = 0;
     DevBuf b_var, b_blocklist, b_bits, b_flags, b_slot, b_tab_key, b_tab_cnt, b_tab_rep, b_ctr, b_groups, b_gather, b_rank, b_hap,
         b_pat, b_cooc, b_bits_t;
+    std::vector<uint32_t> groups_cnt, groups_pat;   // host copy of the last grouping pass (all ranks when a comm is attached)
+    uint64_t groups_marg[4] = {0, 0, 0, 0};
+    bool groups_valid = false;
     void* h_stage = nullptr;      // pinned host staging for small D2H reads
     size_t h_stage_cap = 0;
 

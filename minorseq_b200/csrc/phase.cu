@@ -335,6 +335,8 @@ int ms_comm_allgather_bytes(ms_handle* h, const void* d_send, void* d_recv, size
 
 namespace {
 
+int phase_groups_copy_out(ms_handle* h, uint32_t* patterns, uint64_t* counts, int64_t cap, int64_t* H, ms_phase_counters* ctr);
+
 constexpr int64_t kGroupCapInit = 4096;
 
 int ensure_stage(ms_handle* h, size_t bytes) {
@@ -372,6 +374,21 @@ int build_table(ms_handle* h, int attempt) {
     return MS_OK;
 }
 
+// hand the cached (pattern, count) lists of the last grouping pass to the caller (order: as compacted)
+int phase_groups_copy_out(ms_handle* h, uint32_t* patterns, uint64_t* counts, int64_t cap, int64_t* H, ms_phase_counters* ctr) {
+    const int32_t nw = h->vwords;
+    const int64_t ng = static_cast<int64_t>(h->groups_cnt.size());
+    const int64_t k = std::min<int64_t>(cap, ng);
+    if (patterns && k > 0) memcpy(patterns, h->groups_pat.data(), static_cast<size_t>(k) * nw * 4);
+    if (counts) for (int64_t i = 0; i < k; ++i) counts[i] = h->groups_cnt[i];
+    *H = ng;
+    if (ctr) {
+        ctr->reported = 0; ctr->insufficient = 0;
+        ctr->damaged = h->groups_marg[0]; ctr->gaps = h->groups_marg[1]; ctr->heteroduplex = h->groups_marg[2]; ctr->partial = h->groups_marg[3];
+    }
+    return MS_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -393,6 +410,7 @@ int ms_phase_begin(ms_handle* h, const int32_t* var_col, const int32_t* var_codo
     h->phase_cap = std::max<int64_t>(1, max_reads);
     h->phase_n = 0;
     h->table_valid = false;
+    h->groups_valid = false;
     // distinct 32-column blocks the variants touch
     std::vector<int32_t> blocks;
     for (int32_t v = 0; v < V; ++v) {
@@ -455,6 +473,7 @@ int ms_phase_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     if (R == 0) return MS_OK;
     MS_CUDA(h, cudaSetDevice(h->device));
     h->table_valid = false;
+    h->groups_valid = false;
     uint32_t* bits = h->b_bits.as<uint32_t>() + static_cast<size_t>(h->phase_n) * h->vwords;
     uint8_t* flags = h->b_flags.as<uint8_t>() + h->phase_n;
     const uint4* pk = reinterpret_cast<const uint4*>(d_packed);
@@ -494,6 +513,7 @@ int ms_phase_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
 int ms_phase_groups(ms_handle* h, uint32_t* patterns, uint64_t* counts, int64_t cap, int64_t* H, ms_phase_counters* ctr) {
     if (!h || !h->b_bits.p || !H) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
+    if (h->groups_valid) return phase_groups_copy_out(h, patterns, counts, cap, H, ctr);   // same pass asked again (bigger cap)
     const int32_t nw = h->vwords;
     const int world = h->comm ? h->world : 1;
     int64_t gcap = kGroupCapInit;
@@ -563,52 +583,67 @@ int ms_phase_groups(ms_handle* h, uint32_t* patterns, uint64_t* counts, int64_t 
         }
         break;
     }
-    const int64_t ng = static_cast<int64_t>(all_cnt.size());
-    std::vector<int64_t> order(ng);
-    std::iota(order.begin(), order.end(), 0);
-    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
-        return ms::pattern_less(all_pat.data() + static_cast<size_t>(a) * nw, all_pat.data() + static_cast<size_t>(b) * nw, nw);
-    });
-    for (int64_t i = 0; i < std::min<int64_t>(cap, ng); ++i) {
-        if (patterns) memcpy(patterns + static_cast<size_t>(i) * nw, all_pat.data() + static_cast<size_t>(order[i]) * nw, static_cast<size_t>(nw) * 4);
-        if (counts) counts[i] = all_cnt[order[i]];
-    }
-    *H = ng;
-    if (ctr) {
-        ctr->reported = 0; ctr->insufficient = 0;
-        ctr->damaged = marg[0]; ctr->gaps = marg[1]; ctr->heteroduplex = marg[2]; ctr->partial = marg[3];
-    }
-    return MS_OK;
+    h->groups_cnt.swap(all_cnt);
+    h->groups_pat.swap(all_pat);
+    for (int i = 0; i < 4; ++i) h->groups_marg[i] = marg[i];
+    h->groups_valid = true;
+    return phase_groups_copy_out(h, patterns, counts, cap, H, ctr);
 }
 
 int ms_haplotype_order(uint32_t* patterns, uint64_t* counts, int64_t H, int32_t V, int32_t min_reads, int64_t* Hmerged,
                        int64_t* nreported, ms_phase_counters* ctr) {
     if (H < 0 || (H > 0 && (!patterns || !counts)) || V < 0) return MS_ERR_ARG;
     const int32_t nw = std::max(1, (V + 31) / 32);
-    std::vector<int64_t> order(H);
-    std::iota(order.begin(), order.end(), 0);
     auto pat = [&](int64_t i) { return patterns + static_cast<size_t>(i) * nw; };
-    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return ms::pattern_less(pat(a), pat(b), nw); });
-    // merge equal patterns (same haplotype seen on several ranks)
-    std::vector<uint32_t> mp; std::vector<uint64_t> mc;
+    // 1. merge equal patterns (the same haplotype seen on several ranks) with a hash join: O(H)
+    int64_t ts = 16;
+    while (ts < 2 * H) ts <<= 1;
+    std::vector<int64_t> table(ts, -1);
+    std::vector<int64_t> first;        // merged group -> index of its first occurrence
+    std::vector<uint64_t> mc;
     for (int64_t i = 0; i < H; ++i) {
-        const uint32_t* p = pat(order[i]);
-        if (!mc.empty() && memcmp(mp.data() + (mc.size() - 1) * nw, p, static_cast<size_t>(nw) * 4) == 0) mc.back() += counts[order[i]];
-        else { mp.insert(mp.end(), p, p + nw); mc.push_back(counts[order[i]]); }
+        uint64_t hsh = 0x9E3779B97F4A7C15ULL;
+        for (int32_t w = 0; w < nw; ++w) {
+            hsh ^= pat(i)[w] + 0x9E3779B97F4A7C15ULL + (hsh << 6) + (hsh >> 2);
+            hsh *= 0xbf58476d1ce4e5b9ULL;
+            hsh ^= hsh >> 29;
+        }
+        int64_t slot = static_cast<int64_t>(hsh) & (ts - 1);
+        for (;;) {
+            const int64_t g = table[slot];
+            if (g < 0) { table[slot] = static_cast<int64_t>(first.size()); first.push_back(i); mc.push_back(counts[i]); break; }
+            if (memcmp(pat(first[g]), pat(i), static_cast<size_t>(nw) * 4) == 0) { mc[g] += counts[i]; break; }
+            slot = (slot + 1) & (ts - 1);
+        }
     }
-    const int64_t M = static_cast<int64_t>(mc.size());
-    std::vector<int64_t> ord2(M);
-    std::iota(ord2.begin(), ord2.end(), 0);
-    std::stable_sort(ord2.begin(), ord2.end(), [&](int64_t a, int64_t b) { return mc[a] > mc[b]; });  // ties keep ascending pattern
-    int64_t nrep = 0; uint64_t rep = 0, ins = 0;
-    for (int64_t i = 0; i < M; ++i) {
-        memcpy(patterns + static_cast<size_t>(i) * nw, mp.data() + static_cast<size_t>(ord2[i]) * nw, static_cast<size_t>(nw) * 4);
-        counts[i] = mc[ord2[i]];
-        if (counts[i] >= static_cast<uint64_t>(min_reads)) { ++nrep; rep += counts[i]; } else ins += counts[i];
+    const int64_t M = static_cast<int64_t>(first.size());
+    // 2. juliet's order for the reported ones: count descending, ties by ascending pattern words.
+    //    The unreported rest follows; it is sorted the same way unless it is huge (phasing stress runs
+    //    produce hundreds of thousands of single-read patterns nobody lists).
+    std::vector<int64_t> rep, rest;
+    uint64_t nrep_reads = 0, nins_reads = 0;
+    for (int64_t g = 0; g < M; ++g) {
+        if (mc[g] >= static_cast<uint64_t>(min_reads)) { rep.push_back(g); nrep_reads += mc[g]; }
+        else { rest.push_back(g); nins_reads += mc[g]; }
     }
+    auto by_order = [&](int64_t a, int64_t b) {
+        if (mc[a] != mc[b]) return mc[a] > mc[b];
+        return ms::pattern_less(pat(first[a]), pat(first[b]), nw);
+    };
+    std::sort(rep.begin(), rep.end(), by_order);
+    if (rest.size() <= 65536) std::sort(rest.begin(), rest.end(), by_order);
+    std::vector<uint32_t> op(static_cast<size_t>(M) * nw);
+    std::vector<uint64_t> oc(M);
+    int64_t k = 0;
+    for (const std::vector<int64_t>* part : {&rep, &rest})
+        for (int64_t g : *part) {
+            memcpy(op.data() + static_cast<size_t>(k) * nw, pat(first[g]), static_cast<size_t>(nw) * 4);
+            oc[k++] = mc[g];
+        }
+    if (M) { memcpy(patterns, op.data(), op.size() * 4); memcpy(counts, oc.data(), oc.size() * 8); }
     if (Hmerged) *Hmerged = M;
-    if (nreported) *nreported = nrep;
-    if (ctr) { ctr->reported = rep; ctr->insufficient = ins; }
+    if (nreported) *nreported = static_cast<int64_t>(rep.size());
+    if (ctr) { ctr->reported = nrep_reads; ctr->insufficient = nins_reads; }
     return MS_OK;
 }
 
