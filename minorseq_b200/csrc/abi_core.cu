@@ -151,14 +151,15 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
     if (!h || L < 3) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
     const int32_t nblk = (L + 31) / 32;
-    const int32_t W = (nblk + 31) / 32;
-    if (W > 10) MS_FAIL(h, MS_ERR_ARG, "reference longer than 10240 columns is not supported by this build");
+    // warps per row: 31 counting lanes per warp (lane 31 is the codon look-ahead provider), 32 in the last
+    const int32_t W = nblk <= 32 ? 1 : 1 + (nblk - 32 + 30) / 31;
+    if (W > 12) MS_FAIL(h, MS_ERR_ARG, "reference longer than 11936 columns is not supported by this build");
     MS_CUDA(h, cudaStreamSynchronize(h->stream));
     free_layout(h);
     h->L = L; h->nblk = nblk; h->count_codons = start_mask != nullptr; h->have_pivot = false;
     // CTA shape: G row-groups of W warps; W*G is a multiple of 4 where possible so that every
     // SM sub-partition hosts the same number of consumer warps, plus 1 producer warp
-    static const int kGroups[11] = {0, 12, 6, 4, 3, 2, 2, 1, 1, 1, 1};
+    static const int kGroups[13] = {0, 12, 6, 4, 3, 2, 2, 1, 1, 1, 1, 1, 1};
     h->wpg = W;
     h->groups = kGroups[W];
     const int row_bytes = nblk * 16;

@@ -93,13 +93,14 @@ __device__ __forceinline__ void ripple(Vert<NM>& v, int i, int level, uint32_t x
 
 // Per-thread constants for codon work
 struct CodonCtx {
-    uint32_t r0, r1, r0n, r1n;  // pivot planes of this block and the next
+    uint32_t r0, r1, r0n, r1n;  // pivot planes of this block and the next (the latter only for the rare path)
     uint32_t start;             // codon start columns in this block
-    uint32_t* codon;            // global [L][64]
-    int32_t colbase;            // 32*blk
+    uint32_t cols;              // columns of this block that belong to a codon starting in this block
+    uint32_t lookcols;          // same for the first two columns of the next block (bits 0, 1)
+    uint32_t* codon;            // this block's rows of the global [L][64] histogram
 };
 
-// "codon starting at column j is not the clean pivot codon" for all 32 j, and the clean ones among them
+// exact masks (rare path): "codon starting at column j is not the clean pivot codon" and the clean ones among them
 __device__ __forceinline__ void codon_masks(const uint4& q, const uint4& n, const CodonCtx& cx, uint32_t& np, uint32_t& e) {
     const uint32_t X = ((q.x ^ cx.r0) | q.z) | (q.y ^ cx.r1);  // column is not the clean pivot base
     const uint32_t Xn = ((n.x ^ cx.r0n) | n.z) | (n.y ^ cx.r1n);
@@ -109,6 +110,11 @@ __device__ __forceinline__ void codon_masks(const uint4& q, const uint4& n, cons
 }
 
 // Build the one-bit masks of one read for this thread's 32 columns.
+// Hot path of the codon work: the per-column mismatch mask X is computed once per block; the
+// look-ahead into the next block comes from the neighbouring lane by shuffle (lane 31 of every
+// warp but the last of a row is a pure look-ahead provider, see the lane mapping in pileup_body).
+// A read is flagged for the exact rare path when a clean non-pivot BASE sits in a column that
+// belongs to one of this block's codons -- a superset of "has a clean non-pivot codon".
 template <int MODE>
 __device__ __forceinline__ void read_masks(uint32_t addr, const CodonCtx& cx, uint32_t (&m)[Traits<MODE>::NM], uint32_t& pm,
                                            uint32_t rdbit) {
@@ -122,16 +128,17 @@ __device__ __forceinline__ void read_masks(uint32_t addr, const CodonCtx& cx, ui
     m[5] = q.y & q.z;
     if (T::INS) m[T::iINS] = q.w;
     if (T::CODON) {
-        const uint4 n = lds128(addr + 16);  // look-ahead block (garbage past the row end is masked by `start`)
-        uint32_t np, e;
-        codon_masks(q, n, cx, np, e);
-        m[T::iNP] = np;
-        if (e) pm |= rdbit;
+        const uint32_t X = ((q.x ^ cx.r0) | q.z) | (q.y ^ cx.r1);  // column is not the clean pivot base
+        const uint32_t Xn = __shfl_down_sync(0xffffffffu, X, 1);
+        const uint32_t zn = __shfl_down_sync(0xffffffffu, q.z, 1);
+        m[T::iNP] = X | __funnelshift_r(X, Xn, 1) | __funnelshift_r(X, Xn, 2);
+        const uint32_t trig = (X & ~q.z & cx.cols) | (Xn & ~zn & cx.lookcols);
+        if (trig) pm |= rdbit;
     }
 }
 
-// Rare path: the reads flagged in pm carry clean non-pivot codons; re-read them from the stage
-// (still owned by this CTA) and add each codon to the global 64-bin histogram.
+// Rare path: the reads flagged in pm may carry clean non-pivot codons; re-read them from the slot
+// (still owned by this row-group) and add each such codon to the global 64-bin histogram.
 __device__ __forceinline__ void codon_exceptions(uint32_t addr, uint32_t row_bytes, uint32_t pm, const CodonCtx& cx) {
     while (pm) {
         const int rd = __ffs(pm) - 1;
@@ -147,7 +154,7 @@ __device__ __forceinline__ void codon_exceptions(uint32_t addr, uint32_t row_byt
             const uint32_t b1 = __funnelshift_r(q.y, n.y, j) & 7u;  // bit1 of the 3 states
             const uint32_t cod = ((b0 & 1u) << 4) | ((b1 & 1u) << 5) | ((b0 & 2u) << 1) | ((b1 & 2u) << 2) |
                                  ((b0 & 4u) >> 2) | ((b1 & 4u) >> 1);
-            atomicAdd(cx.codon + (static_cast<size_t>(cx.colbase + j) * 64 + cod), 1u);
+            atomicAdd(cx.codon + (j * 64 + cod), 1u);
         }
     }
 }
@@ -348,21 +355,26 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     __syncthreads();
 
     // ---------------- consumers: group g of W warps walks its 8 reads of every tile
+    // Lane mapping: warp w of a row-group starts at block 31*w, so lane 31 of every warp but the last
+    // re-reads the first block of the next warp and serves only as the look-ahead provider of lane 30
+    // (its counters are ignored).  The last warp of the row uses all 32 lanes.
     const int group = warp / W;
-    const int tig = (warp - group * W) * 32 + lane;  // thread in group
-    int blk = tig;
-    const bool active = blk < a.nblk;
-    if (!active) blk = 0;
+    const int wig = warp - group * W;                // warp in group
+    const int tig = wig * 32 + lane;                 // thread in group
+    int blk = wig * 31 + lane;
+    const bool active = blk < a.nblk && (lane < 31 || wig == W - 1);
+    if (blk >= a.nblk) blk = 0;
 
     CodonCtx cx;
-    cx.codon = a.codon;
-    cx.colbase = blk * 32;
+    cx.codon = a.codon + static_cast<size_t>(blk) * 32 * 64;
     cx.r0 = cx.r1 = cx.r0n = cx.r1n = 0;
-    cx.start = 0;
+    cx.start = cx.cols = cx.lookcols = 0;
     if (T::CODON) {
         const uint2 p = a.pivot[blk], pn = a.pivot[blk + 1];
         cx.r0 = p.x; cx.r1 = p.y; cx.r0n = pn.x; cx.r1n = pn.y;
         cx.start = active ? a.start_mask[blk] : 0u;
+        cx.cols = cx.start | (cx.start << 1) | (cx.start << 2);
+        cx.lookcols = ((cx.start >> 30) ? 1u : 0u) | ((cx.start >> 31) ? 2u : 0u);
     }
 
     Vert<NM> v;
