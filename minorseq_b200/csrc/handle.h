@@ -47,6 +47,7 @@ struct ms_handle {
     uint32_t *d_part_col = nullptr, *d_part_piv = nullptr;
     int32_t groups = 1, wpg = 1, stages = 2, stage_bytes = 0, smem_bytes = 0;
     bool have_pivot = false;
+    DevBuf b_exc_list, b_exc_cnt;  // K1's per-thread exception logs
     std::vector<uint32_t> h_start;
 
     // host-upload staging (ms_pileup_host keeps the rows for phasing)

@@ -160,8 +160,8 @@ __device__ __forceinline__ void codon_exceptions(uint32_t addr, uint32_t row_byt
 }
 
 template <int MODE>
-__device__ __forceinline__ void block8(uint32_t addr, uint32_t row_bytes, const CodonCtx& cx,
-                                       Vert<Traits<MODE>::NM>& v, uint32_t bi) {
+__device__ __forceinline__ uint32_t block8(uint32_t addr, uint32_t row_bytes, const CodonCtx& cx,
+                                           Vert<Traits<MODE>::NM>& v, uint32_t bi) {
     constexpr int NM = Traits<MODE>::NM;
     uint32_t m0[NM], m1[NM], twosA[NM], twosB[NM], foursA[NM], foursB[NM];
     uint32_t pm = 0;
@@ -218,9 +218,21 @@ __device__ __forceinline__ void block8(uint32_t addr, uint32_t row_bytes, const 
 #pragma unroll
         for (int i = 0; i < NM; ++i) v.p3[i] = twosA[i];
     }
-    if (Traits<MODE>::CODON) {
-        if (pm) codon_exceptions(addr, row_bytes, pm, cx);
-    }
+    return pm;  // reads of this block flagged for the exact codon pass
+}
+
+// Flagged reads are logged to this thread's private list in global memory (fire-and-forget stores)
+// and resolved after the kernel by codon_exception_kernel with full parallelism; only when the
+// list is full (dense-variation data) does the thread fall back to the in-kernel rare path.
+struct ExcLog {
+    uint32_t* list;
+    uint32_t cnt, cap;
+};
+// one entry per 8-read chunk with any flagged read: (first read of the chunk / 8) << 8 | flag byte
+__device__ __forceinline__ void log_or_handle(uint32_t pm, uint32_t read0, ExcLog& lg, uint32_t addr, uint32_t row_bytes,
+                                              const CodonCtx& cx) {
+    if (lg.cnt < lg.cap) lg.list[lg.cnt++] = ((read0 >> 3) << 8) | pm;
+    else codon_exceptions(addr, row_bytes, pm, cx);
 }
 
 // ---------------------------------------------------------------- flush (cold path)
@@ -377,6 +389,12 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         cx.lookcols = ((cx.start >> 30) ? 1u : 0u) | ((cx.start >> 31) ? 2u : 0u);
     }
 
+    const size_t list_id = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    ExcLog lg;
+    lg.cap = a.exc_cap;
+    lg.cnt = 0;
+    lg.list = a.exc_list + list_id * a.exc_cap;
+
     Vert<NM> v;
     clear(v);
     uint32_t bi = 0, n = 0, tiles_since_flush = 0;
@@ -430,7 +448,8 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         if (nv > 0) mbar_wait(bar0 + 8 * slot, phase);
         const uint32_t addr = data0 + slot * chunk_bytes + static_cast<uint32_t>(blk) * 16u;
         if (nv == 8) {
-            block8<MODE>(addr, row_bytes, cx, v, bi);
+            const uint32_t pm = block8<MODE>(addr, row_bytes, cx, v, bi);
+            if (T::CODON && pm) log_or_handle(pm, static_cast<uint32_t>(r0), lg, addr, row_bytes, cx);
             ++bi;
             n += 8;
         } else {
@@ -440,7 +459,7 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
                 read_masks<MODE>(addr + i * row_bytes, cx, m, pm, 1u);
 #pragma unroll
                 for (int q = 0; q < NM; ++q) ripple(v, q, 0, m[q]);
-                if (T::CODON && pm) codon_exceptions(addr + i * row_bytes, row_bytes, 1u, cx);
+                if (T::CODON && pm) log_or_handle(1u << i, static_cast<uint32_t>(r0), lg, addr, row_bytes, cx);
                 ++n;
             }
         }
@@ -459,6 +478,8 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         }
         if (++stage == static_cast<uint32_t>(S)) { stage = 0; phase ^= 1u; }
     }
+
+    if (T::CODON) a.exc_cnt[list_id] = lg.cnt;
 
     // ---------------- final merge: groups 1..G-1 hand their planes to group 0 through shared memory
     fold_pendings(v, bi);
@@ -505,6 +526,74 @@ void pileup_launch(int mode, int grid, int threads, int smem, cudaStream_t s, co
     if (mode == kModeJuliet) pileup_csa_kernel<kModeJuliet><<<grid, threads, smem, s>>>(a);
     else if (mode == kModeFuse) pileup_csa_kernel<kModeFuse><<<grid, threads, smem, s>>>(a);
     else pileup_csa_kernel<kModeBoth><<<grid, threads, smem, s>>>(a);
+}
+
+// ---------------------------------------------------------------- logged exceptions
+// One warp per logged list: every entry is a read whose block may hold clean non-pivot codons.  The
+// exact masks are recomputed from global memory (one 32-byte sector per entry) and each such codon
+// goes to the 64-bin histogram with a RED.  ~1.6 % of the (read, block) pairs at CCS error rates.
+__global__ void __launch_bounds__(256) codon_exception_kernel(PileupArgs a, int threads_per_cta) {
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t nlists = static_cast<int64_t>(a.exc_lists);
+    if (warp >= nlists) return;
+    uint32_t cnt = a.exc_cnt[warp];
+    if (cnt > a.exc_cap) cnt = a.exc_cap;
+    if (cnt == 0) return;
+    const int tid = static_cast<int>(warp % threads_per_cta);
+    const int w = tid >> 5, l = tid & 31;
+    const int wig = w % a.warps_per_group;
+    const int blk = wig * 31 + l;
+    if (blk >= a.nblk) return;
+    CodonCtx cx;
+    const uint2 p = a.pivot[blk], pn = a.pivot[blk + 1];
+    cx.r0 = p.x; cx.r1 = p.y; cx.r0n = pn.x; cx.r1n = pn.y;
+    cx.start = a.start_mask[blk];
+    cx.cols = cx.lookcols = 0;
+    cx.codon = a.codon + static_cast<size_t>(blk) * 32 * 64;
+    const uint32_t* list = a.exc_list + static_cast<size_t>(warp) * a.exc_cap;
+    const uint4* rows = reinterpret_cast<const uint4*>(a.packed);
+    // work items = (entry, flagged read); lanes take consecutive entries, then walk their flag bits.
+    // Minor variants make many reads hit the SAME bin, so equal addresses within the warp are merged
+    // (__match_any_sync) and only one lane issues the RED with the group's size.
+    for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        uint32_t ent = i < cnt ? list[i] : 0u;
+        uint32_t pm = ent & 0xffu;
+        const size_t rbase = static_cast<size_t>(ent >> 8) << 3;
+        while (__any_sync(0xffffffffu, pm != 0)) {
+            uint32_t e = 0;
+            uint4 q = make_uint4(0, 0, 0, 0), n = q;
+            if (pm) {
+                const int rd = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const uint4* row = rows + (rbase + rd) * a.nblk;
+                q = row[blk];
+                n = blk + 1 < a.nblk ? row[blk + 1] : make_uint4(0, 0, 0xffffffffu, 0);
+                uint32_t np;
+                codon_masks(q, n, cx, np, e);
+            }
+            while (__any_sync(0xffffffffu, e != 0)) {
+                uint32_t key = 0xffffffffu;
+                if (e) {
+                    const int j = __ffs(e) - 1;
+                    e &= e - 1;
+                    const uint32_t b0 = __funnelshift_r(q.x, n.x, j) & 7u;
+                    const uint32_t b1 = __funnelshift_r(q.y, n.y, j) & 7u;
+                    const uint32_t cod = ((b0 & 1u) << 4) | ((b1 & 1u) << 5) | ((b0 & 2u) << 1) | ((b1 & 2u) << 2) |
+                                         ((b0 & 4u) >> 2) | ((b1 & 4u) >> 1);
+                    key = static_cast<uint32_t>(j) * 64u + cod;
+                }
+                const uint32_t peers = __match_any_sync(0xffffffffu, key);
+                if (key != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(cx.codon + key, static_cast<uint32_t>(__popc(peers)));
+            }
+        }
+    }
+}
+
+void pileup_exceptions_launch(int pileup_grid, int pileup_threads, cudaStream_t s, const PileupArgs& a) {
+    const int64_t nlists = static_cast<int64_t>(pileup_grid) * pileup_threads;
+    codon_exception_kernel<<<static_cast<unsigned>((nlists * 32 + 255) / 256), 256, 0, s>>>(a, pileup_threads);
 }
 
 // ---------------------------------------------------------------- pivot sampling

@@ -48,6 +48,10 @@ struct PileupArgs {
     uint32_t* codon;          // [L][64] global histogram (exceptions land here)
     uint32_t* part_col;       // [gridDim][nblk*32][8]
     uint32_t* part_piv;       // [gridDim][nblk*32]
+    uint32_t* exc_list;       // [gridDim*blockDim][exc_cap] reads logged for the exact codon pass
+    uint32_t* exc_cnt;        // [gridDim*blockDim]
+    uint32_t exc_cap;
+    int64_t exc_lists;        // gridDim*blockDim of the pileup launch
 };
 
 template <int MODE>
@@ -66,5 +70,6 @@ __global__ void coverage_kernel(uint32_t* col, int32_t L);
 
 void pileup_set_smem_attr(int max_smem);
 void pileup_launch(int mode, int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a);
+void pileup_exceptions_launch(int pileup_grid, int pileup_threads, cudaStream_t s, const PileupArgs& a);
 
 }  // namespace ms
