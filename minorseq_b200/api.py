@@ -194,15 +194,18 @@ class Juliet:
         return rows
 
     # -- K2
-    def call(self, cap=4096):
-        genes = (Gene * len(self.genes))(*[Gene(b, e) for (b, e) in self.genes])
-        out = (Variant * cap)()
+    def call(self, cap=1024):
+        if getattr(self, "_call_cap", 0) < cap:          # ctypes buffers are reused from pass to pass
+            self._call_cap = cap
+            self._call_out = (Variant * cap)()
+            self._call_genes = (Gene * len(self.genes))(*[Gene(b, e) for (b, e) in self.genes])
+        cap, out = self._call_cap, self._call_out
         n = C.c_int64()
         ref = self.refseq.encode() if self.refseq else None
-        check(self.lib.ms_call(self.hd.h, genes, len(self.genes), ref, C.byref(self.params), out, cap, C.byref(n)), self.hd.h)
+        check(self.lib.ms_call(self.hd.h, self._call_genes, len(self.genes), ref, C.byref(self.params), out, cap, C.byref(n)), self.hd.h)
         if n.value > cap:
             return self.call(cap=int(n.value))
-        return [out[i] for i in range(n.value)]
+        return [Variant.from_buffer_copy(out[i]) for i in range(n.value)]
 
     # -- K3
     def phase_device(self, variants, d_packed_ptr: int, nreads: int, want_hap_id=True) -> Haplotypes:
@@ -217,14 +220,17 @@ class Juliet:
         check(self.lib.ms_phase_dev(self.hd.h, C.c_void_p(d_packed_ptr), nreads), self.hd.h)
         cap = 4096
         while True:
-            pat = np.zeros((cap, nw), dtype=np.uint32)
-            cnt = np.zeros(cap, dtype=np.uint64)
+            if getattr(self, "_grp_shape", None) != (cap, nw):   # reused from pass to pass
+                self._grp_shape = (cap, nw)
+                self._grp_pat = np.zeros((cap, nw), dtype=np.uint32)
+                self._grp_cnt = np.zeros(cap, dtype=np.uint64)
+            pat, cnt = self._grp_pat, self._grp_cnt
             H, ctr = C.c_int64(), PhaseCounters()
             check(self.lib.ms_phase_groups(self.hd.h, _ptr(pat), _ptr(cnt), cap, C.byref(H), C.byref(ctr)), self.hd.h)
             if H.value <= cap:
                 break
             cap = int(H.value)
-        pat, cnt = pat[:H.value], cnt[:H.value]
+        pat, cnt = pat[:H.value].copy(), cnt[:H.value].copy()
         marg = np.array([ctr.damaged, ctr.gaps, ctr.heteroduplex, ctr.partial], dtype=np.int64)
         if not getattr(self.hd, "native_comm", False) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             pat, cnt, marg = _gather_groups(pat, cnt, marg, self.hd.device)   # torch.distributed fallback (e.g. gloo)

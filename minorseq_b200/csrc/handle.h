@@ -65,7 +65,7 @@ struct ms_handle {
     int32_t V = 0, vwords = 0;
     int64_t phase_cap = 0, phase_n = 0;
     int32_t nblocklist = 0;
-    int64_t tab_size = 0;
+    int64_t tab_size = 0, tab_size_max = 0;
     bool table_valid = false;
     int table_attempt = 0;
     DevBuf b_var, b_blocklist, b_bits, b_flags, b_slot, b_tab_key, b_tab_cnt, b_tab_rep, b_ctr, b_groups, b_gather, b_rank, b_hap,

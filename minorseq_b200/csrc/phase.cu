@@ -188,7 +188,7 @@ __device__ __forceinline__ uint64_t pattern_hash(const uint32_t* w, int32_t vwor
 // lowest read index) which alone touches the table: one CAS probe, one count add, one rep min.
 __global__ void phase_insert_kernel(const uint32_t* __restrict__ bits, const uint8_t* __restrict__ flags, int64_t R,
                                     int32_t vwords, uint64_t seed, unsigned long long* tab_key, uint32_t* tab_cnt,
-                                    long long* tab_rep, int64_t mask, int32_t* __restrict__ slot) {
+                                    long long* tab_rep, int64_t mask, int32_t* __restrict__ slot, unsigned long long* overflow) {
     const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool valid = r < R && flags[r] == 0;
@@ -198,16 +198,20 @@ __global__ void phase_insert_kernel(const uint32_t* __restrict__ bits, const uin
     const uint64_t key = pattern_hash(bits + static_cast<size_t>(r) * vwords, vwords, seed);
     const uint32_t peers = __match_any_sync(vmask, static_cast<unsigned long long>(key));
     const int leader = __ffs(peers) - 1;
-    int64_t idx = 0;
+    int64_t idx = -1;
     if (lane == leader) {
-        idx = static_cast<int64_t>(key) & mask;
-        for (;;) {
-            const unsigned long long prev = atomicCAS(tab_key + idx, 0ULL, static_cast<unsigned long long>(key));
-            if (prev == 0ULL || prev == key) break;
-            idx = (idx + 1) & mask;
+        int64_t probe = static_cast<int64_t>(key) & mask;
+        for (int step = 0; step < 256; ++step) {   // bounded: a (nearly) full table reports overflow instead of spinning
+            const unsigned long long prev = atomicCAS(tab_key + probe, 0ULL, static_cast<unsigned long long>(key));
+            if (prev == 0ULL || prev == key) { idx = probe; break; }
+            probe = (probe + 1) & mask;
         }
-        atomicAdd(tab_cnt + idx, static_cast<uint32_t>(__popc(peers)));
-        atomicMin(tab_rep + idx, static_cast<long long>(r));
+        if (idx >= 0) {
+            atomicAdd(tab_cnt + idx, static_cast<uint32_t>(__popc(peers)));
+            atomicMin(tab_rep + idx, static_cast<long long>(r));
+        } else {
+            atomicAdd(overflow, 1ULL);
+        }
     }
     idx = __shfl_sync(peers, idx, leader);
     slot[r] = static_cast<int32_t>(idx);
@@ -359,12 +363,13 @@ int build_table(ms_handle* h, int attempt) {
     MS_CUDA(h, cudaMemsetAsync(h->b_tab_cnt.p, 0, static_cast<size_t>(h->tab_size) * 4, h->stream));
     MS_CUDA(h, cudaMemsetAsync(h->b_tab_rep.p, 0x7f, static_cast<size_t>(h->tab_size) * 8, h->stream));
     MS_CUDA(h, cudaMemsetAsync(ctr_ptr(h) + 4, 0, 8, h->stream));
+    MS_CUDA(h, cudaMemsetAsync(ctr_ptr(h) + 6, 0, 8, h->stream));
     if (R > 0) {
         const int grid = static_cast<int>((R + 255) / 256);
         ms::phase_insert_kernel<<<grid, 256, 0, h->stream>>>(h->b_bits.as<uint32_t>(), h->b_flags.as<uint8_t>(), R, h->vwords,
                                                              phase_seed(attempt), h->b_tab_key.as<unsigned long long>(),
                                                              h->b_tab_cnt.as<uint32_t>(), h->b_tab_rep.as<long long>(),
-                                                             h->tab_size - 1, h->b_slot.as<int32_t>());
+                                                             h->tab_size - 1, h->b_slot.as<int32_t>(), ctr_ptr(h) + 6);
         ms::phase_verify_kernel<<<grid, 256, 0, h->stream>>>(h->b_bits.as<uint32_t>(), R, h->vwords, h->b_tab_rep.as<long long>(),
                                                              h->b_slot.as<int32_t>(), ctr_ptr(h) + 4);
         h->launches += 2;
@@ -431,8 +436,12 @@ int ms_phase_begin(ms_handle* h, const int32_t* var_col, const int32_t* var_codo
         } else { d.slotA = d.slotB = 0; d.shift = 0; d.codon = -1; }
         vd[v] = d;
     }
-    int64_t ts = 1024;
-    while (ts < 2 * h->phase_cap) ts <<= 1;
+    // The table starts small (distinct patterns are usually a few hundred) and is re-sized by
+    // ms_phase_groups when an insert reports overflow; its upper bound is 2x the reads.
+    int64_t ts_max = 1024;
+    while (ts_max < 2 * h->phase_cap) ts_max <<= 1;
+    h->tab_size_max = ts_max;
+    int64_t ts = std::min<int64_t>(ts_max, 1 << 16);
     h->tab_size = ts;
     // the previous pass may still be reading these buffers on the stream if they have to move
     const bool grow = vd.size() * sizeof(ms::VarDev) > h->b_var.cap || blocks.size() * 4 > h->b_blocklist.cap ||
@@ -452,7 +461,6 @@ int ms_phase_begin(ms_handle* h, const int32_t* var_col, const int32_t* var_codo
     if (rc != MS_OK) return rc;
     // pageable -> device copies of the small tables go through the pinned stage to stay asynchronous
     uint8_t* st = static_cast<uint8_t*>(h->h_stage);
-    MS_CUDA(h, cudaStreamSynchronize(h->stream));  // the stage may still be in flight from the previous pass
     const size_t nb_var = vd.size() * sizeof(ms::VarDev), nb_blk = blocks.size() * 4;
     if (nb_var + nb_blk <= h->h_stage_cap) {
         memcpy(st, vd.data(), nb_var);
@@ -551,13 +559,23 @@ int ms_phase_groups(ms_handle* h, uint32_t* patterns, uint64_t* counts, int64_t 
         }
         MS_CUDA(h, cudaStreamSynchronize(h->stream));
         // every rank sees every header, so all ranks take the same branch below
-        bool any_collision = false;
+        bool any_collision = false, any_overflow = false;
         int64_t max_ng = 0;
         const int me = h->comm ? h->rank : 0;
         for (int r = 0; r < world; ++r) {
             uint64_t hc[8];
             memcpy(hc, st + static_cast<size_t>(r) * block, 64);
-            if (hc[4] != 0) {
+            if (hc[6] != 0) {
+                any_overflow = true;
+                if (r == me) {  // table too small for this rank's distinct patterns: grow and rebuild
+                    if (h->tab_size >= h->tab_size_max) MS_FAIL(h, MS_ERR_CUDA, "haplotype table overflow at maximum size");
+                    h->tab_size = std::min<int64_t>(h->tab_size_max, h->tab_size * 8);
+                    MS_CUDA(h, h->b_tab_key.ensure(static_cast<size_t>(h->tab_size) * 8));
+                    MS_CUDA(h, h->b_tab_cnt.ensure(static_cast<size_t>(h->tab_size) * 4));
+                    MS_CUDA(h, h->b_tab_rep.ensure(static_cast<size_t>(h->tab_size) * 8));
+                    h->table_valid = false;
+                }
+            } else if (hc[4] != 0) {
                 any_collision = true;
                 if (r == me) {  // a 64-bit hash collision between different patterns here: re-hash with another seed
                     if (++attempt >= 4) MS_FAIL(h, MS_ERR_CUDA, "haplotype hash collided under four seeds");
@@ -568,7 +586,7 @@ int ms_phase_groups(ms_handle* h, uint32_t* patterns, uint64_t* counts, int64_t 
             }
             max_ng = std::max<int64_t>(max_ng, static_cast<int64_t>(hc[5]));
         }
-        if (any_collision) continue;
+        if (any_collision || any_overflow) continue;
         if (max_ng > gcap) { gcap = max_ng; continue; }
         all_cnt.clear(); all_pat.clear();
         for (int r = 0; r < world; ++r) {
