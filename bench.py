@@ -266,8 +266,15 @@ def main():
     k1 = float(np.mean(k1_ms))
     alg_bytes = Rg * (L / 2.0)
     achieved = alg_bytes / (k1 / 1e3) / 1e9
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_k1_traffic.json")))
+        if tj["workload"] == {"reads_per_gpu": Rg, "L": L}:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
     roof = {"kernel": "pileup_csa_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_read": L / 2.0, "kernel_ms": k1,
+            "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src, "algorithmic_bytes_per_read": L / 2.0, "kernel_ms": k1,
             "kernel_share_of_step": k1 / ms_per_step}
 
     # ---- CPU restatement beside it (rank 0, N=1)

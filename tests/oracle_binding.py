@@ -126,7 +126,7 @@ class Oracle:
         ctr = PhaseCounters()
         H = self.lib.mso_phase_group(_p(cbits), _p(np.ascontiguousarray(flags)), R, V, min_reads, _p(hap), _p(pat),
                                      _p(cnt), cap, C.byref(nrep), C.byref(ctr))
-        pat = pat[:H].reshape(H, -1)
+        pat = pat[:H].reshape(H, pat.shape[1])
         if V == 0:
             pat = np.zeros((H, nw), dtype=np.uint32)
         return dict(H=H, nreported=nrep.value, patterns=pat, counts=cnt[:H], hap_id=hap,
