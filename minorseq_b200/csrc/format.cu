@@ -3,8 +3,40 @@
 // ms_expand_cigar replaces the per-record walk juliet and fuse do over an aligned
 // BAM record (/root/reference/doc/JULIET.md:49-58: PacBio-compliant BAM, CIGAR 'M'
 // forbidden, QV-filtered bases become 'N' :256-259; /root/reference/doc/FUSE.md:13-15).
+#include <algorithm>
 #include <cstring>
+#include <vector>
 #include "handle.h"
+
+namespace {
+
+// 8 state bytes (one per column, bits 0..3) -> 8 bits of plane p, via the multiply-gather trick
+inline uint32_t gather8(uint64_t x, int p) {
+    return static_cast<uint32_t>((((x >> p) & 0x0101010101010101ULL) * 0x0102040810204080ULL) >> 56);
+}
+
+// L state bytes -> ceil(L/32) blocks of four planes; columns past L are state 7
+void pack_row(const uint8_t* st, int32_t L, uint32_t* row) {
+    const int32_t nblk = (L + 31) / 32;
+    for (int32_t b = 0; b < nblk; ++b) {
+        uint8_t tmp[32];
+        const uint8_t* src = st + static_cast<size_t>(b) * 32;
+        if (b * 32 + 32 > L) {
+            memset(tmp, 7, 32);
+            memcpy(tmp, src, static_cast<size_t>(L - b * 32));
+            src = tmp;
+        }
+        uint32_t pl[4] = {0, 0, 0, 0};
+        for (int g = 0; g < 4; ++g) {
+            uint64_t x;
+            memcpy(&x, src + 8 * g, 8);
+            for (int p = 0; p < 4; ++p) pl[p] |= gather8(x, p) << (8 * g);
+        }
+        row[4 * b] = pl[0]; row[4 * b + 1] = pl[1]; row[4 * b + 2] = pl[2]; row[4 * b + 3] = pl[3];
+    }
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -19,20 +51,9 @@ int ms_pack_states(const uint8_t* states, int64_t R, int32_t L, uint32_t* packed
     const int32_t nblk = (L + 31) / 32;
     for (int64_t r = 0; r < R; ++r) {
         const uint8_t* s = states + static_cast<size_t>(r) * L;
-        uint32_t* row = packed + static_cast<size_t>(r) * 4 * nblk;
-        for (int32_t b = 0; b < nblk; ++b) {
-            uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-            for (int32_t j = 0; j < 32; ++j) {
-                const int32_t c = b * 32 + j;
-                const uint32_t v = c < L ? s[c] : 7u;
-                if ((v & 7u) == 6u) return MS_ERR_FORMAT;
-                p0 |= (v & 1u) << j;
-                p1 |= ((v >> 1) & 1u) << j;
-                p2 |= ((v >> 2) & 1u) << j;
-                p3 |= ((v >> 3) & 1u) << j;
-            }
-            row[4 * b] = p0; row[4 * b + 1] = p1; row[4 * b + 2] = p2; row[4 * b + 3] = p3;
-        }
+        for (int32_t c = 0; c < L; ++c)
+            if ((s[c] & 7u) == 6u || s[c] > 15u) return MS_ERR_FORMAT;
+        pack_row(s, L, packed + static_cast<size_t>(r) * 4 * nblk);
     }
     return MS_OK;
 }
@@ -53,25 +74,15 @@ int ms_unpack_states(const uint32_t* packed, int64_t R, int32_t L, uint8_t* stat
     return MS_OK;
 }
 
-static inline void set_col(uint32_t* row, int32_t c, uint32_t st) {
-    uint32_t* w = row + 4 * (c >> 5);
-    const uint32_t bit = 1u << (c & 31);
-    // row starts as state 7 everywhere: clear the planes that are 0 in st
-    if (!(st & 1u)) w[0] &= ~bit;
-    if (!(st & 2u)) w[1] &= ~bit;
-    if (!(st & 4u)) w[2] &= ~bit;
-}
-
 int ms_expand_cigar(const uint32_t* cigar, int32_t ncigar, int32_t pos, const char* seq, const uint8_t* qv_mask,
                     int32_t lseq, int32_t L, uint32_t* row, int32_t* ins_col, int64_t* ins_off, int32_t* ins_len,
                     int64_t ins_cap, int64_t* nins, char* ins_pool, int64_t pool_cap, int64_t* pool_used) {
     if (!cigar || !seq || !row || L <= 0 || ncigar < 0 || lseq < 0) return MS_ERR_ARG;
-    const int32_t nblk = (L + 31) / 32;
-    for (int32_t b = 0; b < nblk; ++b) {
-        row[4 * b] = row[4 * b + 1] = row[4 * b + 2] = 0xffffffffu;  // not spanned
-        row[4 * b + 3] = 0;
-    }
-    int32_t rc = pos;  // reference column
+    static const struct Lut { uint8_t v[256]; Lut() { memset(v, MS_N, 256); v['A'] = v['a'] = MS_A; v['C'] = v['c'] = MS_C; v['G'] = v['g'] = MS_G; v['T'] = v['t'] = MS_T; } } lut;
+    thread_local std::vector<uint8_t> st_tls;   // one state byte per column (bit 3 = insertion follows), packed at the end
+    st_tls.assign(static_cast<size_t>(L), 7);
+    uint8_t* const st = st_tls.data();         // (a thread_local in a shared object costs a call per access)
+    int64_t rc = pos;  // reference column
     int32_t qi = 0;    // query index
     int64_t ni = nins ? *nins : 0, pu = pool_used ? *pool_used : 0;
     for (int32_t k = 0; k < ncigar; ++k) {
@@ -83,36 +94,31 @@ int ms_expand_cigar(const uint32_t* cigar, int32_t ncigar, int32_t pos, const ch
         case 7:    // =
         case 8: {  // X
             if (qi + len > lseq) return MS_ERR_FORMAT;
-            for (int32_t i = 0; i < len; ++i, ++rc, ++qi) {
-                if (rc < 0 || rc >= L) continue;
-                uint32_t st;
-                switch (seq[qi]) {
-                case 'A': case 'a': st = MS_A; break;
-                case 'C': case 'c': st = MS_C; break;
-                case 'G': case 'g': st = MS_G; break;
-                case 'T': case 't': st = MS_T; break;
-                default: st = MS_N; break;
-                }
-                if (qv_mask && qv_mask[qi]) st = MS_N;
-                set_col(row, rc, st);
+            const int64_t c0 = std::max<int64_t>(rc, 0), c1 = std::min<int64_t>(rc + len, L);
+            for (int64_t c = c0; c < c1; ++c) {
+                const int32_t q = qi + static_cast<int32_t>(c - rc);
+                st[c] = (qv_mask && qv_mask[q]) ? static_cast<uint8_t>(MS_N) : lut.v[static_cast<uint8_t>(seq[q])];
             }
+            rc += len; qi += len;
             break;
         }
-        case 2:  // D
-            for (int32_t i = 0; i < len; ++i, ++rc)
-                if (rc >= 0 && rc < L) set_col(row, rc, MS_DEL);
+        case 2: {  // D
+            const int64_t c0 = std::max<int64_t>(rc, 0), c1 = std::min<int64_t>(rc + len, L);
+            if (c1 > c0) memset(st + c0, MS_DEL, static_cast<size_t>(c1 - c0));
+            rc += len;
             break;
+        }
         case 3:  // N (reference skip): columns stay "not spanned"
             rc += len;
             break;
         case 1: {  // I: attaches to the previous reference column
             if (qi + len > lseq) return MS_ERR_FORMAT;
-            const int32_t c = rc - 1;
-            if (c >= 0 && c < L && c >= pos) {
-                row[4 * (c >> 5) + 3] |= 1u << (c & 31);
+            const int64_t c = rc - 1;
+            if (c >= 0 && c < L && c >= pos && (st[c] & 7u) != 7u) {
+                st[c] |= 8;
                 if (ins_col && ins_off && ins_len && ins_pool) {
                     if (ni >= ins_cap || pu + len > pool_cap) return MS_ERR_CAPACITY;
-                    ins_col[ni] = c; ins_off[ni] = pu; ins_len[ni] = len;
+                    ins_col[ni] = static_cast<int32_t>(c); ins_off[ni] = pu; ins_len[ni] = len;
                     memcpy(ins_pool + pu, seq + qi, static_cast<size_t>(len));
                     pu += len; ++ni;
                 }
@@ -130,6 +136,7 @@ int ms_expand_cigar(const uint32_t* cigar, int32_t ncigar, int32_t pos, const ch
             return MS_ERR_FORMAT;
         }
     }
+    pack_row(st, L, row);
     if (nins) *nins = ni;
     if (pool_used) *pool_used = pu;
     return MS_OK;

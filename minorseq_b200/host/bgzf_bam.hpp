@@ -13,6 +13,8 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 namespace msbam {
@@ -224,7 +226,12 @@ public:
         if (bs < 32) throw Error("BAM record too small");
         raw_.resize(bs);
         z_.read(raw_.data(), bs);
-        const uint8_t* p = raw_.data();
+        parse_record(raw_.data(), bs, r);
+        return true;
+    }
+    // decode one alignment record from its raw bytes (after the 4-byte block_size)
+    static void parse_record(const uint8_t* p, uint32_t bs, Record& r) {
+        if (bs < 32) throw Error("BAM record too small");
         r.ref_id = detail::i32(p); r.pos = detail::i32(p + 4);
         const uint8_t l_name = p[8];
         r.mapq = p[9];
@@ -236,16 +243,17 @@ public:
         r.name.assign(reinterpret_cast<const char*>(p + o), l_name ? l_name - 1 : 0);
         o += l_name;
         r.cigar.resize(ncig);
-        for (uint16_t i = 0; i < ncig; ++i) r.cigar[i] = detail::u32(p + o + 4 * i);
+        if (ncig) memcpy(r.cigar.data(), p + o, 4ull * ncig);   // little-endian host
         o += 4ull * ncig;
         static const char dec[] = "=ACMGRSVTWYHKDBN";
         r.seq.resize(lseq);
-        for (uint32_t i = 0; i < lseq; ++i) r.seq[i] = dec[(p[o + i / 2] >> (i & 1 ? 0 : 4)) & 15];
+        char* sq = lseq ? &r.seq[0] : nullptr;
+        for (uint32_t i = 0; i + 1 < lseq; i += 2) { const uint8_t b = p[o + i / 2]; sq[i] = dec[b >> 4]; sq[i + 1] = dec[b & 15]; }
+        if (lseq & 1) sq[lseq - 1] = dec[p[o + lseq / 2] >> 4];
         o += (lseq + 1) / 2;
         r.qual.assign(p + o, p + o + lseq);
         o += lseq;
         r.aux.assign(p + o, p + bs);
-        return true;
     }
 private:
     BgzfReader z_;
@@ -253,6 +261,103 @@ private:
     std::vector<RefSeq> refs_;
     std::vector<uint8_t> raw_;
 };
+
+// ------------------------------------------------------------------ whole-file parallel inflate
+// BGZF blocks are independent gzip members: read the file, find the block boundaries from the BSIZE fields,
+// inflate all blocks concurrently into one buffer.  Returns the uncompressed BAM stream.
+inline std::vector<uint8_t> inflate_file(const std::string& path, unsigned nthreads) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) throw Error("cannot open " + path);
+    fseek(f, 0, SEEK_END);
+    const long fsz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> file(static_cast<size_t>(fsz));
+    if (fsz && fread(file.data(), 1, file.size(), f) != file.size()) { fclose(f); throw Error("short read on " + path); }
+    fclose(f);
+    struct Blk { size_t cpos, clen, upos; uint32_t isize, crc; };
+    std::vector<Blk> blks;
+    size_t o = 0, utotal = 0;
+    while (o + 18 <= file.size()) {
+        const uint8_t* hd = file.data() + o;
+        if (hd[0] != 31 || hd[1] != 139 || hd[2] != 8 || !(hd[3] & 4)) throw Error("not a BGZF block");
+        const uint16_t xlen = detail::u16(hd + 10);
+        int bsize = -1;
+        for (size_t i = 0; i + 4 <= xlen;) {
+            const uint8_t* x = hd + 12 + i;
+            const uint16_t slen = detail::u16(x + 2);
+            if (x[0] == 66 && x[1] == 67 && slen == 2) bsize = detail::u16(x + 4);
+            i += 4 + slen;
+        }
+        if (bsize < 0 || o + static_cast<size_t>(bsize) + 1 > file.size()) throw Error("bad BGZF block");
+        const size_t total = static_cast<size_t>(bsize) + 1, cpos = o + 12 + xlen, clen = total - 12 - xlen - 8;
+        const uint32_t crc = detail::u32(file.data() + o + total - 8), isize = detail::u32(file.data() + o + total - 4);
+        blks.push_back({cpos, clen, utotal, isize, crc});
+        utotal += isize;
+        o += total;
+    }
+    std::vector<uint8_t> out(utotal);
+    std::vector<std::string> errs(nthreads ? nthreads : 1);
+    auto work = [&](unsigned t, unsigned nt) {
+        for (size_t i = t; i < blks.size(); i += nt) {
+            const Blk& b = blks[i];
+            if (!b.isize) continue;
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, -15) != Z_OK) { errs[t] = "inflateInit2 failed"; return; }
+            zs.next_in = file.data() + b.cpos; zs.avail_in = static_cast<uInt>(b.clen);
+            zs.next_out = out.data() + b.upos; zs.avail_out = b.isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            if (rc != Z_STREAM_END || zs.avail_out != 0) { errs[t] = "BGZF inflate failed"; return; }
+            if (crc32(crc32(0L, Z_NULL, 0), out.data() + b.upos, b.isize) != b.crc) { errs[t] = "BGZF CRC mismatch"; return; }
+        }
+    };
+    if (nthreads <= 1) work(0, 1);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nthreads; ++t) th.emplace_back(work, t, nthreads);
+        for (auto& x : th) x.join();
+    }
+    for (const std::string& e : errs) if (!e.empty()) throw Error(e);
+    return out;
+}
+
+// BAM header + record offsets inside an uncompressed stream
+struct BamIndexed {
+    std::string text;
+    std::vector<RefSeq> refs;
+    std::vector<std::pair<size_t, uint32_t>> records;   // (offset of the record body, block_size)
+};
+inline BamIndexed index_stream(const std::vector<uint8_t>& u) {
+    BamIndexed x;
+    size_t o = 0;
+    auto need = [&](size_t n) { if (o + n > u.size()) throw Error("truncated BAM stream"); };
+    need(12);
+    if (memcmp(u.data(), "BAM\1", 4) != 0) throw Error("not a BAM file");
+    const uint32_t lt = detail::u32(u.data() + 4);
+    o = 8; need(lt + 4);
+    x.text.assign(reinterpret_cast<const char*>(u.data() + o), lt);
+    o += lt;
+    const uint32_t nref = detail::u32(u.data() + o);
+    o += 4;
+    for (uint32_t i = 0; i < nref; ++i) {
+        need(4);
+        const uint32_t ln = detail::u32(u.data() + o);
+        o += 4; need(ln + 4);
+        std::string nm(reinterpret_cast<const char*>(u.data() + o), ln);
+        if (!nm.empty() && nm.back() == '\0') nm.pop_back();
+        o += ln;
+        x.refs.push_back({nm, detail::i32(u.data() + o)});
+        o += 4;
+    }
+    while (o + 4 <= u.size()) {
+        const uint32_t bs = detail::u32(u.data() + o);
+        o += 4; need(bs);
+        x.records.emplace_back(o, bs);
+        o += bs;
+    }
+    return x;
+}
 
 // ------------------------------------------------------------------ BAM writer (fixtures, mixdata)
 class BamWriter {

@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/minorseq_b200.h"
 #include "bgzf_bam.hpp"
@@ -38,69 +40,108 @@ inline void die(const std::string& m) {
     exit(1);
 }
 
+// One record -> one packed row (+ optional insertion events appended to the caller's vectors).
+inline void expand_record(const msbam::Record& rec, const QvFilter& qv, int32_t L, uint32_t* row, bool want_insertions,
+                          std::vector<uint8_t>& mask, std::vector<int32_t>& ic, std::vector<int64_t>& io, std::vector<int32_t>& il,
+                          std::string& pool, std::vector<int32_t>& out_col, std::vector<int32_t>& out_len, std::vector<int64_t>& out_off,
+                          std::string& out_pool) {
+    // rich-QV filter: tracks are stored in native orientation, SEQ in reference orientation
+    const uint8_t* maskp = nullptr;
+    if (qv.threshold > 0) {
+        bool any = false;
+        for (const std::string& t : qv.tags) {
+            std::vector<int> track = rec.tag_per_base(t.c_str());
+            if (track.size() != rec.seq.size() || track.empty()) continue;
+            if (!any) mask.assign(rec.seq.size(), 0);
+            any = true;
+            const bool rev = rec.flag & 0x10;
+            for (size_t i = 0; i < track.size(); ++i)
+                if (track[i] < qv.threshold) mask[rev ? track.size() - 1 - i : i] = 1;
+        }
+        if (any) maskp = mask.data();
+    }
+    int64_t ni = 0, pu = 0;
+    int rc;
+    for (;;) {
+        ni = 0; pu = 0;
+        rc = ms_expand_cigar(rec.cigar.data(), static_cast<int32_t>(rec.cigar.size()), rec.pos, rec.seq.data(), maskp,
+                             static_cast<int32_t>(rec.seq.size()), L, row, want_insertions ? ic.data() : nullptr, io.data(), il.data(),
+                             static_cast<int64_t>(ic.size()), &ni, want_insertions ? &pool[0] : nullptr, static_cast<int64_t>(pool.size()), &pu);
+        if (rc != MS_ERR_CAPACITY) break;
+        ic.resize(ic.size() * 2); io.resize(io.size() * 2); il.resize(il.size() * 2); pool.resize(pool.size() * 2);
+    }
+    if (rc == MS_ERR_FORMAT) die("record " + rec.name + ": BAM files have to be PacBio-compliant, cigar M is forbidden");
+    if (rc != MS_OK) die("record " + rec.name + ": cannot expand CIGAR");
+    for (int64_t i = 0; i < ni; ++i) {
+        out_col.push_back(ic[i]);
+        out_len.push_back(il[i]);
+        out_off.push_back(static_cast<int64_t>(out_pool.size()) + io[i]);
+    }
+    out_pool.append(pool.data(), static_cast<size_t>(pu));
+}
+
+// Whole-file loader: parallel BGZF inflate, one sequential pass for the admission filter, then the
+// records are parsed and expanded by all host threads straight into one pinned row buffer.
 inline void load_alignments(const std::string& path, const QvFilter& qv, bool want_names, bool want_insertions, Alignments& out) {
-    msbam::BamReader bam(path);
-    msbam::Record rec;
-    std::vector<uint8_t> mask;
-    std::vector<int32_t> ic(4096);
-    std::vector<int64_t> io(4096);
-    std::vector<int32_t> il(4096);
-    std::string pool(1 << 16, '\0');
-    while (bam.next(rec)) {
-        if (!ms_read_admitted(rec.flag) || rec.ref_id < 0) { ++out.nskipped; continue; }
+    unsigned nt = std::thread::hardware_concurrency();
+    if (const char* e = getenv("MS_HOST_THREADS")) nt = static_cast<unsigned>(atoi(e));
+    if (nt < 1) nt = 1;
+    const std::vector<uint8_t> u = msbam::inflate_file(path, nt);
+    const msbam::BamIndexed bx = msbam::index_stream(u);
+    // admission (doc/JULIET.md:58) + one reference per run
+    std::vector<size_t> keep;
+    for (size_t i = 0; i < bx.records.size(); ++i) {
+        const uint8_t* p = u.data() + bx.records[i].first;
+        if (bx.records[i].second < 32) die("BAM record too small");
+        const int32_t ref_id = msbam::detail::i32(p);
+        const uint16_t flag = msbam::detail::u16(p + 14);
+        if (!ms_read_admitted(flag) || ref_id < 0) { ++out.nskipped; continue; }
         if (out.ref_id < 0) {
-            out.ref_id = rec.ref_id;
-            if (rec.ref_id >= static_cast<int32_t>(bam.refs().size())) die("record refers to an unknown reference");
-            out.L = bam.refs()[rec.ref_id].length;
-            out.ref_name = bam.refs()[rec.ref_id].name;
+            out.ref_id = ref_id;
+            if (ref_id >= static_cast<int32_t>(bx.refs.size())) die("record refers to an unknown reference");
+            out.L = bx.refs[ref_id].length;
+            out.ref_name = bx.refs[ref_id].name;
             if (out.L < 3) die("reference too short");
         }
-        if (rec.ref_id != out.ref_id) { ++out.nskipped; continue; }   // one reference per run
-        const int32_t rw = ms_row_words(out.L);
-        if (static_cast<size_t>(out.nreads + 1) > out.cap_rows) {
-            const size_t ncap = out.cap_rows ? out.cap_rows * 2 : 4096;
-            uint32_t* nr = static_cast<uint32_t*>(ms_alloc_pinned(ncap * rw * sizeof(uint32_t)));
-            if (!nr) die("out of pinned host memory");
-            if (out.rows) memcpy(nr, out.rows, static_cast<size_t>(out.nreads) * rw * sizeof(uint32_t));
-            ms_free_pinned(out.rows);
-            out.rows = nr; out.cap_rows = ncap;
+        if (ref_id != out.ref_id) { ++out.nskipped; continue; }
+        keep.push_back(i);
+    }
+    out.nreads = static_cast<int64_t>(keep.size());
+    if (keep.empty()) return;
+    const int32_t rw = ms_row_words(out.L);
+    out.rows = static_cast<uint32_t*>(ms_alloc_pinned(keep.size() * rw * sizeof(uint32_t)));
+    if (!out.rows) die("out of pinned host memory");
+    out.cap_rows = keep.size();
+    if (want_names) out.names.resize(keep.size());
+    struct Part { std::vector<int32_t> col, len; std::vector<int64_t> off; std::string pool; };
+    nt = static_cast<unsigned>(std::min<size_t>(nt, keep.size()));
+    std::vector<Part> parts(nt);
+    auto work = [&](unsigned t) {
+        const size_t i0 = keep.size() * t / nt, i1 = keep.size() * (t + 1) / nt;
+        msbam::Record rec;
+        std::vector<uint8_t> mask;
+        std::vector<int32_t> ic(4096), il(4096);
+        std::vector<int64_t> io(4096);
+        std::string pool(1 << 16, '\0');
+        for (size_t k = i0; k < i1; ++k) {
+            const auto& rr = bx.records[keep[k]];
+            msbam::BamReader::parse_record(u.data() + rr.first, rr.second, rec);
+            expand_record(rec, qv, out.L, out.rows + k * rw, want_insertions, mask, ic, io, il, pool, parts[t].col, parts[t].len, parts[t].off, parts[t].pool);
+            if (want_names) out.names[k] = rec.name;
         }
-        // rich-QV filter: tracks are stored in native orientation, SEQ in reference orientation
-        const uint8_t* maskp = nullptr;
-        if (qv.threshold > 0) {
-            bool any = false;
-            mask.assign(rec.seq.size(), 0);
-            for (const std::string& t : qv.tags) {
-                std::vector<int> track = rec.tag_per_base(t.c_str());
-                if (track.size() != rec.seq.size()) continue;
-                any = true;
-                const bool rev = rec.flag & 0x10;
-                for (size_t i = 0; i < track.size(); ++i)
-                    if (track[i] < qv.threshold) mask[rev ? track.size() - 1 - i : i] = 1;
-            }
-            if (any) maskp = mask.data();
-        }
-        int64_t ni = 0, pu = 0;
-        int rc;
-        for (;;) {
-            ni = 0; pu = 0;
-            rc = ms_expand_cigar(rec.cigar.data(), static_cast<int32_t>(rec.cigar.size()), rec.pos, rec.seq.data(), maskp,
-                                 static_cast<int32_t>(rec.seq.size()), out.L, out.rows + static_cast<size_t>(out.nreads) * rw,
-                                 want_insertions ? ic.data() : nullptr, io.data(), il.data(), static_cast<int64_t>(ic.size()), &ni,
-                                 want_insertions ? &pool[0] : nullptr, static_cast<int64_t>(pool.size()), &pu);
-            if (rc != MS_ERR_CAPACITY) break;
-            ic.resize(ic.size() * 2); io.resize(io.size() * 2); il.resize(il.size() * 2); pool.resize(pool.size() * 2);
-        }
-        if (rc == MS_ERR_FORMAT) die("record " + rec.name + ": BAM files have to be PacBio-compliant, cigar M is forbidden");
-        if (rc != MS_OK) die("record " + rec.name + ": cannot expand CIGAR");
-        for (int64_t i = 0; i < ni; ++i) {
-            out.ins_col.push_back(ic[i]);
-            out.ins_len.push_back(il[i]);
-            out.ins_off.push_back(static_cast<int64_t>(out.ins_pool.size()) + io[i]);
-        }
-        out.ins_pool.append(pool.data(), static_cast<size_t>(pu));
-        if (want_names) out.names.push_back(rec.name);
-        ++out.nreads;
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    for (const Part& p : parts) {   // read order is preserved: thread t holds a contiguous range
+        const int64_t base = static_cast<int64_t>(out.ins_pool.size());
+        out.ins_col.insert(out.ins_col.end(), p.col.begin(), p.col.end());
+        out.ins_len.insert(out.ins_len.end(), p.len.begin(), p.len.end());
+        for (int64_t o : p.off) out.ins_off.push_back(base + o);
+        out.ins_pool += p.pool;
     }
 }
 

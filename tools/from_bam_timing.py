@@ -1,0 +1,25 @@
+"""R3: wall-clock of the juliet / fuse binaries starting from a BAM file (inflate + CIGAR walk + H2D + kernels +
+report).  Host-bound by construction; reported, not a target."""
+import json, os, subprocess, sys, tempfile, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from minorseq_b200.synth import SynthConfig, make_tables, pack_states, synth_states
+BIN = os.path.join(ROOT, "minorseq_b200", "bin")
+R = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+t = make_tables(SynthConfig(L=3000, seed=20240003))
+d = tempfile.mkdtemp()
+packed = pack_states(synth_states(t, 0, R))
+packed.tofile(os.path.join(d, "p.bin"))
+open(os.path.join(d, "ref.txt"), "w").write(t.refseq + "\n")
+subprocess.check_call([os.path.join(BIN, "packed2bam"), os.path.join(d, "p.bin"), "3000", str(R), os.path.join(d, "ref.txt"), os.path.join(d, "in.bam")])
+cfg = {"genes": [{"name": "pol", "begin": 1, "end": 3001}], "referenceName": "synthetic_ref", "referenceSequence": t.refseq}
+json.dump(cfg, open(os.path.join(d, "cfg.json"), "w"))
+out = {"reads": R, "bam_bytes": os.path.getsize(os.path.join(d, "in.bam"))}
+for name, cmd in (("juliet", [os.path.join(BIN, "juliet"), "-c", os.path.join(d, "cfg.json"), "--mode-phasing", "--min-perc", "0.5", os.path.join(d, "in.bam"), os.path.join(d, "o.json")]),
+                  ("fuse", [os.path.join(BIN, "fuse"), os.path.join(d, "in.bam"), os.path.join(d, "o.fasta")])):
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter(); subprocess.check_call(cmd, stderr=subprocess.DEVNULL); ts.append(time.perf_counter() - t0)
+    out[name + "_s"] = min(ts); out[name + "_reads_per_s"] = R / min(ts)
+print(json.dumps(out))
