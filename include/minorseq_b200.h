@@ -181,6 +181,26 @@ int ms_phase_device(ms_handle *h, uint32_t **d_bits, uint8_t **d_flags, int64_t 
 /* C[v][w] = #reads carrying both (V*V int32, device buffer owned by the handle). */
 int ms_cooccurrence(ms_handle *h, int32_t **d_C);
 
+/* ---- the whole juliet pass in one call ------------------------------------------------------
+ * reset -> pileup -> (all-reduce when a communicator is attached) -> codon test -> phasing, i.e. everything
+ * juliet does between BAM decode and report writing.  The caller owns the result buffers; on
+ * MS_ERR_CAPACITY the n* fields hold the sizes needed.  patterns/counts come back in juliet's haplotype
+ * order with [0,nreported) reported (rows ceil(nkeys/32) words apart; the buffer must hold
+ * patterns_cap * ceil(keys_cap/32) words); key_col/key_codon is the pooled variant list the bit-vectors refer to.
+ * Afterwards ms_phase_assign / ms_get_counts / ms_cooccurrence can be called as usual.              */
+typedef struct {
+    ms_variant *variants;  int64_t variants_cap, nvariants;
+    int32_t *key_col, *key_codon; int32_t keys_cap, nkeys;
+    uint32_t *patterns; uint64_t *counts; int64_t patterns_cap, npatterns, nreported;
+    ms_phase_counters counters;
+} ms_juliet_result;
+int ms_juliet_pass_dev(ms_handle *h, const uint32_t *d_packed, int64_t R, const ms_gene *genes, int32_t ngenes,
+                       const char *refseq, const ms_call_params *prm, int32_t phase, int32_t min_hap_reads,
+                       ms_juliet_result *out);
+int ms_juliet_pass_host(ms_handle *h, const uint32_t *h_packed, int64_t R, const ms_gene *genes, int32_t ngenes,
+                        const char *refseq, const ms_call_params *prm, int32_t phase, int32_t min_hap_reads,
+                        ms_juliet_result *out);
+
 /* ---- K4: fuse consensus (doc/FUSE.md:17-24) --------------------------------------- */
 typedef struct { int32_t min_coverage; double ins_fraction; int32_t ins_distance; } ms_fuse_params;
 void ms_fuse_params_default(ms_fuse_params *p);

@@ -36,6 +36,13 @@ class FuseParams(C.Structure):
     _fields_ = [("min_coverage", C.c_int32), ("ins_fraction", C.c_double), ("ins_distance", C.c_int32)]
 
 
+class JulietResult(C.Structure):
+    _fields_ = [("variants", C.POINTER(Variant)), ("variants_cap", C.c_int64), ("nvariants", C.c_int64),
+                ("key_col", C.POINTER(C.c_int32)), ("key_codon", C.POINTER(C.c_int32)), ("keys_cap", C.c_int32), ("nkeys", C.c_int32),
+                ("patterns", C.POINTER(C.c_uint32)), ("counts", C.POINTER(C.c_uint64)), ("patterns_cap", C.c_int64),
+                ("npatterns", C.c_int64), ("nreported", C.c_int64), ("counters", PhaseCounters)]
+
+
 class SynthParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("L", C.c_int32), ("nstrains", C.c_int32), ("thr_N", C.c_uint32),
                 ("thr_sub", C.c_uint32), ("thr_ins20", C.c_uint32), ("thr_trunc16", C.c_uint32)]
@@ -85,6 +92,10 @@ _SIGNATURES = {
     "ms_phase_assign": (C.c_int, [_P, _P, C.c_int64, _P]),
     "ms_phase_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
     "ms_cooccurrence": (C.c_int, [_P, C.POINTER(_P)]),
+    "ms_juliet_pass_dev": (C.c_int, [_P, _P, C.c_int64, C.POINTER(Gene), C.c_int32, C.c_char_p, C.POINTER(CallParams), C.c_int32,
+                                   C.c_int32, C.POINTER(JulietResult)]),
+    "ms_juliet_pass_host": (C.c_int, [_P, _P, C.c_int64, C.POINTER(Gene), C.c_int32, C.c_char_p, C.POINTER(CallParams), C.c_int32,
+                                    C.c_int32, C.POINTER(JulietResult)]),
     "ms_fuse_params_default": (None, [C.POINTER(FuseParams)]),
     "ms_fuse": (C.c_int, [_P, C.POINTER(FuseParams), _P, _P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64,
                           C.POINTER(C.c_int64)]),

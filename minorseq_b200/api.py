@@ -48,7 +48,8 @@ class Haplotypes:
 
 @dataclass
 class JulietResult:
-    variants: list = field(default_factory=list)     # list of dict
+    variants: list = field(default_factory=list)     # list of ms_variant records
+    keys: list = field(default_factory=list)         # pooled (start column, codon) list the haplotype bit-vectors refer to
     haplotypes: Haplotypes = None
     col_counts: np.ndarray = None
     codon_counts: np.ndarray = None
@@ -266,24 +267,80 @@ class Juliet:
             torch.cuda.current_stream(self.hd.device).synchronize()
         return t[: self._V * self._V].view(self._V, self._V)
 
-    # -- the whole pass on device-resident reads (what bench.py times)
+    # -- the whole pass in one C-ABI call (what bench.py times)
+    def _pass(self, ptr, nreads, host, want_hap_id):
+        from ._lib import JulietResult as _JR
+        st = getattr(self, "_pass_state", None)
+        if st is None:
+            st = self._pass_state = dict(vcap=1024, kcap=1024, pcap=4096)
+        while True:
+            if st.get("alloc") != (st["vcap"], st["kcap"], st["pcap"]):
+                st["alloc"] = (st["vcap"], st["kcap"], st["pcap"])
+                st["var"] = (Variant * st["vcap"])()
+                st["kc"] = np.zeros(st["kcap"], dtype=np.int32)
+                st["kk"] = np.zeros(st["kcap"], dtype=np.int32)
+                st["pat"] = np.zeros(st["pcap"] * ((st["kcap"] + 31) // 32), dtype=np.uint32)
+                st["cnt"] = np.zeros(st["pcap"], dtype=np.uint64)
+                st["genes"] = (Gene * len(self.genes))(*[Gene(b, e) for (b, e) in self.genes])
+                r = st["res"] = _JR()
+                r.variants = st["var"]; r.variants_cap = st["vcap"]
+                r.key_col = st["kc"].ctypes.data_as(C.POINTER(C.c_int32)); r.key_codon = st["kk"].ctypes.data_as(C.POINTER(C.c_int32)); r.keys_cap = st["kcap"]
+                r.patterns = st["pat"].ctypes.data_as(C.POINTER(C.c_uint32)); r.counts = st["cnt"].ctypes.data_as(C.POINTER(C.c_uint64)); r.patterns_cap = st["pcap"]
+            r = st["res"]
+            fn = self.lib.ms_juliet_pass_host if host else self.lib.ms_juliet_pass_dev
+            rc = fn(self.hd.h, C.c_void_p(ptr), nreads, st["genes"], len(self.genes), self.refseq.encode() if self.refseq else None,
+                    C.byref(self.params), 1 if self.mode_phasing else 0, self.min_hap_reads, C.byref(r))
+            if rc == -4:   # MS_ERR_CAPACITY: grow what was too small and run the pass again
+                st["vcap"] = max(st["vcap"], int(r.nvariants)); st["kcap"] = max(st["kcap"], int(r.nkeys)); st["pcap"] = max(st["pcap"], int(r.npatterns))
+                continue
+            check(rc, self.hd.h)
+            break
+        res = JulietResult(variants=[Variant.from_buffer_copy(st["var"][i]) for i in range(r.nvariants)])
+        res.keys = [(int(st["kc"][i]), int(st["kk"][i])) for i in range(r.nkeys)]
+        if self.mode_phasing:
+            V = int(r.nkeys)
+            self._V = V
+            nw = max(1, (V + 31) // 32)
+            H = int(r.npatterns)
+            pat = st["pat"][: H * nw].reshape(H, nw).copy()
+            cnt = st["cnt"][:H].copy()
+            names = []
+            buf = C.create_string_buffer(3)
+            for i in range(r.nreported):
+                self.lib.ms_haplotype_name(i, buf)
+                names.append(buf.value.decode())
+            c = r.counters
+            counters = dict(reported=int(c.reported), insufficient=int(c.insufficient), damaged=int(c.damaged), gaps=int(c.gaps),
+                            heteroduplex=int(c.heteroduplex), partial=int(c.partial))
+            hap = None
+            if want_hap_id:
+                hap = np.empty(nreads, dtype=np.int32)
+                check(self.lib.ms_phase_assign(self.hd.h, _ptr(pat), H, _ptr(hap)), self.hd.h)
+            res.haplotypes = Haplotypes(patterns=pat, counts=cnt, nreported=int(r.nreported), names=names, counters=counters, hap_id=hap)
+        return res
+
     def run_device(self, d_packed_ptr: int, nreads: int, want_hap_id=False) -> JulietResult:
-        self.reset()
-        self.pileup_device(d_packed_ptr, nreads)
+        """pileup -> all-reduce -> call -> phase on device-resident packed reads (one C-ABI call)."""
+        if not getattr(self.hd, "native_comm", False) and _torch_world() > 1:
+            return self._run_staged(d_packed_ptr, nreads, want_hap_id)     # torch.distributed exchange between the stages
+        return self._pass(d_packed_ptr, nreads, False, want_hap_id)
+
+    def run_host(self, packed: np.ndarray, want_hap_id=False) -> JulietResult:
+        """Reference-facing call with HOST buffers: H2D + kernels + D2H of the results (one C-ABI call)."""
+        if not getattr(self.hd, "native_comm", False) and _torch_world() > 1:
+            self.reset()
+            dptr = self.pileup_host(packed)
+            return self._run_staged(dptr, packed.shape[0], want_hap_id, piled=True)
+        return self._pass(packed.ctypes.data, packed.shape[0], True, want_hap_id)
+
+    def _run_staged(self, d_packed_ptr, nreads, want_hap_id, piled=False) -> JulietResult:
+        if not piled:
+            self.reset()
+            self.pileup_device(d_packed_ptr, nreads)
         self.allreduce_counts()
         res = JulietResult(variants=self.call())
         if self.mode_phasing:
             res.haplotypes, res.keys = self.phase_device(res.variants, d_packed_ptr, nreads, want_hap_id)
-        return res
-
-    def run_host(self, packed: np.ndarray, want_hap_id=False) -> JulietResult:
-        """Reference-facing call with HOST buffers: H2D + kernels + D2H of the results."""
-        self.reset()
-        dptr = self.pileup_host(packed)
-        self.allreduce_counts()
-        res = JulietResult(variants=self.call())
-        if self.mode_phasing:
-            res.haplotypes, res.keys = self.phase_device(res.variants, dptr, packed.shape[0], want_hap_id)
         return res
 
     def variant_dicts(self, variants):
@@ -332,6 +389,14 @@ class Fuse:
         check(self.lib.ms_fuse(self.hd.h, C.byref(self.params), _ptr(ic), _ptr(io), _ptr(il), nins, _ptr(pool),
                                len(ins_pool), _ptr(seq), cap, C.byref(n)), self.hd.h)
         return seq[: n.value].tobytes().decode()
+
+
+def _torch_world():
+    try:
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    except Exception:
+        return 1
 
 
 def _as_tensor(ptr, shape, dtype, device):

@@ -1,0 +1,73 @@
+// pass.cu -- the whole juliet pass behind one C-ABI call: pileup -> (all-reduce) -> codon test -> phasing.
+//
+// What `juliet [--mode-phasing] in.bam out.json` does between BAM decode and report writing
+// (/root/reference/doc/JULIET.md:38-42, :192-211), as one entry point so that a host program pays two small
+// device->host reads per pass instead of a round trip per stage.  Composition only: every stage is the same
+// code as the stand-alone entry points.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+#include "handle.h"
+
+static int juliet_pass(ms_handle* h, const uint32_t* packed, bool host_rows, int64_t R, const ms_gene* genes, int32_t ngenes,
+                       const char* refseq, const ms_call_params* prm, int32_t phase, int32_t min_hap_reads, ms_juliet_result* out) {
+    if (!h || !out || !prm || R < 0) return MS_ERR_ARG;
+    int rc = ms_reset_counts(h);
+    if (rc != MS_OK) return rc;
+    const uint32_t* d_rows = packed;
+    rc = host_rows ? ms_pileup_host(h, packed, R, &d_rows) : ms_pileup_dev(h, packed, R);
+    if (rc != MS_OK) return rc;
+    rc = ms_allreduce_counts(h);
+    if (rc != MS_OK) return rc;
+    rc = ms_call(h, genes, ngenes, refseq, prm, out->variants, out->variants_cap, &out->nvariants);
+    if (rc != MS_OK) return rc;
+    out->nkeys = 0; out->npatterns = 0; out->nreported = 0;
+    memset(&out->counters, 0, sizeof out->counters);
+    if (!phase) return MS_OK;
+    if (out->nvariants > out->variants_cap) return MS_ERR_CAPACITY;   // the caller re-runs with a larger buffer
+    // one pooled, de-duplicated variant list over all genes (screenshot juliet_hiv-phasing.png)
+    std::vector<std::pair<int32_t, int32_t>> keys;
+    keys.reserve(static_cast<size_t>(out->nvariants));
+    for (int64_t i = 0; i < out->nvariants; ++i) keys.emplace_back(out->variants[i].col, out->variants[i].codon);
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    const int32_t V = static_cast<int32_t>(keys.size());
+    out->nkeys = V;
+    if (V > out->keys_cap) return MS_ERR_CAPACITY;
+    std::vector<int32_t> vc(std::max(1, V)), vk(std::max(1, V));
+    for (int32_t i = 0; i < V; ++i) { vc[i] = keys[i].first; vk[i] = keys[i].second; out->key_col[i] = vc[i]; out->key_codon[i] = vk[i]; }
+    rc = ms_phase_begin(h, vc.data(), vk.data(), V, R);
+    if (rc != MS_OK) return rc;
+    rc = ms_phase_dev(h, d_rows, R);
+    if (rc != MS_OK) return rc;
+    int64_t H = 0;
+    ms_phase_counters ctr;
+    rc = ms_phase_groups(h, out->patterns, out->counts, out->patterns_cap, &H, &ctr);
+    if (rc != MS_OK) return rc;
+    out->npatterns = H;
+    if (H > out->patterns_cap) return MS_ERR_CAPACITY;
+    int64_t Hm = 0, nrep = 0;
+    ms_phase_counters c2;
+    rc = ms_haplotype_order(out->patterns, out->counts, H, V, min_hap_reads, &Hm, &nrep, &c2);
+    if (rc != MS_OK) return rc;
+    out->npatterns = Hm;
+    out->nreported = nrep;
+    out->counters = ctr;
+    out->counters.reported = c2.reported;
+    out->counters.insufficient = c2.insufficient;
+    return MS_OK;
+}
+
+extern "C" {
+
+int ms_juliet_pass_dev(ms_handle* h, const uint32_t* d_packed, int64_t R, const ms_gene* genes, int32_t ngenes, const char* refseq,
+                       const ms_call_params* prm, int32_t phase, int32_t min_hap_reads, ms_juliet_result* out) {
+    return juliet_pass(h, d_packed, false, R, genes, ngenes, refseq, prm, phase, min_hap_reads, out);
+}
+
+int ms_juliet_pass_host(ms_handle* h, const uint32_t* h_packed, int64_t R, const ms_gene* genes, int32_t ngenes, const char* refseq,
+                        const ms_call_params* prm, int32_t phase, int32_t min_hap_reads, ms_juliet_result* out) {
+    return juliet_pass(h, h_packed, true, R, genes, ngenes, refseq, prm, phase, min_hap_reads, out);
+}
+
+}  // extern "C"
