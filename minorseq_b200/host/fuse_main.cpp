@@ -5,7 +5,9 @@
 #include <cstdlib>
 #include <fstream>
 #include <string>
+#include <thread>
 #include <vector>
+#include <unistd.h>
 #include "host_common.hpp"
 
 #define CK(h, call)                                                                            \
@@ -40,10 +42,12 @@ int main(int argc, char** argv) {
     }
     if (pos.size() != 2) { puts("Usage: fuse <in.bam> <out.fasta>"); return 1; }
     try {
+        // the CUDA context comes up (~0.5 s) on this thread while a helper thread inflates and indexes the BAM
         ms_handle* h = nullptr;
-        if (ms_create(device, &h) != MS_OK) mshost::die(ms_last_error(nullptr));   // fail before any work: there is no CPU path
         mshost::Alignments aln;
-        mshost::load_alignments(pos[0], qv, false, true, aln);
+        mshost::load_alignments_overlapped(pos[0], qv, false, true, aln, [&] {
+            if (ms_create(device, &h) != MS_OK) mshost::die(ms_last_error(nullptr));   // there is no CPU path
+        });
         if (aln.nreads == 0) mshost::die("no primary or supplementary alignments in " + pos[0]);
         CK(h, ms_set_layout(h, aln.L, nullptr));
         CK(h, ms_pileup_host(h, aln.rows, aln.nreads, nullptr));
@@ -60,6 +64,9 @@ int main(int argc, char** argv) {
         f << ">" << stem << "|fuse|" << aln.ref_name << "\n";
         for (size_t i = 0; i < seq.size(); i += 70) f << seq.substr(i, 70) << "\n";
         fprintf(stderr, "fuse: %lld reads, consensus length %lld\n", static_cast<long long>(aln.nreads), static_cast<long long>(len));
+        f.close();
+        fflush(nullptr);
+        if (!getenv("MS_FULL_TEARDOWN")) _exit(0);
         ms_destroy(h);
     } catch (const std::exception& e) {
         mshost::die(e.what());

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -80,37 +81,52 @@ inline void expand_record(const msbam::Record& rec, const QvFilter& qv, int32_t 
     out_pool.append(pool.data(), static_cast<size_t>(pu));
 }
 
-// Whole-file loader: parallel BGZF inflate, one sequential pass for the admission filter, then the
-// records are parsed and expanded by all host threads straight into one pinned row buffer.
-inline void load_alignments(const std::string& path, const QvFilter& qv, bool want_names, bool want_insertions, Alignments& out) {
+// Whole-file loader in two phases so that the first one (no CUDA involved) can overlap the creation of the
+// CUDA context: decode() = parallel BGZF inflate + record index + admission filter; expand() = all host
+// threads parse and expand the admitted records straight into one pinned row buffer.
+struct Decoded {
+    std::vector<uint8_t> u;
+    msbam::BamIndexed bx;
+    std::vector<size_t> keep;
+    unsigned nt = 1;
+};
+
+inline void decode_alignments(const std::string& path, Decoded& d, Alignments& out) {
     unsigned nt = std::thread::hardware_concurrency();
     if (const char* e = getenv("MS_HOST_THREADS")) nt = static_cast<unsigned>(atoi(e));
     if (nt < 1) nt = 1;
-    const std::vector<uint8_t> u = msbam::inflate_file(path, nt);
-    const msbam::BamIndexed bx = msbam::index_stream(u);
+    d.nt = nt;
+    d.u = msbam::inflate_file(path, nt);
+    d.bx = msbam::index_stream(d.u);
     // admission (doc/JULIET.md:58) + one reference per run
-    std::vector<size_t> keep;
-    for (size_t i = 0; i < bx.records.size(); ++i) {
-        const uint8_t* p = u.data() + bx.records[i].first;
-        if (bx.records[i].second < 32) die("BAM record too small");
+    for (size_t i = 0; i < d.bx.records.size(); ++i) {
+        const uint8_t* p = d.u.data() + d.bx.records[i].first;
+        if (d.bx.records[i].second < 32) throw std::runtime_error("BAM record too small");
         const int32_t ref_id = msbam::detail::i32(p);
         const uint16_t flag = msbam::detail::u16(p + 14);
         if (!ms_read_admitted(flag) || ref_id < 0) { ++out.nskipped; continue; }
         if (out.ref_id < 0) {
             out.ref_id = ref_id;
-            if (ref_id >= static_cast<int32_t>(bx.refs.size())) die("record refers to an unknown reference");
-            out.L = bx.refs[ref_id].length;
-            out.ref_name = bx.refs[ref_id].name;
-            if (out.L < 3) die("reference too short");
+            if (ref_id >= static_cast<int32_t>(d.bx.refs.size())) throw std::runtime_error("record refers to an unknown reference");
+            out.L = d.bx.refs[ref_id].length;
+            out.ref_name = d.bx.refs[ref_id].name;
+            if (out.L < 3) throw std::runtime_error("reference too short");
         }
         if (ref_id != out.ref_id) { ++out.nskipped; continue; }
-        keep.push_back(i);
+        d.keep.push_back(i);
     }
-    out.nreads = static_cast<int64_t>(keep.size());
+    out.nreads = static_cast<int64_t>(d.keep.size());
+}
+
+inline void expand_alignments(const Decoded& d, const QvFilter& qv, bool want_names, bool want_insertions, Alignments& out) {
+    const std::vector<uint8_t>& u = d.u;
+    const msbam::BamIndexed& bx = d.bx;
+    const std::vector<size_t>& keep = d.keep;
+    unsigned nt = d.nt;
     if (keep.empty()) return;
     const int32_t rw = ms_row_words(out.L);
     out.rows = static_cast<uint32_t*>(ms_alloc_pinned(keep.size() * rw * sizeof(uint32_t)));
-    if (!out.rows) die("out of pinned host memory");
+    if (!out.rows) throw std::runtime_error("cannot allocate pinned host memory for the packed rows");
     out.cap_rows = keep.size();
     if (want_names) out.names.resize(keep.size());
     struct Part { std::vector<int32_t> col, len; std::vector<int64_t> off; std::string pool; };
@@ -143,6 +159,25 @@ inline void load_alignments(const std::string& path, const QvFilter& qv, bool wa
         for (int64_t o : p.off) out.ins_off.push_back(base + o);
         out.ins_pool += p.pool;
     }
+}
+
+// decode on a helper thread while the caller brings up the CUDA context, then expand
+template <class CreateFn>
+inline void load_alignments_overlapped(const std::string& path, const QvFilter& qv, bool want_names, bool want_insertions, Alignments& out,
+                                       CreateFn create_context) {
+    Decoded d;
+    std::string err;
+    if (getenv("MS_SERIAL_LOAD")) {   // A/B switch for the overlap (tools/from_bam_timing.py)
+        create_context();
+        decode_alignments(path, d, out);
+        expand_alignments(d, qv, want_names, want_insertions, out);
+        return;
+    }
+    std::thread dec([&] { try { decode_alignments(path, d, out); } catch (const std::exception& e) { err = e.what(); } });
+    create_context();      // dies with the CUDA error when there is no usable GPU: that message wins
+    dec.join();
+    if (!err.empty()) throw std::runtime_error(err);
+    expand_alignments(d, qv, want_names, want_insertions, out);
 }
 
 }  // namespace mshost

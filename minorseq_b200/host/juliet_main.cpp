@@ -12,7 +12,9 @@
 #include <fstream>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
+#include <unistd.h>
 #include "host_common.hpp"
 #include "report.hpp"
 #include "target_config.hpp"
@@ -87,15 +89,25 @@ int main(int argc, char** argv) {
         if (sscanf(region.c_str(), "%d-%d", &rb, &re) != 2 || rb < 1 || re <= rb) mshost::die("--region expects <begin-end>");
     }
 
+    const bool timing = getenv("MS_TIMING") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[timing] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     try {
         mscfg::TargetConfig cfg;
         if (!config.empty()) cfg = mscfg::load(config);
 
+        // the CUDA context comes up (~0.5 s) on this thread while a helper thread inflates and indexes the BAM
         ms_handle* h = nullptr;
-        if (ms_create(device, &h) != MS_OK) mshost::die(ms_last_error(nullptr));   // fail before any work: there is no CPU path
-
         mshost::Alignments aln;
-        mshost::load_alignments(pos[0], qv, phasing, false, aln);
+        mshost::load_alignments_overlapped(pos[0], qv, phasing, false, aln, [&] {
+            if (ms_create(device, &h) != MS_OK) mshost::die(ms_last_error(nullptr));   // there is no CPU path
+        });
+        lap("CUDA context || BAM inflate + CIGAR expansion");
         if (aln.nreads == 0) mshost::die("no primary or supplementary alignments in " + pos[0]);
         const int32_t L = aln.L;
 
@@ -121,6 +133,8 @@ int main(int argc, char** argv) {
         CK(h, ms_set_layout(h, L, start.data()));
         const uint32_t* d_rows = nullptr;
         CK(h, ms_pileup_host(h, aln.rows, aln.nreads, &d_rows));
+        CK(h, ms_synchronize(h));
+        lap("H2D + pileup");
 
         ms_call_params prm;
         ms_call_params_default(&prm);
@@ -150,6 +164,7 @@ int main(int argc, char** argv) {
             rows.push_back(r);
         }
 
+        lap("call + DRM annotation");
         std::vector<uint32_t> col(static_cast<size_t>(L) * 8);
         CK(h, ms_get_counts(h, col.data(), nullptr));
 
@@ -207,6 +222,7 @@ int main(int argc, char** argv) {
             }
         }
 
+        lap("phasing");
         char ts[40];
         const auto now = std::chrono::system_clock::now();
         const std::time_t tt = std::chrono::system_clock::to_time_t(now);
@@ -229,8 +245,11 @@ int main(int argc, char** argv) {
             if (!f) mshost::die("cannot write " + out_html);
             f << msreport::to_html(report);
         }
+        lap("report writing");
         fprintf(stderr, "juliet: %lld reads (%lld skipped), %zu variants%s\n", static_cast<long long>(aln.nreads),
                 static_cast<long long>(aln.nskipped), rows.size(), phasing ? (", " + std::to_string(haps.size()) + " haplotypes").c_str() : "");
+        fflush(nullptr);
+        if (!getenv("MS_FULL_TEARDOWN")) _exit(0);   // outputs are written and closed; skip the ~0.2 s CUDA teardown
         ms_destroy(h);
     } catch (const std::exception& e) {
         mshost::die(e.what());

@@ -18,8 +18,10 @@ json.dump(cfg, open(os.path.join(d, "cfg.json"), "w"))
 out = {"reads": R, "bam_bytes": os.path.getsize(os.path.join(d, "in.bam"))}
 for name, cmd in (("juliet", [os.path.join(BIN, "juliet"), "-c", os.path.join(d, "cfg.json"), "--mode-phasing", "--min-perc", "0.5", os.path.join(d, "in.bam"), os.path.join(d, "o.json")]),
                   ("fuse", [os.path.join(BIN, "fuse"), os.path.join(d, "in.bam"), os.path.join(d, "o.fasta")])):
-    ts = []
-    for _ in range(3):
-        t0 = time.perf_counter(); subprocess.check_call(cmd, stderr=subprocess.DEVNULL); ts.append(time.perf_counter() - t0)
-    out[name + "_s"] = min(ts); out[name + "_reads_per_s"] = R / min(ts)
+    for tag, extra in (("", {}), ("_serial_load", {"MS_SERIAL_LOAD": "1"})):   # context/decode overlap vs serial, same box
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter(); subprocess.check_call(cmd, env=dict(os.environ, MS_TIMING="1", **extra)); ts.append(time.perf_counter() - t0)
+        out[name + tag + "_s"] = min(ts); out[name + tag + "_median_s"] = sorted(ts)[2]
+    out[name + "_reads_per_s"] = R / out[name + "_s"]
 print(json.dumps(out))
