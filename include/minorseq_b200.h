@@ -176,6 +176,17 @@ void ms_haplotype_name(int64_t rank, char buf[3]);      /* [A-Z][a-z]? doc/JULIE
 /* hap_id (host, one per phased read, in upload order): rank in ordered_patterns,
  * or -1 if damaged.                                                               */
 int ms_phase_assign(ms_handle *h, const uint32_t *ordered_patterns, int64_t H, int32_t *hap_id);
+/* Grouping, merge over ranks (with a communicator: one all-gather of the ranks' compact
+ * lists, merged on the device), juliet's haplotype order (count desc, then ascending
+ * words) and the per-read haplotype id in ONE call, without the full pattern list ever
+ * leaving the GPU: patterns/counts receive the first min(cap,*H) haplotypes of the order,
+ * *H the number of distinct patterns, *nreported how many have >= min_reads reads (they
+ * come first), ctr all six read categories of doc/JULIET.md:372-381.  hap_id (host, one per
+ * read phased on this handle, may be NULL): position in that order, -1 if damaged.
+ * Same results as ms_phase_groups + ms_haplotype_order + ms_phase_assign.               */
+int ms_phase_haplotypes(ms_handle *h, int32_t min_reads, uint32_t *patterns, uint64_t *counts,
+                        int64_t cap, int64_t *H, int64_t *nreported, ms_phase_counters *ctr,
+                        int32_t *hap_id);
 /* Device pointers to the per-read results (R*ceil(V/32) words, R bytes).          */
 int ms_phase_device(ms_handle *h, uint32_t **d_bits, uint8_t **d_flags, int64_t *R);
 /* C[v][w] = #reads carrying both (V*V int32, device buffer owned by the handle). */
@@ -184,15 +195,18 @@ int ms_cooccurrence(ms_handle *h, int32_t **d_C);
 /* ---- the whole juliet pass in one call ------------------------------------------------------
  * reset -> pileup -> (all-reduce when a communicator is attached) -> codon test -> phasing, i.e. everything
  * juliet does between BAM decode and report writing.  The caller owns the result buffers; on
- * MS_ERR_CAPACITY the n* fields hold the sizes needed.  patterns/counts come back in juliet's haplotype
- * order with [0,nreported) reported (rows ceil(nkeys/32) words apart; the buffer must hold
- * patterns_cap * ceil(keys_cap/32) words); key_col/key_codon is the pooled variant list the bit-vectors refer to.
- * Afterwards ms_phase_assign / ms_get_counts / ms_cooccurrence can be called as usual.              */
+ * MS_ERR_CAPACITY the n* fields hold the sizes needed.  patterns/counts receive the first
+ * min(patterns_cap, npatterns) haplotypes of juliet's order, [0,nreported) being the reported ones (rows
+ * ceil(nkeys/32) words apart; the buffer must hold patterns_cap * ceil(keys_cap/32) words); npatterns is the
+ * number of distinct patterns, and only nreported > patterns_cap counts as too small.  key_col/key_codon is
+ * the pooled variant list the bit-vectors refer to.  hap_id (host, R entries, may be NULL) as in
+ * ms_phase_haplotypes.  Afterwards ms_get_counts / ms_cooccurrence can be called as usual.            */
 typedef struct {
     ms_variant *variants;  int64_t variants_cap, nvariants;
     int32_t *key_col, *key_codon; int32_t keys_cap, nkeys;
     uint32_t *patterns; uint64_t *counts; int64_t patterns_cap, npatterns, nreported;
     ms_phase_counters counters;
+    int32_t *hap_id;
 } ms_juliet_result;
 int ms_juliet_pass_dev(ms_handle *h, const uint32_t *d_packed, int64_t R, const ms_gene *genes, int32_t ngenes,
                        const char *refseq, const ms_call_params *prm, int32_t phase, int32_t min_hap_reads,

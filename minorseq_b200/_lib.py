@@ -40,7 +40,7 @@ class JulietResult(C.Structure):
     _fields_ = [("variants", C.POINTER(Variant)), ("variants_cap", C.c_int64), ("nvariants", C.c_int64),
                 ("key_col", C.POINTER(C.c_int32)), ("key_codon", C.POINTER(C.c_int32)), ("keys_cap", C.c_int32), ("nkeys", C.c_int32),
                 ("patterns", C.POINTER(C.c_uint32)), ("counts", C.POINTER(C.c_uint64)), ("patterns_cap", C.c_int64),
-                ("npatterns", C.c_int64), ("nreported", C.c_int64), ("counters", PhaseCounters)]
+                ("npatterns", C.c_int64), ("nreported", C.c_int64), ("counters", PhaseCounters), ("hap_id", C.POINTER(C.c_int32))]
 
 
 class SynthParams(C.Structure):
@@ -90,6 +90,7 @@ _SIGNATURES = {
                                      C.POINTER(C.c_int64), C.POINTER(PhaseCounters)]),
     "ms_haplotype_name": (None, [C.c_int64, C.c_char_p]),
     "ms_phase_assign": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "ms_phase_haplotypes": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "ms_phase_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
     "ms_cooccurrence": (C.c_int, [_P, C.POINTER(_P)]),
     "ms_juliet_pass_dev": (C.c_int, [_P, _P, C.c_int64, C.POINTER(Gene), C.c_int32, C.c_char_p, C.POINTER(CallParams), C.c_int32,

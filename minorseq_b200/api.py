@@ -44,6 +44,7 @@ class Haplotypes:
     names: list
     counters: dict
     hap_id: np.ndarray = None       # per local read, -1 = damaged
+    ndistinct: int = -1             # distinct patterns in total (patterns/counts may hold only the first ones of the order)
 
 
 @dataclass
@@ -209,7 +210,7 @@ class Juliet:
         return [Variant.from_buffer_copy(out[i]) for i in range(n.value)]
 
     # -- K3
-    def phase_device(self, variants, d_packed_ptr: int, nreads: int, want_hap_id=True) -> Haplotypes:
+    def phase_device(self, variants, d_packed_ptr: int, nreads: int, want_hap_id=True, host_merge=False, cap=4096) -> Haplotypes:
         import torch.distributed as dist
         keys = sorted({(v.col, v.codon) for v in variants})
         V = len(keys)
@@ -219,7 +220,9 @@ class Juliet:
         self._V = V
         check(self.lib.ms_phase_begin(self.hd.h, _ptr(vc), _ptr(vd), V, nreads), self.hd.h)
         check(self.lib.ms_phase_dev(self.hd.h, C.c_void_p(d_packed_ptr), nreads), self.hd.h)
-        cap = 4096
+        if not host_merge and (getattr(self.hd, "native_comm", False) or _torch_world() == 1):
+            return self._haplotypes_device(V, nw, nreads, want_hap_id, cap), keys
+        # torch.distributed exchange (e.g. gloo in the CPU tests): the three-call protocol with a host merge
         while True:
             if getattr(self, "_grp_shape", None) != (cap, nw):   # reused from pass to pass
                 self._grp_shape = (cap, nw)
@@ -254,6 +257,32 @@ class Juliet:
             check(self.lib.ms_phase_assign(self.hd.h, _ptr(pat), len(cnt), _ptr(hap)), self.hd.h)
         return Haplotypes(patterns=pat, counts=cnt, nreported=int(nrep.value), names=names, counters=counters, hap_id=hap), keys
 
+    def _haplotypes_device(self, V, nw, nreads, want_hap_id, cap=4096) -> Haplotypes:
+        """grouping + merge over ranks + order + per-read ids in one C-ABI call (ms_phase_haplotypes)"""
+        while True:
+            if getattr(self, "_grp_shape", None) != (cap, nw):   # reused from pass to pass
+                self._grp_shape = (cap, nw)
+                self._grp_pat = np.zeros((cap, nw), dtype=np.uint32)
+                self._grp_cnt = np.zeros(cap, dtype=np.uint64)
+            pat, cnt = self._grp_pat, self._grp_cnt
+            H, nrep, ctr = C.c_int64(), C.c_int64(), PhaseCounters()
+            hap = np.empty(nreads, dtype=np.int32) if want_hap_id else None
+            check(self.lib.ms_phase_haplotypes(self.hd.h, self.min_hap_reads, _ptr(pat), _ptr(cnt), cap, C.byref(H), C.byref(nrep), C.byref(ctr),
+                                               _ptr(hap) if want_hap_id else None), self.hd.h)
+            if nrep.value <= cap:
+                break
+            cap = int(nrep.value)
+        k = min(cap, int(H.value))
+        names = []
+        buf = C.create_string_buffer(3)
+        for i in range(nrep.value):
+            self.lib.ms_haplotype_name(i, buf)
+            names.append(buf.value.decode())
+        counters = dict(reported=int(ctr.reported), insufficient=int(ctr.insufficient), damaged=int(ctr.damaged), gaps=int(ctr.gaps),
+                        heteroduplex=int(ctr.heteroduplex), partial=int(ctr.partial))
+        return Haplotypes(patterns=pat[:k].copy(), counts=cnt[:k].copy(), nreported=int(nrep.value), names=names, counters=counters, hap_id=hap,
+                          ndistinct=int(H.value))
+
     def cooccurrence(self):
         """[V, V] int32 torch tensor (device memory owned by the handle), summed over ranks."""
         import torch
@@ -287,11 +316,13 @@ class Juliet:
                 r.key_col = st["kc"].ctypes.data_as(C.POINTER(C.c_int32)); r.key_codon = st["kk"].ctypes.data_as(C.POINTER(C.c_int32)); r.keys_cap = st["kcap"]
                 r.patterns = st["pat"].ctypes.data_as(C.POINTER(C.c_uint32)); r.counts = st["cnt"].ctypes.data_as(C.POINTER(C.c_uint64)); r.patterns_cap = st["pcap"]
             r = st["res"]
+            hap = np.empty(nreads, dtype=np.int32) if (want_hap_id and self.mode_phasing) else None
+            r.hap_id = hap.ctypes.data_as(C.POINTER(C.c_int32)) if hap is not None else None
             fn = self.lib.ms_juliet_pass_host if host else self.lib.ms_juliet_pass_dev
             rc = fn(self.hd.h, C.c_void_p(ptr), nreads, st["genes"], len(self.genes), self.refseq.encode() if self.refseq else None,
                     C.byref(self.params), 1 if self.mode_phasing else 0, self.min_hap_reads, C.byref(r))
             if rc == -4:   # MS_ERR_CAPACITY: grow what was too small and run the pass again
-                st["vcap"] = max(st["vcap"], int(r.nvariants)); st["kcap"] = max(st["kcap"], int(r.nkeys)); st["pcap"] = max(st["pcap"], int(r.npatterns))
+                st["vcap"] = max(st["vcap"], int(r.nvariants)); st["kcap"] = max(st["kcap"], int(r.nkeys)); st["pcap"] = max(st["pcap"], int(r.nreported))
                 continue
             check(rc, self.hd.h)
             break
@@ -301,7 +332,7 @@ class Juliet:
             V = int(r.nkeys)
             self._V = V
             nw = max(1, (V + 31) // 32)
-            H = int(r.npatterns)
+            H = min(int(r.npatterns), st["pcap"])
             pat = st["pat"][: H * nw].reshape(H, nw).copy()
             cnt = st["cnt"][:H].copy()
             names = []
@@ -312,11 +343,8 @@ class Juliet:
             c = r.counters
             counters = dict(reported=int(c.reported), insufficient=int(c.insufficient), damaged=int(c.damaged), gaps=int(c.gaps),
                             heteroduplex=int(c.heteroduplex), partial=int(c.partial))
-            hap = None
-            if want_hap_id:
-                hap = np.empty(nreads, dtype=np.int32)
-                check(self.lib.ms_phase_assign(self.hd.h, _ptr(pat), H, _ptr(hap)), self.hd.h)
-            res.haplotypes = Haplotypes(patterns=pat, counts=cnt, nreported=int(r.nreported), names=names, counters=counters, hap_id=hap)
+            res.haplotypes = Haplotypes(patterns=pat, counts=cnt, nreported=int(r.nreported), names=names, counters=counters, hap_id=hap,
+                                        ndistinct=int(r.npatterns))
         return res
 
     def run_device(self, d_packed_ptr: int, nreads: int, want_hap_id=False) -> JulietResult:

@@ -40,21 +40,12 @@ static int juliet_pass(ms_handle* h, const uint32_t* packed, bool host_rows, int
     if (rc != MS_OK) return rc;
     rc = ms_phase_dev(h, d_rows, R);
     if (rc != MS_OK) return rc;
-    int64_t H = 0;
-    ms_phase_counters ctr;
-    rc = ms_phase_groups(h, out->patterns, out->counts, out->patterns_cap, &H, &ctr);
+    int64_t H = 0, nrep = 0;
+    rc = ms_phase_haplotypes(h, min_hap_reads, out->patterns, out->counts, out->patterns_cap, &H, &nrep, &out->counters, out->hap_id);
     if (rc != MS_OK) return rc;
     out->npatterns = H;
-    if (H > out->patterns_cap) return MS_ERR_CAPACITY;
-    int64_t Hm = 0, nrep = 0;
-    ms_phase_counters c2;
-    rc = ms_haplotype_order(out->patterns, out->counts, H, V, min_hap_reads, &Hm, &nrep, &c2);
-    if (rc != MS_OK) return rc;
-    out->npatterns = Hm;
     out->nreported = nrep;
-    out->counters = ctr;
-    out->counters.reported = c2.reported;
-    out->counters.insufficient = c2.insufficient;
+    if (nrep > out->patterns_cap) return MS_ERR_CAPACITY;
     return MS_OK;
 }
 

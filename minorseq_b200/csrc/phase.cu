@@ -16,7 +16,7 @@
 #include <cstring>
 #include <numeric>
 #include <vector>
-#include "handle.h"
+#include "phase_internal.cuh"
 
 namespace ms {
 
@@ -25,13 +25,6 @@ struct VarDev {
     int32_t shift;         // col & 31
     int32_t codon;         // 0..63, or -1: variant lies outside the reference (always partial)
 };
-
-__device__ __forceinline__ uint64_t mix64d(uint64_t x) {
-    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
-    x ^= x >> 27; x *= 0x94d049bb133111ebULL;
-    x ^= x >> 31;
-    return x;
-}
 
 constexpr int kPhaseWarps = 8;
 
@@ -178,12 +171,6 @@ __global__ void __launch_bounds__(256) phase_bits_sparse_kernel(const uint4* __r
     }
 }
 
-__device__ __forceinline__ uint64_t pattern_hash(const uint32_t* w, int32_t vwords, uint64_t seed) {
-    uint64_t hsh = seed;
-    for (int32_t i = 0; i < vwords; ++i) hsh = mix64d(hsh ^ (static_cast<uint64_t>(w[i]) + 0x9E3779B97F4A7C15ULL * (i + 1)));
-    return hsh ? hsh : 1ULL;
-}
-
 // One thread per read; lanes of a warp that carry the same pattern elect a leader (lowest lane =
 // lowest read index) which alone touches the table: one CAS probe, one count add, one rep min.
 __global__ void phase_insert_kernel(const uint32_t* __restrict__ bits, const uint8_t* __restrict__ flags, int64_t R,
@@ -193,6 +180,12 @@ __global__ void phase_insert_kernel(const uint32_t* __restrict__ bits, const uin
     const int lane = threadIdx.x & 31;
     const bool valid = r < R && flags[r] == 0;
     if (r < R && !valid) slot[r] = -1;
+    // the table already overflowed: this build is void (the host grows the table and rebuilds), so do not keep
+    // probing it.  Decided per warp so that the match below still sees every lane of vmask.
+    if (__any_sync(0xffffffffu, *reinterpret_cast<volatile unsigned long long*>(overflow) != 0ULL)) {
+        if (r < R) slot[r] = -1;
+        return;
+    }
     const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
     if (!valid) return;
     const uint64_t key = pattern_hash(bits + static_cast<size_t>(r) * vwords, vwords, seed);
@@ -234,12 +227,13 @@ __global__ void phase_verify_kernel(const uint32_t* __restrict__ bits, int64_t R
 __global__ void phase_compact_kernel(const uint32_t* __restrict__ tab_cnt, const long long* __restrict__ tab_rep,
                                      int64_t tab_size, const uint32_t* __restrict__ bits, int32_t vwords,
                                      unsigned long long* ngroups, uint32_t* __restrict__ g_cnt,
-                                     uint32_t* __restrict__ g_pat, int64_t cap) {
+                                     uint32_t* __restrict__ g_pat, int32_t* __restrict__ g_slot, int64_t cap) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= tab_size || tab_cnt[i] == 0) return;
     const unsigned long long k = atomicAdd(ngroups, 1ULL);
     if (static_cast<int64_t>(k) < cap) {
         g_cnt[k] = tab_cnt[i];
+        if (g_slot) g_slot[k] = static_cast<int32_t>(i);
         const uint32_t* src = bits + static_cast<size_t>(tab_rep[i]) * vwords;
         for (int32_t w = 0; w < vwords; ++w) g_pat[k * vwords + w] = src[w];
     }
@@ -327,12 +321,6 @@ __global__ void __launch_bounds__(256) cooccurrence_kernel(const uint32_t* __res
     }
 }
 
-static inline bool pattern_less(const uint32_t* a, const uint32_t* b, int32_t nw) {
-    for (int32_t i = 0; i < nw; ++i)
-        if (a[i] != b[i]) return a[i] < b[i];
-    return false;
-}
-
 }  // namespace ms
 
 int ms_comm_allgather_bytes(ms_handle* h, const void* d_send, void* d_recv, size_t bytes_per_rank);
@@ -343,7 +331,11 @@ int phase_groups_copy_out(ms_handle* h, uint32_t* patterns, uint64_t* counts, in
 
 constexpr int64_t kGroupCapInit = 4096;
 
-int ensure_stage(ms_handle* h, size_t bytes) {
+}  // namespace
+
+namespace ms {
+
+int phase_ensure_stage(ms_handle* h, size_t bytes) {
     if (bytes <= h->h_stage_cap) return MS_OK;
     if (h->h_stage) cudaFreeHost(h->h_stage);
     h->h_stage = nullptr; h->h_stage_cap = 0;
@@ -352,32 +344,58 @@ int ensure_stage(ms_handle* h, size_t bytes) {
     return MS_OK;
 }
 
-uint64_t phase_seed(int attempt) { return 0x6d696e6f72736571ULL + 0x9E3779B97F4A7C15ULL * static_cast<uint64_t>(attempt); }
-
-// ctr layout (u64): [0] damaged [1] gaps [2] heteroduplex [3] partial [4] hash collisions [5] ngroups [6..7] spare
-unsigned long long* ctr_ptr(ms_handle* h) { return h->b_ctr.as<unsigned long long>(); }
-
-int build_table(ms_handle* h, int attempt) {
+int phase_build_table(ms_handle* h, int attempt) {
     const int64_t R = h->phase_n;
+    unsigned long long* ctr = phase_ctr(h);
     MS_CUDA(h, cudaMemsetAsync(h->b_tab_key.p, 0, static_cast<size_t>(h->tab_size) * 8, h->stream));
     MS_CUDA(h, cudaMemsetAsync(h->b_tab_cnt.p, 0, static_cast<size_t>(h->tab_size) * 4, h->stream));
     MS_CUDA(h, cudaMemsetAsync(h->b_tab_rep.p, 0x7f, static_cast<size_t>(h->tab_size) * 8, h->stream));
-    MS_CUDA(h, cudaMemsetAsync(ctr_ptr(h) + 4, 0, 8, h->stream));
-    MS_CUDA(h, cudaMemsetAsync(ctr_ptr(h) + 6, 0, 8, h->stream));
+    MS_CUDA(h, cudaMemsetAsync(ctr + 4, 0, 8, h->stream));
+    MS_CUDA(h, cudaMemsetAsync(ctr + 6, 0, 8, h->stream));
     if (R > 0) {
         const int grid = static_cast<int>((R + 255) / 256);
-        ms::phase_insert_kernel<<<grid, 256, 0, h->stream>>>(h->b_bits.as<uint32_t>(), h->b_flags.as<uint8_t>(), R, h->vwords,
-                                                             phase_seed(attempt), h->b_tab_key.as<unsigned long long>(),
-                                                             h->b_tab_cnt.as<uint32_t>(), h->b_tab_rep.as<long long>(),
-                                                             h->tab_size - 1, h->b_slot.as<int32_t>(), ctr_ptr(h) + 6);
-        ms::phase_verify_kernel<<<grid, 256, 0, h->stream>>>(h->b_bits.as<uint32_t>(), R, h->vwords, h->b_tab_rep.as<long long>(),
-                                                             h->b_slot.as<int32_t>(), ctr_ptr(h) + 4);
+        phase_insert_kernel<<<grid, 256, 0, h->stream>>>(h->b_bits.as<uint32_t>(), h->b_flags.as<uint8_t>(), R, h->vwords,
+                                                         phase_seed(attempt), h->b_tab_key.as<unsigned long long>(),
+                                                         h->b_tab_cnt.as<uint32_t>(), h->b_tab_rep.as<long long>(),
+                                                         h->tab_size - 1, h->b_slot.as<int32_t>(), ctr + 6);
+        phase_verify_kernel<<<grid, 256, 0, h->stream>>>(h->b_bits.as<uint32_t>(), R, h->vwords, h->b_tab_rep.as<long long>(),
+                                                         h->b_slot.as<int32_t>(), ctr + 4);
         h->launches += 2;
     }
     h->table_attempt = attempt;
     MS_CUDA(h, cudaGetLastError());
     return MS_OK;
 }
+
+int phase_compact(ms_handle* h, uint32_t* g_cnt, uint32_t* g_pat, int32_t* g_slot, int64_t cap) {
+    MS_CUDA(h, cudaMemsetAsync(phase_ctr(h) + 5, 0, 8, h->stream));
+    phase_compact_kernel<<<static_cast<int>((h->tab_size + 255) / 256), 256, 0, h->stream>>>(
+        h->b_tab_cnt.as<uint32_t>(), h->b_tab_rep.as<long long>(), h->tab_size, h->b_bits.as<uint32_t>(), h->vwords, phase_ctr(h) + 5,
+        g_cnt, g_pat, g_slot, cap);
+    h->launches++;
+    MS_CUDA(h, cudaGetLastError());
+    return MS_OK;
+}
+
+int phase_grow_table(ms_handle* h) {
+    if (h->tab_size >= h->tab_size_max) MS_FAIL(h, MS_ERR_CUDA, "haplotype table overflow at maximum size");
+    h->tab_size = std::min<int64_t>(h->tab_size_max, h->tab_size * 8);
+    h->tab_hint = h->tab_size;
+    MS_CUDA(h, h->b_tab_key.ensure(static_cast<size_t>(h->tab_size) * 8));
+    MS_CUDA(h, h->b_tab_cnt.ensure(static_cast<size_t>(h->tab_size) * 4));
+    MS_CUDA(h, h->b_tab_rep.ensure(static_cast<size_t>(h->tab_size) * 8));
+    h->table_valid = false;
+    return MS_OK;
+}
+
+}  // namespace ms
+
+namespace {
+
+using ms::phase_seed;
+inline unsigned long long* ctr_ptr(ms_handle* h) { return ms::phase_ctr(h); }
+inline int ensure_stage(ms_handle* h, size_t bytes) { return ms::phase_ensure_stage(h, bytes); }
+inline int build_table(ms_handle* h, int attempt) { return ms::phase_build_table(h, attempt); }
 
 // hand the cached (pattern, count) lists of the last grouping pass to the caller (order: as compacted)
 int phase_groups_copy_out(ms_handle* h, uint32_t* patterns, uint64_t* counts, int64_t cap, int64_t* H, ms_phase_counters* ctr) {
@@ -400,7 +418,9 @@ extern "C" {
 
 void ms_phase_free_internal(ms_handle* h) {
     DevBuf* all[] = {&h->b_var, &h->b_blocklist, &h->b_bits, &h->b_flags, &h->b_slot, &h->b_tab_key, &h->b_tab_cnt, &h->b_tab_rep,
-                     &h->b_ctr, &h->b_groups, &h->b_gather, &h->b_rank, &h->b_hap, &h->b_pat, &h->b_cooc, &h->b_bits_t};
+                     &h->b_ctr, &h->b_groups, &h->b_gather, &h->b_rank, &h->b_hap, &h->b_pat, &h->b_cooc, &h->b_bits_t,
+                     &h->b_gslot, &h->b_mt_key, &h->b_mt_cnt, &h->b_mt_rep, &h->b_mslot, &h->b_mindex, &h->b_m_cnt, &h->b_m_pat, &h->b_m_rank,
+                     &h->b_ord, &h->b_out};
     for (DevBuf* b : all) b->release();
     if (h->h_stage) cudaFreeHost(h->h_stage);
     h->h_stage = nullptr; h->h_stage_cap = 0;
@@ -441,7 +461,7 @@ int ms_phase_begin(ms_handle* h, const int32_t* var_col, const int32_t* var_codo
     int64_t ts_max = 1024;
     while (ts_max < 2 * h->phase_cap) ts_max <<= 1;
     h->tab_size_max = ts_max;
-    int64_t ts = std::min<int64_t>(ts_max, 1 << 16);
+    int64_t ts = std::min<int64_t>(ts_max, std::max<int64_t>(1 << 16, h->tab_hint));   // last pass's grown size is the hint
     h->tab_size = ts;
     // the previous pass may still be reading these buffers on the stream if they have to move
     const bool grow = vd.size() * sizeof(ms::VarDev) > h->b_var.cap || blocks.size() * 4 > h->b_blocklist.cap ||
@@ -542,11 +562,8 @@ int ms_phase_groups(ms_handle* h, uint32_t* patterns, uint64_t* counts, int64_t 
         uint8_t* blk = h->b_groups.as<uint8_t>();
         uint32_t* g_cnt = reinterpret_cast<uint32_t*>(blk + 64);
         uint32_t* g_pat = g_cnt + gcap;
-        MS_CUDA(h, cudaMemsetAsync(ctr_ptr(h) + 5, 0, 8, h->stream));
-        ms::phase_compact_kernel<<<static_cast<int>((h->tab_size + 255) / 256), 256, 0, h->stream>>>(
-            h->b_tab_cnt.as<uint32_t>(), h->b_tab_rep.as<long long>(), h->tab_size, h->b_bits.as<uint32_t>(), nw, ctr_ptr(h) + 5,
-            g_cnt, g_pat, gcap);
-        h->launches++;
+        rc = ms::phase_compact(h, g_cnt, g_pat, nullptr, gcap);
+        if (rc != MS_OK) return rc;
         MS_CUDA(h, cudaMemcpyAsync(blk, h->b_ctr.p, 64, cudaMemcpyDeviceToDevice, h->stream));
         uint8_t* st = static_cast<uint8_t*>(h->h_stage);
         if (world > 1) {
@@ -568,11 +585,8 @@ int ms_phase_groups(ms_handle* h, uint32_t* patterns, uint64_t* counts, int64_t 
             if (hc[6] != 0) {
                 any_overflow = true;
                 if (r == me) {  // table too small for this rank's distinct patterns: grow and rebuild
-                    if (h->tab_size >= h->tab_size_max) MS_FAIL(h, MS_ERR_CUDA, "haplotype table overflow at maximum size");
-                    h->tab_size = std::min<int64_t>(h->tab_size_max, h->tab_size * 8);
-                    MS_CUDA(h, h->b_tab_key.ensure(static_cast<size_t>(h->tab_size) * 8));
-                    MS_CUDA(h, h->b_tab_cnt.ensure(static_cast<size_t>(h->tab_size) * 4));
-                    MS_CUDA(h, h->b_tab_rep.ensure(static_cast<size_t>(h->tab_size) * 8));
+                    rc = ms::phase_grow_table(h);
+                    if (rc != MS_OK) return rc;
                     h->table_valid = false;
                 }
             } else if (hc[4] != 0) {

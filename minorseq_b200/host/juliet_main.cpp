@@ -182,24 +182,21 @@ int main(int argc, char** argv) {
             for (int32_t i = 0; i < V; ++i) { vc[i] = keys[i].first; vk[i] = keys[i].second; }
             CK(h, ms_phase_begin(h, vc.data(), vk.data(), V, aln.nreads));
             CK(h, ms_phase_dev(h, d_rows, aln.nreads));
-            int64_t H = 0, cap = 4096;
+            // grouping, haplotype order and per-read ids in one device-side call; only the reported haplotypes are read back
+            int64_t H = 0, nrep = 0, cap = 256;
             std::vector<uint32_t> pat;
             std::vector<uint64_t> cnt;
-            ms_phase_counters ctr;
+            std::vector<int32_t> hap(aln.nreads);
+            ms_phase_counters c2;
             for (;;) {
                 pat.assign(static_cast<size_t>(cap) * nw, 0u);
                 cnt.assign(cap, 0);
-                CK(h, ms_phase_groups(h, pat.data(), cnt.data(), cap, &H, &ctr));
-                if (H <= cap) break;
-                cap = H;
+                CK(h, ms_phase_haplotypes(h, min_hap, pat.data(), cnt.data(), cap, &H, &nrep, &c2, hap.data()));
+                if (nrep <= cap) break;
+                cap = nrep;
             }
-            int64_t Hm = 0, nrep = 0;
-            ms_phase_counters c2;
-            if (ms_haplotype_order(pat.data(), cnt.data(), H, V, min_hap, &Hm, &nrep, &c2) != MS_OK) mshost::die("ms_haplotype_order failed");
-            std::vector<int32_t> hap(aln.nreads);
-            CK(h, ms_phase_assign(h, pat.data(), Hm, hap.data()));
-            counters[0] = c2.reported; counters[1] = c2.insufficient; counters[2] = ctr.damaged;
-            counters[3] = ctr.gaps; counters[4] = ctr.heteroduplex; counters[5] = ctr.partial;
+            counters[0] = c2.reported; counters[1] = c2.insufficient; counters[2] = c2.damaged;
+            counters[3] = c2.gaps; counters[4] = c2.heteroduplex; counters[5] = c2.partial;
             haps.resize(nrep);
             for (int64_t k = 0; k < nrep; ++k) {
                 char nb[3];

@@ -221,13 +221,13 @@ def test_call_multi_gene_frames_and_big_counts(oracle, hd):
     variants_equal(j.call(), oracle.call(codon, genes, refseq=ref))
 
 
-def phase_equal(oracle, hd, st, L, var_col, var_codon, packed_dev=None):
+def phase_equal(oracle, hd, st, L, var_col, var_codon, packed_dev=None, host_merge=False, cap=4096):
     class V:  # minimal variant record for Juliet.phase_device
         def __init__(self, c, k):
             self.col, self.codon = c, k
     j = Juliet(L, [(1, L + 1)], mode_phasing=True, handle=hd)
     d = packed_dev if packed_dev is not None else to_dev(pack_states(st))
-    hap, keys = j.phase_device([V(c, k) for c, k in zip(var_col, var_codon)], d.data_ptr(), st.shape[0])
+    hap, keys = j.phase_device([V(c, k) for c, k in zip(var_col, var_codon)], d.data_ptr(), st.shape[0], host_merge=host_merge, cap=cap)
     kc = [k[0] for k in keys]
     kd = [k[1] for k in keys]
     obits, oflags = oracle.phase_bits(st, kc, kd)
@@ -240,8 +240,10 @@ def phase_equal(oracle, hd, st, L, var_col, var_codon, packed_dev=None):
     gflags = _as_tensor(pf.value, (st.shape[0],), torch.uint8, 0).cpu().numpy()
     assert np.array_equal(gflags, oflags)
     assert np.array_equal(gbits, obits)
-    assert len(hap.counts) == g["H"] and hap.nreported == g["nreported"]
-    assert np.array_equal(hap.counts, g["counts"]) and np.array_equal(hap.patterns, g["patterns"])
+    k = len(hap.counts)       # the device-ordered path hands back the first min(cap, H) haplotypes of the order
+    assert hap.nreported == g["nreported"] and k >= hap.nreported
+    assert (k == g["H"]) if host_merge else (hap.ndistinct == g["H"] and k == min(g["H"], max(cap, hap.nreported)))
+    assert np.array_equal(hap.counts, g["counts"][:k]) and np.array_equal(hap.patterns, g["patterns"][:k])
     assert hap.counters == {k: int(v) for k, v in g["counters"].items()}
     assert np.array_equal(hap.hap_id, g["hap_id"])
     assert hap.names == [oracle.hap_name(i) for i in range(g["nreported"])]
@@ -285,6 +287,43 @@ def test_phase_dense_and_cooccurrence(oracle, hd):
     Cg = j.cooccurrence().cpu().numpy()
     assert np.array_equal(Cg, oracle.cooccurrence(obits, len(sites)))
     assert (np.diag(Cg) > 0).all()
+
+
+def _many_pattern_states(R, L, V, ndup, seed):
+    """Reads that are either one of `ndup` recurring site patterns or a random one: thousands of distinct
+    single-read haplotypes next to a few reported ones, as in BASELINE configs[4]."""
+    rng = np.random.default_rng(seed)
+    ref = rng.integers(0, 4, size=L, dtype=np.uint8)
+    cols = np.sort(rng.choice(np.arange(0, L - 2, 3), size=V, replace=False))
+    alt = (ref[cols] + 1 + rng.integers(0, 3, size=V, dtype=np.uint8)) % 4       # variant codon differs in its first base
+    cods = [16 * int(alt[i]) + 4 * int(ref[c + 1]) + int(ref[c + 2]) for i, c in enumerate(cols)]
+    st = np.tile(ref, (R, 1))
+    carry = rng.random((R, V)) < 0.5
+    proto = rng.random((ndup, V)) < 0.5
+    which = rng.integers(0, ndup, size=R)
+    recurring = rng.random(R) < 0.3
+    carry[recurring] = proto[which[recurring]]
+    st[:, cols] = np.where(carry, alt[None, :], ref[cols][None, :])
+    st[rng.random(R) < 0.05, cols[0]] = 4          # some gapped reads
+    st[rng.random(R) < 0.05, cols[-1] + 1] = 5     # some heteroduplex reads
+    return st, list(cols), cods
+
+
+@pytest.mark.parametrize("R,V,cap", [(12000, 40, 4096), (12000, 70, 20000), (3000, 70, 100)])
+def test_phase_many_distinct_patterns(oracle, hd, R, V, cap):
+    """More distinct patterns than the counting rank takes (4096): the bitonic path; and fewer: the counting path
+    with two-word patterns.  Either way the full oracle order (count desc, pattern asc) and every read's id match."""
+    st, cols, cods = _many_pattern_states(R, 900, V, 25, seed=R + V)
+    _, hap, _ = phase_equal(oracle, hd, st, 900, cols, cods, cap=cap)
+    assert hap.nreported >= 20 and hap.ndistinct > (4096 if R > 5000 else 1000)
+
+
+def test_phase_host_merge_protocol(oracle, hd):
+    """ms_phase_groups + ms_haplotype_order + ms_phase_assign (the three-call protocol the torch.distributed
+    fallback uses) gives the same answer as the device-ordered call."""
+    st, cols, cods = _many_pattern_states(3000, 900, 40, 25, seed=7)
+    phase_equal(oracle, hd, st, 900, cols, cods, host_merge=True)
+    phase_equal(oracle, hd, st, 900, cols, cods)
 
 
 def test_fuse_consensus(oracle, hd):

@@ -101,9 +101,16 @@ if "C5" in which:
     pile = k1_ms(hd)
     vs = [V(c, k) for c, k in sites]
     ms_phase, (hap, keys) = timed(hd, lambda: j.phase_device(vs, d.data_ptr(), R, want_hap_id=False), reps=2, warm=1)
+    ms_phase_ids, _ = timed(hd, lambda: j.phase_device(vs, d.data_ptr(), R, want_hap_id=True), reps=2, warm=1)
+    ms_phase_host, (hap_h, _) = timed(hd, lambda: j.phase_device(vs, d.data_ptr(), R, want_hap_id=False, host_merge=True), reps=1, warm=1)
+    assert hap_h.nreported == hap.nreported and hap_h.counters == hap.counters
+    assert np.array_equal(hap_h.counts[: hap.nreported], hap.counts[: hap.nreported]) and np.array_equal(hap_h.patterns[: hap.nreported], hap.patterns[: hap.nreported])
+    # stage split of the device-ordered pass
+    t0 = time.perf_counter(); j.phase_device(vs, d.data_ptr(), R, want_hap_id=False); lib.ms_synchronize(hd.h); t_all = (time.perf_counter() - t0) * 1e3
     ms_co, Cm = timed(hd, lambda: j.cooccurrence(), reps=2, warm=1)
     rows.append(dict(config="C5 phasing stress 500k reads, V=%d sites (dense)" % len(sites), reads=R, L=6144, k1_ms=pile, phase_ms=ms_phase,
-                     cooccurrence_ms=ms_co, word_ops=len(sites) * (len(sites) + 1) / 2 * ((R + 31) // 32), distinct_patterns=len(hap.counts),
+                     phase_with_read_ids_ms=ms_phase_ids, phase_host_merge_ms=ms_phase_host, phase_wall_ms=t_all,
+                     cooccurrence_ms=ms_co, word_ops=len(sites) * (len(sites) + 1) / 2 * ((R + 31) // 32), distinct_patterns=hap.ndistinct,
                      haplotypes=hap.nreported, counters=hap.counters, diag_sum=int(Cm.diagonal().sum().item())))
 for r in rows:
     print(json.dumps(r))
