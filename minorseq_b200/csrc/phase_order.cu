@@ -61,14 +61,6 @@ __device__ __forceinline__ void emit_ranked(const uint32_t* __restrict__ cnt, co
     }
 }
 
-__device__ __forceinline__ bool precedes(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ pat, int32_t nw, uint32_t a, uint32_t b) {
-    if (a == kSentinel) return false;
-    if (b == kSentinel) return true;
-    const uint32_t ca = cnt[a], cb = cnt[b];
-    if (ca != cb) return ca > cb;
-    return pattern_less(pat + static_cast<size_t>(a) * nw, pat + static_cast<size_t>(b) * nw, nw);
-}
-
 // Counting rank for M <= kSmallSort entries (M is read on the device).  Also copies the ranks' 64-byte headers
 // behind the result header so that one device->host read brings everything the host has to look at.
 __global__ void __launch_bounds__(256) rank_small_kernel(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ pat, int32_t nw,
@@ -101,41 +93,71 @@ __global__ void __launch_bounds__(256) rank_small_kernel(const uint32_t* __restr
     emit_ranked(cnt, pat, nw, gid, r, active, o);
 }
 
-__global__ void order_init_kernel(uint32_t* __restrict__ ord, int64_t n_pad, int64_t M) {
+// The sort runs on (64-bit key, entry index) pairs: key = (~count) << 32 | pattern word 0, so that almost every
+// comparison is decided in registers / shared memory; only equal keys look at the remaining pattern words.
+__global__ void order_init_kernel(uint32_t* __restrict__ ord, unsigned long long* __restrict__ key, const uint32_t* __restrict__ cnt,
+                                  const uint32_t* __restrict__ pat, int32_t nw, int64_t n_pad, int64_t M) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n_pad) ord[i] = i < M ? static_cast<uint32_t>(i) : kSentinel;
+    if (i >= n_pad) return;
+    if (i < M) {
+        ord[i] = static_cast<uint32_t>(i);
+        key[i] = (static_cast<unsigned long long>(~cnt[i]) << 32) | pat[static_cast<size_t>(i) * nw];   // count >= 1, so never all ones
+    } else {
+        ord[i] = kSentinel;
+        key[i] = ~0ULL;
+    }
+}
+
+__device__ __forceinline__ bool key_precedes(const uint32_t* __restrict__ pat, int32_t nw, unsigned long long ka, uint32_t a,
+                                             unsigned long long kb, uint32_t b) {
+    if (ka != kb) return ka < kb;
+    if (nw == 1 || a == kSentinel) return false;   // distinct patterns differ in word 0 when there is only one word
+    return pattern_less(pat + static_cast<size_t>(a) * nw + 1, pat + static_cast<size_t>(b) * nw + 1, nw - 1);
 }
 
 // all compare-exchange stages with distance < kLocalSpan of the merges k_begin..k_end, one CTA per kLocalSpan elements
-__global__ void __launch_bounds__(kLocalSpan / 2) bitonic_local_kernel(uint32_t* __restrict__ ord, const uint32_t* __restrict__ cnt,
+__global__ void __launch_bounds__(kLocalSpan / 2) bitonic_local_kernel(uint32_t* __restrict__ ord, unsigned long long* __restrict__ key,
                                                                        const uint32_t* __restrict__ pat, int32_t nw, int64_t k_begin, int64_t k_end) {
+    __shared__ unsigned long long sk[kLocalSpan];
     __shared__ uint32_t s[kLocalSpan];
     const int64_t base = static_cast<int64_t>(blockIdx.x) * kLocalSpan;
     const int t = threadIdx.x;
     s[t] = ord[base + t];
     s[t + kLocalSpan / 2] = ord[base + t + kLocalSpan / 2];
+    sk[t] = key[base + t];
+    sk[t + kLocalSpan / 2] = key[base + t + kLocalSpan / 2];
     __syncthreads();
     for (int64_t k = k_begin; k <= k_end; k <<= 1) {
         for (int j = (k >> 1) < kLocalSpan / 2 ? static_cast<int>(k >> 1) : kLocalSpan / 2; j > 0; j >>= 1) {
             const int i = 2 * t - (t & (j - 1)), l = i + j;
             const bool asc = ((base + i) & k) == 0;
             const uint32_t a = s[i], b = s[l];
-            if (asc ? precedes(cnt, pat, nw, b, a) : precedes(cnt, pat, nw, a, b)) { s[i] = b; s[l] = a; }
+            const unsigned long long ka = sk[i], kb = sk[l];
+            if (asc ? key_precedes(pat, nw, kb, b, ka, a) : key_precedes(pat, nw, ka, a, kb, b)) {
+                s[i] = b; s[l] = a;
+                sk[i] = kb; sk[l] = ka;
+            }
             __syncthreads();
         }
     }
     ord[base + t] = s[t];
     ord[base + t + kLocalSpan / 2] = s[t + kLocalSpan / 2];
+    key[base + t] = sk[t];
+    key[base + t + kLocalSpan / 2] = sk[t + kLocalSpan / 2];
 }
 
-__global__ void bitonic_global_kernel(uint32_t* __restrict__ ord, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ pat,
+__global__ void bitonic_global_kernel(uint32_t* __restrict__ ord, unsigned long long* __restrict__ key, const uint32_t* __restrict__ pat,
                                       int32_t nw, int64_t n_pad, int64_t k, int64_t j) {
     const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= n_pad / 2) return;
     const int64_t i = 2 * t - (t & (j - 1)), l = i + j;
     const bool asc = (i & k) == 0;
     const uint32_t a = ord[i], b = ord[l];
-    if (asc ? precedes(cnt, pat, nw, b, a) : precedes(cnt, pat, nw, a, b)) { ord[i] = b; ord[l] = a; }
+    const unsigned long long ka = key[i], kb = key[l];
+    if (asc ? key_precedes(pat, nw, kb, b, ka, a) : key_precedes(pat, nw, ka, a, kb, b)) {
+        ord[i] = b; ord[l] = a;
+        key[i] = kb; key[l] = ka;
+    }
 }
 
 __global__ void __launch_bounds__(256) emit_sorted_kernel(const uint32_t* __restrict__ ord, const uint32_t* __restrict__ cnt,
@@ -237,17 +259,19 @@ int sort_big(ms_handle* h, const uint32_t* cnt, const uint32_t* pat, int32_t nw,
     int64_t n_pad = ms::kLocalSpan;
     while (n_pad < M) n_pad <<= 1;
     MS_CUDA(h, h->b_ord.ensure(static_cast<size_t>(n_pad) * 4));
+    MS_CUDA(h, h->b_keys.ensure(static_cast<size_t>(n_pad) * 8));
     uint32_t* ord = h->b_ord.as<uint32_t>();
-    ms::order_init_kernel<<<grid_for(n_pad, 256), 256, 0, h->stream>>>(ord, n_pad, M);
+    unsigned long long* key = h->b_keys.as<unsigned long long>();
+    ms::order_init_kernel<<<grid_for(n_pad, 256), 256, 0, h->stream>>>(ord, key, cnt, pat, nw, n_pad, M);
     const unsigned nloc = static_cast<unsigned>(n_pad / ms::kLocalSpan);
-    ms::bitonic_local_kernel<<<nloc, ms::kLocalSpan / 2, 0, h->stream>>>(ord, cnt, pat, nw, 2, ms::kLocalSpan);
+    ms::bitonic_local_kernel<<<nloc, ms::kLocalSpan / 2, 0, h->stream>>>(ord, key, pat, nw, 2, ms::kLocalSpan);
     h->launches += 2;
     for (int64_t k = 2 * ms::kLocalSpan; k <= n_pad; k <<= 1) {
         for (int64_t j = k >> 1; j >= ms::kLocalSpan; j >>= 1) {
-            ms::bitonic_global_kernel<<<grid_for(n_pad / 2, 256), 256, 0, h->stream>>>(ord, cnt, pat, nw, n_pad, k, j);
+            ms::bitonic_global_kernel<<<grid_for(n_pad / 2, 256), 256, 0, h->stream>>>(ord, key, pat, nw, n_pad, k, j);
             h->launches++;
         }
-        ms::bitonic_local_kernel<<<nloc, ms::kLocalSpan / 2, 0, h->stream>>>(ord, cnt, pat, nw, k, k);
+        ms::bitonic_local_kernel<<<nloc, ms::kLocalSpan / 2, 0, h->stream>>>(ord, key, pat, nw, k, k);
         h->launches++;
     }
     MS_CUDA(h, cudaGetLastError());

@@ -236,10 +236,11 @@ def phase_equal(oracle, hd, st, L, var_col, var_codon, packed_dev=None, host_mer
     _lib.check(j.lib.ms_phase_device(hd.h, C.byref(pb), C.byref(pf), C.byref(pn)), hd.h)
     nw = max(1, (len(keys) + 31) // 32)
     from minorseq_b200.api import _as_tensor
-    gbits = _as_tensor(pb.value, (st.shape[0] * nw,), torch.int32, 0).cpu().numpy().view(np.uint32).reshape(-1, nw)
-    gflags = _as_tensor(pf.value, (st.shape[0],), torch.uint8, 0).cpu().numpy()
-    assert np.array_equal(gflags, oflags)
-    assert np.array_equal(gbits, obits)
+    if st.shape[0]:
+        gbits = _as_tensor(pb.value, (st.shape[0] * nw,), torch.int32, 0).cpu().numpy().view(np.uint32).reshape(-1, nw)
+        gflags = _as_tensor(pf.value, (st.shape[0],), torch.uint8, 0).cpu().numpy()
+        assert np.array_equal(gflags, oflags)
+        assert np.array_equal(gbits, obits)
     k = len(hap.counts)       # the device-ordered path hands back the first min(cap, H) haplotypes of the order
     assert hap.nreported == g["nreported"] and k >= hap.nreported
     assert (k == g["H"]) if host_merge else (hap.ndistinct == g["H"] and k == min(g["H"], max(cap, hap.nreported)))
@@ -324,6 +325,36 @@ def test_phase_host_merge_protocol(oracle, hd):
     st, cols, cods = _many_pattern_states(3000, 900, 40, 25, seed=7)
     phase_equal(oracle, hd, st, 900, cols, cods, host_merge=True)
     phase_equal(oracle, hd, st, 900, cols, cods)
+
+
+def test_phase_haplotypes_edge_cases(oracle, hd):
+    """ms_phase_haplotypes: no reads, every read damaged, cap = 0 / no read ids, fewer slots than reported haplotypes."""
+    lib = _lib.load()
+    st, cols, cods = _many_pattern_states(2000, 900, 40, 25, seed=3)
+    phase_equal(oracle, hd, st[:0], 900, cols, cods)                       # no reads at all
+    dead = st.copy()
+    dead[:, cols[3]] = 4
+    _, hap, _ = phase_equal(oracle, hd, dead, 900, cols, cods)             # every read has a gap in a variant codon
+    assert hap.ndistinct == 0 and hap.counters["damaged"] == 2000 and (hap.hap_id == -1).all()
+    _, hap, _ = phase_equal(oracle, hd, st, 900, cols, cods, cap=3)        # the API grows cap to the reported count
+    assert len(hap.counts) == hap.nreported > 3
+    # raw call: cap 0, no buffers, no ids -> only the tallies
+    vc, vk = np.array(cols, dtype=np.int32), np.array(cods, dtype=np.int32)
+    d = to_dev(pack_states(st))
+    _lib.check(lib.ms_set_layout(hd.h, 900, None), hd.h)
+    _lib.check(lib.ms_phase_begin(hd.h, vc.ctypes.data_as(C.c_void_p), vk.ctypes.data_as(C.c_void_p), 40, 2000), hd.h)
+    _lib.check(lib.ms_phase_dev(hd.h, C.c_void_p(d.data_ptr()), 2000), hd.h)
+    H, nrep, ctr = C.c_int64(), C.c_int64(), _lib.PhaseCounters()
+    _lib.check(lib.ms_phase_haplotypes(hd.h, 10, None, None, 0, C.byref(H), C.byref(nrep), C.byref(ctr), None), hd.h)
+    ob, of = oracle.phase_bits(st, cols, cods)
+    g = oracle.phase_group(ob, of, 40)
+    assert (H.value, nrep.value) == (g["H"], g["nreported"])
+    assert {k: getattr(ctr, k) for k, _ in _lib.PhaseCounters._fields_} == {k: int(v) for k, v in g["counters"].items()}
+    # a different threshold on the same grouping (cached table): juliet's 10 is a parameter here
+    _lib.check(lib.ms_phase_haplotypes(hd.h, 1, None, None, 0, C.byref(H), C.byref(nrep), C.byref(ctr), None), hd.h)
+    assert nrep.value == g["H"] and ctr.insufficient == 0 and ctr.reported == 2000 - ctr.damaged
+    assert lib.ms_phase_haplotypes(hd.h, -1, None, None, 0, C.byref(H), C.byref(nrep), C.byref(ctr), None) == -1
+    assert lib.ms_phase_haplotypes(hd.h, 10, None, None, 5, C.byref(H), C.byref(nrep), C.byref(ctr), None) == -1
 
 
 def test_fuse_consensus(oracle, hd):
