@@ -189,8 +189,12 @@ int ms_phase_haplotypes(ms_handle *h, int32_t min_reads, uint32_t *patterns, uin
                         int32_t *hap_id);
 /* Device pointers to the per-read results (R*ceil(V/32) words, R bytes).          */
 int ms_phase_device(ms_handle *h, uint32_t **d_bits, uint8_t **d_flags, int64_t *R);
-/* C[v][w] = #reads carrying both (V*V int32, device buffer owned by the handle). */
+/* C[v][w] = #reads carrying both (V*V int32, device buffer owned by the handle).
+ * Popcount-AND over the transposed bit matrix, or -- when the contraction is large (V >= 256 and
+ * >= 32768 reads) -- u8 x u8 -> s32 tcgen05 MMA with the accumulator in tensor memory; same integers. */
 int ms_cooccurrence(ms_handle *h, int32_t **d_C);
+/* 0 = choose by size (default), 1 = popcount-AND kernel, 2 = tensor-core kernel (A/B measurements, tests) */
+int ms_set_cooccurrence_variant(ms_handle *h, int32_t variant);
 
 /* ---- the whole juliet pass in one call ------------------------------------------------------
  * reset -> pileup -> (all-reduce when a communicator is attached) -> codon test -> phasing, i.e. everything

@@ -72,7 +72,8 @@ struct ms_handle {
     DevBuf b_var, b_blocklist, b_bits, b_flags, b_slot, b_tab_key, b_tab_cnt, b_tab_rep, b_ctr, b_groups, b_gather, b_rank, b_hap,
         b_pat, b_cooc, b_bits_t;
     // device-side merge + ordering (phase_order.cu)
-    DevBuf b_gslot, b_mt_key, b_mt_cnt, b_mt_rep, b_mslot, b_mindex, b_m_cnt, b_m_pat, b_m_rank, b_ord, b_keys, b_out;
+    DevBuf b_gslot, b_mt_key, b_mt_cnt, b_mt_rep, b_mslot, b_mindex, b_m_cnt, b_m_pat, b_m_rank, b_ord, b_keys, b_out, b_tc_tiles;
+    int cooc_variant = 0;        // 0 auto, 1 popcount-AND, 2 tcgen05 int8
     std::vector<uint32_t> groups_cnt, groups_pat;   // host copy of the last grouping pass (all ranks when a comm is attached)
     uint64_t groups_marg[4] = {0, 0, 0, 0};
     bool groups_valid = false;

@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(256) cooccurrence_kernel(const uint32_t* __res
 }  // namespace ms
 
 int ms_comm_allgather_bytes(ms_handle* h, const void* d_send, void* d_recv, size_t bytes_per_rank);
+int ms_cooccurrence_tc_launch(ms_handle* h, const uint32_t* bt, int32_t V, int64_t rstride, int64_t R, int32_t* C);
 
 namespace {
 
@@ -420,7 +421,7 @@ void ms_phase_free_internal(ms_handle* h) {
     DevBuf* all[] = {&h->b_var, &h->b_blocklist, &h->b_bits, &h->b_flags, &h->b_slot, &h->b_tab_key, &h->b_tab_cnt, &h->b_tab_rep,
                      &h->b_ctr, &h->b_groups, &h->b_gather, &h->b_rank, &h->b_hap, &h->b_pat, &h->b_cooc, &h->b_bits_t,
                      &h->b_gslot, &h->b_mt_key, &h->b_mt_cnt, &h->b_mt_rep, &h->b_mslot, &h->b_mindex, &h->b_m_cnt, &h->b_m_pat, &h->b_m_rank,
-                     &h->b_ord, &h->b_keys, &h->b_out};
+                     &h->b_ord, &h->b_keys, &h->b_out, &h->b_tc_tiles};
     for (DevBuf* b : all) b->release();
     if (h->h_stage) cudaFreeHost(h->h_stage);
     h->h_stage = nullptr; h->h_stage_cap = 0;
@@ -725,22 +726,39 @@ int ms_phase_device(ms_handle* h, uint32_t** d_bits, uint8_t** d_flags, int64_t*
     return MS_OK;
 }
 
+int ms_set_cooccurrence_variant(ms_handle* h, int32_t variant) {
+    if (!h || variant < 0 || variant > 2) return MS_ERR_ARG;
+    h->cooc_variant = variant;
+    return MS_OK;
+}
+
 int ms_cooccurrence(ms_handle* h, int32_t** d_C) {
     if (!h || !h->b_bits.p || !d_C) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
     const int32_t V = h->V, nw = h->vwords;
-    const int64_t R = h->phase_n, rwords = std::max<int64_t>(1, (R + 31) / 32);
+    const int64_t R = h->phase_n;
+    // the contraction goes to the tensor cores when it is big enough to be one (cooc_tc.cu); the popcount-AND
+    // kernel serves the usual few-dozen-variant case, where the matrix is tiny
+    const bool tensor = h->cooc_variant == 2 || (h->cooc_variant == 0 && V >= 256 && R >= 32768);
+    // row stride of the transposed bit matrix: whole 128-read stages for the tensor path (zero padded)
+    const int64_t rwords = tensor ? 4 * ((R + 127) / 128) : std::max<int64_t>(1, (R + 31) / 32);
     const size_t cbytes = std::max<size_t>(4, static_cast<size_t>(V) * V * 4);
     MS_CUDA(h, h->b_cooc.ensure(cbytes));
-    MS_CUDA(h, h->b_bits_t.ensure(static_cast<size_t>(nw) * 32 * rwords * 4));
+    MS_CUDA(h, h->b_bits_t.ensure(std::max<size_t>(16, static_cast<size_t>(nw) * 32 * rwords * 4)));
     MS_CUDA(h, cudaMemsetAsync(h->b_cooc.p, 0, cbytes, h->stream));
-    if (V > 0) {
+    if (V > 0 && rwords > 0) {
         const int64_t nwarps = rwords * nw;
         ms::bits_transpose_kernel<<<static_cast<unsigned>((nwarps * 32 + 255) / 256), 256, 0, h->stream>>>(h->b_bits.as<uint32_t>(), R, nw, rwords,
                                                                                                          h->b_bits_t.as<uint32_t>());
-        dim3 grid((V + ms::kCoTile - 1) / ms::kCoTile, (V + ms::kCoTile - 1) / ms::kCoTile);
-        ms::cooccurrence_kernel<<<grid, 256, 0, h->stream>>>(h->b_bits_t.as<uint32_t>(), V, rwords, h->b_cooc.as<int32_t>());
-        h->launches += 2;
+        h->launches++;
+        if (tensor) {
+            int rc = ms_cooccurrence_tc_launch(h, h->b_bits_t.as<uint32_t>(), V, rwords, R, h->b_cooc.as<int32_t>());
+            if (rc != MS_OK) return rc;
+        } else {
+            dim3 grid((V + ms::kCoTile - 1) / ms::kCoTile, (V + ms::kCoTile - 1) / ms::kCoTile);
+            ms::cooccurrence_kernel<<<grid, 256, 0, h->stream>>>(h->b_bits_t.as<uint32_t>(), V, rwords, h->b_cooc.as<int32_t>());
+            h->launches++;
+        }
     }
     MS_CUDA(h, cudaGetLastError());
     *d_C = h->b_cooc.as<int32_t>();

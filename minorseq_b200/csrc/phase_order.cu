@@ -112,7 +112,20 @@ __device__ __forceinline__ bool key_precedes(const uint32_t* __restrict__ pat, i
                                              unsigned long long kb, uint32_t b) {
     if (ka != kb) return ka < kb;
     if (nw == 1 || a == kSentinel) return false;   // distinct patterns differ in word 0 when there is only one word
-    return pattern_less(pat + static_cast<size_t>(a) * nw + 1, pat + static_cast<size_t>(b) * nw + 1, nw - 1);
+    const uint32_t *pa = pat + static_cast<size_t>(a) * nw, *pb = pat + static_cast<size_t>(b) * nw;
+    if ((nw & 3) == 0 && (reinterpret_cast<uintptr_t>(pat) & 15) == 0) {
+        // patterns of a phasing stress run share long prefixes (a strain's sites plus a few flipped bits): 16 bytes per load
+        const uint4 *qa = reinterpret_cast<const uint4*>(pa), *qb = reinterpret_cast<const uint4*>(pb);
+        for (int32_t i = 0; i < nw / 4; ++i) {
+            const uint4 x = qa[i], y = qb[i];
+            if (x.x != y.x) return x.x < y.x;
+            if (x.y != y.y) return x.y < y.y;
+            if (x.z != y.z) return x.z < y.z;
+            if (x.w != y.w) return x.w < y.w;
+        }
+        return false;
+    }
+    return pattern_less(pa + 1, pb + 1, nw - 1);
 }
 
 // all compare-exchange stages with distance < kLocalSpan of the merges k_begin..k_end, one CTA per kLocalSpan elements
@@ -408,7 +421,7 @@ extern "C" int ms_phase_haplotypes(ms_handle* h, int32_t min_reads, uint32_t* pa
             for (int i = 0; i < 4; ++i) marg[i] += hc[i];
         }
         if (any_collision || any_overflow) continue;
-        if (max_ng > gcap) { gcap = max_ng; h->gcap_hint = gcap; continue; }
+        if (max_ng > gcap) { gcap = (max_ng + 3) & ~int64_t(3); h->gcap_hint = gcap; continue; }   // multiple of 4: pattern rows stay 16-byte aligned
         if (res[6] != 0) MS_FAIL(h, MS_ERR_CUDA, "haplotype merge table overflow");
         if (res[5] != 0) {
             if (++merge_attempt >= 4) MS_FAIL(h, MS_ERR_CUDA, "haplotype merge hash collided under four seeds");
