@@ -327,6 +327,23 @@ def test_phase_host_merge_protocol(oracle, hd):
     phase_equal(oracle, hd, st, 900, cols, cods)
 
 
+@pytest.mark.parametrize("R,V", [(300, 40), (5000, 300), (33000, 257)])
+def test_cooccurrence_tensor_core_equals_popcount_and_oracle(oracle, hd, R, V):
+    """a13 on tcgen05 (u8 x u8 -> s32 UMMA, cooc_tc.cu): same integers as the popcount-AND kernel and the oracle, for
+    read counts that are not a multiple of the 128-read stage and variant counts that are not a multiple of the tile."""
+    lib = _lib.load()
+    st, cols, cods = _many_pattern_states(R, 3 * V + 60, V, 25, seed=R + V)
+    j, hap, obits = phase_equal(oracle, hd, st, 3 * V + 60, cols, cods)
+    want = oracle.cooccurrence(obits, V)
+    try:
+        for variant in (1, 2, 0):
+            _lib.check(lib.ms_set_cooccurrence_variant(hd.h, variant), hd.h)
+            assert np.array_equal(j.cooccurrence().cpu().numpy(), want), variant
+    finally:
+        _lib.check(lib.ms_set_cooccurrence_variant(hd.h, 0), hd.h)
+    assert lib.ms_set_cooccurrence_variant(hd.h, 3) == -1
+
+
 def test_phase_haplotypes_edge_cases(oracle, hd):
     """ms_phase_haplotypes: no reads, every read damaged, cap = 0 / no read ids, fewer slots than reported haplotypes."""
     lib = _lib.load()
