@@ -118,7 +118,7 @@ def load():
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -m minorseq_b200.build` "
             "(minorseq_b200 has no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(os.environ.get("MS_LIB_PATH", LIB_PATH))   # the override is for A/B builds of the same ABI (tools/)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res

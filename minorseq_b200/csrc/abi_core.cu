@@ -1,6 +1,7 @@
 // abi_core.cu -- lifecycle, layout and the K1 launchers of the C ABI (include/minorseq_b200.h).
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 #include "handle.h"
 #include "pileup.cuh"
 
@@ -165,19 +166,41 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
     h->groups = kGroups[W];
     const int row_bytes = nblk * 16;
     h->stage_bytes = h->groups * 8 * row_bytes;
+    // Clean non-pivot codons: with one reading frame they are resolved inside K1 from shared memory;
+    // with overlapping frames every substituted base makes up to three of them, and it is cheaper
+    // to log the flagged 8-read chunks per thread and resolve them afterwards in codon_exception_kernel
+    // (measured on 1M x 3 kb: 1 frame 0.374 vs 0.345+0.065 ms, 3 frames 0.591 vs 0.421+0.07 ms).
+    int64_t nstarts = 0;
+    if (start_mask)
+        for (int32_t j = 0; j + 2 < L; ++j) nstarts += (start_mask[j >> 5] >> (j & 31)) & 1u;
+    h->log_mode = start_mask != nullptr && nstarts * 20 > static_cast<int64_t>(L) * 9;   // > 0.45 starts per column
+    const int merge_bytes = (h->groups - 1) * 8 * ms::kPlanes * W * 32 * 4 + 64;  // end-of-kernel group merge reuses the ring
     const int budget = h->max_smem - ms::kPileupSmemHeader - 16;
     h->stages = std::max(3, std::min(8, budget / h->stage_bytes));
-    const int merge_bytes = (h->groups - 1) * 8 * ms::kPlanes * W * 32 * 4 + 64;  // end-of-kernel group merge reuses the ring
     h->smem_bytes = ms::kPileupSmemHeader + std::max(h->stages * h->stage_bytes + 16, merge_bytes);
+    // DENSE variant of the in-kernel rare path (pileup.cu, exception_add): one second-codon counter per column in
+    // shared memory behind the ring; chosen at the first pile-up after this call from the pivot sample's statistics
+    h->dense_known = false; h->dense = false;
+    h->stages_dense = 0; h->alt_off = 0; h->smem_bytes_dense = 0;
+    if (start_mask && !h->log_mode) {
+        const int alt_bytes = nblk * 32 * 4;
+        const int stages_d = std::min(8, (budget - alt_bytes - 128) / h->stage_bytes);
+        if (stages_d >= 3) {
+            const int ring_bytes = (std::max(stages_d * h->stage_bytes + 16, merge_bytes) + 127) & ~127;
+            h->stages_dense = stages_d;
+            h->alt_off = ms::kPileupSmemHeader + ring_bytes;
+            h->smem_bytes_dense = h->alt_off + alt_bytes;
+        }
+    }
     if (h->smem_bytes > h->max_smem) MS_FAIL(h, MS_ERR_ARG, "row too long for the shared-memory ring");
     const size_t ncounts = static_cast<size_t>(L) * 72;
     MS_CUDA(h, cudaMalloc(&h->d_counts, ncounts * 4));
     MS_CUDA(h, cudaMemsetAsync(h->d_counts, 0, ncounts * 4, h->stream));
     MS_CUDA(h, cudaMalloc(&h->d_start, nblk * 4));
     MS_CUDA(h, cudaMalloc(&h->d_pivot, (nblk + 1) * sizeof(uint2)));
-    MS_CUDA(h, cudaMalloc(&h->d_pivot_state, nblk * 32 + 4));
+    MS_CUDA(h, cudaMalloc(&h->d_pivot_state, nblk * 32 + 16));   // + {non-pivot, all} sample statistics behind the states
     MS_CUDA(h, cudaMemsetAsync(h->d_pivot, 0, (nblk + 1) * sizeof(uint2), h->stream));
-    MS_CUDA(h, cudaMemsetAsync(h->d_pivot_state, 0, nblk * 32 + 4, h->stream));
+    MS_CUDA(h, cudaMemsetAsync(h->d_pivot_state, 0, nblk * 32 + 16, h->stream));
     h->h_start.assign(nblk, 0u);
     if (start_mask) {
         for (int32_t b = 0; b < nblk; ++b) h->h_start[b] = start_mask[b];
@@ -217,14 +240,29 @@ int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
         return MS_OK;
     }
     if (h->count_codons && !h->have_pivot) {
-        ms::pivot_sample_kernel<<<h->nblk, 256, 0, h->stream>>>(d_packed, R, h->nblk, h->L, h->d_pivot, h->d_pivot_state);
+        const bool want_stat = !h->dense_known && h->stages_dense > 0;
+        uint32_t* dense_stat = reinterpret_cast<uint32_t*>(h->d_pivot_state + static_cast<size_t>(h->nblk) * 32 + 8);
+        if (want_stat) MS_CUDA(h, cudaMemsetAsync(dense_stat, 0, 8, h->stream));
+        ms::pivot_sample_kernel<<<h->nblk, 256, 0, h->stream>>>(d_packed, R, h->nblk, h->L, h->d_pivot, h->d_pivot_state,
+                                                               want_stat ? dense_stat : nullptr);
+        if (want_stat) {
+            // once per layout: are non-pivot bases the exception (sequencing errors, low-frequency variants) or the rule
+            // (dense high-frequency variants, > 2 % of the sampled clean bases)?  One 8-byte read decides which K1 runs.
+            uint32_t st[2] = {0, 0};
+            MS_CUDA(h, cudaMemcpyAsync(st, dense_stat, 8, cudaMemcpyDeviceToHost, h->stream));
+            MS_CUDA(h, cudaStreamSynchronize(h->stream));
+            h->dense = static_cast<uint64_t>(st[0]) * 50u > st[1];
+            h->dense_known = true;
+        }
         h->launches++;
         h->have_pivot = true;
     }
     ms::PileupArgs a;
     a.packed = d_packed; a.R = R; a.L = h->L; a.nblk = h->nblk;
     a.warps_per_group = h->wpg; a.groups = h->groups;
-    a.stages = h->stages; a.stage_bytes = h->stage_bytes;
+    const bool dense = h->count_codons && h->dense && h->stages_dense > 0;
+    a.stages = dense ? h->stages_dense : h->stages; a.stage_bytes = h->stage_bytes;
+    a.alt_off = dense ? static_cast<uint32_t>(h->alt_off) : 0u;
     a.pivot = h->d_pivot; a.start_mask = h->d_start; a.codon = codon;
     a.part_col = h->d_part_col; a.part_piv = h->d_part_piv;
     const int mode = !h->count_codons ? ms::kModeFuse : (h->count_ins ? ms::kModeBoth : ms::kModeJuliet);
@@ -233,13 +271,7 @@ int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     const int grid = static_cast<int>(std::min<int64_t>(h->num_sms, ntiles));
     const int threads = h->wpg * h->groups * 32;
     if (R > (1LL << 27)) MS_FAIL(h, MS_ERR_ARG, "more than 2^27 reads in one ms_pileup_dev call: split the batch");
-    // Clean non-pivot codons: with one reading frame they are resolved inside K1 from shared memory;
-    // with overlapping frames every substituted base makes up to three of them, and it is cheaper
-    // to log the flagged 8-read chunks per thread and resolve them afterwards in codon_exception_kernel
-    // (measured on 1M x 3 kb: 1 frame 0.374 vs 0.345+0.065 ms, 3 frames 0.591 vs 0.421+0.07 ms).
-    int64_t nstarts = 0;
-    for (uint32_t w : h->h_start) nstarts += __builtin_popcount(w);
-    const bool log_mode = mode != ms::kModeFuse && nstarts * 20 > static_cast<int64_t>(h->L) * 9;   // > 0.45 starts per column
+    const bool log_mode = mode != ms::kModeFuse && h->log_mode;   // decided with the layout (ms_set_layout)
     const int64_t reads_per_group = (R + static_cast<int64_t>(grid) * h->groups - 1) / (static_cast<int64_t>(grid) * h->groups);
     const uint32_t exc_cap = log_mode ? static_cast<uint32_t>(std::min<int64_t>(8192, std::max<int64_t>(64, reads_per_group / 8 / 3))) : 0u;
     const int64_t nlists = static_cast<int64_t>(grid) * threads;
@@ -249,7 +281,7 @@ int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     }
     a.exc_list = h->b_exc_list.as<uint32_t>(); a.exc_cnt = h->b_exc_cnt.as<uint32_t>(); a.exc_cap = exc_cap; a.exc_lists = nlists;
     if (h->timing) MS_CUDA(h, cudaEventRecord(h->ev_k1[0], h->stream));
-    ms::pileup_launch(mode, grid, threads, h->smem_bytes, h->stream, a);
+    ms::pileup_launch(mode, dense, grid, threads, dense ? h->smem_bytes_dense : h->smem_bytes, h->stream, a);
     if (h->timing) { MS_CUDA(h, cudaEventRecord(h->ev_k1[1], h->stream)); h->k1_reads = R; }
     if (log_mode) { ms::pileup_exceptions_launch(grid, threads, h->stream, a); h->launches++; }
     const int64_t nfin = static_cast<int64_t>(h->L) * 9 * 4;

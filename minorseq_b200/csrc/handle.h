@@ -47,6 +47,10 @@ struct ms_handle {
     uint32_t *d_part_col = nullptr, *d_part_piv = nullptr;
     int32_t groups = 1, wpg = 1, stages = 2, stage_bytes = 0, smem_bytes = 0;
     bool have_pivot = false;
+    bool log_mode = false;       // K1 logs flagged chunks for codon_exception_kernel (dense start masks)
+    // DENSE variant of K1 (second-codon counters in shared memory): its own ring depth and shared-memory size
+    int32_t alt_off = 0, stages_dense = 0, smem_bytes_dense = 0;
+    bool dense_known = false, dense = false;
     DevBuf b_exc_list, b_exc_cnt;  // K1's per-thread exception logs
     std::vector<uint32_t> h_start;
 

@@ -137,9 +137,39 @@ __device__ __forceinline__ void read_masks(uint32_t addr, const CodonCtx& cx, ui
     }
 }
 
+// One clean non-pivot codon (start column j of this block) goes to the histogram.  A frequent minor variant makes
+// the SAME (column, codon) bin come up in a sizeable share of all reads -- in a phasing stress run in half of them at
+// every site -- and global REDs on a few thousand hot addresses then dominate the kernel.  So every CTA keeps one
+// second-codon counter per column in shared memory, word = codon << 26 | count: the first non-pivot codon seen at a
+// column claims it, later sightings of that codon are shared-memory REDs, and only other codons (sequencing errors)
+// go to global memory.  The counters are added to the global histogram once, at the end of the kernel.
+constexpr uint32_t kAltEmpty = 0xFFFFFFFFu;
+// This costs the ordinary kernel 3-8 % (code generation at its register limit, 12 KB less L1), so it is a separate
+// instantiation (DENSE) that the launcher picks when the pivot sample finds more than 2 % non-pivot bases.
+// alt: shared address of this block's 32 counters.
+__device__ __forceinline__ void exception_add(uint32_t* codon, uint32_t alt, int j, uint32_t cod) {
+    {
+        const uint32_t addr = alt + static_cast<uint32_t>(j) * 4u;
+        uint32_t v = lds32(addr);
+        if (v == kAltEmpty) {
+            asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(v) : "r"(addr), "r"(kAltEmpty), "r"((cod << 26) | 1u) : "memory");
+            if (v == kAltEmpty) return;   // claimed, count 1
+        }
+        if ((v >> 26) == cod) {
+            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+            return;
+        }
+    }
+    atomicAdd(codon + (j * 64 + cod), 1u);
+}
+
 // Rare path: the reads flagged in pm may carry clean non-pivot codons; re-read them from the slot
 // (still owned by this row-group) and add each such codon to the global 64-bin histogram.
-__device__ __forceinline__ void codon_exceptions(uint32_t addr, uint32_t row_bytes, uint32_t pm, const CodonCtx& cx) {
+template <bool DENSE>
+__device__ __forceinline__ void codon_exceptions(uint32_t addr, uint32_t row_bytes, uint32_t pm, const CodonCtx& cx,
+                                                 const uint32_t* codon_base, uint32_t alt0) {
+    // this block's second-codon counters (block index from the histogram pointer); compiled out of the ordinary kernel
+    const uint32_t alt = DENSE ? alt0 + static_cast<uint32_t>((cx.codon - codon_base) >> 11) * 128u : 0u;
     while (pm) {
         const int rd = __ffs(pm) - 1;
         pm &= pm - 1;
@@ -154,7 +184,8 @@ __device__ __forceinline__ void codon_exceptions(uint32_t addr, uint32_t row_byt
             const uint32_t b1 = __funnelshift_r(q.y, n.y, j) & 7u;  // bit1 of the 3 states
             const uint32_t cod = ((b0 & 1u) << 4) | ((b1 & 1u) << 5) | ((b0 & 2u) << 1) | ((b1 & 2u) << 2) |
                                  ((b0 & 4u) >> 2) | ((b1 & 4u) >> 1);
-            atomicAdd(cx.codon + (j * 64 + cod), 1u);
+            if (DENSE) exception_add(cx.codon, alt, j, cod);
+            else atomicAdd(cx.codon + (j * 64 + cod), 1u);
         }
     }
 }
@@ -229,10 +260,11 @@ struct ExcLog {
     uint32_t cnt, cap;
 };
 // one entry per 8-read chunk with any flagged read: (first read of the chunk / 8) << 8 | flag byte
+template <bool DENSE>
 __device__ __forceinline__ void log_or_handle(uint32_t pm, uint32_t read0, ExcLog& lg, uint32_t addr, uint32_t row_bytes,
-                                              const CodonCtx& cx) {
+                                              const CodonCtx& cx, const uint32_t* codon_base, uint32_t alt0) {
     if (lg.cnt < lg.cap) lg.list[lg.cnt++] = ((read0 >> 3) << 8) | pm;
-    else codon_exceptions(addr, row_bytes, pm, cx);
+    else codon_exceptions<DENSE>(addr, row_bytes, pm, cx, codon_base, alt0);
 }
 
 // ---------------------------------------------------------------- flush (cold path)
@@ -340,7 +372,7 @@ __device__ __forceinline__ void clear(Vert<NM>& v) {
     }
 }
 
-template <int MODE>
+template <int MODE, bool DENSE>
 __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     using T = Traits<MODE>;
     constexpr int NM = T::NM;
@@ -364,6 +396,11 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    // second-codon counters, one per column: only when the pivot sample says that non-pivot bases are common (> 2 % of
+    // the clean bases); on ordinary data the extra shared-memory probe per rare codon costs more than it saves
+    const uint32_t alt0 = DENSE ? bar0 + a.alt_off : 0u;   // second-codon counters, one per column
+    if (DENSE)
+        for (int i = threadIdx.x; i < a.nblk * 32; i += blockDim.x) sts32(alt0 + 4u * i, kAltEmpty);
     __syncthreads();
 
     // ---------------- consumers: group g of W warps walks its 8 reads of every tile
@@ -449,7 +486,7 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         const uint32_t addr = data0 + slot * chunk_bytes + static_cast<uint32_t>(blk) * 16u;
         if (nv == 8) {
             const uint32_t pm = block8<MODE>(addr, row_bytes, cx, v, bi);
-            if (T::CODON && pm) log_or_handle(pm, static_cast<uint32_t>(r0), lg, addr, row_bytes, cx);
+            if (T::CODON && pm) log_or_handle<DENSE>(pm, static_cast<uint32_t>(r0), lg, addr, row_bytes, cx, a.codon, alt0);
             ++bi;
             n += 8;
         } else {
@@ -459,7 +496,7 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
                 read_masks<MODE>(addr + i * row_bytes, cx, m, pm, 1u);
 #pragma unroll
                 for (int q = 0; q < NM; ++q) ripple(v, q, 0, m[q]);
-                if (T::CODON && pm) log_or_handle(1u << i, static_cast<uint32_t>(r0), lg, addr, row_bytes, cx);
+                if (T::CODON && pm) log_or_handle<DENSE>(1u << i, static_cast<uint32_t>(r0), lg, addr, row_bytes, cx, a.codon, alt0);
                 ++n;
             }
         }
@@ -485,6 +522,12 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     fold_pendings(v, bi);
     // all tiles are consumed and every bulk copy has landed, so the stage ring is free to reuse
     consumer_barrier(nct);
+    if (DENSE) {   // the CTA's second-codon counters join the global histogram
+        for (int i = threadIdx.x; i < a.nblk * 32; i += nct) {
+            const uint32_t v = lds32(alt0 + 4u * i);
+            if (v != kAltEmpty) atomicAdd(a.codon + (static_cast<size_t>(i) * 64 + (v >> 26)), v & 0x03FFFFFFu);
+        }
+    }
     const uint32_t tg = static_cast<uint32_t>(W) * 32u;           // threads per group
     const uint32_t thread_stride = tg * 4u;                       // bytes between planes
     const uint32_t group_stride = static_cast<uint32_t>(NM * kPlanes) * thread_stride;
@@ -511,21 +554,25 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     }
 }
 
-template <int MODE>
+template <int MODE, bool DENSE>
 __global__ void __launch_bounds__(kPileupMaxThreads, 1) pileup_csa_kernel(PileupArgs a) {
-    pileup_body<MODE>(a);
+    pileup_body<MODE, DENSE>(a);
 }
 
 void pileup_set_smem_attr(int max_smem) {
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeJuliet>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeFuse>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeBoth>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeJuliet, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeFuse, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeBoth, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeJuliet, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeBoth, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
 }
 
-void pileup_launch(int mode, int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a) {
-    if (mode == kModeJuliet) pileup_csa_kernel<kModeJuliet><<<grid, threads, smem, s>>>(a);
-    else if (mode == kModeFuse) pileup_csa_kernel<kModeFuse><<<grid, threads, smem, s>>>(a);
-    else pileup_csa_kernel<kModeBoth><<<grid, threads, smem, s>>>(a);
+void pileup_launch(int mode, bool dense, int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a) {
+    if (mode == kModeFuse) pileup_csa_kernel<kModeFuse, false><<<grid, threads, smem, s>>>(a);
+    else if (mode == kModeJuliet && !dense) pileup_csa_kernel<kModeJuliet, false><<<grid, threads, smem, s>>>(a);
+    else if (mode == kModeJuliet) pileup_csa_kernel<kModeJuliet, true><<<grid, threads, smem, s>>>(a);
+    else if (!dense) pileup_csa_kernel<kModeBoth, false><<<grid, threads, smem, s>>>(a);
+    else pileup_csa_kernel<kModeBoth, true><<<grid, threads, smem, s>>>(a);
 }
 
 // ---------------------------------------------------------------- logged exceptions
@@ -601,7 +648,7 @@ void pileup_exceptions_launch(int pileup_grid, int pileup_threads, cudaStream_t 
 // majority of A/C/G/T among the sample becomes the pivot base.  The pivot only decides which
 // codon is counted by the bit-sliced fast path; results are exact for any pivot.
 __global__ void pivot_sample_kernel(const uint32_t* packed, int64_t R, int32_t nblk, int32_t L, uint2* pivot,
-                                    uint8_t* pivot_state) {
+                                    uint8_t* pivot_state, uint32_t* dense_stat) {
     __shared__ uint32_t cnt[32][4];
     const int blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     if (tid < 128) cnt[tid >> 2][tid & 3] = 0;
@@ -631,6 +678,14 @@ __global__ void pivot_sample_kernel(const uint32_t* packed, int64_t R, int32_t n
         if (tid == 0) pivot[blk] = make_uint2(r0, r1);
         if (blk * 32 + tid < L) pivot_state[blk * 32 + tid] = static_cast<uint8_t>(best);
         if (blk == 0 && tid == 0) pivot[nblk] = make_uint2(0, 0);  // look-ahead of the last block
+        // how often a sampled clean base is not the pivot: tells K1 whether non-pivot codons are rare (sequencing errors,
+        // low-frequency variants) or the rule (dense high-frequency variants), see exception_add
+        uint32_t total = cnt[tid][0] + cnt[tid][1] + cnt[tid][2] + cnt[tid][3];
+        uint32_t dev = total - cnt[tid][best];
+        if (blk * 32 + tid >= L) total = dev = 0;
+        total = __reduce_add_sync(0xffffffffu, total);
+        dev = __reduce_add_sync(0xffffffffu, dev);
+        if (tid == 0 && dense_stat) { atomicAdd(dense_stat, dev); atomicAdd(dense_stat + 1, total); }
     }
 }
 

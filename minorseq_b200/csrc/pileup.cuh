@@ -51,14 +51,15 @@ struct PileupArgs {
     uint32_t* exc_list;       // [gridDim*blockDim][exc_cap] reads logged for the exact codon pass
     uint32_t* exc_cnt;        // [gridDim*blockDim]
     uint32_t exc_cap;
+    uint32_t alt_off;         // DENSE kernels: byte offset (from the start of shared memory) of the per-column second-codon counters
     int64_t exc_lists;        // gridDim*blockDim of the pileup launch
 };
 
-template <int MODE>
+template <int MODE, bool DENSE>
 __global__ void pileup_csa_kernel(PileupArgs a);
 
 __global__ void pivot_sample_kernel(const uint32_t* packed, int64_t R, int32_t nblk, int32_t L,
-                                    uint2* pivot, uint8_t* pivot_state);
+                                    uint2* pivot, uint8_t* pivot_state, uint32_t* dense_stat);
 __global__ void pileup_finalize_kernel(const uint32_t* part_col, const uint32_t* part_piv, int32_t slices,
                                        int32_t nblk, int32_t L, const uint8_t* pivot_state,
                                        const uint32_t* start_mask, uint32_t* col, uint32_t* codon,
@@ -69,7 +70,7 @@ __global__ void pileup_atomic_kernel(const uint32_t* packed, int64_t R, int32_t 
 __global__ void coverage_kernel(uint32_t* col, int32_t L);
 
 void pileup_set_smem_attr(int max_smem);
-void pileup_launch(int mode, int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a);
+void pileup_launch(int mode, bool dense, int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a);
 void pileup_exceptions_launch(int pileup_grid, int pileup_threads, cudaStream_t s, const PileupArgs& a);
 
 }  // namespace ms

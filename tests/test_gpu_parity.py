@@ -125,6 +125,27 @@ def test_pileup_reference_differs_from_sample(oracle, hd):
     check_pileup(oracle, hd, st, L, [(1, L + 1), (2, L + 1), (3, L + 1)])
 
 
+def test_pileup_dense_high_frequency_variants(oracle, hd):
+    """Phasing-stress style data: a variant codon in half of the reads at every third codon.  The pivot sample sees
+    > 2 % non-pivot bases and K1 runs its DENSE instantiation (second-codon counters in shared memory); counts
+    must not care.  Also with ragged read counts and across two accumulated batches."""
+    cfg = SynthConfig(L=960, seed=56, dense_sites=150, dense_strains=16, n_rate=1e-3, dele=1e-3, trunc=0.02)
+    t = make_tables(cfg)
+    st = synth_states(t, 0, 6001)
+    check_pileup(oracle, hd, st, 960, [(1, 961)])
+    check_pileup(oracle, hd, st[:777], 960, [(1, 961)], count_ins=True)
+    j = Juliet(960, [(1, 961)], handle=hd)
+    j.reset()
+    d = to_dev(pack_states(st))
+    j.pileup_device(d.data_ptr(), 4000)
+    j.pileup_device(d.data_ptr() + 4000 * j.row_words * 4, 2001)
+    col, codon = j.get_counts()
+    ocol, ocodon = oracle.pileup(st, mask_bytes(j.start_mask, 960))
+    ocol = ocol.copy()
+    ocol[:, 6] = 0
+    assert np.array_equal(col, ocol) and np.array_equal(codon, ocodon)
+
+
 def test_pileup_accumulates_batches_and_host_path(oracle, hd, c1):
     t, st, packed = c1
     L = 3000
