@@ -161,6 +161,26 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this rank's threads to the CPUs NVML names as local to its GPU (when the container's cpuset allows), so that
+    the pinned staging buffers of the e2e path are first-touched on that GPU's NUMA node.  Returns the CPU count or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        ideal = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = ideal & allowed
+        if len(cpus) >= 2 and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def main():
     args = parse()
     if os.environ.get("BENCH_WATCHDOG"):
@@ -173,6 +193,7 @@ def main():
         run_reference(args, rank)
         return
 
+    affinity = bind_to_gpu_numa(local_rank) if world > 1 else None   # pinned buffers land on the GPU's NUMA node
     sampler = ClockSampler(local_rank)   # before CUDA / NCCL come up
     sampler.start()
     import torch
@@ -296,7 +317,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u32 counts / f64 p-values", "data": "synthetic", "config": workload_config(args),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+                "clocks": clocks, "e2e": e2e, "host_affinity_cpus": affinity, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
                 "result_check": {"variants": len(res.variants), "haplotypes_reported": hp.nreported if hp else None,
                                  "counters": hp.counters if hp else None}}
         print(json.dumps(line), flush=True)

@@ -28,44 +28,75 @@ struct VarDev {
 
 constexpr int kPhaseWarps = 8;
 
+// packed per-variant record of the staged kernel: slot of the first block (13 bits) | second block is the next slot (1)
+// | first column in its block (5) | plane-0 bits of the three bases (3) | plane-1 bits (3) | variant inside the reference (1)
+__host__ __device__ inline uint32_t pack_var(int32_t slotA, int32_t slotB, int32_t shift, int32_t codon) {
+    if (codon < 0) return 0u;
+    const uint32_t b0 = (codon >> 4) & 3u, b1 = (codon >> 2) & 3u, b2 = codon & 3u;
+    const uint32_t k0 = (b0 & 1u) | ((b1 & 1u) << 1) | ((b2 & 1u) << 2);
+    const uint32_t k1 = (b0 >> 1) | ((b1 >> 1) << 1) | ((b2 >> 1) << 2);
+    return static_cast<uint32_t>(slotA) | (static_cast<uint32_t>(slotB - slotA) << 13) | (static_cast<uint32_t>(shift) << 14) | (k0 << 19) |
+           (k1 << 22) | (1u << 25);
+}
+
+// V > 32: one warp per read.  The touched 32-column blocks are staged in shared memory as three plane arrays (so a
+// lane's three words come from consecutive banks and neighbouring variants broadcast), the variant records sit in
+// shared memory once per CTA, one lane per variant, a ballot per 32 variants; the lane whose index equals the word
+// index keeps the word, so the bit-vector leaves as full 128-byte lines.  LSU-bound: 7 shared-memory wavefronts per 32
+// (read, variant) pairs.
 __global__ void __launch_bounds__(kPhaseWarps * 32) phase_bits_kernel(
     const uint4* __restrict__ packed, int64_t R, int32_t nblk, const int32_t* __restrict__ blocklist, int32_t NB,
     const VarDev* __restrict__ vars, int32_t V, int32_t vwords, uint32_t* __restrict__ bits, uint8_t* __restrict__ flags,
     unsigned long long* __restrict__ ctr) {
-    extern __shared__ uint4 sm[];  // [kPhaseWarps][NB]
+    extern __shared__ uint32_t smw[];   // [vwords*32] records | [kPhaseWarps][3][NB] planes
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint4* my = sm + static_cast<size_t>(warp) * NB;
+    uint32_t* meta = smw;
+    uint32_t* px = smw + static_cast<size_t>(vwords) * 32 + static_cast<size_t>(warp) * 3 * NB;
+    uint32_t* py = px + NB;
+    uint32_t* pz = py + NB;
+    for (int v = threadIdx.x; v < vwords * 32; v += blockDim.x) {
+        uint32_t m = 0u;
+        bool outside = false;
+        if (v < V) {
+            const VarDev vd = vars[v];
+            m = pack_var(vd.slotA, vd.slotB, vd.shift, vd.codon);
+            outside = vd.codon < 0;
+        }
+        meta[v] = m | (outside ? (1u << 26) : 0u);   // bit 26: variant lies outside the reference (always partial)
+    }
+    __syncthreads();
     unsigned long long c_dam = 0, c_gap = 0, c_het = 0, c_par = 0;
     for (int64_t r = static_cast<int64_t>(blockIdx.x) * kPhaseWarps + warp; r < R;
          r += static_cast<int64_t>(gridDim.x) * kPhaseWarps) {
         const uint4* row = packed + static_cast<size_t>(r) * nblk;
-        for (int i = lane; i < NB; i += 32) my[i] = row[blocklist[i]];
-        __syncwarp();
-        uint32_t f = 0;
-        for (int w = 0; w < vwords; ++w) {
-            const int v = w * 32 + lane;
-            bool bit = false;
-            if (v < V) {
-                const VarDev vd = vars[v];
-                if (vd.codon < 0) {
-                    f |= MS_FLAG_PARTIAL;
-                } else {
-                    const uint4 a = my[vd.slotA], b = my[vd.slotB];
-                    const uint32_t b0 = __funnelshift_r(a.x, b.x, vd.shift) & 7u;
-                    const uint32_t b1 = __funnelshift_r(a.y, b.y, vd.shift) & 7u;
-                    const uint32_t z = __funnelshift_r(a.z, b.z, vd.shift) & 7u;
-                    if (z & ~b0 & ~b1) f |= MS_FLAG_GAP;      // 100
-                    if (z & b0 & ~b1) f |= MS_FLAG_HET;       // 101
-                    if (z & b1) f |= MS_FLAG_PARTIAL;         // 11x
-                    const uint32_t cod = ((b0 & 1u) << 4) | ((b1 & 1u) << 5) | ((b0 & 2u) << 1) | ((b1 & 2u) << 2) |
-                                         ((b0 & 4u) >> 2) | ((b1 & 4u) >> 1);
-                    bit = (z == 0u) && (cod == static_cast<uint32_t>(vd.codon));
-                }
-            }
-            const uint32_t word = __ballot_sync(0xffffffffu, bit);
-            if (lane == 0) bits[static_cast<size_t>(r) * vwords + w] = word;
+        for (int i = lane; i < NB; i += 32) {
+            const uint4 q = row[blocklist[i]];
+            px[i] = q.x; py[i] = q.y; pz[i] = q.z;
         }
-        f = __reduce_or_sync(0xffffffffu, f);
+        __syncwarp();
+        uint32_t fg = 0, fh = 0, fp = 0, keep = 0;
+        for (int w = 0; w < vwords; ++w) {
+            const uint32_t m = meta[w * 32 + lane];
+            const uint32_t sa = m & 0x1FFFu, sb = sa + ((m >> 13) & 1u), sh = (m >> 14) & 31u;
+            const uint32_t b0 = __funnelshift_r(px[sa], px[sb], sh) & 7u;
+            const uint32_t b1 = __funnelshift_r(py[sa], py[sb], sh) & 7u;
+            const uint32_t z = __funnelshift_r(pz[sa], pz[sb], sh) & 7u;
+            const bool in = (m >> 25) & 1u;
+            if (in) {
+                fg |= z & ~b0 & ~b1;      // 100
+                fh |= z & b0 & ~b1;       // 101
+                fp |= z & b1;             // 11x
+            }
+            fp |= (m >> 26) & 1u;
+            const bool bit = in && (((b0 ^ ((m >> 19) & 7u)) | (b1 ^ ((m >> 22) & 7u)) | z) == 0u);
+            const uint32_t word = __ballot_sync(0xffffffffu, bit);
+            if (lane == (w & 31)) keep = word;
+            if ((w & 31) == 31 || w + 1 == vwords) {
+                if (lane <= (w & 31)) bits[static_cast<size_t>(r) * vwords + (w & ~31) + lane] = keep;
+            }
+        }
+        const uint32_t f = (__any_sync(0xffffffffu, fg != 0) ? MS_FLAG_GAP : 0) | (__any_sync(0xffffffffu, fh != 0) ? MS_FLAG_HET : 0) |
+                           (__any_sync(0xffffffffu, fp != 0) ? MS_FLAG_PARTIAL : 0);
         if (lane == 0) {
             flags[r] = static_cast<uint8_t>(f);
             if (f) {
@@ -525,7 +556,8 @@ int ms_phase_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
         }
 #undef MS_SPARSE
     } else {
-        const size_t smem = static_cast<size_t>(ms::kPhaseWarps) * h->nblocklist * sizeof(uint4);
+        const size_t smem = (static_cast<size_t>(h->vwords) * 32 + static_cast<size_t>(ms::kPhaseWarps) * 3 * h->nblocklist) * sizeof(uint32_t);
+        if (smem > static_cast<size_t>(h->max_smem)) MS_FAIL(h, MS_ERR_CAPACITY, "too many variants / touched blocks for the phasing kernel's shared memory");
         if (smem > 48 * 1024)
             MS_CUDA(h, cudaFuncSetAttribute(ms::phase_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         const int64_t want = (R + ms::kPhaseWarps - 1) / ms::kPhaseWarps;
