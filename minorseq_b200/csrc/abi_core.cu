@@ -153,18 +153,53 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
     if (!h || L < 3) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
     const int32_t nblk = (L + 31) / 32;
-    // warps per row: 31 counting lanes per warp (lane 31 is the codon look-ahead provider), 32 in the last
-    const int32_t W = nblk <= 32 ? 1 : 1 + (nblk - 32 + 30) / 31;
-    if (W > 12) MS_FAIL(h, MS_ERR_ARG, "reference longer than 11936 columns is not supported by this build");
+    // CTA shape.  W warps span a row (31 counting lanes per warp -- lane 31 is the codon look-ahead provider -- and 32 in
+    // the last), G row-groups per CTA with W*G <= 12.  A row can also be cut into nseg column segments (CTA c then handles
+    // segment c % nseg of its reads, every segment but the last carrying one look-ahead block of the next).  Whole rows
+    // are the efficient unit -- one bulk copy per 8-read chunk, whole DRAM pages -- and a sweep over nseg at 3, 5, 6.1,
+    // 8 and 9.7 kb (tools/k1_segments.py, profiles/r1_k1_segments_sweep.txt) found segments slower everywhere except where
+    // the unsegmented shape leaves five of the twelve warps idle (W = 7, G = 1: 6.0-7.0 kb, where twelve single-warp
+    // segments are 1.36x faster).  So: segments only there, and when a whole row needs more than 12 warps (L > 11936).
+    static const int kGroups[13] = {0, 12, 6, 4, 3, 2, 2, 1, 1, 1, 1, 1, 1};
+    const int budget = h->max_smem - ms::kPileupSmemHeader - 16;
+    const int forced = getenv("MS_K1_NSEG") ? atoi(getenv("MS_K1_NSEG")) : 0;   // tuning knob (tools/k1_segments.py)
+    auto shape = [&](int nseg, int& W, int& need) {
+        const int seg_len = (nblk + nseg - 1) / nseg;
+        if (nseg > 1 && seg_len * (nseg - 1) >= nblk) return false;        // an empty last segment
+        need = seg_len + (nseg > 1 ? 1 : 0);
+        W = need <= 32 ? 1 : 1 + (need - 32 + 30) / 31;
+        return W <= 12 && budget / (kGroups[W] * 8 * need * 16) >= 3;    // the ring needs three slots per row-group
+    };
+    int best_nseg = 0, best_W = 0;
+    {
+        int W1 = 0, need1 = 0;
+        const bool whole = shape(1, W1, need1);
+        if (forced > 0) {
+            int Wf, nf;
+            if (shape(forced, Wf, nf)) { best_nseg = forced; best_W = Wf; }
+        } else if (whole && !(kGroups[W1] == 1 && W1 <= 7)) {
+            best_nseg = 1; best_W = W1;
+        } else {
+            // W = 7 row: the all-single-warp shape; longer than 12 warps: the fewest (largest) segments that fit
+            for (int nseg = 2; nseg <= 64 && best_nseg == 0; ++nseg) {
+                int Wn, nn;
+                if (!shape(nseg, Wn, nn)) continue;
+                if (whole && Wn != 1) continue;
+                best_nseg = nseg; best_W = Wn;
+            }
+            if (best_nseg == 0 && whole) { best_nseg = 1; best_W = W1; }
+        }
+    }
+    if (best_nseg == 0) MS_FAIL(h, MS_ERR_ARG, "reference too long for this build's pile-up kernel");
+    const int32_t W = best_W;
     MS_CUDA(h, cudaStreamSynchronize(h->stream));
     free_layout(h);
     h->L = L; h->nblk = nblk; h->count_codons = start_mask != nullptr; h->have_pivot = false;
-    // CTA shape: G row-groups of W warps; W*G is a multiple of 4 where possible so that every
-    // SM sub-partition hosts the same number of consumer warps, plus 1 producer warp
-    static const int kGroups[13] = {0, 12, 6, 4, 3, 2, 2, 1, 1, 1, 1, 1, 1};
     h->wpg = W;
     h->groups = kGroups[W];
-    const int row_bytes = nblk * 16;
+    h->nseg = best_nseg;
+    h->seg_len = (nblk + best_nseg - 1) / best_nseg;
+    const int row_bytes = (h->seg_len + (best_nseg > 1 ? 1 : 0)) * 16;   // bytes of one read in a ring slot
     h->stage_bytes = h->groups * 8 * row_bytes;
     // Clean non-pivot codons: with one reading frame they are resolved inside K1 from shared memory;
     // with overlapping frames every substituted base makes up to three of them, and it is cheaper
@@ -175,7 +210,6 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
         for (int32_t j = 0; j + 2 < L; ++j) nstarts += (start_mask[j >> 5] >> (j & 31)) & 1u;
     h->log_mode = start_mask != nullptr && nstarts * 20 > static_cast<int64_t>(L) * 9;   // > 0.45 starts per column
     const int merge_bytes = (h->groups - 1) * 8 * ms::kPlanes * W * 32 * 4 + 64;  // end-of-kernel group merge reuses the ring
-    const int budget = h->max_smem - ms::kPileupSmemHeader - 16;
     h->stages = std::max(3, std::min(8, budget / h->stage_bytes));
     h->smem_bytes = ms::kPileupSmemHeader + std::max(h->stages * h->stage_bytes + 16, merge_bytes);
     // DENSE variant of the in-kernel rare path (pileup.cu, exception_add): one second-codon counter per column in
@@ -260,6 +294,7 @@ int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     ms::PileupArgs a;
     a.packed = d_packed; a.R = R; a.L = h->L; a.nblk = h->nblk;
     a.warps_per_group = h->wpg; a.groups = h->groups;
+    a.nseg = h->nseg; a.seg_len = h->seg_len;
     const bool dense = h->count_codons && h->dense && h->stages_dense > 0;
     a.stages = dense ? h->stages_dense : h->stages; a.stage_bytes = h->stage_bytes;
     a.alt_off = dense ? static_cast<uint32_t>(h->alt_off) : 0u;
@@ -268,11 +303,12 @@ int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     const int mode = !h->count_codons ? ms::kModeFuse : (h->count_ins ? ms::kModeBoth : ms::kModeJuliet);
     const int64_t T = static_cast<int64_t>(h->groups) * 8;
     const int64_t ntiles = (R + T - 1) / T;
-    const int grid = static_cast<int>(std::min<int64_t>(h->num_sms, ntiles));
+    const int grid = static_cast<int>(std::min<int64_t>(h->num_sms, ntiles * h->nseg));   // >= nseg: every segment has a CTA
     const int threads = h->wpg * h->groups * 32;
     if (R > (1LL << 27)) MS_FAIL(h, MS_ERR_ARG, "more than 2^27 reads in one ms_pileup_dev call: split the batch");
     const bool log_mode = mode != ms::kModeFuse && h->log_mode;   // decided with the layout (ms_set_layout)
-    const int64_t reads_per_group = (R + static_cast<int64_t>(grid) * h->groups - 1) / (static_cast<int64_t>(grid) * h->groups);
+    const int64_t groups_per_seg = static_cast<int64_t>(std::max(1, grid / h->nseg)) * h->groups;
+    const int64_t reads_per_group = (R + groups_per_seg - 1) / groups_per_seg;
     const uint32_t exc_cap = log_mode ? static_cast<uint32_t>(std::min<int64_t>(8192, std::max<int64_t>(64, reads_per_group / 8 / 3))) : 0u;
     const int64_t nlists = static_cast<int64_t>(grid) * threads;
     if (mode != ms::kModeFuse) {
@@ -287,7 +323,7 @@ int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     const int64_t nfin = static_cast<int64_t>(h->L) * 9 * 4;
     ms::pileup_finalize_kernel<<<static_cast<int>((nfin + 255) / 256), 256, 0, h->stream>>>(
         h->d_part_col, h->d_part_piv, grid, h->nblk, h->L, h->d_pivot_state, h->d_start, col, codon,
-        h->count_codons ? 1 : 0);
+        h->count_codons ? 1 : 0, h->nseg, h->seg_len);
     h->launches += 2;
     MS_CUDA(h, cudaGetLastError());
     return MS_OK;

@@ -46,6 +46,7 @@ struct ms_handle {
     uint8_t* d_pivot_state = nullptr;  // [nblk*32 + 2]
     uint32_t *d_part_col = nullptr, *d_part_piv = nullptr;
     int32_t groups = 1, wpg = 1, stages = 2, stage_bytes = 0, smem_bytes = 0;
+    int32_t nseg = 1, seg_len = 0;   // column segments of K1 (abi_core.cu, ms_set_layout)
     bool have_pivot = false;
     bool log_mode = false;       // K1 logs flagged chunks for codon_exception_kernel (dense start masks)
     // DENSE variant of K1 (second-codon counters in shared memory): its own ring depth and shared-memory size

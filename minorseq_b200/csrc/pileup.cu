@@ -380,7 +380,18 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = a.warps_per_group, G = a.groups, S = a.stages;
     const int ncw = W * G;  // all warps are consumers; lane 0 of warp 0 also produces
-    const uint32_t row_bytes = static_cast<uint32_t>(a.nblk) * 16u;
+    // Column segments: with nseg > 1 a CTA handles only the blocks [blk0, blk0 + seg_nblk) of its reads (plus one
+    // look-ahead block of the next segment), so that row lengths whose warp count per row does not divide 12 still
+    // fill the CTA with row-groups, and rows longer than 12 warps fit at all.  CTA c works on segment c % nseg.
+    const int nseg = a.nseg;
+    const int seg = static_cast<int>(blockIdx.x) % nseg;
+    const int cta_in_seg = static_cast<int>(blockIdx.x) / nseg;
+    const int ctas_in_seg = (static_cast<int>(gridDim.x) - seg + nseg - 1) / nseg;
+    const int blk0 = seg * a.seg_len;
+    const int seg_nblk = a.nblk - blk0 < a.seg_len ? a.nblk - blk0 : a.seg_len;
+    const int load_nblk = seg_nblk + (blk0 + seg_nblk < a.nblk ? 1 : 0);
+    const uint32_t row_bytes = static_cast<uint32_t>(load_nblk) * 16u;            // row stride inside a slot
+    const size_t grow_bytes = static_cast<size_t>(a.nblk) * 16u;                  // row stride in global memory
     const uint32_t bar0 = smem_u32(smem);          // full barrier of slot (g,s) at bar0 + 8*(g*S+s)
     const uint32_t cnt0 = bar0 + 1024;             // release counter of slot (g,s) at cnt0 + 4*(g*S+s)
     const uint32_t data0 = bar0 + kPileupSmemHeader;  // slot (g,s) at data0 + (g*S+s)*chunk_bytes
@@ -410,9 +421,10 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     const int group = warp / W;
     const int wig = warp - group * W;                // warp in group
     const int tig = wig * 32 + lane;                 // thread in group
-    int blk = wig * 31 + lane;
-    const bool active = blk < a.nblk && (lane < 31 || wig == W - 1);
-    if (blk >= a.nblk) blk = 0;
+    int lblk = wig * 31 + lane;                      // block within the segment (seg_nblk = the next segment's first: look-ahead only)
+    const bool active = lblk < seg_nblk && (lane < 31 || wig == W - 1);
+    if (lblk >= load_nblk) lblk = 0;
+    const int blk = blk0 + lblk;                     // block within the reference
 
     CodonCtx cx;
     cx.codon = a.codon + static_cast<size_t>(blk) * 32 * 64;
@@ -445,7 +457,7 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     // once (one cp.async.bulk), so S-1 chunks per group stay in flight, nobody blocks on an "empty"
     // barrier, and a slow group never holds back the others.
     auto issue_chunk = [&](int64_t k) {  // k = index among this CTA's tiles
-        const int64_t t = static_cast<int64_t>(blockIdx.x) + k * gridDim.x;
+        const int64_t t = static_cast<int64_t>(cta_in_seg) + k * ctas_in_seg;
         if (t >= ntiles) return;
         const int64_t r0 = t * Tr + group * 8;
         if (r0 >= a.R) return;
@@ -454,15 +466,20 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         const uint32_t full = bar0 + 8 * slot;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads of the slot before the async write
         mbar_expect_tx(full, valid * row_bytes);
-        bulk_g2s(data0 + slot * chunk_bytes, reinterpret_cast<const uint8_t*>(a.packed) + static_cast<size_t>(r0) * row_bytes,
-                 valid * row_bytes, full);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.packed) + static_cast<size_t>(r0) * grow_bytes + static_cast<size_t>(blk0) * 16u;
+        if (nseg == 1) {
+            bulk_g2s(data0 + slot * chunk_bytes, src, valid * row_bytes, full);       // whole rows: one copy per chunk
+        } else {
+            for (uint32_t i = 0; i < valid; ++i)                                      // this segment of every row
+                bulk_g2s(data0 + slot * chunk_bytes + i * row_bytes, src + i * grow_bytes, row_bytes, full);
+        }
     };
     if (tig == 0)
         for (int k = 0; k < S; ++k) issue_chunk(k);
 
     uint32_t stage = 0, phase = 0;
     int64_t kt = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++kt) {
+    for (int64_t t = cta_in_seg; t < ntiles; t += ctas_in_seg, ++kt) {
         if (8u * (tiles_since_flush + 1u) > static_cast<uint32_t>(kMaxReadsPerFlush)) {
             // counters would overflow: every group adds its integers into the slice, one group at a time
             fold_pendings(v, bi);
@@ -483,7 +500,7 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         const int nv = left <= 0 ? 0 : (left > 8 ? 8 : static_cast<int>(left));
         const uint32_t slot = static_cast<uint32_t>(group * S) + stage;
         if (nv > 0) mbar_wait(bar0 + 8 * slot, phase);
-        const uint32_t addr = data0 + slot * chunk_bytes + static_cast<uint32_t>(blk) * 16u;
+        const uint32_t addr = data0 + slot * chunk_bytes + static_cast<uint32_t>(lblk) * 16u;
         if (nv == 8) {
             const uint32_t pm = block8<MODE>(addr, row_bytes, cx, v, bi);
             if (T::CODON && pm) log_or_handle<DENSE>(pm, static_cast<uint32_t>(r0), lg, addr, row_bytes, cx, a.codon, alt0);
@@ -590,8 +607,11 @@ __global__ void __launch_bounds__(256) codon_exception_kernel(PileupArgs a, int 
     const int tid = static_cast<int>(warp % threads_per_cta);
     const int w = tid >> 5, l = tid & 31;
     const int wig = w % a.warps_per_group;
-    const int blk = wig * 31 + l;
-    if (blk >= a.nblk) return;
+    const int cta = static_cast<int>(warp / threads_per_cta);
+    const int blk0 = (cta % a.nseg) * a.seg_len;
+    const int seg_nblk = a.nblk - blk0 < a.seg_len ? a.nblk - blk0 : a.seg_len;
+    if (wig * 31 + l >= seg_nblk) return;
+    const int blk = blk0 + wig * 31 + l;
     CodonCtx cx;
     const uint2 p = a.pivot[blk], pn = a.pivot[blk + 1];
     cx.r0 = p.x; cx.r1 = p.y; cx.r0n = pn.x; cx.r1n = pn.y;
@@ -695,7 +715,7 @@ __global__ void pivot_sample_kernel(const uint32_t* packed, int64_t R, int32_t n
 __global__ void pileup_finalize_kernel(const uint32_t* part_col, const uint32_t* part_piv, int32_t slices,
                                        int32_t nblk, int32_t L, const uint8_t* pivot_state,
                                        const uint32_t* start_mask, uint32_t* col, uint32_t* codon,
-                                       int32_t count_codons) {
+                                       int32_t count_codons, int32_t nseg, int32_t seg_len) {
     const int64_t gt = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t i = gt >> 2;
     const int part = static_cast<int>(gt & 3);
@@ -704,13 +724,16 @@ __global__ void pileup_finalize_kernel(const uint32_t* part_col, const uint32_t*
     uint32_t s = 0;
     bool is_col = i < ncol, is_piv = false;
     int64_t j = 0;
+    // CTA k wrote the blocks of segment k % nseg only
     if (is_col) {
-        for (int k = part; k < slices; k += 4) s += part_col[k * cstride + i];
+        const int sg = static_cast<int>((i >> 8) / seg_len);
+        for (int k = sg + nseg * part; k < slices; k += 4 * nseg) s += part_col[k * cstride + i];
     } else if (count_codons && i < ncol + L) {
         j = i - ncol;
         is_piv = j + 2 < L && ((start_mask[j >> 5] >> (j & 31)) & 1u);
+        const int sg = static_cast<int>((j >> 5) / seg_len);
         if (is_piv)
-            for (int k = part; k < slices; k += 4) s += part_piv[k * pstride + j];
+            for (int k = sg + nseg * part; k < slices; k += 4 * nseg) s += part_piv[k * pstride + j];
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);

@@ -41,6 +41,7 @@ struct PileupArgs {
     int32_t nblk;             // ceil(L/32)
     int32_t warps_per_group;  // W = ceil(nblk/32)
     int32_t groups;           // G row-groups per CTA
+    int32_t nseg, seg_len;    // column segments: CTA c handles blocks [seg_len*(c%nseg), +seg_len) of its reads
     int32_t stages;
     int32_t stage_bytes;      // G*8*row_bytes
     const uint2* pivot;       // [nblk+1] {r0, r1} planes of the pivot base
@@ -63,7 +64,7 @@ __global__ void pivot_sample_kernel(const uint32_t* packed, int64_t R, int32_t n
 __global__ void pileup_finalize_kernel(const uint32_t* part_col, const uint32_t* part_piv, int32_t slices,
                                        int32_t nblk, int32_t L, const uint8_t* pivot_state,
                                        const uint32_t* start_mask, uint32_t* col, uint32_t* codon,
-                                       int32_t count_codons);
+                                       int32_t count_codons, int32_t nseg, int32_t seg_len);
 __global__ void pileup_atomic_kernel(const uint32_t* packed, int64_t R, int32_t L, int32_t nblk,
                                      const uint32_t* start_mask, uint32_t* col, uint32_t* codon,
                                      int32_t count_codons);

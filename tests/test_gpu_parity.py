@@ -95,7 +95,7 @@ def test_pileup_ragged_read_counts(oracle, hd, c1, R):
     check_pileup(oracle, hd, st[:R], 3000, [(1, 3001)])
 
 
-@pytest.mark.parametrize("L", [3, 5, 32, 33, 64, 95, 96, 97, 1000, 1024, 1025, 4096, 9719])
+@pytest.mark.parametrize("L", [3, 5, 32, 33, 64, 95, 96, 97, 1000, 1024, 1025, 4096, 4100, 6144, 7000, 9719, 11936, 12001, 20000])
 def test_pileup_reference_lengths(oracle, hd, L):
     cfg = SynthConfig(L=L, seed=77 + L, trunc=0.2, variants_per_minor=(1, 2) if L >= 30 else (0, 0),
                       minor_fracs=(0.1, 0.05) if L >= 30 else ())
@@ -338,6 +338,19 @@ def test_phase_many_distinct_patterns(oracle, hd, R, V, cap):
     st, cols, cods = _many_pattern_states(R, 900, V, 25, seed=R + V)
     _, hap, _ = phase_equal(oracle, hd, st, 900, cols, cods, cap=cap)
     assert hap.nreported >= 20 and hap.ndistinct > (4096 if R > 5000 else 1000)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_phase_order_randomised(oracle, hd, seed):
+    """Random read counts, variant counts and recurrence levels: few variants give heavy ties in the counts (order decided
+    by the pattern words), many give long bit-vectors; every case must reproduce the oracle's full order and read ids."""
+    rng = np.random.default_rng(1000 + seed)
+    R = int(rng.integers(50, 6000))
+    V = int(rng.choice([1, 2, 3, 5, 9, 31, 32, 33, 64, 65, 90]))
+    ndup = int(rng.integers(1, 40))
+    L = 3 * V + 30 + int(rng.integers(0, 50))
+    st, cols, cods = _many_pattern_states(R, L, V, ndup, seed=seed)
+    phase_equal(oracle, hd, st, L, cols, cods, cap=int(rng.choice([1, 50, 4096, 10000])))
 
 
 def test_phase_host_merge_protocol(oracle, hd):
