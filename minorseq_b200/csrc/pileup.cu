@@ -372,7 +372,7 @@ __device__ __forceinline__ void clear(Vert<NM>& v) {
     }
 }
 
-template <int MODE, bool DENSE>
+template <int MODE, bool DENSE, bool SEG>
 __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     using T = Traits<MODE>;
     constexpr int NM = T::NM;
@@ -383,13 +383,15 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     // Column segments: with nseg > 1 a CTA handles only the blocks [blk0, blk0 + seg_nblk) of its reads (plus one
     // look-ahead block of the next segment), so that row lengths whose warp count per row does not divide 12 still
     // fill the CTA with row-groups, and rows longer than 12 warps fit at all.  CTA c works on segment c % nseg.
-    const int nseg = a.nseg;
-    const int seg = static_cast<int>(blockIdx.x) % nseg;
-    const int cta_in_seg = static_cast<int>(blockIdx.x) / nseg;
-    const int ctas_in_seg = (static_cast<int>(gridDim.x) - seg + nseg - 1) / nseg;
-    const int blk0 = seg * a.seg_len;
-    const int seg_nblk = a.nblk - blk0 < a.seg_len ? a.nblk - blk0 : a.seg_len;
-    const int load_nblk = seg_nblk + (blk0 + seg_nblk < a.nblk ? 1 : 0);
+    // SEG is a template parameter: the whole-row kernel must not carry any of this (K1 sits at its register limit and
+    // lost 4 % to the mere presence of the segment arithmetic).
+    const int nseg = SEG ? a.nseg : 1;
+    const int seg = SEG ? static_cast<int>(blockIdx.x) % nseg : 0;
+    const int cta_in_seg = SEG ? static_cast<int>(blockIdx.x) / nseg : static_cast<int>(blockIdx.x);
+    const int ctas_in_seg = SEG ? (static_cast<int>(gridDim.x) - seg + nseg - 1) / nseg : static_cast<int>(gridDim.x);
+    const int blk0 = SEG ? seg * a.seg_len : 0;
+    const int seg_nblk = SEG ? (a.nblk - blk0 < a.seg_len ? a.nblk - blk0 : a.seg_len) : a.nblk;
+    const int load_nblk = SEG ? seg_nblk + (blk0 + seg_nblk < a.nblk ? 1 : 0) : a.nblk;
     const uint32_t row_bytes = static_cast<uint32_t>(load_nblk) * 16u;            // row stride inside a slot
     const size_t grow_bytes = static_cast<size_t>(a.nblk) * 16u;                  // row stride in global memory
     const uint32_t bar0 = smem_u32(smem);          // full barrier of slot (g,s) at bar0 + 8*(g*S+s)
@@ -467,7 +469,7 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads of the slot before the async write
         mbar_expect_tx(full, valid * row_bytes);
         const uint8_t* src = reinterpret_cast<const uint8_t*>(a.packed) + static_cast<size_t>(r0) * grow_bytes + static_cast<size_t>(blk0) * 16u;
-        if (nseg == 1) {
+        if (!SEG) {
             bulk_g2s(data0 + slot * chunk_bytes, src, valid * row_bytes, full);       // whole rows: one copy per chunk
         } else {
             for (uint32_t i = 0; i < valid; ++i)                                      // this segment of every row
@@ -571,25 +573,35 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     }
 }
 
-template <int MODE, bool DENSE>
+template <int MODE, bool DENSE, bool SEG>
 __global__ void __launch_bounds__(kPileupMaxThreads, 1) pileup_csa_kernel(PileupArgs a) {
-    pileup_body<MODE, DENSE>(a);
+    pileup_body<MODE, DENSE, SEG>(a);
 }
 
-void pileup_set_smem_attr(int max_smem) {
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeJuliet, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeFuse, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeBoth, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeJuliet, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeBoth, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+template <int MODE, bool DENSE, bool SEG>
+static void launch_one(int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a) {
+    static bool attr_done = false;   // one opt-in to the large dynamic shared memory per instantiation
+    if (!attr_done) {
+        cudaFuncSetAttribute(pileup_csa_kernel<MODE, DENSE, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_done = true;
+    }
+    pileup_csa_kernel<MODE, DENSE, SEG><<<grid, threads, smem, s>>>(a);
 }
+
+void pileup_set_smem_attr(int) {}   // kept for the ABI of this translation unit: attributes are set at first launch
 
 void pileup_launch(int mode, bool dense, int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a) {
-    if (mode == kModeFuse) pileup_csa_kernel<kModeFuse, false><<<grid, threads, smem, s>>>(a);
-    else if (mode == kModeJuliet && !dense) pileup_csa_kernel<kModeJuliet, false><<<grid, threads, smem, s>>>(a);
-    else if (mode == kModeJuliet) pileup_csa_kernel<kModeJuliet, true><<<grid, threads, smem, s>>>(a);
-    else if (!dense) pileup_csa_kernel<kModeBoth, false><<<grid, threads, smem, s>>>(a);
-    else pileup_csa_kernel<kModeBoth, true><<<grid, threads, smem, s>>>(a);
+    const bool seg = a.nseg > 1;
+    if (mode == kModeFuse) {
+        if (seg) launch_one<kModeFuse, false, true>(grid, threads, smem, s, a);
+        else launch_one<kModeFuse, false, false>(grid, threads, smem, s, a);
+    } else if (mode == kModeJuliet) {
+        if (dense) { if (seg) launch_one<kModeJuliet, true, true>(grid, threads, smem, s, a); else launch_one<kModeJuliet, true, false>(grid, threads, smem, s, a); }
+        else { if (seg) launch_one<kModeJuliet, false, true>(grid, threads, smem, s, a); else launch_one<kModeJuliet, false, false>(grid, threads, smem, s, a); }
+    } else {
+        if (dense) { if (seg) launch_one<kModeBoth, true, true>(grid, threads, smem, s, a); else launch_one<kModeBoth, true, false>(grid, threads, smem, s, a); }
+        else { if (seg) launch_one<kModeBoth, false, true>(grid, threads, smem, s, a); else launch_one<kModeBoth, false, false>(grid, threads, smem, s, a); }
+    }
 }
 
 // ---------------------------------------------------------------- logged exceptions

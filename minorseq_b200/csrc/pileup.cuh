@@ -56,7 +56,7 @@ struct PileupArgs {
     int64_t exc_lists;        // gridDim*blockDim of the pileup launch
 };
 
-template <int MODE, bool DENSE>
+template <int MODE, bool DENSE, bool SEG>
 __global__ void pileup_csa_kernel(PileupArgs a);
 
 __global__ void pivot_sample_kernel(const uint32_t* packed, int64_t R, int32_t nblk, int32_t L,
