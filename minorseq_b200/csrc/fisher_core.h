@@ -96,15 +96,18 @@ MS_HD double dhyper(double x, double r, double b, double n) {
     return p1 * p2 / p3;
 }
 
-// one-sided "greater" p-value of the 2x2 table [[a,b],[c,d]]
-MS_HD double fisher_greater(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+// one-sided "greater" p-value of the 2x2 table [[a,b],[c,d]].  `enough`: the caller only needs to know whether
+// p < enough, so the (monotone) partial sum is returned as soon as it reaches it.  Codons at their expected
+// sequencing-error count have p ~ 0.5 and a tail of a few hundred slowly falling terms; their first term alone is
+// orders of magnitude above a Bonferroni threshold, and they are most of what K2 would otherwise spend its time on.
+MS_HD double fisher_greater(uint32_t a, uint32_t b, uint32_t c, uint32_t d, double enough = 2.0) {
     const double white = static_cast<double>(a) + c, black = static_cast<double>(b) + d;
     const double draws = static_cast<double>(a) + b;
     const double xmax = white < draws ? white : draws;
     double x = a;
     double term = dhyper(x, white, black, draws);
     double sum = term;
-    while (x < xmax && term > 0.0) {
+    while (x < xmax && term > 0.0 && sum < enough) {
         const double ratio = (white - x) * (draws - x) / ((x + 1.0) * (black - draws + x + 1.0));
         term *= ratio;
         sum += term;
