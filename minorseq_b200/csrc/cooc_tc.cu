@@ -6,32 +6,37 @@
 // popcount-AND kernel of phase.cu.  Here the same contraction runs as u8 x u8 -> s32 UMMA with the accumulator
 // tile in tensor memory; integer arithmetic, so the result is bit-identical to the popcount kernel.
 //
-// Shape of one CTA: a 128 (variants v) x 256 (variants w) tile of C and a contiguous range of reads (split-K over
-// reads so that tiles x splits fills the 148 SMs; partial tiles are combined with red.global.add.s32).  Only tiles
-// that touch the upper triangle are launched and only v <= w is written (mirrored), like the popcount kernel.
+// Shape of one CTA: a 256 (variants v) x 256 (variants w) tile of C as two 128 x 256 accumulators that fill tensor
+// memory (2 x 256 columns) and share the expanded B rows, and a contiguous range of reads (split-K over reads so that
+// tiles x splits fills the 148 SMs; partial tiles are combined with red.global.add.s32).  Only tiles that touch the
+// upper triangle are launched and only v <= w is written (mirrored), like the popcount kernel.
 //
-//   12 expander warps : one operand row each (128 rows of A, 256 of B).  Per stage a thread loads 128 reads of its
+//   16 expander warps : one operand row each (256 rows of A, 256 of B).  Per stage a thread loads 128 reads of its
 //                       variant as 16 bytes of the transposed bit matrix and expands them to 128 bytes of 0/1 in
 //                       shared memory, in the K-major SWIZZLE_128B canonical layout the UMMA descriptor names
 //                       (16-byte chunk c of row r lives at chunk c ^ (r & 7) of the row's 128-byte line).
-//    1 MMA warp       : one elected lane issues 4 x tcgen05.mma (M128 N256 K32) per stage and commits the stage's
-//                       "empty" mbarrier; after the last stage it commits the accumulator barrier.
-//   epilogue          : the expander warps read the accumulator with tcgen05.ld (32 lanes x 32 columns per
-//                       instruction, warp w owns TMEM lanes 32*(w%4)..) and add it into C.
+//    1 MMA warp       : one elected lane issues 8 x tcgen05.mma (M128 N256 K32; 4 K-steps x 2 accumulators) per stage
+//                       and commits the stage's "empty" mbarrier; after the last stage it commits the accumulator
+//                       barrier.
+//   epilogue          : the expander warps read the accumulators with tcgen05.ld (32 lanes x 32 columns per
+//                       instruction, warp w owns TMEM lanes 32*(w%4)..) and add them into C.
 //
-// Shared-memory bandwidth (48 KB written and 48 KB read per stage) bounds this at roughly 2/3 of the int8 peak;
-// the bit -> byte expansion costs 3 integer instructions per 4 bytes ((nibble * 0x00204081) & 0x01010101).
+// What bounds it is the expansion (3 integer instructions per 4 bytes: (nibble * 0x00204081) & 0x01010101) and
+// shared-memory bandwidth (64 KB written, 96 KB read per stage); one accumulator per CTA ran the tensor pipe at 47 %.
 #include <algorithm>
 #include <vector>
 #include "handle.h"
 
 namespace ms {
 
-constexpr int kTcM = 128, kTcN = 256, kTcKStage = 128;       // reads per stage = one 128-byte swizzle line of u8
-constexpr int kTcStages = 4;
-constexpr int kTcExpanders = kTcM + kTcN;                      // 384 threads, one operand row each
+constexpr int kTcAcc = 2;                                      // accumulator tiles per CTA (they share the expanded B rows)
+constexpr int kTcMma = 128;                                    // M of one MMA
+constexpr int kTcM = kTcAcc * kTcMma, kTcN = 256, kTcKStage = 128;   // reads per stage = one 128-byte swizzle line of u8
+constexpr int kTcStages = 3;
+constexpr int kTcExpanders = kTcM + kTcN;                      // 512 threads, one operand row each
 constexpr int kTcThreads = kTcExpanders + 32;                  // + the MMA warp
-constexpr uint32_t kTcStageBytes = kTcExpanders * 128;         // 48 KB: A rows then B rows
+constexpr uint32_t kTcStageBytes = kTcExpanders * 128;         // 64 KB: A rows then B rows
+constexpr uint32_t kTcTmemCols = kTcAcc * kTcN;                // 512: all of tensor memory
 constexpr uint32_t kTcSmemBytes = kTcStages * kTcStageBytes + 1024 /* alignment slack */ + 256 /* barriers, tmem address */;
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -73,7 +78,7 @@ __host__ __device__ constexpr uint32_t tc_instr_desc() {
            | (0u << 7)            // a_format: unsigned 8 bit
            | (0u << 10)           // b_format: unsigned 8 bit
            | (0u << 15) | (0u << 16)   // K-major A and B
-           | (static_cast<uint32_t>(kTcN >> 3) << 17) | (static_cast<uint32_t>(kTcM >> 4) << 24);
+           | (static_cast<uint32_t>(kTcN >> 3) << 17) | (static_cast<uint32_t>(kTcMma >> 4) << 24);
 }
 
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -120,7 +125,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cooccurrence_tc_kernel(const ui
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kTcExpanders / 32) {                            // the MMA warp owns the tensor-memory allocation
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(static_cast<uint32_t>(kTcN)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTcTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -173,7 +178,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) cooccurrence_tc_kernel(const ui
                 const uint32_t a0 = data0 + static_cast<uint32_t>(s) * kTcStageBytes, b0 = a0 + kTcM * 128;
 #pragma unroll
                 for (int k = 0; k < kTcKStage / 32; ++k)
-                    tc_mma(tmem_base, tc_smem_desc(a0 + k * 32), tc_smem_desc(b0 + k * 32), idesc, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int acc = 0; acc < kTcAcc; ++acc)   // accumulator `acc`: A rows 128*acc.., TMEM columns 256*acc..
+                        tc_mma(tmem_base + static_cast<uint32_t>(acc * kTcN), tc_smem_desc(a0 + acc * kTcMma * 128 + k * 32),
+                               tc_smem_desc(b0 + k * 32), idesc, (i > 0 || k > 0) ? 1u : 0u);
                 tc_commit(empty0 + 8 * s);                       // arrives when these MMAs have read the slot
                 if (i + 1 == my_stages) tc_commit(accbar);       // ... and when the accumulator is final
             }
@@ -186,11 +194,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) cooccurrence_tc_kernel(const ui
         tc_mbar_wait(accbar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
-        const int part = warp >> 2;             // 0..2: column range of this warp
-        const int32_t v = tile.m0 + q * 32 + lane;
-        for (int c0 = part * 32; c0 < kTcN; c0 += 96) {
+        const int part = warp >> 2;             // column range of this warp
+        constexpr int kParts = kTcExpanders / 128;
+        for (int it = 0; it < kTcAcc * (kTcN / 32) / kParts; ++it) {
+            const int idx = it * kParts + part;                 // (accumulator, 32-column group)
+            const int acc = idx / (kTcN / 32), c0 = (idx % (kTcN / 32)) * 32;
+            const int32_t v = tile.m0 + acc * kTcMma + q * 32 + lane;
             uint32_t r[32];
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kTcN + c0);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -217,7 +228,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cooccurrence_tc_kernel(const ui
     __syncthreads();
     if (warp == kTcExpanders / 32) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(static_cast<uint32_t>(kTcN)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcTmemCols) : "memory");
     }
 }
 
@@ -227,7 +238,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cooccurrence_tc_kernel(const ui
 int ms_cooccurrence_tc_launch(ms_handle* h, const uint32_t* bt, int32_t V, int64_t rstride, int64_t R, int32_t* C) {
     const int64_t nstages = (R + ms::kTcKStage - 1) / ms::kTcKStage;
     if (V <= 0 || nstages <= 0) return MS_OK;
-    // tiles that touch the upper triangle: rows [m0, m0+128) x columns [n0, n0+256) with n0 + 255 >= m0
+    // tiles that touch the upper triangle: rows [m0, m0+256) x columns [n0, n0+256) with n0 + 255 >= m0
     std::vector<ms::TcTile> tiles;
     for (int32_t n0 = 0; n0 < V; n0 += ms::kTcN)
         for (int32_t m0 = 0; m0 < V && m0 <= n0 + ms::kTcN - 1; m0 += ms::kTcM) tiles.push_back({m0, n0});

@@ -341,12 +341,12 @@ extern "C" int ms_phase_haplotypes(ms_handle* h, int32_t min_reads, uint32_t* pa
         MS_CUDA(h, cudaMemsetAsync(o.res, 0, 64, h->stream));
         rc = ms::phase_compact(h, g_cnt, g_pat, h->b_gslot.as<int32_t>(), gcap);
         if (rc != MS_OK) return rc;
-        MS_CUDA(h, cudaMemcpyAsync(blk, h->b_ctr.p, 64, cudaMemcpyDeviceToDevice, h->stream));
+        if (world > 1) MS_CUDA(h, cudaMemcpyAsync(blk, h->b_ctr.p, 64, cudaMemcpyDeviceToDevice, h->stream));   // header of the block to exchange
 
         // the list the order is computed over: this rank's own, or the merge of everybody's
         const uint32_t *v_cnt = g_cnt, *v_pat = g_pat;
         const unsigned long long* Mptr = lctr + 5;
-        const uint8_t* hdr_src = blk;
+        const uint8_t* hdr_src = reinterpret_cast<const uint8_t*>(lctr);   // single rank: the counters themselves are the header
         size_t hdr_stride = 0;
         const int32_t* mslot_me = nullptr;
         int64_t tsize = 0;
