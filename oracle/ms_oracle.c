@@ -440,3 +440,144 @@ int64_t mso_fuse(const uint32_t *col, int32_t L, const int32_t *ins_col, const i
     free(ev); free(acc);
     return n;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * cleric restatement (doc/CLERIC.md:19-23,41-44), choices U13 in the header.
+ * ------------------------------------------------------------------------------------------------ */
+enum { NW_MATCH = 2, NW_MISMATCH = -3, NW_GAP = -4 };
+
+int64_t mso_nw_align(const char *a, int32_t la, const char *b, int32_t lb, char *ops, int64_t cap, int64_t *score)
+{
+    if (la < 0 || lb < 0) return -1;
+    const size_t W = (size_t)lb + 1;
+    int32_t *prev = (int32_t *)malloc(W * sizeof(int32_t)), *cur = (int32_t *)malloc(W * sizeof(int32_t));
+    uint8_t *dir = (uint8_t *)malloc(((size_t)la + 1) * W);      /* 0 diagonal, 1 up (consume A), 2 left (consume B) */
+    if (!prev || !cur || !dir) { free(prev); free(cur); free(dir); return -1; }
+    for (int32_t j = 0; j <= lb; ++j) { prev[j] = j * NW_GAP; dir[j] = 2; }
+    for (int32_t i = 1; i <= la; ++i) {
+        cur[0] = i * NW_GAP;
+        dir[(size_t)i * W] = 1;
+        for (int32_t j = 1; j <= lb; ++j) {
+            const int32_t d = prev[j - 1] + (a[i - 1] == b[j - 1] ? NW_MATCH : NW_MISMATCH);
+            const int32_t u = prev[j] + NW_GAP, l = cur[j - 1] + NW_GAP;
+            int32_t best = d; uint8_t k = 0;
+            if (u > best) { best = u; k = 1; }
+            if (l > best) { best = l; k = 2; }
+            cur[j] = best;
+            dir[(size_t)i * W + j] = k;
+        }
+        int32_t *t = prev; prev = cur; cur = t;
+    }
+    if (score) *score = prev[lb];
+    /* trace back, then reverse */
+    int64_t n = 0;
+    int32_t i = la, j = lb;
+    int64_t rc = 0;
+    while (i > 0 || j > 0) {
+        const uint8_t k = dir[(size_t)i * W + j];
+        if (n >= cap) { rc = -1; break; }
+        if (k == 0) { ops[n++] = 'M'; --i; --j; }
+        else if (k == 1) { ops[n++] = 'D'; --i; }
+        else { ops[n++] = 'I'; --j; }
+    }
+    free(prev); free(cur); free(dir);
+    if (rc < 0) return -1;
+    for (int64_t x = 0, y = n - 1; x < y; ++x, --y) { const char t = ops[x]; ops[x] = ops[y]; ops[y] = t; }
+    return n;
+}
+
+/* append one op of length len, merging with the previous one */
+static int push_op(char *op, int32_t *len, int64_t cap, int64_t *n, char c, int32_t l)
+{
+    if (l <= 0) return 0;
+    if (*n > 0 && op[*n - 1] == c) { len[*n - 1] += l; return 0; }
+    if (*n >= cap) return -1;
+    op[*n] = c; len[*n] = l; ++*n;
+    return 0;
+}
+
+int64_t mso_project_read(const char *ops, int64_t nops, const char *b, int32_t lb,
+                         int32_t pos, const char *cig_op, const int32_t *cig_len, int32_t ncig,
+                         const char *seq, int32_t lseq,
+                         char *new_op, int32_t *new_len, int64_t cap, int32_t *new_pos)
+{
+    /* per-op coordinates of the path: ai/bj = A and B columns consumed BEFORE op x */
+    int32_t la = 0;
+    for (int64_t x = 0; x < nops; ++x) la += ops[x] != 'I';
+    /* first path op that consumes A column `pos` */
+    if (pos < 0 || pos > la) return -1;
+    /* middle part of the CIGAR: between the leading and trailing clips */
+    int32_t c0 = 0, c1 = ncig;
+    while (c0 < c1 && (cig_op[c0] == 'S' || cig_op[c0] == 'H')) ++c0;
+    while (c1 > c0 && (cig_op[c1 - 1] == 'S' || cig_op[c1 - 1] == 'H')) --c1;
+    /* raw projected ops (1 column each, merged on the fly) in a scratch list */
+    const int64_t scap = (int64_t)lseq + nops + 8;
+    char *rop = (char *)malloc((size_t)scap);
+    int32_t *rlen = (int32_t *)malloc((size_t)scap * sizeof(int32_t));
+    int32_t *rb = (int32_t *)malloc((size_t)scap * sizeof(int32_t));     /* B column of the op's first base (ref-consuming ops) */
+    if (!rop || !rlen || !rb) { free(rop); free(rlen); free(rb); return -1; }
+    int64_t rn = 0;
+    int rc = 0;
+#define RAW(c, l, bj) do { if ((l) > 0) { if (rn > 0 && rop[rn - 1] == (c)) rlen[rn - 1] += (l); \
+        else if (rn >= scap) rc = -1; else { rop[rn] = (c); rlen[rn] = (l); rb[rn] = (bj); ++rn; } } } while (0)
+    int64_t x = 0;
+    int32_t ai = 0, bj = 0, q = 0;
+    /* skip the path up to A column pos (B columns before it do not belong to the read) */
+    while (x < nops && !(ops[x] != 'I' && ai == pos)) { if (ops[x] != 'I') ++ai; if (ops[x] != 'D') ++bj; ++x; }
+    for (int32_t c = 0; c < c0; ++c) if (cig_op[c] == 'S') q += cig_len[c];
+    int started = 0;
+    for (int32_t c = c0; c < c1 && rc == 0; ++c) {
+        const char o = cig_op[c];
+        const int32_t l = cig_len[c];
+        if (o == 'I') { RAW('I', l, -1); q += l; continue; }
+        if (o != '=' && o != 'X' && o != 'D') { rc = -1; break; }
+        for (int32_t t = 0; t < l && rc == 0; ++t) {
+            /* B-only columns in front of the next A column lie inside the read once it has started */
+            while (x < nops && ops[x] == 'I') { if (started) RAW('D', 1, bj); ++bj; ++x; }
+            if (x >= nops) { rc = -1; break; }              /* the read runs past the end of A */
+            if (ops[x] == 'M') {
+                if (o == 'D') RAW('D', 1, bj);
+                else {
+                    if (q >= lseq || bj >= lb) { rc = -1; break; }
+                    RAW(seq[q] == b[bj] ? '=' : 'X', 1, bj);
+                    ++q;
+                }
+                ++bj;
+            } else {                                        /* 'D': this A column has no partner on B */
+                if (o != 'D') { RAW('I', 1, -1); ++q; }
+            }
+            ++ai; ++x;
+            started = 1;
+        }
+    }
+#undef RAW
+    if (rc == 0) {
+        for (int32_t c = c1; c < ncig; ++c) if (cig_op[c] == 'S') q += cig_len[c];
+        if (q != lseq) rc = -1;                             /* CIGAR and sequence disagree */
+    }
+    int64_t n = 0;
+    if (rc == 0) {
+        /* trim: leading / trailing D dropped, leading / trailing I become clips */
+        int64_t lo = 0, hi = rn;
+        int32_t lead_clip = 0, tail_clip = 0;
+        while (lo < hi && (rop[lo] == 'D' || rop[lo] == 'I')) { if (rop[lo] == 'I') lead_clip += rlen[lo]; ++lo; }
+        while (hi > lo && (rop[hi - 1] == 'D' || rop[hi - 1] == 'I')) { if (rop[hi - 1] == 'I') tail_clip += rlen[hi - 1]; --hi; }
+        if (lo == hi) { n = 0; }
+        else {
+            *new_pos = rb[lo];
+            /* leading clips: hard clips first, then soft */
+            for (int32_t c = 0; c < c0 && rc == 0; ++c) if (cig_op[c] == 'H') rc = push_op(new_op, new_len, cap, &n, 'H', cig_len[c]);
+            int32_t s0 = lead_clip;
+            for (int32_t c = 0; c < c0; ++c) if (cig_op[c] == 'S') s0 += cig_len[c];
+            if (rc == 0) rc = push_op(new_op, new_len, cap, &n, 'S', s0);
+            for (int64_t k = lo; k < hi && rc == 0; ++k) rc = push_op(new_op, new_len, cap, &n, rop[k], rlen[k]);
+            int32_t s1 = tail_clip;
+            for (int32_t c = c1; c < ncig; ++c) if (cig_op[c] == 'S') s1 += cig_len[c];
+            if (rc == 0) rc = push_op(new_op, new_len, cap, &n, 'S', s1);
+            for (int32_t c = c1; c < ncig && rc == 0; ++c) if (cig_op[c] == 'H') rc = push_op(new_op, new_len, cap, &n, 'H', cig_len[c]);
+            if (rc != 0) { free(rop); free(rlen); free(rb); return -2; }
+        }
+    }
+    free(rop); free(rlen); free(rb);
+    return rc == 0 ? n : -1;
+}

@@ -119,6 +119,30 @@ int64_t mso_fuse(const uint32_t *col /* L*8 */, int32_t L,
                  int64_t nins, const char *ins_pool,
                  const mso_fuse_params *prm, char *seq, int64_t cap);
 
+/* ---- cleric: "converting a given alignment to a different reference ... by aligning the original
+ * and target reference sequences.  A transitive alignment is used to generate the new alignment"; "The alignment
+ * step runs a Needleman-Wunsch; with NxM runtime" (/root/reference/doc/CLERIC.md:19-23,41-44).  Nothing in the
+ * reference pins the scoring or the projection rules: restatement choice U13 --
+ *   global alignment, match +2, mismatch -3, linear gap -4; cell = max(diagonal, up (consume A), left (consume B)),
+ *   ties resolved in that order; the path is read back from (N,M) to (0,0).
+ * ops (forward order): 'M' A and B advance, 'D' only A advances (base of A absent from B), 'I' only B advances.
+ * Returns the number of ops written (<= la+lb), or -1 if cap is too small; *score = alignment score. */
+int64_t mso_nw_align(const char *a, int32_t la, const char *b, int32_t lb, char *ops, int64_t cap, int64_t *score);
+
+/* One read, aligned to A at 0-based `pos` with CIGAR ops `cig_op` (chars of "=XIDSH"; 'M', 'N', 'P' are refused, doc
+ * CLERIC.md:14-15) and lengths `cig_len`, re-expressed against B through the A/B path `ops`:
+ *   A column paired with a B column: read base -> '=' / 'X' against B, read deletion -> 'D'
+ *   A column without a partner:      read base -> 'I' (extra relative to B), read deletion -> nothing
+ *   B column without a partner strictly inside the read's span -> 'D'
+ *   read insertions stay 'I'; clips stay; leading/trailing 'I' become 'S', leading/trailing 'D' are dropped;
+ *   neighbouring equal ops are merged.
+ * Writes up to cap new ops; returns their number, 0 if nothing of the read lands on B (the record becomes unmapped),
+ * -1 on an unsupported CIGAR op or inconsistent input, -2 if cap is too small.  *new_pos = 0-based start on B. */
+int64_t mso_project_read(const char *ops, int64_t nops, const char *b, int32_t lb,
+                         int32_t pos, const char *cig_op, const int32_t *cig_len, int32_t ncig,
+                         const char *seq, int32_t lseq,
+                         char *new_op, int32_t *new_len, int64_t cap, int32_t *new_pos);
+
 #ifdef __cplusplus
 }
 #endif

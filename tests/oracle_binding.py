@@ -142,6 +142,33 @@ class Oracle:
         self.lib.mso_cooccurrence(_p(np.ascontiguousarray(bits)), bits.shape[0], V, _p(Cm))
         return Cm
 
+    # ---- cleric restatement
+    def nw_align(self, a: str, b: str):
+        cap = len(a) + len(b) + 1
+        ops = C.create_string_buffer(cap)
+        score = C.c_int64()
+        self.lib.mso_nw_align.restype = C.c_int64
+        n = self.lib.mso_nw_align(a.encode(), len(a), b.encode(), len(b), ops, cap, C.byref(score))
+        assert n >= 0
+        return ops.raw[:n].decode(), score.value
+
+    def project_read(self, ops: str, b: str, pos: int, cigar, seq: str):
+        """cigar: list of (len, op-char).  Returns (new_pos, new cigar list) or None when nothing lands on B."""
+        co = "".join(o for _, o in cigar).encode()
+        cl = np.array([l for l, _ in cigar], dtype=np.int32)
+        cap = len(seq) + len(ops) + 8
+        no = C.create_string_buffer(cap)
+        nl = np.zeros(cap, dtype=np.int32)
+        npos = C.c_int32(-1)
+        self.lib.mso_project_read.restype = C.c_int64
+        n = self.lib.mso_project_read(ops.encode(), len(ops), b.encode(), len(b), pos, co, _p(cl), len(cigar), seq.encode(), len(seq),
+                                      no, _p(nl), cap, C.byref(npos))
+        if n < 0:
+            raise ValueError(f"mso_project_read failed ({n})")
+        if n == 0:
+            return None
+        return npos.value, [(int(nl[i]), no.raw[i:i + 1].decode()) for i in range(n)]
+
     def fuse(self, col, ins_col=None, ins_off=None, ins_len=None, pool=b"", min_coverage=50, ins_fraction=0.5,
              ins_distance=20):
         L = col.shape[0]
