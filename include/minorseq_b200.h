@@ -229,6 +229,15 @@ int ms_fuse(ms_handle *h, const ms_fuse_params *prm,
             int64_t nins, const char *ins_pool, int64_t pool_len,
             char *seq, int64_t cap, int64_t *len);
 
+/* ---- cleric's alignment step (doc/CLERIC.md:19-23,41-44) ------------------------
+ * Global Needleman-Wunsch of the original reference a against the target reference b on the GPU
+ * (tiled wavefront, N x M cells; match +2, mismatch -3, linear gap -4, ties diagonal > consume-a >
+ * consume-b -- restatement choice U13).  ops receives the path in forward order: 'M' both advance,
+ * 'D' only a advances (a base of a that b lacks), 'I' only b advances; cap must be >= la + lb.
+ * The per-read CIGAR projection through this path is host code (minorseq_b200/host/cleric.hpp).   */
+int ms_align_refs(ms_handle *h, const char *a, int32_t la, const char *b, int32_t lb,
+                  char *ops, int64_t cap, int64_t *nops, int64_t *score);
+
 /* ---- synthetic amplicon generator (bench/tests) ------------------------- */
 typedef struct {
     uint64_t seed;

@@ -90,6 +90,7 @@ _SIGNATURES = {
                                      C.POINTER(C.c_int64), C.POINTER(PhaseCounters)]),
     "ms_haplotype_name": (None, [C.c_int64, C.c_char_p]),
     "ms_phase_assign": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "ms_align_refs": (C.c_int, [_P, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, _P, C.c_int64, _P, _P]),
     "ms_set_cooccurrence_variant": (C.c_int, [_P, C.c_int32]),
     "ms_phase_haplotypes": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "ms_phase_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),

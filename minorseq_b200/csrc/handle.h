@@ -78,6 +78,7 @@ struct ms_handle {
         b_pat, b_cooc, b_bits_t;
     // device-side merge + ordering (phase_order.cu)
     DevBuf b_gslot, b_mt_key, b_mt_cnt, b_mt_rep, b_mslot, b_mindex, b_m_cnt, b_m_pat, b_m_rank, b_ord, b_keys, b_out, b_tc_tiles;
+    DevBuf b_nw_seq, b_nw_hrow, b_nw_hcol, b_nw_dir;   // nw.cu (cleric's reference-to-reference alignment)
     int cooc_variant = 0;        // 0 auto, 1 popcount-AND, 2 tcgen05 int8
     std::vector<uint32_t> groups_cnt, groups_pat;   // host copy of the last grouping pass (all ranks when a comm is attached)
     uint64_t groups_marg[4] = {0, 0, 0, 0};

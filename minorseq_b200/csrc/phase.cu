@@ -452,7 +452,8 @@ void ms_phase_free_internal(ms_handle* h) {
     DevBuf* all[] = {&h->b_var, &h->b_blocklist, &h->b_bits, &h->b_flags, &h->b_slot, &h->b_tab_key, &h->b_tab_cnt, &h->b_tab_rep,
                      &h->b_ctr, &h->b_groups, &h->b_gather, &h->b_rank, &h->b_hap, &h->b_pat, &h->b_cooc, &h->b_bits_t,
                      &h->b_gslot, &h->b_mt_key, &h->b_mt_cnt, &h->b_mt_rep, &h->b_mslot, &h->b_mindex, &h->b_m_cnt, &h->b_m_pat, &h->b_m_rank,
-                     &h->b_ord, &h->b_keys, &h->b_out, &h->b_tc_tiles};
+                     &h->b_ord, &h->b_keys, &h->b_out, &h->b_tc_tiles,
+                     &h->b_nw_seq, &h->b_nw_hrow, &h->b_nw_hcol, &h->b_nw_dir};
     for (DevBuf* b : all) b->release();
     if (h->h_stage) cudaFreeHost(h->h_stage);
     h->h_stage = nullptr; h->h_stage_cap = 0;

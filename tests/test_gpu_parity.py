@@ -480,3 +480,39 @@ def test_full_size_properties(hd):
     fr = dict(zip(range(1, 4), cfg.minor_fracs))
     for strain, c, k in t.truth:
         assert abs(found[(c, k)] / fr[strain] - 1) < 0.1
+
+
+# ---- cleric's alignment step: GPU Needleman-Wunsch against the restatement
+def _mutate(rng, a, indel=0.02, sub=0.04):
+    b = []
+    for ch in a:
+        u = rng.random()
+        if u < indel:
+            continue
+        if u < 2 * indel:
+            b.append(str(rng.choice(list("ACGT"))))
+        b.append(ch if rng.random() > sub else str(rng.choice(list("ACGT"))))
+    return "".join(b)
+
+
+def gpu_nw(hd, a, b):
+    lib = _lib.load()
+    cap = len(a) + len(b) + 1
+    ops = C.create_string_buffer(cap)
+    n, score = C.c_int64(), C.c_int64()
+    _lib.check(lib.ms_align_refs(hd.h, a.encode(), len(a), b.encode(), len(b), ops, cap, C.byref(n), C.byref(score)), hd.h)
+    return ops.raw[: n.value].decode(), score.value
+
+
+@pytest.mark.parametrize("la", [0, 1, 5, 127, 128, 129, 255, 257, 700, 3000])
+def test_nw_align_equals_oracle(oracle, hd, la):
+    """Same path (so: same tie-breaking in every cell) and same score as the CPU restatement, for lengths around the
+    128-cell tile edges, unrelated sequences, and references that differ by indels and substitutions."""
+    rng = np.random.default_rng(la)
+    a = "".join(rng.choice(list("ACGT"), size=la))
+    for b in (_mutate(rng, a), a, "".join(rng.choice(list("ACGT"), size=max(0, la - 3))), a[: la // 2], "ACGT" * 40):
+        assert gpu_nw(hd, a, b) == oracle.nw_align(a, b)
+        assert gpu_nw(hd, b, a) == oracle.nw_align(b, a)
+    lib = _lib.load()
+    n = C.c_int64()
+    assert lib.ms_align_refs(hd.h, b"ACGT", 4, b"ACG", 3, C.create_string_buffer(3), 3, C.byref(n), None) == -4 and n.value == 7
