@@ -41,7 +41,7 @@ def build_library(force=False, verbose=False):
 
 HOST = os.path.join(HERE, "host")
 BIN = os.path.join(HERE, "bin")
-HOST_PROGRAMS = {"juliet": "juliet_main.cpp", "fuse": "fuse_main.cpp", "host_selftest": "host_selftest.cpp", "mixdata": "mixdata_main.cpp", "packed2bam": "packed2bam_main.cpp"}
+HOST_PROGRAMS = {"juliet": "juliet_main.cpp", "fuse": "fuse_main.cpp", "host_selftest": "host_selftest.cpp", "mixdata": "mixdata_main.cpp", "packed2bam": "packed2bam_main.cpp", "cleric": "cleric_main.cpp"}
 
 
 def build_host(force=False):
@@ -53,7 +53,7 @@ def build_host(force=False):
         if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in hdrs if os.path.exists(d)):
             continue
         cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-o", out, os.path.join(HOST, src), "-lz", "-pthread"]
-        if name in ("juliet", "fuse"):
+        if name in ("juliet", "fuse", "cleric"):
             cmd += ["-L" + HERE, "-lminorseq_b200", "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath," + HERE]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:

@@ -88,3 +88,33 @@ def states_to_record(name, st, ref, insertions=None, flag=0, n_via_qv=False):
     if flag & 0x10 and aux:
         aux = aux_z("sq", "".join(qv)[::-1])   # per-base tags are stored in native orientation
     return record(name, flag, b, cigar, seq, aux)
+
+
+def read_bam(path):
+    """Independent minimal BAM reader (BGZF = multi-member gzip): returns (header text, [(name, length)], records) with
+    records as dicts(name, flag, ref_id, pos, mapq, cigar [(len, op)], seq)."""
+    import gzip
+    raw = gzip.decompress(open(path, "rb").read())
+    assert raw[:4] == b"BAM\x01"
+    lt = struct.unpack_from("<I", raw, 4)[0]
+    text = raw[8:8 + lt].decode()
+    o = 8 + lt
+    nref = struct.unpack_from("<I", raw, o)[0]; o += 4
+    refs = []
+    for _ in range(nref):
+        ln = struct.unpack_from("<I", raw, o)[0]; o += 4
+        nm = raw[o:o + ln - 1].decode(); o += ln
+        refs.append((nm, struct.unpack_from("<I", raw, o)[0])); o += 4
+    ops = "MIDNSHP=X"
+    dec = "=ACMGRSVTWYHKDBN"
+    recs = []
+    while o < len(raw):
+        bs = struct.unpack_from("<I", raw, o)[0]; o += 4
+        ref_id, pos, lname, mapq, _bin, ncig, flag, lseq = struct.unpack_from("<iiBBHHHI", raw, o)
+        p = o + 32
+        name = raw[p:p + lname - 1].decode(); p += lname
+        cig = [((v >> 4), ops[v & 15]) for v in struct.unpack_from("<%dI" % ncig, raw, p)]; p += 4 * ncig
+        sq = "".join(dec[(raw[p + i // 2] >> (0 if i & 1 else 4)) & 15] for i in range(lseq))
+        recs.append(dict(name=name, flag=flag, ref_id=ref_id, pos=pos, mapq=mapq, cigar=cig, seq=sq))
+        o += bs
+    return text, refs, recs

@@ -182,3 +182,73 @@ def test_fuse_cli_matches_oracle(binaries, oracle, tmp_path):
     want = oracle.fuse(ocol, [c for c, _ in ev], io, il, pool)
     assert got == want
     assert "GGC" in got and len(got) == 900 - 3 + 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("combined", [False, True])
+def test_cleric_cli_matches_oracle(binaries, oracle, tmp_path, combined):
+    """`cleric in.bam reference.fasta new_ref.fasta out.bam` and the combined-FASTA form (doc/CLERIC.md:27-38): GPU
+    Needleman-Wunsch of the two references + host projection, every output record against the restatement."""
+    from test_oracle_cleric import _random_case
+    rng = np.random.default_rng(77)
+    a = "".join(rng.choice(list("ACGT"), size=1500))
+    b = []
+    for ch in a:
+        u = rng.random()
+        if u < 0.01: continue
+        if u < 0.02: b.append(str(rng.choice(list("ACGT"))))
+        b.append(ch if rng.random() > 0.03 else str(rng.choice(list("ACGT"))))
+    b = "".join(b)
+    recs, meta = [], []
+    for r in range(300):
+        pos = int(rng.integers(0, len(a) - 400))
+        span = int(rng.integers(50, 400))
+        cig, seq, i = [], [], pos
+        if r % 5 == 0:
+            cig.append((3, "S")); seq.append("NNN")
+        while i < pos + span:
+            u = rng.random()
+            if u < 0.02 and cig and cig[-1][1] in "=X" and i + 1 < pos + span: cig.append((1, "D")); i += 1
+            elif u < 0.04 and cig and cig[-1][1] in "=X": cig.append((2, "I")); seq.append("GT")
+            elif u < 0.06: cig.append((1, "X")); seq.append([c for c in "ACGT" if c != a[i]][0]); i += 1
+            else: cig.append((1, "=")); seq.append(a[i]); i += 1
+        while cig[-1][1] in "DI":
+            if cig[-1][1] == "I": seq.pop()
+            cig.pop()
+        merged = []
+        for l, o in cig:
+            if merged and merged[-1][1] == o: merged[-1] = (merged[-1][0] + l, o)
+            else: merged.append((l, o))
+        seq = "".join(seq)
+        recs.append(bam_util.record(f"read/{r}/ccs", 0 if r % 7 else 2048, pos, merged, seq))
+        meta.append((pos, merged, seq))
+    recs.append(bam_util.record("unmapped/1/ccs", 4, -1, [], "ACGT", ref_id=-1))
+    bam_util.write_bam(str(tmp_path / "in.bam"), "orig", len(a), recs)
+    (tmp_path / "a.fa").write_text(">orig some description\n" + "\n".join(a[i:i + 60] for i in range(0, len(a), 60)) + "\n")
+    (tmp_path / "b.fa").write_text(">target\n" + b.lower() + "\n")
+    if combined:
+        (tmp_path / "c.fa").write_text((tmp_path / "b.fa").read_text() + (tmp_path / "a.fa").read_text())   # order must not matter
+        cmd = [os.path.join(binaries, "cleric"), str(tmp_path / "in.bam"), str(tmp_path / "c.fa"), str(tmp_path / "out.bam")]
+    else:
+        cmd = [os.path.join(binaries, "cleric"), str(tmp_path / "in.bam"), str(tmp_path / "a.fa"), str(tmp_path / "b.fa"), str(tmp_path / "out.bam")]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    text, refs, got = bam_util.read_bam(str(tmp_path / "out.bam"))
+    assert refs == [("target", len(b))] and "SN:target" in text and "SN:orig" not in text and "ID:cleric" in text
+    assert len(got) == len(recs)
+    ops, score = oracle.nw_align(a, b)
+    assert f"alignment score {score})" in out.stderr
+    for g, (pos, cig, seq) in zip(got[:-1], meta):
+        want = oracle.project_read(ops, b, pos, cig, seq)
+        assert want is not None
+        assert (g["pos"], g["cigar"], g["seq"], g["ref_id"]) == (want[0], want[1], seq, 0), g["name"]
+    assert got[-1]["flag"] & 4 and got[-1]["ref_id"] == -1 and got[0]["flag"] == 2048
+    # the BAM's reference must be one of the two sequences (doc/CLERIC.md:16-17); cigar M is refused (:14-15)
+    (tmp_path / "x.fa").write_text(">other\nACGT\n")
+    bad = subprocess.run([os.path.join(binaries, "cleric"), str(tmp_path / "in.bam"), str(tmp_path / "x.fa"), str(tmp_path / "b.fa"), str(tmp_path / "o2.bam")],
+                         capture_output=True, text=True)
+    assert bad.returncode != 0 and "must match the reference name" in bad.stderr
+    bam_util.write_bam(str(tmp_path / "m.bam"), "orig", len(a), [bam_util.record("m/1/ccs", 0, 0, [(4, "M")], "ACGT")])
+    bad = subprocess.run([os.path.join(binaries, "cleric"), str(tmp_path / "m.bam"), str(tmp_path / "a.fa"), str(tmp_path / "b.fa"), str(tmp_path / "o3.bam")],
+                         capture_output=True, text=True)
+    assert bad.returncode != 0 and "cigar M is forbidden" in bad.stderr

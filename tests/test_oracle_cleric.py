@@ -143,3 +143,65 @@ def test_projection_invariants_random(oracle):
                     for t in range(l):
                         assert (seq[q + t] == b[j + t]) == (o == "=")
                     q += l; j += l
+
+
+def _random_case(rng):
+    a = "".join(rng.choice(list("ACGT"), size=int(rng.integers(40, 160))))
+    b = []
+    for ch in a:
+        u = rng.random()
+        if u < 0.04: continue
+        if u < 0.08: b.append(str(rng.choice(list("ACGT"))))
+        b.append(ch if rng.random() > 0.05 else str(rng.choice(list("ACGT"))))
+    b = "".join(b)
+    pos = int(rng.integers(0, len(a) - 20))
+    span = int(rng.integers(5, len(a) - pos + 1))
+    cig, seq, i = [], [], pos
+    if rng.random() < 0.3:
+        k = int(rng.integers(1, 5)); cig.append((k, "H" if rng.random() < 0.3 else "S"))
+        if cig[-1][1] == "S": seq.append("N" * k)
+    if rng.random() < 0.15:
+        k = int(rng.integers(1, 3)); cig.append((k, "I")); seq.append("".join(rng.choice(list("ACGT"), size=k)))
+    while i < pos + span:
+        u = rng.random()
+        if u < 0.07:
+            cig.append((1, "D")); i += 1
+        elif u < 0.13:
+            k = int(rng.integers(1, 4)); cig.append((k, "I")); seq.append("".join(rng.choice(list("ACGT"), size=k)))
+        elif u < 0.2:
+            cig.append((1, "X")); seq.append([c for c in "ACGT" if c != a[i]][int(rng.integers(0, 3))]); i += 1
+        else:
+            cig.append((1, "=")); seq.append(a[i]); i += 1
+    if rng.random() < 0.3:
+        k = int(rng.integers(1, 5)); cig.append((k, "S")); seq.append("N" * k)
+    merged = []
+    for l, o in cig:
+        if merged and merged[-1][1] == o: merged[-1] = (merged[-1][0] + l, o)
+        else: merged.append((l, o))
+    return a, b, pos, merged, "".join(seq)
+
+
+def test_host_projection_equals_oracle(oracle, tmp_path):
+    """The product's C++ projection (minorseq_b200/host/cleric.hpp) against the restatement on random alignments,
+    including reads that begin / end with insertions or deletions and reads made of clips only around a tiny body."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "cleric_project_tool")
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-o", exe, os.path.join(root, "tests", "cleric_project_tool.cpp"), "-lz"])
+    rng = np.random.default_rng(2024)
+    cases, want = [], []
+    for _ in range(400):
+        a, b, pos, cig, seq = _random_case(rng)
+        ops, _ = oracle.nw_align(a, b)
+        try:
+            out = oracle.project_read(ops, b, pos, cig, seq)
+            want.append("unmapped" if out is None else "ok %d %s" % (out[0], "".join("%d%s" % (l, o) for l, o in out[1])))
+        except ValueError:
+            want.append("inconsistent")
+        cases.append("%s %s %d %s %s" % (ops or "-", b or "-", pos, "".join("%d%s" % (l, o) for l, o in cig), seq or "-"))
+    cases.append("MMMM ACGT 0 4M ACGT"); want.append("unsupported")
+    got = subprocess.run([exe], input="\n".join(cases) + "\n", capture_output=True, text=True, check=True).stdout.strip().split("\n")
+    assert len(got) == len(want)
+    bad = [(c, g, w) for c, g, w in zip(cases, got, want) if g != w]
+    assert not bad, bad[:3]
+    assert sum(w.startswith("ok") for w in want) > 300
