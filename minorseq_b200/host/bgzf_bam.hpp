@@ -365,21 +365,18 @@ public:
     BamWriter(const std::string& path, const std::string& header_text, const std::vector<RefSeq>& refs) : f_(fopen(path.c_str(), "wb")) {
         if (!f_) throw Error("cannot create " + path);
         std::vector<uint8_t> h;
-        h.insert(h.end(), {'B', 'A', 'M', 1});
-        detail::put32(h, static_cast<uint32_t>(header_text.size()));
-        h.insert(h.end(), header_text.begin(), header_text.end());
-        detail::put32(h, static_cast<uint32_t>(refs.size()));
-        for (const RefSeq& r : refs) {
-            detail::put32(h, static_cast<uint32_t>(r.name.size() + 1));
-            h.insert(h.end(), r.name.begin(), r.name.end());
-            h.push_back(0);
-            detail::put32(h, static_cast<uint32_t>(r.length));
-        }
+        encode_header(header_text, refs, h);
         append(h.data(), h.size());
     }
     ~BamWriter() { close(); }
     void write(const Record& r) {
         std::vector<uint8_t> b;
+        encode(r, b);
+        append(b.data(), b.size());
+    }
+    // one alignment record in BAM's binary layout, appended to b
+    static void encode(const Record& r, std::vector<uint8_t>& b) {
+        const size_t at = b.size();
         const uint32_t lseq = static_cast<uint32_t>(r.seq.size());
         detail::put32(b, 0);  // block size, patched below
         detail::put32(b, static_cast<uint32_t>(r.ref_id));
@@ -405,9 +402,41 @@ public:
         if (r.qual.size() == lseq) b.insert(b.end(), r.qual.begin(), r.qual.end());
         else b.insert(b.end(), lseq, 0xff);
         b.insert(b.end(), r.aux.begin(), r.aux.end());
-        const uint32_t bs = static_cast<uint32_t>(b.size() - 4);
-        for (int i = 0; i < 4; ++i) b[i] = (bs >> (8 * i)) & 0xff;
-        append(b.data(), b.size());
+        const uint32_t bs = static_cast<uint32_t>(b.size() - at - 4);
+        for (int i = 0; i < 4; ++i) b[at + i] = (bs >> (8 * i)) & 0xff;
+    }
+    // the BAM header block (magic, text, reference list), uncompressed
+    static void encode_header(const std::string& header_text, const std::vector<RefSeq>& refs, std::vector<uint8_t>& h) {
+        h.insert(h.end(), {'B', 'A', 'M', 1});
+        detail::put32(h, static_cast<uint32_t>(header_text.size()));
+        h.insert(h.end(), header_text.begin(), header_text.end());
+        detail::put32(h, static_cast<uint32_t>(refs.size()));
+        for (const RefSeq& r : refs) {
+            detail::put32(h, static_cast<uint32_t>(r.name.size() + 1));
+            h.insert(h.end(), r.name.begin(), r.name.end());
+            h.push_back(0);
+            detail::put32(h, static_cast<uint32_t>(r.length));
+        }
+    }
+    // one BGZF member holding n <= 0xff00 bytes, appended to out
+    static void bgzf_member(const uint8_t* p, size_t n, std::vector<uint8_t>& out, int level = 6) {
+        std::vector<uint8_t> z(compressBound(static_cast<uLong>(n)) + 64);
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw Error("deflateInit2 failed");
+        zs.next_in = const_cast<uint8_t*>(p); zs.avail_in = static_cast<uInt>(n);
+        zs.next_out = z.data(); zs.avail_out = static_cast<uInt>(z.size());
+        if (deflate(&zs, Z_FINISH) != Z_STREAM_END) throw Error("deflate failed");
+        const size_t clen = zs.total_out;
+        deflateEnd(&zs);
+        const size_t total = 18 + clen + 8;
+        if (total - 1 > 0xffff) throw Error("BGZF block too large");
+        const uint8_t hd[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, static_cast<uint8_t>((total - 1) & 0xff),
+                                static_cast<uint8_t>((total - 1) >> 8)};
+        out.insert(out.end(), hd, hd + 18);
+        out.insert(out.end(), z.data(), z.data() + clen);
+        detail::put32(out, static_cast<uint32_t>(crc32(crc32(0L, Z_NULL, 0), p, static_cast<uInt>(n))));
+        detail::put32(out, static_cast<uint32_t>(n));
     }
     void close() {
         if (!f_) return;
@@ -438,29 +467,52 @@ private:
     }
     void flush_block() {
         if (pend_.empty()) return;
-        std::vector<uint8_t> out(compressBound(static_cast<uLong>(pend_.size())) + 64);
-        z_stream zs;
-        memset(&zs, 0, sizeof zs);
-        if (deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw Error("deflateInit2 failed");
-        zs.next_in = pend_.data(); zs.avail_in = static_cast<uInt>(pend_.size());
-        zs.next_out = out.data(); zs.avail_out = static_cast<uInt>(out.size());
-        if (deflate(&zs, Z_FINISH) != Z_STREAM_END) throw Error("deflate failed");
-        const size_t clen = zs.total_out;
-        deflateEnd(&zs);
-        const size_t total = 18 + clen + 8;
-        if (total - 1 > 0xffff) throw Error("BGZF block too large");
-        uint8_t hd[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 0, 0};
-        hd[16] = static_cast<uint8_t>((total - 1) & 0xff); hd[17] = static_cast<uint8_t>((total - 1) >> 8);
-        fwrite(hd, 1, 18, f_);
-        fwrite(out.data(), 1, clen, f_);
-        std::vector<uint8_t> tail;
-        detail::put32(tail, static_cast<uint32_t>(crc32(crc32(0L, Z_NULL, 0), pend_.data(), static_cast<uInt>(pend_.size()))));
-        detail::put32(tail, static_cast<uint32_t>(pend_.size()));
-        fwrite(tail.data(), 1, 8, f_);
+        std::vector<uint8_t> out;
+        bgzf_member(pend_.data(), pend_.size(), out);
+        fwrite(out.data(), 1, out.size(), f_);
         pend_.clear();
     }
     FILE* f_;
     std::vector<uint8_t> pend_;
 };
+
+// Whole-file writer for tools that hold every record in memory (cleric): records are encoded and the stream is
+// compressed in 0xff00-byte BGZF members on all host threads, then written in order.
+inline void write_bam_parallel(const std::string& path, const std::string& header_text, const std::vector<RefSeq>& refs,
+                               const std::vector<const Record*>& recs, unsigned nthreads) {
+    nthreads = std::max(1u, nthreads);
+    std::vector<std::vector<uint8_t>> part(nthreads);
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nthreads; ++t)
+            th.emplace_back([&, t] {
+                for (size_t k = recs.size() * t / nthreads; k < recs.size() * (t + 1) / nthreads; ++k) BamWriter::encode(*recs[k], part[t]);
+            });
+        for (auto& x : th) x.join();
+    }
+    std::vector<uint8_t> u;
+    BamWriter::encode_header(header_text, refs, u);
+    size_t total = u.size();
+    for (auto& p : part) total += p.size();
+    u.reserve(total);
+    for (auto& p : part) { u.insert(u.end(), p.begin(), p.end()); std::vector<uint8_t>().swap(p); }
+    const size_t nblocks = (u.size() + 0xff00 - 1) / 0xff00;
+    std::vector<std::vector<uint8_t>> z(nthreads);
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nthreads; ++t)
+            th.emplace_back([&, t] {
+                for (size_t b = nblocks * t / nthreads; b < nblocks * (t + 1) / nthreads; ++b)
+                    BamWriter::bgzf_member(u.data() + b * 0xff00, std::min<size_t>(0xff00, u.size() - b * 0xff00), z[t]);
+            });
+        for (auto& x : th) x.join();
+    }
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) throw Error("cannot create " + path);
+    for (auto& p : z) fwrite(p.data(), 1, p.size(), f);
+    static const uint8_t eof[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    fwrite(eof, 1, 28, f);
+    fclose(f);
+}
 
 }  // namespace msbam

@@ -35,23 +35,35 @@ int main(int argc, char** argv) {
     }
     if (pos.size() != 3 && pos.size() != 4) { puts("Usage: cleric <in.bam> <reference.fasta> <new_ref.fasta> <out.bam>"); return 1; }
     try {
+        unsigned nt = std::thread::hardware_concurrency();
+        if (const char* e = getenv("MS_HOST_THREADS")) nt = static_cast<unsigned>(atoi(e));
+        nt = std::max(1u, nt);
+        // whole file: parallel BGZF inflate + record index on a helper thread while the CUDA context comes up
+        std::vector<uint8_t> stream;
+        msbam::BamIndexed in;
+        std::string read_err;
+        std::thread reader([&] {
+            try { stream = msbam::inflate_file(pos[0], nt); in = msbam::index_stream(stream); } catch (const std::exception& e) { read_err = e.what(); }
+        });
         ms_handle* h = nullptr;
-        if (ms_create(device, &h) != MS_OK) mshost::die(ms_last_error(nullptr));   // the alignment step runs on the GPU; there is no CPU path
+        const int create_rc = ms_create(device, &h);   // the alignment step runs on the GPU; there is no CPU path
+        reader.join();
+        if (create_rc != MS_OK) mshost::die(ms_last_error(nullptr));
+        if (!read_err.empty()) mshost::die(read_err);
         std::vector<mscleric::Fasta> fa = mscleric::read_fasta(pos[1]);
         if (pos.size() == 4) {
             std::vector<mscleric::Fasta> fb = mscleric::read_fasta(pos[2]);
             fa.insert(fa.end(), fb.begin(), fb.end());
         }
         if (fa.size() != 2) mshost::die("two sequences have to be provided, either in individual files or combined in one");
-        msbam::BamReader in(pos[0]);
         // the original reference is the one the BAM names
         int orig = -1, ref_id = -1;
-        for (size_t r = 0; r < in.refs().size() && orig < 0; ++r)
+        for (size_t r = 0; r < in.refs.size() && orig < 0; ++r)
             for (int k = 0; k < 2; ++k)
-                if (in.refs()[r].name == fa[k].name) { orig = k; ref_id = static_cast<int>(r); break; }
+                if (in.refs[r].name == fa[k].name) { orig = k; ref_id = static_cast<int>(r); break; }
         if (orig < 0) mshost::die("the header of the original reference must match the reference name in the BAM");
         const mscleric::Fasta &A = fa[orig], &B = fa[1 - orig];
-        if (static_cast<int64_t>(A.seq.size()) != in.refs()[ref_id].length) mshost::die("the original reference's length differs from the BAM header's");
+        if (static_cast<int64_t>(A.seq.size()) != in.refs[ref_id].length) mshost::die("the original reference's length differs from the BAM header's");
         std::string ops(A.seq.size() + B.seq.size() + 1, '\0');
         int64_t nops = 0, score = 0;
         CK(h, ms_align_refs(h, A.seq.data(), static_cast<int32_t>(A.seq.size()), B.seq.data(), static_cast<int32_t>(B.seq.size()), &ops[0],
@@ -59,13 +71,7 @@ int main(int argc, char** argv) {
         ops.resize(static_cast<size_t>(nops));
         const mscleric::Path path(ops);
 
-        std::vector<msbam::Record> recs;
-        {
-            msbam::Record r;
-            while (in.next(r)) recs.push_back(r);
-        }
-        unsigned nt = std::thread::hardware_concurrency();
-        if (const char* e = getenv("MS_HOST_THREADS")) nt = static_cast<unsigned>(atoi(e));
+        std::vector<msbam::Record> recs(in.records.size());
         nt = std::max(1u, std::min<unsigned>(nt, static_cast<unsigned>(recs.size() / 256 + 1)));
         std::atomic<int64_t> n_ok{0}, n_unmapped{0}, n_other{0};
         std::atomic<int> bad{0};
@@ -73,6 +79,7 @@ int main(int argc, char** argv) {
         auto work = [&](unsigned t) {
             for (size_t k = recs.size() * t / nt; k < recs.size() * (t + 1) / nt; ++k) {
                 msbam::Record& r = recs[k];
+                msbam::BamReader::parse_record(stream.data() + in.records[k].first, in.records[k].second, r);
                 if (r.ref_id < 0 || (r.flag & 0x4)) continue;                     // unmapped records pass through
                 if (r.ref_id != ref_id) { ++n_other; r.ref_id = -2; continue; }   // aligned to something else: dropped
                 switch (mscleric::project_read(path, B.seq, r)) {
@@ -96,7 +103,7 @@ int main(int argc, char** argv) {
         // header: every @SQ line gives way to the target reference; everything else is kept
         std::string text;
         {
-            std::istringstream hs(in.header_text());
+            std::istringstream hs(in.text);
             std::string line;
             bool sq_done = false;
             while (std::getline(hs, line)) {
@@ -109,9 +116,10 @@ int main(int argc, char** argv) {
             text += "@PG\tID:cleric\tPN:cleric\tVN:minorseq_b200-0.1.0\n";
         }
         {
-            msbam::BamWriter out(pos.back(), text, {{B.name, static_cast<int32_t>(B.seq.size())}});
+            std::vector<const msbam::Record*> keep;
             for (const msbam::Record& r : recs)
-                if (r.ref_id != -2) out.write(r);
+                if (r.ref_id != -2) keep.push_back(&r);
+            msbam::write_bam_parallel(pos.back(), text, {{B.name, static_cast<int32_t>(B.seq.size())}}, keep, nt);
         }
         fprintf(stderr, "cleric: %lld records re-expressed against %s (alignment score %lld), %lld became unmapped, %lld on other references dropped\n",
                 static_cast<long long>(n_ok.load()), B.name.c_str(), static_cast<long long>(score), static_cast<long long>(n_unmapped.load()),
