@@ -13,6 +13,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <memory>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -262,16 +263,28 @@ private:
     std::vector<uint8_t> raw_;
 };
 
+// Byte buffer that is NOT zero-filled on allocation: the inflated stream of a large BAM is hundreds of megabytes, and a
+// std::vector would first write all of it serially; here the inflating threads are the first to touch their pages.
+struct Bytes {
+    std::unique_ptr<uint8_t[]> p;
+    size_t n = 0;
+    Bytes() = default;
+    explicit Bytes(size_t size) : p(new uint8_t[size ? size : 1]), n(size) {}
+    uint8_t* data() { return p.get(); }
+    const uint8_t* data() const { return p.get(); }
+    size_t size() const { return n; }
+};
+
 // ------------------------------------------------------------------ whole-file parallel inflate
 // BGZF blocks are independent gzip members: read the file, find the block boundaries from the BSIZE fields,
 // inflate all blocks concurrently into one buffer.  Returns the uncompressed BAM stream.
-inline std::vector<uint8_t> inflate_file(const std::string& path, unsigned nthreads) {
+inline Bytes inflate_file(const std::string& path, unsigned nthreads) {
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) throw Error("cannot open " + path);
     fseek(f, 0, SEEK_END);
     const long fsz = ftell(f);
     fseek(f, 0, SEEK_SET);
-    std::vector<uint8_t> file(static_cast<size_t>(fsz));
+    Bytes file(static_cast<size_t>(fsz));
     if (fsz && fread(file.data(), 1, file.size(), f) != file.size()) { fclose(f); throw Error("short read on " + path); }
     fclose(f);
     struct Blk { size_t cpos, clen, upos; uint32_t isize, crc; };
@@ -295,7 +308,7 @@ inline std::vector<uint8_t> inflate_file(const std::string& path, unsigned nthre
         utotal += isize;
         o += total;
     }
-    std::vector<uint8_t> out(utotal);
+    Bytes out(utotal);
     std::vector<std::string> errs(nthreads ? nthreads : 1);
     auto work = [&](unsigned t, unsigned nt) {
         for (size_t i = t; i < blks.size(); i += nt) {
@@ -328,7 +341,7 @@ struct BamIndexed {
     std::vector<RefSeq> refs;
     std::vector<std::pair<size_t, uint32_t>> records;   // (offset of the record body, block_size)
 };
-inline BamIndexed index_stream(const std::vector<uint8_t>& u) {
+inline BamIndexed index_stream(const Bytes& u) {
     BamIndexed x;
     size_t o = 0;
     auto need = [&](size_t n) { if (o + n > u.size()) throw Error("truncated BAM stream"); };

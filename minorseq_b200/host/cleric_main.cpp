@@ -39,7 +39,7 @@ int main(int argc, char** argv) {
         if (const char* e = getenv("MS_HOST_THREADS")) nt = static_cast<unsigned>(atoi(e));
         nt = std::max(1u, nt);
         // whole file: parallel BGZF inflate + record index on a helper thread while the CUDA context comes up
-        std::vector<uint8_t> stream;
+        msbam::Bytes stream;
         msbam::BamIndexed in;
         std::string read_err;
         std::thread reader([&] {

@@ -85,7 +85,7 @@ inline void expand_record(const msbam::Record& rec, const QvFilter& qv, int32_t 
 // CUDA context: decode() = parallel BGZF inflate + record index + admission filter; expand() = all host
 // threads parse and expand the admitted records straight into one pinned row buffer.
 struct Decoded {
-    std::vector<uint8_t> u;
+    msbam::Bytes u;
     msbam::BamIndexed bx;
     std::vector<size_t> keep;
     unsigned nt = 1;
@@ -119,7 +119,7 @@ inline void decode_alignments(const std::string& path, Decoded& d, Alignments& o
 }
 
 inline void expand_alignments(const Decoded& d, const QvFilter& qv, bool want_names, bool want_insertions, Alignments& out) {
-    const std::vector<uint8_t>& u = d.u;
+    const msbam::Bytes& u = d.u;
     const msbam::BamIndexed& bx = d.bx;
     const std::vector<size_t>& keep = d.keep;
     unsigned nt = d.nt;
