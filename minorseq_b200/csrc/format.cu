@@ -95,9 +95,16 @@ int ms_expand_cigar(const uint32_t* cigar, int32_t ncigar, int32_t pos, const ch
         case 8: {  // X
             if (qi + len > lseq) return MS_ERR_FORMAT;
             const int64_t c0 = std::max<int64_t>(rc, 0), c1 = std::min<int64_t>(rc + len, L);
-            for (int64_t c = c0; c < c1; ++c) {
-                const int32_t q = qi + static_cast<int32_t>(c - rc);
-                st[c] = (qv_mask && qv_mask[q]) ? static_cast<uint8_t>(MS_N) : lut.v[static_cast<uint8_t>(seq[q])];
+            const char* sq = seq + (qi - rc);          // query base of column c is sq[c]
+            if (qv_mask) {                                // branch-free select: low-QV bases are not predictable
+                const uint8_t* mk = qv_mask + (qi - rc);
+                for (int64_t c = c0; c < c1; ++c) {
+                    const uint8_t b = lut.v[static_cast<uint8_t>(sq[c])];
+                    const uint8_t m = static_cast<uint8_t>(-static_cast<int8_t>(mk[c] != 0));   // 0x00 or 0xff
+                    st[c] = static_cast<uint8_t>((b & ~m) | (MS_N & m));
+                }
+            } else {
+                for (int64_t c = c0; c < c1; ++c) st[c] = lut.v[static_cast<uint8_t>(sq[c])];
             }
             rc += len; qi += len;
             break;

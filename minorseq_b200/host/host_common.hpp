@@ -19,6 +19,45 @@ namespace mshost {
 struct QvFilter {                      // restatement choice U4: which per-base tracks, which threshold
     std::vector<std::string> tags{"dq", "iq", "sq"};
     int threshold = 20;                // a base whose QV in any present track is below this becomes 'N'; 0 = off
+
+    // mask[i] = 1 for every base of rec (SEQ orientation) whose value in any present per-base track is below the
+    // threshold; returns false when no usable track exists (doc/JULIET.md:256-259,273-276: no filter then).  Tracks
+    // are stored in native orientation, SEQ in reference orientation.  Works on the raw tag bytes: this runs once per
+    // read and track on the decode path, which is what bounds the tools end to end.
+    bool apply(const msbam::Record& rec, std::vector<uint8_t>& mask) const {
+        if (threshold <= 0) return false;
+        const size_t n = rec.seq.size();
+        const bool rev = rec.flag & 0x10;
+        bool any = false;
+        for (const std::string& tg : tags) {
+            const uint8_t* t = rec.find_tag(tg.c_str());
+            if (!t || n == 0) continue;
+            auto track = [&](auto value) {     // value(i) = QV of native base i; branch-free so that the loops vectorise
+                if (!any) mask.assign(n, 0);
+                any = true;
+                uint8_t* m = mask.data();
+                const int thr = threshold;
+                if (rev) { for (size_t i = 0; i < n; ++i) m[n - 1 - i] |= static_cast<uint8_t>(value(i) < thr); }
+                else { for (size_t i = 0; i < n; ++i) m[i] |= static_cast<uint8_t>(value(i) < thr); }
+            };
+            if (*t == 'Z') {
+                const uint8_t* p = t + 1;
+                if (strnlen(reinterpret_cast<const char*>(p), n + 1) != n) continue;
+                track([&](size_t i) { return static_cast<int>(p[i]) - 33; });
+            } else if (*t == 'B') {
+                if (msbam::detail::u32(t + 2) != n) continue;
+                const uint8_t* p = t + 6;
+                switch (t[1]) {
+                case 'c': track([&](size_t i) { return static_cast<int>(static_cast<int8_t>(p[i])); }); break;
+                case 'C': track([&](size_t i) { return static_cast<int>(p[i]); }); break;
+                case 's': track([&](size_t i) { return static_cast<int>(static_cast<int16_t>(msbam::detail::u16(p + 2 * i))); }); break;
+                case 'S': track([&](size_t i) { return static_cast<int>(msbam::detail::u16(p + 2 * i)); }); break;
+                default: break;
+                }
+            }
+        }
+        return any;
+    }
 };
 
 struct Alignments {
@@ -46,21 +85,7 @@ inline void expand_record(const msbam::Record& rec, const QvFilter& qv, int32_t 
                           std::vector<uint8_t>& mask, std::vector<int32_t>& ic, std::vector<int64_t>& io, std::vector<int32_t>& il,
                           std::string& pool, std::vector<int32_t>& out_col, std::vector<int32_t>& out_len, std::vector<int64_t>& out_off,
                           std::string& out_pool) {
-    // rich-QV filter: tracks are stored in native orientation, SEQ in reference orientation
-    const uint8_t* maskp = nullptr;
-    if (qv.threshold > 0) {
-        bool any = false;
-        for (const std::string& t : qv.tags) {
-            std::vector<int> track = rec.tag_per_base(t.c_str());
-            if (track.size() != rec.seq.size() || track.empty()) continue;
-            if (!any) mask.assign(rec.seq.size(), 0);
-            any = true;
-            const bool rev = rec.flag & 0x10;
-            for (size_t i = 0; i < track.size(); ++i)
-                if (track[i] < qv.threshold) mask[rev ? track.size() - 1 - i : i] = 1;
-        }
-        if (any) maskp = mask.data();
-    }
+    const uint8_t* maskp = qv.apply(rec, mask) ? mask.data() : nullptr;   // rich-QV filter
     int64_t ni = 0, pu = 0;
     int rc;
     for (;;) {

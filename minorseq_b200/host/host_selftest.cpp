@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <string>
 #include "bgzf_bam.hpp"
+#include "host_common.hpp"
 #include "json.hpp"
 #include "report.hpp"
 #include "target_config.hpp"
@@ -46,6 +47,39 @@ int main(int argc, char** argv) {
             ++n;
         }
         REQUIRE(n == 3000);
+    }
+    {   // ---- rich-QV filter (doc/JULIET.md:256-259): raw-byte implementation against the per-base accessor
+        msbam::Record r;
+        r.seq = "ACGTACGTACGTACGTACGTACGTA";
+        const size_t n = r.seq.size();
+        std::string dq(n, 'I'), sq(n, 'I');
+        dq[2] = '+'; dq[7] = '4'; sq[7] = '5'; sq[20] = '!';            // QVs 10, 19 | 20, 0
+        msbam::BamWriter::aux_string(r.aux, "dq", dq);
+        msbam::BamWriter::aux_string(r.aux, "sq", sq);
+        r.aux.insert(r.aux.end(), {'i', 'q', 'B', 'C'});                  // a B:C array track, one low value
+        msbam::detail::put32(r.aux, static_cast<uint32_t>(n));
+        for (size_t i = 0; i < n; ++i) r.aux.push_back(i == 11 ? 3 : 60);
+        msbam::BamWriter::aux_string(r.aux, "xq", std::string(n - 1, '!'));   // wrong length: ignored
+        mshost::QvFilter qv;
+        qv.tags = {"dq", "iq", "sq", "xq", "zz"};
+        for (int rev = 0; rev < 2; ++rev) {
+            r.flag = rev ? 0x10 : 0;
+            std::vector<uint8_t> want(n, 0), got;
+            for (const std::string& t : qv.tags) {
+                const std::vector<int> tr = r.tag_per_base(t.c_str());
+                if (tr.size() != n) continue;
+                for (size_t i = 0; i < n; ++i) if (tr[i] < qv.threshold) want[rev ? n - 1 - i : i] = 1;
+            }
+            REQUIRE(qv.apply(r, got) && got == want);
+            REQUIRE(want[rev ? n - 1 - 2 : 2] == 1 && want[rev ? n - 1 - 7 : 7] == 1 && want[rev ? n - 1 - 11 : 11] == 1 && want[rev ? n - 1 - 20 : 20] == 1);
+            size_t ones = 0; for (uint8_t m : want) ones += m;
+            REQUIRE(ones == 4);
+        }
+        std::vector<uint8_t> m;
+        mshost::QvFilter off; off.threshold = 0;
+        REQUIRE(!off.apply(r, m));
+        msbam::Record bare; bare.seq = "ACGT";
+        REQUIRE(!qv.apply(bare, m));                                     // no tracks: no filtering
     }
     {   // ---- target config: the example of doc/JULIET.md:138-157 and the DRM grammar of :167-176
         const std::string text = R"({"genes":[{"begin":2550,"drms":[{"name":"fancy drug","positions":["M41L"]},

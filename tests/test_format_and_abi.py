@@ -135,3 +135,52 @@ def test_start_mask_words():
     m2 = start_mask_words(100, [(1, 31)], region=(4, 20))
     bits2 = [j for j in range(128) if (int(m2[j >> 5]) >> (j & 31)) & 1]
     assert bits2 == [3, 6, 9, 12, 15]
+
+
+def test_expand_cigar_randomised_against_python(mslib):
+    """Random =/X/I/D/S alignments with and without a QV mask, including reads that start left of the reference
+    window (negative pos is impossible in BAM, so: pos 0 with the window cut on the right) -- against a plain Python walk."""
+    rng = np.random.default_rng(31)
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    for _ in range(200):
+        L = int(rng.integers(20, 120))
+        pos = int(rng.integers(0, L))
+        cig, seq = [], []
+        span = int(rng.integers(1, 100))
+        used = 0
+        if rng.random() < 0.3:
+            cig.append((2, "S")); seq.append("GG")
+        while used < span:
+            u = rng.random()
+            l = int(rng.integers(1, 6))
+            if u < 0.15 and cig and cig[-1][1] in "=X":
+                cig.append((l, "D")); used += l
+            elif u < 0.3 and cig and cig[-1][1] in "=X":
+                cig.append((l, "I")); seq.append("".join(rng.choice(list("ACGT"), size=l)))
+            else:
+                cig.append((l, "=" if u < 0.8 else "X")); seq.append("".join(rng.choice(list("ACGTN"), size=l))); used += l
+        seq = "".join(seq)
+        qv = None if rng.random() < 0.4 else (rng.random(len(seq)) < 0.3).astype(np.uint8)
+        want = np.full(L, 7, dtype=np.uint8)
+        c, q = pos, 0
+        for l, o in cig:
+            if o in "=X":
+                for t in range(l):
+                    if 0 <= c + t < L:
+                        want[c + t] = 5 if (qv is not None and qv[q + t]) else code.get(seq[q + t], 5)
+                c += l; q += l
+            elif o == "D":
+                for t in range(l):
+                    if 0 <= c + t < L: want[c + t] = 4
+                c += l
+            elif o == "I":
+                if pos <= c - 1 < L and (want[c - 1] & 7) != 7: want[c - 1] |= 8
+                q += l
+            else:
+                q += l
+        merged = []
+        for l, o in cig:
+            if merged and merged[-1][1] == o: merged[-1] = (merged[-1][0] + l, o)
+            else: merged.append((l, o))
+        rc, st, _ = _expand(mslib, merged, pos, seq, L, qv=qv)
+        assert rc == 0 and np.array_equal(st, want), (merged, pos, seq)
