@@ -22,6 +22,20 @@ def test_header_symbols_exported(mslib):
     assert names == set(_lib.EXPORTED_SYMBOLS)
 
 
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99 and as C++ on its own (no torch / CUDA types)."""
+    import shutil, subprocess
+    hdr = os.path.join(ROOT, "include", "minorseq_b200.h")
+    for cc, lang, std in (("gcc", "c", "c99"), ("g++", "c++", "c++11")):
+        exe = shutil.which(cc, path="/usr/bin") or shutil.which(cc)
+        if not exe:
+            pytest.skip(f"{cc} not found")
+        out = subprocess.run([exe, "-x", lang, f"-std={std}", "-fsyntax-only", "-Wall", "-Werror", hdr], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+    text = open(hdr).read()
+    assert "torch" not in text and "cuda_runtime" not in text
+
+
 def test_create_fails_loudly_without_gpu(mslib):
     import torch
     if torch.cuda.is_available():
