@@ -33,7 +33,7 @@ def test_header_is_plain_c():
         out = subprocess.run([exe, "-x", lang, f"-std={std}", "-fsyntax-only", "-Wall", "-Werror", hdr], capture_output=True, text=True)
         assert out.returncode == 0, out.stderr
     text = open(hdr).read()
-    assert "torch" not in text and "cuda_runtime" not in text
+    assert "#include <torch" not in text and "cuda_runtime" not in text and "ATen" not in text
 
 
 def test_create_fails_loudly_without_gpu(mslib):
