@@ -248,11 +248,8 @@ int ms_cooccurrence_tc_launch(ms_handle* h, const uint32_t* bt, int32_t V, int64
     MS_CUDA(h, h->b_tc_tiles.ensure(tiles.size() * sizeof(ms::TcTile)));
     MS_CUDA(h, cudaMemcpyAsync(h->b_tc_tiles.p, tiles.data(), tiles.size() * sizeof(ms::TcTile), cudaMemcpyHostToDevice, h->stream));
     MS_CUDA(h, cudaStreamSynchronize(h->stream));    // `tiles` is pageable host memory about to go out of scope
-    static bool attr_set = false;
-    if (!attr_set) {
-        MS_CUDA(h, cudaFuncSetAttribute(ms::cooccurrence_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ms::kTcSmemBytes)));
-        attr_set = true;
-    }
+    // per device (a process may hold handles on several GPUs), cheap enough to repeat per call
+    MS_CUDA(h, cudaFuncSetAttribute(ms::cooccurrence_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ms::kTcSmemBytes)));
     ms::cooccurrence_tc_kernel<<<static_cast<unsigned>(ntiles * splits), ms::kTcThreads, ms::kTcSmemBytes, h->stream>>>(
         bt, V, rstride, nstages, static_cast<int32_t>(splits), h->b_tc_tiles.as<ms::TcTile>(), C);
     h->launches++;

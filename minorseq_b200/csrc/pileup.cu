@@ -580,15 +580,22 @@ __global__ void __launch_bounds__(kPileupMaxThreads, 1) pileup_csa_kernel(Pileup
 
 template <int MODE, bool DENSE, bool SEG>
 static void launch_one(int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a) {
-    static bool attr_done = false;   // one opt-in to the large dynamic shared memory per instantiation
-    if (!attr_done) {
-        cudaFuncSetAttribute(pileup_csa_kernel<MODE, DENSE, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_done = true;
-    }
     pileup_csa_kernel<MODE, DENSE, SEG><<<grid, threads, smem, s>>>(a);
 }
 
-void pileup_set_smem_attr(int) {}   // kept for the ABI of this translation unit: attributes are set at first launch
+// opt every instantiation in to the large dynamic shared memory, on the current device (called by ms_create)
+void pileup_set_smem_attr(int max_smem) {
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeFuse, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeFuse, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeJuliet, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeJuliet, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeJuliet, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeJuliet, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeBoth, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeBoth, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeBoth, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    cudaFuncSetAttribute(pileup_csa_kernel<kModeBoth, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+}
 
 void pileup_launch(int mode, bool dense, int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a) {
     const bool seg = a.nseg > 1;

@@ -146,6 +146,17 @@ def test_pileup_dense_high_frequency_variants(oracle, hd):
     assert np.array_equal(col, ocol) and np.array_equal(codon, ocodon)
 
 
+def test_pileup_dense_variants_on_segmented_rows(oracle, hd):
+    """BASELINE configs[4] shape at reduced read count: L = 6144 rows are cut into twelve single-warp column segments AND
+    the data make K1 pick its DENSE instantiation -- the one combination of the two template switches the other tests
+    do not reach.  Also a 3-frame layout on the same rows (logged rare path + segments)."""
+    cfg = SynthConfig(L=6144, seed=20240005, dense_sites=2048, dense_strains=64, n_rate=2e-5, dele=2e-5, trunc=0.0)
+    t = make_tables(cfg)
+    st = synth_states(t, 0, 1501)
+    check_pileup(oracle, hd, st, 6144, [(1, 6145)])
+    check_pileup(oracle, hd, st[:300], 6144, [(1, 6145), (2, 6145), (3, 6145)])
+
+
 def test_pileup_accumulates_batches_and_host_path(oracle, hd, c1):
     t, st, packed = c1
     L = 3000
