@@ -13,10 +13,13 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <cstdlib>
 #include <memory>
 #include <thread>
 #include <utility>
 #include <vector>
+
+#include "fast_inflate.hpp"
 
 namespace msbam {
 
@@ -309,11 +312,17 @@ inline Bytes inflate_file(const std::string& path, unsigned nthreads) {
         o += total;
     }
     Bytes out(utotal);
+    const bool use_fast = getenv("MS_ZLIB_INFLATE") == nullptr;
     std::vector<std::string> errs(nthreads ? nthreads : 1);
     auto work = [&](unsigned t, unsigned nt) {
         for (size_t i = t; i < blks.size(); i += nt) {
             const Blk& b = blks[i];
             if (!b.isize) continue;
+            // the project's own decoder first (about twice zlib's speed on BAM blocks); the block's CRC-32 decides whether
+            // its output stands, zlib decodes the block again otherwise
+            if (use_fast && msinflate::fast_inflate(file.data() + b.cpos, b.clen, out.data() + b.upos, b.isize) &&
+                crc32(crc32(0L, Z_NULL, 0), out.data() + b.upos, b.isize) == b.crc)
+                continue;
             z_stream zs;
             memset(&zs, 0, sizeof zs);
             if (inflateInit2(&zs, -15) != Z_OK) { errs[t] = "inflateInit2 failed"; return; }

@@ -3,6 +3,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <vector>
+#include <zlib.h>
 #include "bgzf_bam.hpp"
 #include "host_common.hpp"
 #include "json.hpp"
@@ -47,6 +49,52 @@ int main(int argc, char** argv) {
             ++n;
         }
         REQUIRE(n == 3000);
+    }
+    {   // ---- the project's DEFLATE decoder against zlib: every level and strategy, sizes around the edge cases
+        uint64_t x = 88172645463325252ULL;
+        auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+        int tested = 0;
+        for (int trial = 0; trial < 400; ++trial) {
+            const size_t n = trial < 8 ? static_cast<size_t>(trial) : static_cast<size_t>(rnd() % 70000);
+            std::vector<uint8_t> data(n);
+            const int kind = trial % 5;            // random bytes / 4-letter text / long runs / BAM-like mix / all zero
+            for (size_t i = 0; i < n; ++i) {
+                switch (kind) {
+                case 0: data[i] = static_cast<uint8_t>(rnd()); break;
+                case 1: data[i] = "ACGT"[rnd() & 3]; break;
+                case 2: data[i] = static_cast<uint8_t>((i / (1 + trial % 97)) & 0xff); break;
+                case 3: data[i] = (i % 1000 < 500) ? "ACGT"[rnd() & 3] : static_cast<uint8_t>(33 + rnd() % 60); break;
+                default: data[i] = 0;
+                }
+            }
+            const int level = trial % 10, strategy = (trial / 10) % 5;     // Z_DEFAULT, FILTERED, HUFFMAN_ONLY, RLE, FIXED
+            std::vector<uint8_t> comp(compressBound(static_cast<uLong>(n)) + 64);
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            REQUIRE(deflateInit2(&zs, level, Z_DEFLATED, -15, 8, strategy) == Z_OK);
+            zs.next_in = data.data(); zs.avail_in = static_cast<uInt>(n);
+            zs.next_out = comp.data(); zs.avail_out = static_cast<uInt>(comp.size());
+            REQUIRE(deflate(&zs, Z_FINISH) == Z_STREAM_END);
+            const size_t clen = zs.total_out;
+            deflateEnd(&zs);
+            std::vector<uint8_t> back(n + 1, 0xAB);
+            REQUIRE(msinflate::fast_inflate(comp.data(), clen, back.data(), n));
+            REQUIRE((n == 0 || memcmp(back.data(), data.data(), n) == 0) && back[n] == 0xAB);
+            // wrong expected size and truncated input must be refused, not crash
+            if (n > 0) {
+                REQUIRE(!msinflate::fast_inflate(comp.data(), clen, back.data(), n - 1));
+                REQUIRE(!msinflate::fast_inflate(comp.data(), clen / 2, back.data(), n));
+            }
+            ++tested;
+        }
+        REQUIRE(tested == 400);
+        // garbage input never reads or writes out of bounds (run under the sanitizers in development) and is refused or
+        // caught by the caller's CRC check
+        std::vector<uint8_t> junk(4096), sink(65536);
+        for (int t = 0; t < 200; ++t) {
+            for (auto& c : junk) c = static_cast<uint8_t>(rnd());
+            (void)msinflate::fast_inflate(junk.data(), junk.size(), sink.data(), 1 + rnd() % sink.size());
+        }
     }
     {   // ---- rich-QV filter (doc/JULIET.md:256-259): raw-byte implementation against the per-base accessor
         msbam::Record r;
