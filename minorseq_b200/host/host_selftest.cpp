@@ -49,6 +49,22 @@ int main(int argc, char** argv) {
             ++n;
         }
         REQUIRE(n == 3000);
+        // the whole-file path the tools use (parallel inflate with the project's decoder, record index, parse) sees the
+        // same records as the sequential zlib reader -- with either decoder
+        for (int use_zlib = 0; use_zlib < 2; ++use_zlib) {
+            if (use_zlib) setenv("MS_ZLIB_INFLATE", "1", 1); else unsetenv("MS_ZLIB_INFLATE");
+            const msbam::Bytes u = msbam::inflate_file(tmp, 3);
+            const msbam::BamIndexed bx = msbam::index_stream(u);
+            REQUIRE(bx.refs.size() == 1 && bx.refs[0].name == "ref" && bx.records.size() == 3000);
+            msbam::BamReader again(tmp);
+            msbam::Record a, b;
+            for (size_t k = 0; k < bx.records.size(); ++k) {
+                REQUIRE(again.next(a));
+                msbam::BamReader::parse_record(u.data() + bx.records[k].first, bx.records[k].second, b);
+                REQUIRE(a.name == b.name && a.pos == b.pos && a.flag == b.flag && a.cigar == b.cigar && a.seq == b.seq && a.qual == b.qual && a.aux == b.aux);
+            }
+        }
+        unsetenv("MS_ZLIB_INFLATE");
     }
     {   // ---- the project's DEFLATE decoder against zlib: every level and strategy, sizes around the edge cases
         uint64_t x = 88172645463325252ULL;
