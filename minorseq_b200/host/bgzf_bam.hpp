@@ -19,6 +19,7 @@
 #include <utility>
 #include <vector>
 
+#include "fast_crc32.hpp"
 #include "fast_inflate.hpp"
 
 namespace msbam {
@@ -321,7 +322,7 @@ inline Bytes inflate_file(const std::string& path, unsigned nthreads) {
             // the project's own decoder first (about twice zlib's speed on BAM blocks); the block's CRC-32 decides whether
             // its output stands, zlib decodes the block again otherwise
             if (use_fast && msinflate::fast_inflate(file.data() + b.cpos, b.clen, out.data() + b.upos, b.isize) &&
-                crc32(crc32(0L, Z_NULL, 0), out.data() + b.upos, b.isize) == b.crc)
+                mscrc::crc32(out.data() + b.upos, b.isize) == b.crc)
                 continue;
             z_stream zs;
             memset(&zs, 0, sizeof zs);
