@@ -65,6 +65,27 @@ int main(int argc, char** argv) {
             }
         }
         unsetenv("MS_ZLIB_INFLATE");
+        // the parallel whole-file writer (cleric) produces a BAM the sequential reader reads back record for record
+        {
+            std::vector<msbam::Record> recs;
+            msbam::BamReader src(tmp);
+            msbam::Record r2;
+            while (src.next(r2)) recs.push_back(r2);
+            std::vector<const msbam::Record*> ptrs;
+            for (const auto& x : recs) ptrs.push_back(&x);
+            const std::string tmp2 = tmp + ".parallel.bam";
+            msbam::write_bam_parallel(tmp2, "@HD\tVN:1.5\n@SQ\tSN:other\tLN:777\n", {{"other", 777}}, ptrs, 5);
+            msbam::BamReader back(tmp2);
+            REQUIRE(back.refs().size() == 1 && back.refs()[0].name == "other" && back.refs()[0].length == 777);
+            size_t k = 0;
+            while (back.next(r2)) {
+                REQUIRE(k < recs.size());
+                const msbam::Record& w0 = recs[k++];
+                REQUIRE(r2.name == w0.name && r2.pos == w0.pos && r2.flag == w0.flag && r2.cigar == w0.cigar && r2.seq == w0.seq && r2.qual == w0.qual && r2.aux == w0.aux);
+            }
+            REQUIRE(k == recs.size());
+            remove(tmp2.c_str());
+        }
     }
     {   // ---- the project's DEFLATE decoder against zlib: every level and strategy, sizes around the edge cases
         uint64_t x = 88172645463325252ULL;
