@@ -35,6 +35,7 @@ static void usage() {
          "      --min-haplotype-reads <n>      reads needed to report a haplotype (default 10)\n"
          "      --qv-threshold <q>             rich-QV base filter, 0 = off (default 20 on dq,iq,sq when present)\n"
          "      --device <n>                   CUDA device (default 0)\n"
+         "      --timing-json <file>           write the wall-clock time of every stage as JSON\n"
          "  -h, --help / --version");
 }
 
@@ -47,7 +48,7 @@ static bool ends_with(const std::string& s, const std::string& e) { return s.siz
     } while (0)
 
 int main(int argc, char** argv) {
-    std::string config, region, cmdline;
+    std::string config, region, cmdline, timing_json;
     bool phasing = false, drm_only = false;
     double min_perc = -1, max_perc = -1, sub = 5e-4, del = 3e-3, alpha = 0.01;
     int min_hap = 10, device = 0;
@@ -74,6 +75,7 @@ int main(int argc, char** argv) {
         else if (a == "--min-haplotype-reads") min_hap = atoi(need("--min-haplotype-reads").c_str());
         else if (a == "--qv-threshold") qv.threshold = atoi(need("--qv-threshold").c_str());
         else if (a == "--device") device = atoi(need("--device").c_str());
+        else if (a == "--timing-json") timing_json = need("--timing-json");
         else if (!a.empty() && a[0] == '-') mshost::die("unknown option " + a);
         else pos.push_back(a);
     }
@@ -90,11 +92,14 @@ int main(int argc, char** argv) {
     }
 
     const bool timing = getenv("MS_TIMING") != nullptr;
-    auto t_prev = std::chrono::steady_clock::now();
+    const auto t_start = std::chrono::steady_clock::now();
+    auto t_prev = t_start;
+    std::vector<std::pair<std::string, double>> laps;     // for --timing-json
     auto lap = [&](const char* what) {
-        if (!timing) return;
         const auto now = std::chrono::steady_clock::now();
-        fprintf(stderr, "[timing] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        const double ms = std::chrono::duration<double, std::milli>(now - t_prev).count();
+        laps.emplace_back(what, ms);
+        if (timing) fprintf(stderr, "[timing] %-28s %8.1f ms\n", what, ms);
         t_prev = now;
     };
     try {
@@ -243,6 +248,22 @@ int main(int argc, char** argv) {
             f << msreport::to_html(report);
         }
         lap("report writing");
+        if (!timing_json.empty()) {
+            msjson::Value t = msjson::Value::object();
+            msjson::Value st = msjson::Value::array();
+            for (const auto& l : laps) {
+                msjson::Value e = msjson::Value::object();
+                e.set("stage", msjson::Value::string(l.first));
+                e.set("ms", msjson::Value::number(l.second));
+                st.push(e);
+            }
+            t.set("reads", msjson::Value::integer(aln.nreads));
+            t.set("stages", st);
+            t.set("total_ms", msjson::Value::number(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count()));
+            std::ofstream f(timing_json);
+            if (!f) mshost::die("cannot write " + timing_json);
+            f << msjson::dump(t);
+        }
         fprintf(stderr, "juliet: %lld reads (%lld skipped), %zu variants%s\n", static_cast<long long>(aln.nreads),
                 static_cast<long long>(aln.nskipped), rows.size(), phasing ? (", " + std::to_string(haps.size()) + " haplotypes").c_str() : "");
         fflush(nullptr);

@@ -83,7 +83,9 @@ def test_juliet_cli_matches_oracle(binaries, oracle, tmp_path, n_via_qv):
     cpath = tmp_path / "cfg.json"
     cpath.write_text(json.dumps(conf))
     oj, oh = str(tmp_path / "out.json"), str(tmp_path / "out.html")
-    res = subprocess.run([os.path.join(binaries, "juliet"), "--config", str(cpath), "--mode-phasing", bam, oj, oh], capture_output=True, text=True)
+    tj = str(tmp_path / "timing.json")
+    res = subprocess.run([os.path.join(binaries, "juliet"), "--config", str(cpath), "--mode-phasing", "--timing-json", tj, bam, oj, oh],
+                         capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     rep = json.load(open(oj))
     genes = [(1, 301), (302, 599)]
@@ -92,6 +94,9 @@ def test_juliet_cli_matches_oracle(binaries, oracle, tmp_path, n_via_qv):
     mask = np.zeros(600, dtype=np.uint8)
     for (b, e) in genes:
         mask[b - 1: e - 3: 3] = 1
+    if res.returncode == 0:
+        tim = json.load(open(tj))
+        assert tim["reads"] > 0 and len(tim["stages"]) >= 4 and tim["total_ms"] >= sum(x["ms"] for x in tim["stages"]) * 0.99
     col, codon = oracle.pileup(sto, mask)
     ov = oracle.call(codon, genes, refseq=t.refseq)
     got = []
