@@ -7,7 +7,7 @@
  *
  * PARITY UNPINNED: /root/reference ships documentation only (7 markdown files,
  * 21 screenshots; no source, tests or fixtures), so this file restates the
- * algorithm from doc/JULIET.md and doc/FUSE.md.  Behaviour the docs do not pin
+ * algorithm from doc/JULIET.md, doc/FUSE.md and doc/CLERIC.md.  Behaviour the docs do not pin
  * (U13 for cleric) is a named "restatement choice" below.  The only
  * pins are the screenshot-derived known answers of SURVEY.md App. C, checked in
  * tests/test_oracle_doc_kats.py.
