@@ -43,6 +43,10 @@ class JulietResult(C.Structure):
                 ("npatterns", C.c_int64), ("nreported", C.c_int64), ("counters", PhaseCounters), ("hap_id", C.POINTER(C.c_int32))]
 
 
+class ReadHdr(C.Structure):
+    _fields_ = [("ev_off", C.c_uint32), ("begin", C.c_uint16), ("end", C.c_uint16)]
+
+
 class SynthParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("L", C.c_int32), ("nstrains", C.c_int32), ("thr_N", C.c_uint32),
                 ("thr_sub", C.c_uint32), ("thr_ins20", C.c_uint32), ("thr_trunc16", C.c_uint32)]
@@ -68,6 +72,7 @@ _SIGNATURES = {
     "ms_timer_start": (C.c_int, [_P]),
     "ms_timer_stop": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "ms_pileup_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "ms_stage_kernel_ms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "ms_set_layout": (C.c_int, [_P, C.c_int32, _P]),
     "ms_set_count_insertions": (C.c_int, [_P, C.c_int]),
     "ms_reset_counts": (C.c_int, [_P]),
@@ -99,6 +104,17 @@ _SIGNATURES = {
                                    C.c_int32, C.POINTER(JulietResult)]),
     "ms_juliet_pass_host": (C.c_int, [_P, _P, C.c_int64, C.POINTER(Gene), C.c_int32, C.c_char_p, C.POINTER(CallParams), C.c_int32,
                                     C.c_int32, C.POINTER(JulietResult)]),
+    "ms_events_bound": (C.c_int64, [C.c_int32]),
+    "ms_encode_states": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "ms_encode_rows": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "ms_base_planes": (C.c_int, [_P, C.c_int32, _P]),
+    "ms_encode_row": (C.c_int, [_P, C.c_int32, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "ms_events_seal": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int32]),
+    "ms_set_base": (C.c_int, [_P, _P]),
+    "ms_expand_events_dev": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    "ms_pileup_events_host": (C.c_int, [_P, _P, _P, C.c_int64, C.POINTER(_P)]),
+    "ms_juliet_pass_events_host": (C.c_int, [_P, _P, _P, C.c_int64, C.POINTER(Gene), C.c_int32, C.c_char_p, C.POINTER(CallParams), C.c_int32,
+                                           C.c_int32, C.POINTER(JulietResult)]),
     "ms_fuse_params_default": (None, [C.POINTER(FuseParams)]),
     "ms_fuse": (C.c_int, [_P, C.POINTER(FuseParams), _P, _P, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64,
                           C.POINTER(C.c_int64)]),

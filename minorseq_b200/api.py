@@ -297,7 +297,7 @@ class Juliet:
         return t[: self._V * self._V].view(self._V, self._V)
 
     # -- the whole pass in one C-ABI call (what bench.py times)
-    def _pass(self, ptr, nreads, host, want_hap_id):
+    def _pass(self, ptr, nreads, host, want_hap_id, events=None):
         from ._lib import JulietResult as _JR
         st = getattr(self, "_pass_state", None)
         if st is None:
@@ -318,9 +318,13 @@ class Juliet:
             r = st["res"]
             hap = np.empty(nreads, dtype=np.int32) if (want_hap_id and self.mode_phasing) else None
             r.hap_id = hap.ctypes.data_as(C.POINTER(C.c_int32)) if hap is not None else None
-            fn = self.lib.ms_juliet_pass_host if host else self.lib.ms_juliet_pass_dev
-            rc = fn(self.hd.h, C.c_void_p(ptr), nreads, st["genes"], len(self.genes), self.refseq.encode() if self.refseq else None,
+            tail = (nreads, st["genes"], len(self.genes), self.refseq.encode() if self.refseq else None,
                     C.byref(self.params), 1 if self.mode_phasing else 0, self.min_hap_reads, C.byref(r))
+            if events is not None:
+                rc = self.lib.ms_juliet_pass_events_host(self.hd.h, C.c_void_p(ptr), _ptr(events), *tail)
+            else:
+                fn = self.lib.ms_juliet_pass_host if host else self.lib.ms_juliet_pass_dev
+                rc = fn(self.hd.h, C.c_void_p(ptr), *tail)
             if rc == -4:   # MS_ERR_CAPACITY: grow what was too small and run the pass again
                 st["vcap"] = max(st["vcap"], int(r.nvariants)); st["kcap"] = max(st["kcap"], int(r.nkeys)); st["pcap"] = max(st["pcap"], int(r.nreported))
                 continue
@@ -352,6 +356,23 @@ class Juliet:
         if not getattr(self.hd, "native_comm", False) and _torch_world() > 1:
             return self._run_staged(d_packed_ptr, nreads, want_hap_id)     # torch.distributed exchange between the stages
         return self._pass(d_packed_ptr, nreads, False, want_hap_id)
+
+    # -- event rows (the compact host->device form, csrc/events.cu)
+    def set_base(self, base):
+        """base: the sequence the event rows are encoded against -- a string over ACGT or an array of 0..3, L long
+        (the configured referenceSequence, or any sequence close to the reads)."""
+        self.base = base_array(base, self.L)
+        check(self.lib.ms_set_base(self.hd.h, _ptr(self.base)), self.hd.h)
+
+    def run_events_host(self, hdr: np.ndarray, events: np.ndarray, want_hap_id=False) -> JulietResult:
+        """Reference-facing call with HOST event rows (encode_rows / encode_states): H2D of the events, expansion on the GPU,
+        pileup -> call -> phase, D2H of the results (one C-ABI call, ms_juliet_pass_events_host)."""
+        if not getattr(self.hd, "native_comm", False) and _torch_world() > 1:
+            self.reset()
+            keep = C.c_void_p()
+            check(self.lib.ms_pileup_events_host(self.hd.h, _ptr(hdr), _ptr(events), len(hdr) - 1, C.byref(keep)), self.hd.h)
+            return self._run_staged(keep.value, len(hdr) - 1, want_hap_id, piled=True)
+        return self._pass(hdr.ctypes.data, len(hdr) - 1, True, want_hap_id, events=events)
 
     def run_host(self, packed: np.ndarray, want_hap_id=False) -> JulietResult:
         """Reference-facing call with HOST buffers: H2D + kernels + D2H of the results (one C-ABI call)."""
@@ -401,6 +422,7 @@ class Fuse:
 
     allreduce_counts = Juliet.allreduce_counts
     counts_tensor = Juliet.counts_tensor
+    set_base = Juliet.set_base
 
     def reset(self):
         check(self.lib.ms_reset_counts(self.hd.h), self.hd.h)
@@ -417,6 +439,65 @@ class Fuse:
         check(self.lib.ms_fuse(self.hd.h, C.byref(self.params), _ptr(ic), _ptr(io), _ptr(il), nins, _ptr(pool),
                                len(ins_pool), _ptr(seq), cap, C.byref(n)), self.hd.h)
         return seq[: n.value].tobytes().decode()
+
+
+HDR_DTYPE = np.dtype([("ev_off", "<u4"), ("begin", "<u2"), ("end", "<u2")])
+
+
+def base_array(base, L):
+    if isinstance(base, str):
+        lut = np.full(256, 0, dtype=np.uint8)
+        for i, ch in enumerate("ACGT"):
+            lut[ord(ch)] = i
+            lut[ord(ch.lower())] = i
+        base = lut[np.frombuffer(base.encode(), dtype=np.uint8)]
+    base = np.ascontiguousarray(base, dtype=np.uint8)
+    if base.shape != (L,):
+        raise ValueError(f"base sequence must have {L} entries")
+    return base
+
+
+def _encode(fn_name, src, R, L, base):
+    """-> (hdr[R+1] structured array, events uint16 array)"""
+    lib = _lib.load()
+    base = base_array(base, L)
+    cap = max(1024, int(R) * 64)
+    while True:
+        hdr = np.zeros(R + 1, dtype=HDR_DTYPE)
+        ev = np.empty(cap, dtype=np.uint16)
+        n = C.c_int64()
+        rc = getattr(lib, fn_name)(_ptr(src), R, L, _ptr(base), _ptr(hdr), _ptr(ev), cap, C.byref(n))
+        if rc == -4:
+            cap *= 4
+            continue
+        check(rc)
+        return hdr, ev[: n.value].copy()
+
+
+def encode_states(states: np.ndarray, base):
+    """[R, L] uint8 column states -> event rows against `base` (ms_encode_states)."""
+    states = np.ascontiguousarray(states, dtype=np.uint8)
+    return _encode("ms_encode_states", states, states.shape[0], states.shape[1], base)
+
+
+def encode_rows(packed: np.ndarray, L: int, base):
+    """[R, row_words] uint32 planar rows -> event rows against `base` (ms_encode_rows)."""
+    packed = np.ascontiguousarray(packed, dtype=np.uint32)
+    return _encode("ms_encode_rows", packed, packed.shape[0], L, base)
+
+
+def decode_events(hdr, events, L, base):
+    """numpy decoder of the event-row format (tests only; the product expands on the GPU): -> [R, L] uint8 states."""
+    base = base_array(base, L)
+    R = len(hdr) - 1
+    out = np.full((R, L), 7, dtype=np.uint8)
+    for r in range(R):
+        b, e = int(hdr["begin"][r]), int(hdr["end"][r])
+        out[r, b:e] = base[b:e]
+        ev = events[int(hdr["ev_off"][r]): int(hdr["ev_off"][r + 1])].astype(np.int64)
+        cols = b + np.cumsum(ev >> 4)
+        out[r, cols] = (ev & 15).astype(np.uint8)
+    return out
 
 
 def _torch_world():

@@ -6,6 +6,8 @@
 #include "pileup.cuh"
 
 static std::string g_create_error;
+void ms_events_set_smem_attr(int max_smem);
+void ms_cooc_tc_set_smem_attr();
 
 extern "C" {
 
@@ -38,13 +40,24 @@ int ms_create(int device, ms_handle** out) {
         cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&h->ev_k1[0]) != cudaSuccess || cudaEventCreate(&h->ev_k1[1]) != cudaSuccess ||
-        cudaEventCreate(&h->ev_timer[0]) != cudaSuccess || cudaEventCreate(&h->ev_timer[1]) != cudaSuccess) {
+        cudaEventCreate(&h->ev_timer[0]) != cudaSuccess || cudaEventCreate(&h->ev_timer[1]) != cudaSuccess ||
+        cudaEventCreate(&h->ev_stage[1][0]) != cudaSuccess || cudaEventCreate(&h->ev_stage[1][1]) != cudaSuccess ||
+        cudaEventCreate(&h->ev_stage[2][0]) != cudaSuccess || cudaEventCreate(&h->ev_stage[2][1]) != cudaSuccess ||
+        cudaEventCreate(&h->ev_stage[3][0]) != cudaSuccess || cudaEventCreate(&h->ev_stage[3][1]) != cudaSuccess) {
         g_create_error = cudaGetErrorString(cudaGetLastError());
         delete h;
         return MS_ERR_CUDA;
     }
+    for (cudaEvent_t& ev : h->ev_chunk)
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+            g_create_error = cudaGetErrorString(cudaGetLastError());
+            delete h;
+            return MS_ERR_CUDA;
+        }
     h->stream = h->own_stream;
     ms::pileup_set_smem_attr(h->max_smem);
+    ms_events_set_smem_attr(h->max_smem);
+    ms_cooc_tc_set_smem_attr();
     *out = h;
     return MS_OK;
 }
@@ -68,10 +81,13 @@ void ms_destroy(ms_handle* h) {
     ms_phase_free_internal(h);
     cudaFree(h->d_upload); cudaFree(h->d_call_buf); cudaFree(h->d_seq);
     h->b_exc_list.release(); h->b_exc_cnt.release();
+    h->b_base.release(); h->b_ev_hdr.release(); h->b_ev.release();
+    for (cudaEvent_t ev : h->ev_chunk) cudaEventDestroy(ev);
     if (h->call_stage) cudaFreeHost(h->call_stage);
     cudaEventDestroy(h->ev_copy[0]); cudaEventDestroy(h->ev_copy[1]);
     cudaEventDestroy(h->ev_k1[0]); cudaEventDestroy(h->ev_k1[1]);
     cudaEventDestroy(h->ev_timer[0]); cudaEventDestroy(h->ev_timer[1]);
+    for (int s = 1; s < 4; ++s) { cudaEventDestroy(h->ev_stage[s][0]); cudaEventDestroy(h->ev_stage[s][1]); }
     cudaStreamDestroy(h->own_stream); cudaStreamDestroy(h->copy_stream);
     delete h;
 }
@@ -137,6 +153,16 @@ int ms_pileup_kernel_ms(ms_handle* h, double* ms, int64_t* reads) {
     return MS_OK;
 }
 
+int ms_stage_kernel_ms(ms_handle* h, int stage, double* ms) {
+    if (!h || !ms || stage < 1 || stage > 3 || !h->timing || !h->stage_seen[stage]) return MS_ERR_ARG;
+    MS_CUDA(h, cudaSetDevice(h->device));
+    MS_CUDA(h, cudaEventSynchronize(h->ev_stage[stage][1]));
+    float f = 0.f;
+    MS_CUDA(h, cudaEventElapsedTime(&f, h->ev_stage[stage][0], h->ev_stage[stage][1]));
+    *ms = f;
+    return MS_OK;
+}
+
 int ms_set_count_insertions(ms_handle* h, int on) {
     if (!h) return MS_ERR_ARG;
     h->count_ins = on != 0;
@@ -195,6 +221,7 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
     MS_CUDA(h, cudaStreamSynchronize(h->stream));
     free_layout(h);
     h->L = L; h->nblk = nblk; h->count_codons = start_mask != nullptr; h->have_pivot = false;
+    h->have_base = false;
     h->wpg = W;
     h->groups = kGroups[W];
     h->nseg = best_nseg;
@@ -346,21 +373,18 @@ int ms_pileup_host(ms_handle* h, const uint32_t* h_packed, int64_t R, const uint
     // the copy stream must not start overwriting d_upload before earlier work on the main stream is done
     MS_CUDA(h, cudaEventRecord(h->ev_copy[1], h->stream));
     MS_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_copy[1], 0));
-    std::vector<cudaEvent_t> evs;
-    for (int64_t r0 = 0; r0 < R; r0 += chunk_rows) {
+    int k = 0;
+    for (int64_t r0 = 0; r0 < R; r0 += chunk_rows, ++k) {
         const int64_t nr = std::min(chunk_rows, R - r0);
         uint8_t* dst = reinterpret_cast<uint8_t*>(h->d_upload) + static_cast<size_t>(r0) * row_bytes;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(h_packed) + static_cast<size_t>(r0) * row_bytes;
         MS_CUDA(h, cudaMemcpyAsync(dst, src, static_cast<size_t>(nr) * row_bytes, cudaMemcpyHostToDevice, h->copy_stream));
-        cudaEvent_t ev;
-        MS_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        evs.push_back(ev);
+        cudaEvent_t ev = h->ev_chunk[k & 15];   // a wait snapshots the record it follows, so the ring can be reused at once
         MS_CUDA(h, cudaEventRecord(ev, h->copy_stream));
         MS_CUDA(h, cudaStreamWaitEvent(h->stream, ev, 0));
         int rc = ms_pileup_dev(h, reinterpret_cast<const uint32_t*>(dst), nr);
         if (rc != MS_OK) return rc;
     }
-    for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
     if (keep_dev) *keep_dev = h->d_upload;
     return MS_OK;
 }

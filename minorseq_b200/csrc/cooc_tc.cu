@@ -234,6 +234,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) cooccurrence_tc_kernel(const ui
 
 }  // namespace ms
 
+// opt in to the large dynamic shared memory on the current device (called once per handle by ms_create)
+void ms_cooc_tc_set_smem_attr() {
+    cudaFuncSetAttribute(ms::cooccurrence_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ms::kTcSmemBytes));
+}
+
 // C (V*V int32, zeroed by the caller) += B^T B over the transposed bit matrix; enqueued on the handle's stream
 int ms_cooccurrence_tc_launch(ms_handle* h, const uint32_t* bt, int32_t V, int64_t rstride, int64_t R, int32_t* C) {
     const int64_t nstages = (R + ms::kTcKStage - 1) / ms::kTcKStage;
@@ -245,11 +250,12 @@ int ms_cooccurrence_tc_launch(ms_handle* h, const uint32_t* bt, int32_t V, int64
     const int64_t ntiles = static_cast<int64_t>(tiles.size());
     int64_t splits = std::max<int64_t>(1, h->num_sms / ntiles);
     splits = std::min<int64_t>(splits, std::max<int64_t>(1, nstages / 8));      // at least 8 stages per CTA
-    MS_CUDA(h, h->b_tc_tiles.ensure(tiles.size() * sizeof(ms::TcTile)));
-    MS_CUDA(h, cudaMemcpyAsync(h->b_tc_tiles.p, tiles.data(), tiles.size() * sizeof(ms::TcTile), cudaMemcpyHostToDevice, h->stream));
-    MS_CUDA(h, cudaStreamSynchronize(h->stream));    // `tiles` is pageable host memory about to go out of scope
-    // per device (a process may hold handles on several GPUs), cheap enough to repeat per call
-    MS_CUDA(h, cudaFuncSetAttribute(ms::cooccurrence_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ms::kTcSmemBytes)));
+    if (h->tc_tiles_V != V) {   // the tile list depends on V only: uploaded once per variant count, not per call
+        MS_CUDA(h, h->b_tc_tiles.ensure(tiles.size() * sizeof(ms::TcTile)));
+        MS_CUDA(h, cudaMemcpyAsync(h->b_tc_tiles.p, tiles.data(), tiles.size() * sizeof(ms::TcTile), cudaMemcpyHostToDevice, h->stream));
+        MS_CUDA(h, cudaStreamSynchronize(h->stream));    // `tiles` is pageable host memory about to go out of scope
+        h->tc_tiles_V = V;
+    }
     ms::cooccurrence_tc_kernel<<<static_cast<unsigned>(ntiles * splits), ms::kTcThreads, ms::kTcSmemBytes, h->stream>>>(
         bt, V, rstride, nstages, static_cast<int32_t>(splits), h->b_tc_tiles.as<ms::TcTile>(), C);
     h->launches++;

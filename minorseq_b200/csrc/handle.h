@@ -28,8 +28,11 @@ struct ms_handle {
     int max_smem = 0;
     cudaStream_t own_stream = nullptr, copy_stream = nullptr, stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    cudaEvent_t ev_chunk[16] = {};              // upload pipeline: one per in-flight chunk, reused round-robin
     cudaEvent_t ev_k1[2] = {nullptr, nullptr};  // around the last K1 launch when timing is on
     cudaEvent_t ev_timer[2] = {nullptr, nullptr};  // ms_timer_start / ms_timer_stop
+    cudaEvent_t ev_stage[4][2] = {};               // when timing is on: around the last launch of MS_STAGE_* (ms_stage_kernel_ms)
+    bool stage_seen[4] = {false, false, false, false};
     bool timing = false;
     int64_t k1_reads = 0;
     std::string err;
@@ -55,6 +58,11 @@ struct ms_handle {
     DevBuf b_exc_list, b_exc_cnt;  // K1's per-thread exception logs
     std::vector<uint32_t> h_start;
 
+    // event rows (events.cu): base sequence planes, staging of the uploaded headers and events
+    DevBuf b_base, b_ev_hdr, b_ev;
+    uint32_t base_hash = 0;
+    bool have_base = false;
+
     // host-upload staging (ms_pileup_host keeps the rows for phasing)
     uint32_t* d_upload = nullptr;
     size_t upload_cap = 0;
@@ -79,6 +87,7 @@ struct ms_handle {
     // device-side merge + ordering (phase_order.cu)
     DevBuf b_gslot, b_mt_key, b_mt_cnt, b_mt_rep, b_mslot, b_mindex, b_m_cnt, b_m_pat, b_m_rank, b_ord, b_keys, b_out, b_tc_tiles;
     DevBuf b_nw_seq, b_nw_hrow, b_nw_hcol, b_nw_dir;   // nw.cu (cleric's reference-to-reference alignment)
+    int32_t tc_tiles_V = -1;     // variant count the uploaded tcgen05 tile list belongs to
     int cooc_variant = 0;        // 0 auto, 1 popcount-AND, 2 tcgen05 int8
     std::vector<uint32_t> groups_cnt, groups_pat;   // host copy of the last grouping pass (all ranks when a comm is attached)
     uint64_t groups_marg[4] = {0, 0, 0, 0};
@@ -102,6 +111,10 @@ struct ms_handle {
             return MS_ERR_CUDA;                                                             \
         }                                                                                   \
     } while (0)
+
+// bench.py's per-kernel rooflines: CUDA events on the handle's stream around the dominant kernel of a stage
+#define MS_STAGE_BEGIN(h, s) do { if ((h)->timing) cudaEventRecord((h)->ev_stage[s][0], (h)->stream); } while (0)
+#define MS_STAGE_END(h, s) do { if ((h)->timing) { cudaEventRecord((h)->ev_stage[s][1], (h)->stream); (h)->stage_seen[s] = true; } } while (0)
 
 #define MS_FAIL(h, code, msg) \
     do {                      \

@@ -9,13 +9,17 @@
 #include <vector>
 #include "handle.h"
 
-static int juliet_pass(ms_handle* h, const uint32_t* packed, bool host_rows, int64_t R, const ms_gene* genes, int32_t ngenes,
+enum RowSource { kDeviceRows, kHostRows, kHostEvents };
+
+static int juliet_pass(ms_handle* h, const void* src, const uint16_t* events, RowSource from, int64_t R, const ms_gene* genes, int32_t ngenes,
                        const char* refseq, const ms_call_params* prm, int32_t phase, int32_t min_hap_reads, ms_juliet_result* out) {
     if (!h || !out || !prm || R < 0) return MS_ERR_ARG;
     int rc = ms_reset_counts(h);
     if (rc != MS_OK) return rc;
-    const uint32_t* d_rows = packed;
-    rc = host_rows ? ms_pileup_host(h, packed, R, &d_rows) : ms_pileup_dev(h, packed, R);
+    const uint32_t* d_rows = static_cast<const uint32_t*>(src);
+    if (from == kHostRows) rc = ms_pileup_host(h, static_cast<const uint32_t*>(src), R, &d_rows);
+    else if (from == kHostEvents) rc = ms_pileup_events_host(h, static_cast<const ms_read_hdr*>(src), events, R, &d_rows);
+    else rc = ms_pileup_dev(h, d_rows, R);
     if (rc != MS_OK) return rc;
     rc = ms_allreduce_counts(h);
     if (rc != MS_OK) return rc;
@@ -53,12 +57,17 @@ extern "C" {
 
 int ms_juliet_pass_dev(ms_handle* h, const uint32_t* d_packed, int64_t R, const ms_gene* genes, int32_t ngenes, const char* refseq,
                        const ms_call_params* prm, int32_t phase, int32_t min_hap_reads, ms_juliet_result* out) {
-    return juliet_pass(h, d_packed, false, R, genes, ngenes, refseq, prm, phase, min_hap_reads, out);
+    return juliet_pass(h, d_packed, nullptr, kDeviceRows, R, genes, ngenes, refseq, prm, phase, min_hap_reads, out);
 }
 
 int ms_juliet_pass_host(ms_handle* h, const uint32_t* h_packed, int64_t R, const ms_gene* genes, int32_t ngenes, const char* refseq,
                         const ms_call_params* prm, int32_t phase, int32_t min_hap_reads, ms_juliet_result* out) {
-    return juliet_pass(h, h_packed, true, R, genes, ngenes, refseq, prm, phase, min_hap_reads, out);
+    return juliet_pass(h, h_packed, nullptr, kHostRows, R, genes, ngenes, refseq, prm, phase, min_hap_reads, out);
+}
+
+int ms_juliet_pass_events_host(ms_handle* h, const ms_read_hdr* hdr, const uint16_t* events, int64_t R, const ms_gene* genes, int32_t ngenes,
+                               const char* refseq, const ms_call_params* prm, int32_t phase, int32_t min_hap_reads, ms_juliet_result* out) {
+    return juliet_pass(h, hdr, events, kHostEvents, R, genes, ngenes, refseq, prm, phase, min_hap_reads, out);
 }
 
 }  // extern "C"

@@ -540,6 +540,7 @@ int ms_phase_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     const uint4* pk = reinterpret_cast<const uint4*>(d_packed);
     const ms::VarDev* vars = h->b_var.as<ms::VarDev>();
     unsigned long long* ctr = ctr_ptr(h);
+    MS_STAGE_BEGIN(h, MS_STAGE_PHASE_BITS);
     if (h->V <= 32) {
         int lpr = 1;
         while (lpr < h->V) lpr <<= 1;
@@ -566,6 +567,7 @@ int ms_phase_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
         ms::phase_bits_kernel<<<grid, ms::kPhaseWarps * 32, smem, h->stream>>>(pk, R, h->nblk, h->b_blocklist.as<int32_t>(), h->nblocklist,
                                                                               vars, h->V, h->vwords, bits, flags, ctr);
     }
+    MS_STAGE_END(h, MS_STAGE_PHASE_BITS);
     h->launches++;
     MS_CUDA(h, cudaGetLastError());
     h->phase_n += R;
@@ -784,6 +786,7 @@ int ms_cooccurrence(ms_handle* h, int32_t** d_C) {
         ms::bits_transpose_kernel<<<static_cast<unsigned>((nwarps * 32 + 255) / 256), 256, 0, h->stream>>>(h->b_bits.as<uint32_t>(), R, nw, rwords,
                                                                                                          h->b_bits_t.as<uint32_t>());
         h->launches++;
+        MS_STAGE_BEGIN(h, MS_STAGE_COOCCURRENCE);
         if (tensor) {
             int rc = ms_cooccurrence_tc_launch(h, h->b_bits_t.as<uint32_t>(), V, rwords, R, h->b_cooc.as<int32_t>());
             if (rc != MS_OK) return rc;
@@ -792,6 +795,7 @@ int ms_cooccurrence(ms_handle* h, int32_t** d_C) {
             ms::cooccurrence_kernel<<<grid, 256, 0, h->stream>>>(h->b_bits_t.as<uint32_t>(), V, rwords, h->b_cooc.as<int32_t>());
             h->launches++;
         }
+        MS_STAGE_END(h, MS_STAGE_COOCCURRENCE);
     }
     MS_CUDA(h, cudaGetLastError());
     *d_C = h->b_cooc.as<int32_t>();

@@ -581,3 +581,53 @@ int64_t mso_project_read(const char *ops, int64_t nops, const char *b, int32_t l
     free(rop); free(rlen); free(rb);
     return rc == 0 ? n : -1;
 }
+
+/* ---- workload generator: C twin of minorseq_b200/synth.py (see ms_oracle.h) ---------------------------------- */
+static uint64_t synth_mix64(uint64_t x)
+{
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
+    x ^= x >> 27; x *= 0x94d049bb133111ebULL;
+    x ^= x >> 31;
+    return x;
+}
+
+void mso_synth_states(const mso_synth_params *p, const uint8_t *strain_base, const uint32_t *thr_del,
+                      const uint32_t *strain_cum, int64_t read0, int64_t R, uint8_t *states, int nthreads)
+{
+    const uint64_t K1 = 0x9E3779B97F4A7C15ULL, K2 = 0xD1B54A32D192ED03ULL;
+    (void)nthreads;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads > 1 ? nthreads : 1) schedule(static)
+#endif
+    for (int64_t i = 0; i < R; ++i) {
+        const uint64_t r = (uint64_t)(read0 + i);
+        const uint64_t y = synth_mix64(p->seed + r * K1);
+        const uint32_t us = (uint32_t)y;
+        int32_t strain = p->nstrains - 1;
+        for (int32_t s = 0; s < p->nstrains; ++s)
+            if (us < strain_cum[s]) { strain = s; break; }
+        int32_t begin = 0, end = p->L;
+        if (((y >> 32) & 0xffffu) < p->thr_trunc16) {
+            const uint32_t z = (uint32_t)(y >> 48);
+            const int32_t amount = (int32_t)(((uint64_t)(z >> 1) * (uint64_t)(p->L / 2)) >> 15);
+            if (z & 1u) begin = amount; else end = p->L - amount;
+        }
+        const uint8_t *sb = strain_base + (size_t)strain * p->L;
+        uint8_t *out = states + (size_t)i * p->L;
+        for (int32_t c = 0; c < p->L; ++c) {
+            uint32_t st = 7, ins = 0;
+            if (c >= begin && c < end) {
+                const uint64_t x = synth_mix64(p->seed + r * K1 + (uint64_t)(c + 1) * K2);
+                const uint64_t u = x & 0xffffffffULL;
+                const uint64_t tN = p->thr_N, tD = tN + thr_del[c], tS = tD + p->thr_sub;
+                const uint32_t base = sb[c];
+                if (u < tN) st = 5;
+                else if (u < tD) st = 4;
+                else if (u < tS) st = (base + 1u + (uint32_t)((x >> 32) % 3ULL)) & 3u;
+                else st = base;
+                ins = ((x >> 44) & 0xfffffULL) < p->thr_ins20 ? 1u : 0u;
+            }
+            out[c] = (uint8_t)(st == 7 ? 7 : (st | (ins << 3)));
+        }
+    }
+}

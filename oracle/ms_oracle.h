@@ -143,6 +143,17 @@ int64_t mso_project_read(const char *ops, int64_t nops, const char *b, int32_t l
                          const char *seq, int32_t lseq,
                          char *new_op, int32_t *new_len, int64_t cap, int32_t *new_pos);
 
+/* ---- workload generator (not a restatement of anything in the reference): C twin of minorseq_b200/synth.py and
+ * csrc/synth.cu -- the same pure function of (seed, read, column) -- so that the CPU arm of bench.py can produce its own
+ * reads at full size without the GPU.  tests/test_oracle_properties.py checks it against the numpy generator.        */
+typedef struct {
+    uint64_t seed;
+    int32_t L, nstrains;
+    uint32_t thr_N, thr_sub, thr_ins20, thr_trunc16;
+} mso_synth_params;
+void mso_synth_states(const mso_synth_params *p, const uint8_t *strain_base, const uint32_t *thr_del,
+                      const uint32_t *strain_cum, int64_t read0, int64_t R, uint8_t *states, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,11 @@ class PhaseCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("reported", "insufficient", "damaged", "gaps", "heteroduplex", "partial")]
 
 
+class SynthParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("L", C.c_int32), ("nstrains", C.c_int32), ("thr_N", C.c_uint32),
+                ("thr_sub", C.c_uint32), ("thr_ins20", C.c_uint32), ("thr_trunc16", C.c_uint32)]
+
+
 class FuseParams(C.Structure):
     _fields_ = [("min_coverage", C.c_int32), ("ins_fraction", C.c_double), ("ins_distance", C.c_int32)]
 
@@ -69,6 +74,14 @@ class Oracle:
         L.mso_cooccurrence.argtypes = [_P, C.c_int64, C.c_int32, _P]
         L.mso_fuse.restype = C.c_int64
         L.mso_fuse.argtypes = [_P, C.c_int32, _P, _P, _P, C.c_int64, _P, C.POINTER(FuseParams), _P, C.c_int64]
+
+    def synth_states(self, t, read0, R, nthreads=1):
+        """C twin of minorseq_b200.synth.synth_states (t: SynthTables) -- the CPU arm's own workload generator."""
+        p = SynthParams(t.cfg.seed, t.cfg.L, t.nstrains, t.thr_N, t.thr_sub, t.thr_ins20, t.thr_trunc16)
+        out = np.empty((R, t.cfg.L), dtype=np.uint8)
+        self.lib.mso_synth_states(C.byref(p), _p(np.ascontiguousarray(t.strain_base)), _p(np.ascontiguousarray(t.thr_del)),
+                                  _p(np.ascontiguousarray(t.strain_cum)), C.c_int64(read0), C.c_int64(R), _p(out), nthreads)
+        return out
 
     def unpack(self, packed, L, nthreads=1):
         R = packed.shape[0]

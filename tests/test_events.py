@@ -1,0 +1,183 @@
+"""Event rows (csrc/events.cu): the compact host->device form of an aligned read.
+
+CPU part: the host encoders against an independent numpy decoder (minorseq_b200.api.decode_events) on generator reads,
+random states, fillers (> 4095 unchanged columns between two events), unspanned reads, reference skips inside a read.
+GPU part: expand_events_kernel rebuilds exactly the planar rows ms_pack_states / ms_expand_cigar would have produced, and
+the pass from event rows gives the pass from rows (counts, variants, haplotypes, read ids) and the oracle's.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from minorseq_b200 import _lib, decode_events, encode_rows, encode_states
+from minorseq_b200.api import HDR_DTYPE
+from minorseq_b200.synth import SynthConfig, make_tables, pack_states, synth_states
+
+
+def _random_states(rng, R, L, p_event):
+    base = rng.integers(0, 4, size=L, dtype=np.uint8)
+    st = np.tile(base, (R, 1))
+    ev = rng.random((R, L)) < p_event
+    st[ev] = rng.choice(np.array([0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 12, 13, 15], dtype=np.uint8), size=int(ev.sum()))
+    for r in range(R):       # ragged spans, some reads empty
+        b, e = sorted(rng.integers(0, L + 1, size=2))
+        if r % 7 == 0:
+            b = e
+        st[r, :b] = 7
+        st[r, e:] = 7
+    return base, st
+
+
+@pytest.mark.parametrize("L", [3, 31, 32, 33, 100, 3000, 9719])
+def test_encode_decode_roundtrip_random(L):
+    rng = np.random.default_rng(L)
+    base, st = _random_states(rng, 60, L, 0.03)
+    hdr, ev = encode_states(st, base)
+    assert hdr.dtype == HDR_DTYPE and len(hdr) == 61 and int(hdr["ev_off"][-1]) == len(ev)
+    assert np.array_equal(decode_events(hdr, ev, L, base), st)
+    hdr2, ev2 = encode_rows(pack_states(st), L, base)
+    assert np.array_equal(hdr2, hdr) and np.array_equal(ev2, ev)
+
+
+def test_encode_generator_reads_are_compact():
+    """CCS-like reads against the major strain: ~85 events (N 2 %, deletions, substitutions, insertion flags) per 3 kb read,
+    i.e. ~180 B instead of the 1504-byte planar row."""
+    t = make_tables(SynthConfig(L=3000, seed=20240003))
+    st = synth_states(t, 0, 500)
+    hdr, ev = encode_states(st, t.refseq)
+    assert np.array_equal(decode_events(hdr, ev, 3000, t.refseq), st)
+    per_read = (2 * len(ev) + 8 * len(hdr)) / 500
+    assert 120 < per_read < 260, per_read
+    # lossless for ANY base: a wrong base only makes the list longer
+    rng = np.random.default_rng(1)
+    other = rng.integers(0, 4, size=3000, dtype=np.uint8)
+    hdr2, ev2 = encode_states(st[:50], other)
+    assert np.array_equal(decode_events(hdr2, ev2, 3000, other), st[:50]) and len(ev2) > 50 * 2000
+
+
+def test_encode_fillers_and_edges():
+    L = 20000
+    base = np.zeros(L, dtype=np.uint8)
+    st = np.tile(base, (6, 1))
+    st[0, 19999] = 2                      # one event 19999 columns after begin: four fillers
+    st[1, 4095] = 1                       # exactly the largest delta: no filler
+    st[2, 4096] = 1                       # one more: one filler
+    st[3, :] = 7                          # spans nothing
+    st[4, :100] = 7; st[4, 150:] = 7; st[4, 120:125] = 7     # reference skip (CIGAR N) inside the read
+    st[5, 0] = 15; st[5, 1] = 8           # insertion flags on an unspanned-looking and on an unchanged column
+    hdr, ev = encode_states(st, base)
+    n = np.diff(hdr["ev_off"].astype(np.int64))
+    assert list(n[:4]) == [5, 1, 2, 0]
+    assert (int(hdr["begin"][3]), int(hdr["end"][3])) == (0, 0)
+    assert (int(hdr["begin"][4]), int(hdr["end"][4])) == (100, 150) and n[4] == 5
+    assert np.array_equal(decode_events(hdr, ev, L, base), st)
+
+
+def test_encode_errors(mslib):
+    base = np.zeros(100, dtype=np.uint8)
+    st = np.full((3, 100), 1, dtype=np.uint8)
+    hdr = np.zeros(4, dtype=HDR_DTYPE)
+    ev = np.zeros(10, dtype=np.uint16)
+    n = C.c_int64()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert mslib.ms_encode_states(p(st), 3, 100, p(base), p(hdr), p(ev), 10, C.byref(n)) == -4      # MS_ERR_CAPACITY
+    assert mslib.ms_encode_states(p(st), 3, 70000, p(base), p(hdr), p(ev), 10, C.byref(n)) == -1    # L > 65535
+    st[1, 5] = 6
+    big = np.zeros(400, dtype=np.uint16)
+    assert mslib.ms_encode_states(p(st), 3, 100, p(base), p(hdr), p(big), 400, C.byref(n)) == -5    # reserved state
+    assert mslib.ms_events_bound(3000) == 3001 and mslib.ms_events_bound(20000) == 20005
+
+
+def test_encode_row_incremental_matches_batch(mslib):
+    """The per-record form the BAM loop uses (ms_base_planes + ms_encode_row + ms_events_seal) == the batch encoder."""
+    rng = np.random.default_rng(3)
+    base, st = _random_states(rng, 40, 777, 0.05)
+    rows = pack_states(st)
+    want_hdr, want_ev = encode_states(st, base)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    planes = np.zeros(2 * ((777 + 31) // 32), dtype=np.uint32)
+    assert mslib.ms_base_planes(p(base), 777, p(planes)) == 0
+    hdr = np.zeros(41, dtype=HDR_DTYPE)
+    ev = np.zeros(len(want_ev) + 8, dtype=np.uint16)
+    n = C.c_int64(0)
+    for r in range(40):
+        assert mslib.ms_encode_row(p(rows[r]), 777, p(planes), C.c_void_p(hdr.ctypes.data + 8 * r), p(ev), len(ev), C.byref(n)) == 0
+    assert mslib.ms_events_seal(p(hdr), 40, n.value, p(base), 777) == 0
+    assert np.array_equal(hdr, want_hdr) and np.array_equal(ev[: n.value], want_ev)
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+gpu = pytest.mark.gpu
+
+
+def _dev(a, torch):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8)).cuda()
+
+
+@gpu
+@pytest.mark.parametrize("L,R", [(3, 5), (32, 40), (33, 100), (97, 1000), (3000, 3000), (6144, 300), (9719, 700), (20000, 200)])
+def test_expand_events_equals_packed_rows(L, R):
+    import torch
+    from minorseq_b200 import Handle, Juliet
+    rng = np.random.default_rng(L + R)
+    base, st = _random_states(rng, R, L, 0.03 if L < 10000 else 0.002)
+    hdr, ev = encode_states(st, base)
+    hd = Handle(0)
+    try:
+        j = Juliet(L, [(1, L + 1)], handle=hd)
+        lib = j.lib
+        dh, de = _dev(hdr, torch), _dev(ev if len(ev) else np.zeros(1, np.uint16), torch)
+        out = torch.zeros((R, j.row_words), dtype=torch.int32, device="cuda")
+        assert lib.ms_expand_events_dev(hd.h, C.c_void_p(dh.data_ptr()), C.c_void_p(de.data_ptr()), R, C.c_void_p(out.data_ptr())) == -1  # no base yet
+        j.set_base(base)
+        _lib.check(lib.ms_expand_events_dev(hd.h, C.c_void_p(dh.data_ptr()), C.c_void_p(de.data_ptr()), R, C.c_void_p(out.data_ptr())), hd.h)
+        _lib.check(lib.ms_synchronize(hd.h), hd.h)
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), pack_states(st))
+    finally:
+        hd.close()
+
+
+@gpu
+def test_pass_from_event_rows_equals_pass_from_rows_and_oracle(oracle):
+    """juliet --mode-phasing through ms_juliet_pass_events_host: same counts, variants, haplotypes and read ids as the pass from
+    planar rows, and the oracle's counts.  Small chunk size so that the chunked upload pipeline has several chunks."""
+    import torch
+    from minorseq_b200 import Handle, Juliet
+    cfg = SynthConfig(L=3000, seed=20240003, n_rate=5e-3)
+    t = make_tables(cfg)
+    R = 150_001
+    st = synth_states(t, 0, R)
+    packed = pack_states(st)
+    hdr, ev = encode_rows(packed, 3000, t.refseq)
+    hd = Handle(0)
+    try:
+        genes = [(1, 3001)]
+        j = Juliet(3000, genes, refseq=t.refseq, mode_phasing=True, min_perc=0.5, handle=hd)
+        a = j.run_host(packed, want_hap_id=True)
+        col_a, codon_a = j.get_counts()
+        with pytest.raises(_lib.MsError):
+            j.run_events_host(hdr, ev)          # no base yet
+        j.set_base(t.refseq)
+        b = j.run_events_host(hdr, ev, want_hap_id=True)
+        col_b, codon_b = j.get_counts()
+        assert np.array_equal(col_a, col_b) and np.array_equal(codon_a, codon_b)
+        mask = np.array([(int(j.start_mask[i >> 5]) >> (i & 31)) & 1 for i in range(3000)], dtype=np.uint8)
+        ocol, ocodon = oracle.pileup(st, mask, nthreads=8)
+        ocol[:, 6] = 0
+        assert np.array_equal(col_b, ocol) and np.array_equal(codon_b, ocodon)
+        assert [(v.col, v.codon, v.count, v.coverage, v.pvalue) for v in a.variants] == [(v.col, v.codon, v.count, v.coverage, v.pvalue) for v in b.variants]
+        assert len(b.variants) >= 8 and a.keys == b.keys
+        assert np.array_equal(a.haplotypes.patterns, b.haplotypes.patterns) and np.array_equal(a.haplotypes.counts, b.haplotypes.counts)
+        assert a.haplotypes.counters == b.haplotypes.counters and np.array_equal(a.haplotypes.hap_id, b.haplotypes.hap_id)
+        # rows encoded against another base are rejected, not mis-expanded
+        other = np.roll(j.base, 1)
+        hdr2, ev2 = encode_rows(packed[:100], 3000, other)
+        with pytest.raises(_lib.MsError, match="different base"):
+            j.run_events_host(hdr2, ev2)
+        # zero reads
+        hdr0, ev0 = encode_rows(packed[:0], 3000, t.refseq)
+        z = j.run_events_host(hdr0, ev0)
+        assert len(z.variants) == 0
+    finally:
+        hd.close()
