@@ -95,8 +95,7 @@ constexpr int kExpandMaxWarps = 16;
 
 // One warp per read.  The row is built in the warp's shared-memory slice: base planes masked by the span, then the
 // events are applied 32 at a time -- a warp scan turns the deltas into columns, lanes whose events fall into the same
-// 32-column block (consecutive lanes: the events are sorted) OR their one-bit plane masks with a group reduction
-// (MATCH + REDUX), and one lane per block does the only read-modify-write.  No atomics; the finished row leaves with
+// 32-column block (consecutive lanes: the events are sorted) take turns, one read-modify-write per event.  No atomics; the finished row leaves with
 // 16-byte stores, 512 contiguous bytes per warp instruction.
 __global__ void __launch_bounds__(kExpandMaxWarps * 32) expand_events_kernel(const ms_read_hdr* __restrict__ hdr,
                                                                            const uint16_t* __restrict__ events, int64_t R,
@@ -142,19 +141,23 @@ __global__ void __launch_bounds__(kExpandMaxWarps * 32) expand_events_kernel(con
                 const uint32_t basenib = (c >= begin && c < end) ? (((bp.x >> bit) & 1u) | (((bp.y >> bit) & 1u) << 1)) : 7u;
                 x = (e & 15u) ^ basenib;
             }
-            uint32_t m0 = (x & 1u) << bit, m1 = ((x >> 1) & 1u) << bit, m2 = ((x >> 2) & 1u) << bit, m3 = ((x >> 3) & 1u) << bit;
-            const uint32_t key = ok ? static_cast<uint32_t>(blk) : (0x80000000u | static_cast<uint32_t>(lane));
-            const uint32_t peers = __match_any_sync(0xffffffffu, key);
-            m0 = __reduce_or_sync(peers, m0);
-            m1 = __reduce_or_sync(peers, m1);
-            m2 = __reduce_or_sync(peers, m2);
-            m3 = __reduce_or_sync(peers, m3);
-            if (ok && lane == __ffs(peers) - 1 && (m0 | m1 | m2 | m3)) {
-                uint4 v = row[blk];
-                v.x ^= m0; v.y ^= m1; v.z ^= m2; v.w ^= m3;
-                row[blk] = v;
+            // lanes of one 32-column block are consecutive (the events are sorted): a lane's position inside its block's run comes
+            // from one ballot of the run heads; the lanes then update shared memory in rounds, round k = the k-th event of every
+            // block, so no two lanes of a round touch the same block.  Runs are 1-3 lanes long at CCS error rates.  (MATCH.ANY and
+            // REDUX on per-group masks both serialise over the ~25 distinct groups of a batch and were ~30x slower.)
+            const int32_t key = ok ? blk : -1;
+            const int32_t left = __shfl_up_sync(0xffffffffu, key, 1);
+            const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || key != left);
+            const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+            const int rank = (ok && x) ? lane - start : -1;
+            for (int k = 0; __any_sync(0xffffffffu, rank >= k); ++k) {
+                if (rank == k) {
+                    uint4 v = row[blk];
+                    v.x ^= (x & 1u) << bit; v.y ^= ((x >> 1) & 1u) << bit; v.z ^= ((x >> 2) & 1u) << bit; v.w ^= ((x >> 3) & 1u) << bit;
+                    row[blk] = v;
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
         uint4* dst = out + static_cast<size_t>(r) * nblk;
         for (int32_t b = lane; b < nblk; b += 32) dst[b] = row[b];
@@ -168,7 +171,8 @@ static int expand_launch(ms_handle* h, const ms_read_hdr* d_hdr, const uint16_t*
     const int row_bytes = h->nblk * 16;
     int wpc = std::min(ms::kExpandMaxWarps, std::max(1, (64 << 10) / row_bytes));
     const int64_t want = (R + wpc - 1) / wpc;
-    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(h->num_sms) * 6)));
+    const int ctas_per_sm = std::max(1, 64 / wpc);      // 64 resident warps per SM (40 registers), grid-stride over the reads
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(h->num_sms) * ctas_per_sm)));
     MS_STAGE_BEGIN(h, MS_STAGE_EXPAND);
     ms::expand_events_kernel<<<grid, wpc * 32, wpc * row_bytes, h->stream>>>(d_hdr, d_events, R, h->nblk, h->b_base.as<uint2>(),
                                                                              reinterpret_cast<uint4*>(d_packed));
