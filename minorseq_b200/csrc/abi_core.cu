@@ -64,9 +64,11 @@ int ms_create(int device, ms_handle** out) {
 
 static void free_layout(ms_handle* h) {
     cudaFree(h->d_counts); cudaFree(h->d_start); cudaFree(h->d_pivot); cudaFree(h->d_pivot_state);
-    cudaFree(h->d_part_col); cudaFree(h->d_part_piv);
+    cudaFree(h->d_pivot2); cudaFree(h->d_pivot2_state);
+    cudaFree(h->d_part_col); cudaFree(h->d_part_piv); cudaFree(h->d_part_piv2);
     h->d_counts = nullptr; h->d_start = nullptr; h->d_pivot = nullptr; h->d_pivot_state = nullptr;
-    h->d_part_col = h->d_part_piv = nullptr;
+    h->d_pivot2 = nullptr; h->d_pivot2_state = nullptr;
+    h->d_part_col = h->d_part_piv = h->d_part_piv2 = nullptr;
 }
 
 void ms_phase_free_internal(ms_handle* h);
@@ -236,23 +238,12 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
     if (start_mask)
         for (int32_t j = 0; j + 2 < L; ++j) nstarts += (start_mask[j >> 5] >> (j & 31)) & 1u;
     h->log_mode = start_mask != nullptr && nstarts * 20 > static_cast<int64_t>(L) * 9;   // > 0.45 starts per column
-    const int merge_bytes = (h->groups - 1) * 8 * ms::kPlanes * W * 32 * 4 + 64;  // end-of-kernel group merge reuses the ring
+    const int merge_bytes = (h->groups - 1) * 9 * ms::kPlanes * W * 32 * 4 + 64;  // end-of-kernel group merge reuses the ring (up to 9 masks)
     h->stages = std::max(3, std::min(8, budget / h->stage_bytes));
     h->smem_bytes = ms::kPileupSmemHeader + std::max(h->stages * h->stage_bytes + 16, merge_bytes);
-    // DENSE variant of the in-kernel rare path (pileup.cu, exception_add): one second-codon counter per column in
-    // shared memory behind the ring; chosen at the first pile-up after this call from the pivot sample's statistics
+    // DENSE variant (pileup.cu, read_masks): a second bit-sliced codon count per start column; chosen at the first pile-up
+    // after this call from the pivot sample's statistics
     h->dense_known = false; h->dense = false;
-    h->stages_dense = 0; h->alt_off = 0; h->smem_bytes_dense = 0;
-    if (start_mask && !h->log_mode) {
-        const int alt_bytes = nblk * 32 * 4;
-        const int stages_d = std::min(8, (budget - alt_bytes - 128) / h->stage_bytes);
-        if (stages_d >= 3) {
-            const int ring_bytes = (std::max(stages_d * h->stage_bytes + 16, merge_bytes) + 127) & ~127;
-            h->stages_dense = stages_d;
-            h->alt_off = ms::kPileupSmemHeader + ring_bytes;
-            h->smem_bytes_dense = h->alt_off + alt_bytes;
-        }
-    }
     if (h->smem_bytes > h->max_smem) MS_FAIL(h, MS_ERR_ARG, "row too long for the shared-memory ring");
     const size_t ncounts = static_cast<size_t>(L) * 72;
     MS_CUDA(h, cudaMalloc(&h->d_counts, ncounts * 4));
@@ -260,7 +251,11 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
     MS_CUDA(h, cudaMalloc(&h->d_start, nblk * 4));
     MS_CUDA(h, cudaMalloc(&h->d_pivot, (nblk + 1) * sizeof(uint2)));
     MS_CUDA(h, cudaMalloc(&h->d_pivot_state, nblk * 32 + 16));   // + {non-pivot, all} sample statistics behind the states
+    MS_CUDA(h, cudaMalloc(&h->d_pivot2, (nblk + 1) * sizeof(uint2)));
+    MS_CUDA(h, cudaMalloc(&h->d_pivot2_state, nblk * 32 + 16));
     MS_CUDA(h, cudaMemsetAsync(h->d_pivot, 0, (nblk + 1) * sizeof(uint2), h->stream));
+    MS_CUDA(h, cudaMemsetAsync(h->d_pivot2, 0, (nblk + 1) * sizeof(uint2), h->stream));
+    MS_CUDA(h, cudaMemsetAsync(h->d_pivot2_state, 0, nblk * 32 + 16, h->stream));
     MS_CUDA(h, cudaMemsetAsync(h->d_pivot_state, 0, nblk * 32 + 16, h->stream));
     h->h_start.assign(nblk, 0u);
     if (start_mask) {
@@ -272,6 +267,7 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
     const size_t slices = static_cast<size_t>(h->num_sms);
     MS_CUDA(h, cudaMalloc(&h->d_part_col, slices * nblk * 256 * 4));
     MS_CUDA(h, cudaMalloc(&h->d_part_piv, slices * nblk * 32 * 4));
+    MS_CUDA(h, cudaMalloc(&h->d_part_piv2, slices * nblk * 32 * 4));
     MS_CUDA(h, cudaStreamSynchronize(h->stream));
     return MS_OK;
 }
@@ -301,11 +297,11 @@ int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
         return MS_OK;
     }
     if (h->count_codons && !h->have_pivot) {
-        const bool want_stat = !h->dense_known && h->stages_dense > 0;
+        const bool want_stat = !h->dense_known;
         uint32_t* dense_stat = reinterpret_cast<uint32_t*>(h->d_pivot_state + static_cast<size_t>(h->nblk) * 32 + 8);
         if (want_stat) MS_CUDA(h, cudaMemsetAsync(dense_stat, 0, 8, h->stream));
         ms::pivot_sample_kernel<<<h->nblk, 256, 0, h->stream>>>(d_packed, R, h->nblk, h->L, h->d_pivot, h->d_pivot_state,
-                                                               want_stat ? dense_stat : nullptr);
+                                                               h->d_pivot2, h->d_pivot2_state, want_stat ? dense_stat : nullptr);
         if (want_stat) {
             // once per layout: are non-pivot bases the exception (sequencing errors, low-frequency variants) or the rule
             // (dense high-frequency variants, > 2 % of the sampled clean bases)?  One 8-byte read decides which K1 runs.
@@ -322,11 +318,10 @@ int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     a.packed = d_packed; a.R = R; a.L = h->L; a.nblk = h->nblk;
     a.warps_per_group = h->wpg; a.groups = h->groups;
     a.nseg = h->nseg; a.seg_len = h->seg_len;
-    const bool dense = h->count_codons && h->dense && h->stages_dense > 0;
-    a.stages = dense ? h->stages_dense : h->stages; a.stage_bytes = h->stage_bytes;
-    a.alt_off = dense ? static_cast<uint32_t>(h->alt_off) : 0u;
-    a.pivot = h->d_pivot; a.start_mask = h->d_start; a.codon = codon;
-    a.part_col = h->d_part_col; a.part_piv = h->d_part_piv;
+    const bool dense = h->count_codons && h->dense;
+    a.stages = h->stages; a.stage_bytes = h->stage_bytes;
+    a.pivot = h->d_pivot; a.pivot2 = h->d_pivot2; a.start_mask = h->d_start; a.codon = codon;
+    a.part_col = h->d_part_col; a.part_piv = h->d_part_piv; a.part_piv2 = h->d_part_piv2;
     const int mode = !h->count_codons ? ms::kModeFuse : (h->count_ins ? ms::kModeBoth : ms::kModeJuliet);
     const int64_t T = static_cast<int64_t>(h->groups) * 8;
     const int64_t ntiles = (R + T - 1) / T;
@@ -344,12 +339,12 @@ int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     }
     a.exc_list = h->b_exc_list.as<uint32_t>(); a.exc_cnt = h->b_exc_cnt.as<uint32_t>(); a.exc_cap = exc_cap; a.exc_lists = nlists;
     if (h->timing) MS_CUDA(h, cudaEventRecord(h->ev_k1[0], h->stream));
-    ms::pileup_launch(mode, dense, grid, threads, dense ? h->smem_bytes_dense : h->smem_bytes, h->stream, a);
+    ms::pileup_launch(mode, dense, grid, threads, h->smem_bytes, h->stream, a);
     if (h->timing) { MS_CUDA(h, cudaEventRecord(h->ev_k1[1], h->stream)); h->k1_reads = R; }
-    if (log_mode) { ms::pileup_exceptions_launch(grid, threads, h->stream, a); h->launches++; }
+    if (log_mode) { ms::pileup_exceptions_launch(dense, grid, threads, h->stream, a); h->launches++; }
     const int64_t nfin = static_cast<int64_t>(h->L) * 9 * 4;
     ms::pileup_finalize_kernel<<<static_cast<int>((nfin + 255) / 256), 256, 0, h->stream>>>(
-        h->d_part_col, h->d_part_piv, grid, h->nblk, h->L, h->d_pivot_state, h->d_start, col, codon,
+        h->d_part_col, h->d_part_piv, dense ? h->d_part_piv2 : nullptr, grid, h->nblk, h->L, h->d_pivot_state, h->d_pivot2_state, h->d_start, col, codon,
         h->count_codons ? 1 : 0, h->nseg, h->seg_len);
     h->launches += 2;
     MS_CUDA(h, cudaGetLastError());

@@ -47,13 +47,14 @@ struct ms_handle {
     uint32_t* d_start = nullptr;   // [nblk]
     uint2* d_pivot = nullptr;      // [nblk+1]
     uint8_t* d_pivot_state = nullptr;  // [nblk*32 + 2]
-    uint32_t *d_part_col = nullptr, *d_part_piv = nullptr;
+    uint2* d_pivot2 = nullptr;         // [nblk+1] designated base of the DENSE kernel (runner-up of the sample where frequent)
+    uint8_t* d_pivot2_state = nullptr;
+    uint32_t *d_part_col = nullptr, *d_part_piv = nullptr, *d_part_piv2 = nullptr;
     int32_t groups = 1, wpg = 1, stages = 2, stage_bytes = 0, smem_bytes = 0;
     int32_t nseg = 1, seg_len = 0;   // column segments of K1 (abi_core.cu, ms_set_layout)
     bool have_pivot = false;
     bool log_mode = false;       // K1 logs flagged chunks for codon_exception_kernel (dense start masks)
-    // DENSE variant of K1 (second-codon counters in shared memory): its own ring depth and shared-memory size
-    int32_t alt_off = 0, stages_dense = 0, smem_bytes_dense = 0;
+    // DENSE variant of K1 (a second bit-sliced codon count): picked once per layout from the pivot sample
     bool dense_known = false, dense = false;
     DevBuf b_exc_list, b_exc_cnt;  // K1's per-thread exception logs
     std::vector<uint32_t> h_start;

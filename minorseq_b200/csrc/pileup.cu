@@ -63,13 +63,16 @@ __device__ __forceinline__ void csa(uint32_t& h, uint32_t& l, uint32_t a, uint32
     l = u ^ c;
 }
 
-template <int MODE>
+// DENSE: a second bit-sliced codon count per start column -- the "designated" codon (runner-up base of the pivot sample
+// wherever it holds > 2 % of the sample, the pivot base elsewhere), see the DENSE notes at read_masks.
+template <int MODE, bool DENSE>
 struct Traits {
-    static constexpr int NM = MODE == kModeBoth ? 8 : 7;
+    static constexpr int NM = (MODE == kModeBoth ? 8 : 7) + (DENSE ? 1 : 0);
     static constexpr bool CODON = MODE != kModeFuse;
     static constexpr bool INS = MODE != kModeJuliet;
     static constexpr int iINS = 6;
     static constexpr int iNP = MODE == kModeBoth ? 7 : 6;  // "not the pivot codon"
+    static constexpr int iND = iNP + 1;                    // "not the designated codon" (DENSE only)
 };
 
 // ---------------------------------------------------------------- per-thread state
@@ -94,6 +97,7 @@ __device__ __forceinline__ void ripple(Vert<NM>& v, int i, int level, uint32_t x
 // Per-thread constants for codon work
 struct CodonCtx {
     uint32_t r0, r1, r0n, r1n;  // pivot planes of this block and the next (the latter only for the rare path)
+    uint32_t d0, d1, d0n, d1n;  // DENSE: planes of the designated base (second pivot where there is one)
     uint32_t start;             // codon start columns in this block
     uint32_t cols;              // columns of this block that belong to a codon starting in this block
     uint32_t lookcols;          // same for the first two columns of the next block (bits 0, 1)
@@ -101,12 +105,18 @@ struct CodonCtx {
 };
 
 // exact masks (rare path): "codon starting at column j is not the clean pivot codon" and the clean ones among them
+template <bool DENSE>
 __device__ __forceinline__ void codon_masks(const uint4& q, const uint4& n, const CodonCtx& cx, uint32_t& np, uint32_t& e) {
     const uint32_t X = ((q.x ^ cx.r0) | q.z) | (q.y ^ cx.r1);  // column is not the clean pivot base
     const uint32_t Xn = ((n.x ^ cx.r0n) | n.z) | (n.y ^ cx.r1n);
     np = X | __funnelshift_r(X, Xn, 1) | __funnelshift_r(X, Xn, 2);
     const uint32_t dirty = q.z | __funnelshift_r(q.z, n.z, 1) | __funnelshift_r(q.z, n.z, 2);
     e = ~dirty & np & cx.start;  // clean codon that is not the pivot codon: rare
+    if (DENSE) {                 // ... and not the designated codon either (that one is counted bit-sliced as well)
+        const uint32_t D = ((q.x ^ cx.d0) | q.z) | (q.y ^ cx.d1);
+        const uint32_t Dn = ((n.x ^ cx.d0n) | n.z) | (n.y ^ cx.d1n);
+        e &= D | __funnelshift_r(D, Dn, 1) | __funnelshift_r(D, Dn, 2);
+    }
 }
 
 // Build the one-bit masks of one read for this thread's 32 columns.
@@ -115,10 +125,14 @@ __device__ __forceinline__ void codon_masks(const uint4& q, const uint4& n, cons
 // warp but the last of a row is a pure look-ahead provider, see the lane mapping in pileup_body).
 // A read is flagged for the exact rare path when a clean non-pivot BASE sits in a column that
 // belongs to one of this block's codons -- a superset of "has a clean non-pivot codon".
-template <int MODE>
-__device__ __forceinline__ void read_masks(uint32_t addr, const CodonCtx& cx, uint32_t (&m)[Traits<MODE>::NM], uint32_t& pm,
+// DENSE (frequent variants: a second codon in a sizeable share of the reads at many positions -- phasing stress data): the
+// designated codon is counted exactly like the pivot codon, as one more carry-save mask, and a read is flagged for the rare
+// path only when one of this block's start columns holds a clean codon that is NEITHER (exact, three more LOP3/SHF than the
+// conservative trigger).  Results stay exact for any choice of the two bases per column.
+template <int MODE, bool DENSE>
+__device__ __forceinline__ void read_masks(uint32_t addr, const CodonCtx& cx, uint32_t (&m)[Traits<MODE, DENSE>::NM], uint32_t& pm,
                                            uint32_t rdbit) {
-    using T = Traits<MODE>;
+    using T = Traits<MODE, DENSE>;
     const uint4 q = lds128(addr);
     m[0] = q.x;
     m[1] = q.y;
@@ -131,52 +145,33 @@ __device__ __forceinline__ void read_masks(uint32_t addr, const CodonCtx& cx, ui
         const uint32_t X = ((q.x ^ cx.r0) | q.z) | (q.y ^ cx.r1);  // column is not the clean pivot base
         const uint32_t Xn = __shfl_down_sync(0xffffffffu, X, 1);
         const uint32_t zn = __shfl_down_sync(0xffffffffu, q.z, 1);
-        m[T::iNP] = X | __funnelshift_r(X, Xn, 1) | __funnelshift_r(X, Xn, 2);
-        const uint32_t trig = (X & ~q.z & cx.cols) | (Xn & ~zn & cx.lookcols);
-        if (trig) pm |= rdbit;
-    }
-}
-
-// One clean non-pivot codon (start column j of this block) goes to the histogram.  A frequent minor variant makes
-// the SAME (column, codon) bin come up in a sizeable share of all reads -- in a phasing stress run in half of them at
-// every site -- and global REDs on a few thousand hot addresses then dominate the kernel.  So every CTA keeps one
-// second-codon counter per column in shared memory, word = codon << 26 | count: the first non-pivot codon seen at a
-// column claims it, later sightings of that codon are shared-memory REDs, and only other codons (sequencing errors)
-// go to global memory.  The counters are added to the global histogram once, at the end of the kernel.
-constexpr uint32_t kAltEmpty = 0xFFFFFFFFu;
-// This costs the ordinary kernel 3-8 % (code generation at its register limit, 12 KB less L1), so it is a separate
-// instantiation (DENSE) that the launcher picks when the pivot sample finds more than 2 % non-pivot bases.
-// alt: shared address of this block's 32 counters.
-__device__ __forceinline__ void exception_add(uint32_t* codon, uint32_t alt, int j, uint32_t cod) {
-    {
-        const uint32_t addr = alt + static_cast<uint32_t>(j) * 4u;
-        uint32_t v = lds32(addr);
-        if (v == kAltEmpty) {
-            asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(v) : "r"(addr), "r"(kAltEmpty), "r"((cod << 26) | 1u) : "memory");
-            if (v == kAltEmpty) return;   // claimed, count 1
-        }
-        if ((v >> 26) == cod) {
-            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
-            return;
+        const uint32_t np = X | __funnelshift_r(X, Xn, 1) | __funnelshift_r(X, Xn, 2);
+        m[T::iNP] = np;
+        if (DENSE) {
+            const uint32_t D = ((q.x ^ cx.d0) | q.z) | (q.y ^ cx.d1);  // column is not the clean designated base
+            const uint32_t Dn = __shfl_down_sync(0xffffffffu, D, 1);
+            const uint32_t nd = D | __funnelshift_r(D, Dn, 1) | __funnelshift_r(D, Dn, 2);
+            m[T::iND] = nd;
+            const uint32_t dirty = q.z | __funnelshift_r(q.z, zn, 1) | __funnelshift_r(q.z, zn, 2);
+            if (np & nd & ~dirty & cx.start) pm |= rdbit;
+        } else {
+            const uint32_t trig = (X & ~q.z & cx.cols) | (Xn & ~zn & cx.lookcols);
+            if (trig) pm |= rdbit;
         }
     }
-    atomicAdd(codon + (j * 64 + cod), 1u);
 }
 
 // Rare path: the reads flagged in pm may carry clean non-pivot codons; re-read them from the slot
 // (still owned by this row-group) and add each such codon to the global 64-bin histogram.
 template <bool DENSE>
-__device__ __forceinline__ void codon_exceptions(uint32_t addr, uint32_t row_bytes, uint32_t pm, const CodonCtx& cx,
-                                                 const uint32_t* codon_base, uint32_t alt0) {
-    // this block's second-codon counters (block index from the histogram pointer); compiled out of the ordinary kernel
-    const uint32_t alt = DENSE ? alt0 + static_cast<uint32_t>((cx.codon - codon_base) >> 11) * 128u : 0u;
+__device__ __forceinline__ void codon_exceptions(uint32_t addr, uint32_t row_bytes, uint32_t pm, const CodonCtx& cx) {
     while (pm) {
         const int rd = __ffs(pm) - 1;
         pm &= pm - 1;
         const uint32_t a = addr + static_cast<uint32_t>(rd) * row_bytes;
         const uint4 q = lds128(a), n = lds128(a + 16);
         uint32_t np, e;
-        codon_masks(q, n, cx, np, e);
+        codon_masks<DENSE>(q, n, cx, np, e);
         while (e) {
             const int j = __ffs(e) - 1;
             e &= e - 1;
@@ -184,37 +179,36 @@ __device__ __forceinline__ void codon_exceptions(uint32_t addr, uint32_t row_byt
             const uint32_t b1 = __funnelshift_r(q.y, n.y, j) & 7u;  // bit1 of the 3 states
             const uint32_t cod = ((b0 & 1u) << 4) | ((b1 & 1u) << 5) | ((b0 & 2u) << 1) | ((b1 & 2u) << 2) |
                                  ((b0 & 4u) >> 2) | ((b1 & 4u) >> 1);
-            if (DENSE) exception_add(cx.codon, alt, j, cod);
-            else atomicAdd(cx.codon + (j * 64 + cod), 1u);
+            atomicAdd(cx.codon + (j * 64 + cod), 1u);
         }
     }
 }
 
-template <int MODE>
+template <int MODE, bool DENSE>
 __device__ __forceinline__ uint32_t block8(uint32_t addr, uint32_t row_bytes, const CodonCtx& cx,
-                                           Vert<Traits<MODE>::NM>& v, uint32_t bi) {
-    constexpr int NM = Traits<MODE>::NM;
+                                           Vert<Traits<MODE, DENSE>::NM>& v, uint32_t bi) {
+    constexpr int NM = Traits<MODE, DENSE>::NM;
     uint32_t m0[NM], m1[NM], twosA[NM], twosB[NM], foursA[NM], foursB[NM];
     uint32_t pm = 0;
     // reads 0..3
-    read_masks<MODE>(addr, cx, m0, pm, 1u);
-    read_masks<MODE>(addr + row_bytes, cx, m1, pm, 2u);
+    read_masks<MODE, DENSE>(addr, cx, m0, pm, 1u);
+    read_masks<MODE, DENSE>(addr + row_bytes, cx, m1, pm, 2u);
 #pragma unroll
     for (int i = 0; i < NM; ++i) csa(twosA[i], v.c[i][0], v.c[i][0], m0[i], m1[i]);
-    read_masks<MODE>(addr + 2 * row_bytes, cx, m0, pm, 4u);
-    read_masks<MODE>(addr + 3 * row_bytes, cx, m1, pm, 8u);
+    read_masks<MODE, DENSE>(addr + 2 * row_bytes, cx, m0, pm, 4u);
+    read_masks<MODE, DENSE>(addr + 3 * row_bytes, cx, m1, pm, 8u);
 #pragma unroll
     for (int i = 0; i < NM; ++i) {
         csa(twosB[i], v.c[i][0], v.c[i][0], m0[i], m1[i]);
         csa(foursA[i], v.c[i][1], v.c[i][1], twosA[i], twosB[i]);
     }
     // reads 4..7
-    read_masks<MODE>(addr + 4 * row_bytes, cx, m0, pm, 16u);
-    read_masks<MODE>(addr + 5 * row_bytes, cx, m1, pm, 32u);
+    read_masks<MODE, DENSE>(addr + 4 * row_bytes, cx, m0, pm, 16u);
+    read_masks<MODE, DENSE>(addr + 5 * row_bytes, cx, m1, pm, 32u);
 #pragma unroll
     for (int i = 0; i < NM; ++i) csa(twosA[i], v.c[i][0], v.c[i][0], m0[i], m1[i]);
-    read_masks<MODE>(addr + 6 * row_bytes, cx, m0, pm, 64u);
-    read_masks<MODE>(addr + 7 * row_bytes, cx, m1, pm, 128u);
+    read_masks<MODE, DENSE>(addr + 6 * row_bytes, cx, m0, pm, 64u);
+    read_masks<MODE, DENSE>(addr + 7 * row_bytes, cx, m1, pm, 128u);
 #pragma unroll
     for (int i = 0; i < NM; ++i) {
         csa(twosB[i], v.c[i][0], v.c[i][0], m0[i], m1[i]);
@@ -262,9 +256,9 @@ struct ExcLog {
 // one entry per 8-read chunk with any flagged read: (first read of the chunk / 8) << 8 | flag byte
 template <bool DENSE>
 __device__ __forceinline__ void log_or_handle(uint32_t pm, uint32_t read0, ExcLog& lg, uint32_t addr, uint32_t row_bytes,
-                                              const CodonCtx& cx, const uint32_t* codon_base, uint32_t alt0) {
+                                              const CodonCtx& cx) {
     if (lg.cnt < lg.cap) lg.list[lg.cnt++] = ((read0 >> 3) << 8) | pm;
-    else codon_exceptions<DENSE>(addr, row_bytes, pm, cx, codon_base, alt0);
+    else codon_exceptions<DENSE>(addr, row_bytes, pm, cx);
 }
 
 // ---------------------------------------------------------------- flush (cold path)
@@ -287,11 +281,11 @@ __device__ __forceinline__ void transpose16x2(uint32_t (&a)[16]) {
 // planes: this thread's counters (pendings already folded), [NM][kPlanes] in local memory.
 // Adds the other groups' planes from shared memory (bit-sliced ripple-carry), transposes to
 // per-column integers and stores / adds them into the CTA's slice.
-template <int MODE>
+template <int MODE, bool DENSE>
 __device__ __noinline__ void emit_slice(const uint32_t* planes, uint32_t merge_base, int other_groups, uint32_t group_stride,
-                                        uint32_t thread_stride, uint32_t n, uint32_t start, uint32_t* pc, uint32_t* pp,
+                                        uint32_t thread_stride, uint32_t n, uint32_t start, uint32_t* pc, uint32_t* pp, uint32_t* pd,
                                         bool add) {
-    using T = Traits<MODE>;
+    using T = Traits<MODE, DENSE>;
     constexpr int NM = T::NM;
     uint32_t tr[NM][16];
 #pragma unroll
@@ -347,6 +341,11 @@ __device__ __noinline__ void emit_slice(const uint32_t* planes, uint32_t merge_b
                 uint32_t piv = ((start >> colj) & 1u) ? n - s[T::iNP] : 0u;
                 if (add) piv += pp[colj];
                 pp[colj] = piv;
+                if (DENSE) {
+                    uint32_t des = ((start >> colj) & 1u) ? n - s[T::iND] : 0u;
+                    if (add) des += pd[colj];
+                    pd[colj] = des;
+                }
             }
         }
     }
@@ -374,7 +373,7 @@ __device__ __forceinline__ void clear(Vert<NM>& v) {
 
 template <int MODE, bool DENSE, bool SEG>
 __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
-    using T = Traits<MODE>;
+    using T = Traits<MODE, DENSE>;
     constexpr int NM = T::NM;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -409,11 +408,6 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    // second-codon counters, one per column: only when the pivot sample says that non-pivot bases are common (> 2 % of
-    // the clean bases); on ordinary data the extra shared-memory probe per rare codon costs more than it saves
-    const uint32_t alt0 = DENSE ? bar0 + a.alt_off : 0u;   // second-codon counters, one per column
-    if (DENSE)
-        for (int i = threadIdx.x; i < a.nblk * 32; i += blockDim.x) sts32(alt0 + 4u * i, kAltEmpty);
     __syncthreads();
 
     // ---------------- consumers: group g of W warps walks its 8 reads of every tile
@@ -431,10 +425,15 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     CodonCtx cx;
     cx.codon = a.codon + static_cast<size_t>(blk) * 32 * 64;
     cx.r0 = cx.r1 = cx.r0n = cx.r1n = 0;
+    cx.d0 = cx.d1 = cx.d0n = cx.d1n = 0;
     cx.start = cx.cols = cx.lookcols = 0;
     if (T::CODON) {
         const uint2 p = a.pivot[blk], pn = a.pivot[blk + 1];
         cx.r0 = p.x; cx.r1 = p.y; cx.r0n = pn.x; cx.r1n = pn.y;
+        if (DENSE) {
+            const uint2 d = a.pivot2[blk], dn = a.pivot2[blk + 1];
+            cx.d0 = d.x; cx.d1 = d.y; cx.d0n = dn.x; cx.d1n = dn.y;
+        }
         cx.start = active ? a.start_mask[blk] : 0u;
         cx.cols = cx.start | (cx.start << 1) | (cx.start << 2);
         cx.lookcols = ((cx.start >> 30) ? 1u : 0u) | ((cx.start >> 31) ? 2u : 0u);
@@ -452,6 +451,7 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     bool mid = false;
     uint32_t* pc = a.part_col + (static_cast<size_t>(blockIdx.x) * a.nblk + blk) * 256;
     uint32_t* pp = a.part_piv + (static_cast<size_t>(blockIdx.x) * a.nblk + blk) * 32;
+    uint32_t* pd = DENSE ? a.part_piv2 + (static_cast<size_t>(blockIdx.x) * a.nblk + blk) * 32 : nullptr;
     const int nct = ncw * 32;
 
     // Chunk rings without a producer warp.  Every row-group owns S slots of 8 reads; the warp of the
@@ -491,7 +491,7 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
 #pragma unroll
                 for (int k = 0; k < kPlanes; ++k) planes[i * kPlanes + k] = v.c[i][k];
             for (int g = 0; g < G; ++g) {
-                if (g == group && active) emit_slice<MODE>(planes, 0u, 0, 0u, 0u, n, cx.start, pc, pp, mid || g > 0);
+                if (g == group && active) emit_slice<MODE, DENSE>(planes, 0u, 0, 0u, 0u, n, cx.start, pc, pp, pd, mid || g > 0);
                 consumer_barrier(nct);
             }
             clear(v);
@@ -504,18 +504,18 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         if (nv > 0) mbar_wait(bar0 + 8 * slot, phase);
         const uint32_t addr = data0 + slot * chunk_bytes + static_cast<uint32_t>(lblk) * 16u;
         if (nv == 8) {
-            const uint32_t pm = block8<MODE>(addr, row_bytes, cx, v, bi);
-            if (T::CODON && pm) log_or_handle<DENSE>(pm, static_cast<uint32_t>(r0), lg, addr, row_bytes, cx, a.codon, alt0);
+            const uint32_t pm = block8<MODE, DENSE>(addr, row_bytes, cx, v, bi);
+            if (T::CODON && pm) log_or_handle<DENSE>(pm, static_cast<uint32_t>(r0), lg, addr, row_bytes, cx);
             ++bi;
             n += 8;
         } else {
             for (int i = 0; i < nv; ++i) {
                 uint32_t m[NM];
                 uint32_t pm = 0;
-                read_masks<MODE>(addr + i * row_bytes, cx, m, pm, 1u);
+                read_masks<MODE, DENSE>(addr + i * row_bytes, cx, m, pm, 1u);
 #pragma unroll
                 for (int q = 0; q < NM; ++q) ripple(v, q, 0, m[q]);
-                if (T::CODON && pm) log_or_handle<DENSE>(1u << i, static_cast<uint32_t>(r0), lg, addr, row_bytes, cx, a.codon, alt0);
+                if (T::CODON && pm) log_or_handle<DENSE>(1u << i, static_cast<uint32_t>(r0), lg, addr, row_bytes, cx);
                 ++n;
             }
         }
@@ -541,12 +541,6 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     fold_pendings(v, bi);
     // all tiles are consumed and every bulk copy has landed, so the stage ring is free to reuse
     consumer_barrier(nct);
-    if (DENSE) {   // the CTA's second-codon counters join the global histogram
-        for (int i = threadIdx.x; i < a.nblk * 32; i += nct) {
-            const uint32_t v = lds32(alt0 + 4u * i);
-            if (v != kAltEmpty) atomicAdd(a.codon + (static_cast<size_t>(i) * 64 + (v >> 26)), v & 0x03FFFFFFu);
-        }
-    }
     const uint32_t tg = static_cast<uint32_t>(W) * 32u;           // threads per group
     const uint32_t thread_stride = tg * 4u;                       // bytes between planes
     const uint32_t group_stride = static_cast<uint32_t>(NM * kPlanes) * thread_stride;
@@ -568,8 +562,8 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         for (int i = 0; i < NM; ++i)
 #pragma unroll
             for (int k = 0; k < kPlanes; ++k) planes[i * kPlanes + k] = v.c[i][k];
-        emit_slice<MODE>(planes, data0 + static_cast<uint32_t>(tig) * 4u, G - 1, group_stride, thread_stride, ntot, cx.start,
-                         pc, pp, mid);
+        emit_slice<MODE, DENSE>(planes, data0 + static_cast<uint32_t>(tig) * 4u, G - 1, group_stride, thread_stride, ntot, cx.start,
+                                pc, pp, pd, mid);
     }
 }
 
@@ -615,6 +609,7 @@ void pileup_launch(int mode, bool dense, int grid, int threads, int smem, cudaSt
 // One warp per logged list: every entry is a read whose block may hold clean non-pivot codons.  The
 // exact masks are recomputed from global memory (one 32-byte sector per entry) and each such codon
 // goes to the 64-bin histogram with a RED.  ~1.6 % of the (read, block) pairs at CCS error rates.
+template <bool DENSE>
 __global__ void __launch_bounds__(256) codon_exception_kernel(PileupArgs a, int threads_per_cta) {
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -634,6 +629,11 @@ __global__ void __launch_bounds__(256) codon_exception_kernel(PileupArgs a, int 
     CodonCtx cx;
     const uint2 p = a.pivot[blk], pn = a.pivot[blk + 1];
     cx.r0 = p.x; cx.r1 = p.y; cx.r0n = pn.x; cx.r1n = pn.y;
+    cx.d0 = cx.d1 = cx.d0n = cx.d1n = 0;
+    if (DENSE) {
+        const uint2 d = a.pivot2[blk], dn = a.pivot2[blk + 1];
+        cx.d0 = d.x; cx.d1 = d.y; cx.d0n = dn.x; cx.d1n = dn.y;
+    }
     cx.start = a.start_mask[blk];
     cx.cols = cx.lookcols = 0;
     cx.codon = a.codon + static_cast<size_t>(blk) * 32 * 64;
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(256) codon_exception_kernel(PileupArgs a, int 
                 q = row[blk];
                 n = blk + 1 < a.nblk ? row[blk + 1] : make_uint4(0, 0, 0xffffffffu, 0);
                 uint32_t np;
-                codon_masks(q, n, cx, np, e);
+                codon_masks<DENSE>(q, n, cx, np, e);
             }
             while (__any_sync(0xffffffffu, e != 0)) {
                 uint32_t key = 0xffffffffu;
@@ -677,9 +677,11 @@ __global__ void __launch_bounds__(256) codon_exception_kernel(PileupArgs a, int 
     }
 }
 
-void pileup_exceptions_launch(int pileup_grid, int pileup_threads, cudaStream_t s, const PileupArgs& a) {
+void pileup_exceptions_launch(bool dense, int pileup_grid, int pileup_threads, cudaStream_t s, const PileupArgs& a) {
     const int64_t nlists = static_cast<int64_t>(pileup_grid) * pileup_threads;
-    codon_exception_kernel<<<static_cast<unsigned>((nlists * 32 + 255) / 256), 256, 0, s>>>(a, pileup_threads);
+    const unsigned grid = static_cast<unsigned>((nlists * 32 + 255) / 256);
+    if (dense) codon_exception_kernel<true><<<grid, 256, 0, s>>>(a, pileup_threads);
+    else codon_exception_kernel<false><<<grid, 256, 0, s>>>(a, pileup_threads);
 }
 
 // ---------------------------------------------------------------- pivot sampling
@@ -687,7 +689,7 @@ void pileup_exceptions_launch(int pileup_grid, int pileup_threads, cudaStream_t 
 // majority of A/C/G/T among the sample becomes the pivot base.  The pivot only decides which
 // codon is counted by the bit-sliced fast path; results are exact for any pivot.
 __global__ void pivot_sample_kernel(const uint32_t* packed, int64_t R, int32_t nblk, int32_t L, uint2* pivot,
-                                    uint8_t* pivot_state, uint32_t* dense_stat) {
+                                    uint8_t* pivot_state, uint2* pivot2, uint8_t* pivot2_state, uint32_t* dense_stat) {
     __shared__ uint32_t cnt[32][4];
     const int blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     if (tid < 128) cnt[tid >> 2][tid & 3] = 0;
@@ -716,10 +718,22 @@ __global__ void pivot_sample_kernel(const uint32_t* packed, int64_t R, int32_t n
         const uint32_t r1 = __ballot_sync(0xffffffffu, best & 2u);
         if (tid == 0) pivot[blk] = make_uint2(r0, r1);
         if (blk * 32 + tid < L) pivot_state[blk * 32 + tid] = static_cast<uint8_t>(best);
-        if (blk == 0 && tid == 0) pivot[nblk] = make_uint2(0, 0);  // look-ahead of the last block
-        // how often a sampled clean base is not the pivot: tells K1 whether non-pivot codons are rare (sequencing errors,
-        // low-frequency variants) or the rule (dense high-frequency variants), see exception_add
+        if (blk == 0 && tid == 0) { pivot[nblk] = make_uint2(0, 0); pivot2[nblk] = make_uint2(0, 0); }  // look-ahead of the last block
         uint32_t total = cnt[tid][0] + cnt[tid][1] + cnt[tid][2] + cnt[tid][3];
+        // designated base of the DENSE kernel: the runner-up where it holds more than 2 % of the sampled clean bases
+        // (a frequent variant), the pivot elsewhere
+        uint32_t second = best;
+        uint32_t second_cnt = 0;
+#pragma unroll
+        for (uint32_t s = 0; s < 4; ++s)
+            if (s != best && cnt[tid][s] > second_cnt) { second = s; second_cnt = cnt[tid][s]; }
+        if (second_cnt * 50u <= total) second = best;
+        const uint32_t d0 = __ballot_sync(0xffffffffu, second & 1u);
+        const uint32_t d1 = __ballot_sync(0xffffffffu, second & 2u);
+        if (tid == 0) pivot2[blk] = make_uint2(d0, d1);
+        if (blk * 32 + tid < L) pivot2_state[blk * 32 + tid] = static_cast<uint8_t>(second);
+        // how often a sampled clean base is not the pivot: tells K1 whether non-pivot codons are rare (sequencing errors,
+        // low-frequency variants) or the rule (dense high-frequency variants)
         uint32_t dev = total - cnt[tid][best];
         if (blk * 32 + tid >= L) total = dev = 0;
         total = __reduce_add_sync(0xffffffffu, total);
@@ -731,8 +745,8 @@ __global__ void pivot_sample_kernel(const uint32_t* packed, int64_t R, int32_t n
 // ---------------------------------------------------------------- finalize
 // counts += sum over the CTAs' slices; pivot-codon bin of every start column += its bit-sliced count.
 // Four lanes share one output element and split the slices between them.
-__global__ void pileup_finalize_kernel(const uint32_t* part_col, const uint32_t* part_piv, int32_t slices,
-                                       int32_t nblk, int32_t L, const uint8_t* pivot_state,
+__global__ void pileup_finalize_kernel(const uint32_t* part_col, const uint32_t* part_piv, const uint32_t* part_piv2, int32_t slices,
+                                       int32_t nblk, int32_t L, const uint8_t* pivot_state, const uint8_t* pivot2_state,
                                        const uint32_t* start_mask, uint32_t* col, uint32_t* codon,
                                        int32_t count_codons, int32_t nseg, int32_t seg_len) {
     const int64_t gt = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -740,7 +754,7 @@ __global__ void pileup_finalize_kernel(const uint32_t* part_col, const uint32_t*
     const int part = static_cast<int>(gt & 3);
     const int64_t ncol = static_cast<int64_t>(L) * 8;
     const size_t cstride = static_cast<size_t>(nblk) * 256, pstride = static_cast<size_t>(nblk) * 32;
-    uint32_t s = 0;
+    uint32_t s = 0, s2 = 0;
     bool is_col = i < ncol, is_piv = false;
     int64_t j = 0;
     // CTA k wrote the blocks of segment k % nseg only
@@ -751,16 +765,25 @@ __global__ void pileup_finalize_kernel(const uint32_t* part_col, const uint32_t*
         j = i - ncol;
         is_piv = j + 2 < L && ((start_mask[j >> 5] >> (j & 31)) & 1u);
         const int sg = static_cast<int>((j >> 5) / seg_len);
-        if (is_piv)
+        if (is_piv) {
             for (int k = sg + nseg * part; k < slices; k += 4 * nseg) s += part_piv[k * pstride + j];
+            if (part_piv2)
+                for (int k = sg + nseg * part; k < slices; k += 4 * nseg) s2 += part_piv2[k * pstride + j];
+        }
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
     if (part == 0) {
         if (is_col) col[i] += s;
         else if (is_piv) {
             const uint32_t cod = 16u * pivot_state[j] + 4u * pivot_state[j + 1] + pivot_state[j + 2];
             codon[j * 64 + cod] += s;
+            if (part_piv2) {   // DENSE: the designated codon, where it is another codon than the pivot codon
+                const uint32_t des = 16u * pivot2_state[j] + 4u * pivot2_state[j + 1] + pivot2_state[j + 2];
+                if (des != cod) codon[j * 64 + des] += s2;
+            }
         }
     }
 }

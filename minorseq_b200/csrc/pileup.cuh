@@ -45,14 +45,15 @@ struct PileupArgs {
     int32_t stages;
     int32_t stage_bytes;      // G*8*row_bytes
     const uint2* pivot;       // [nblk+1] {r0, r1} planes of the pivot base
+    const uint2* pivot2;      // [nblk+1] DENSE: planes of the designated base (runner-up of the sample where frequent, else the pivot)
     const uint32_t* start_mask; // [nblk] codon start columns
     uint32_t* codon;          // [L][64] global histogram (exceptions land here)
     uint32_t* part_col;       // [gridDim][nblk*32][8]
     uint32_t* part_piv;       // [gridDim][nblk*32]
+    uint32_t* part_piv2;      // [gridDim][nblk*32] DENSE: designated-codon counts
     uint32_t* exc_list;       // [gridDim*blockDim][exc_cap] reads logged for the exact codon pass
     uint32_t* exc_cnt;        // [gridDim*blockDim]
     uint32_t exc_cap;
-    uint32_t alt_off;         // DENSE kernels: byte offset (from the start of shared memory) of the per-column second-codon counters
     int64_t exc_lists;        // gridDim*blockDim of the pileup launch
 };
 
@@ -60,9 +61,9 @@ template <int MODE, bool DENSE, bool SEG>
 __global__ void pileup_csa_kernel(PileupArgs a);
 
 __global__ void pivot_sample_kernel(const uint32_t* packed, int64_t R, int32_t nblk, int32_t L,
-                                    uint2* pivot, uint8_t* pivot_state, uint32_t* dense_stat);
-__global__ void pileup_finalize_kernel(const uint32_t* part_col, const uint32_t* part_piv, int32_t slices,
-                                       int32_t nblk, int32_t L, const uint8_t* pivot_state,
+                                    uint2* pivot, uint8_t* pivot_state, uint2* pivot2, uint8_t* pivot2_state, uint32_t* dense_stat);
+__global__ void pileup_finalize_kernel(const uint32_t* part_col, const uint32_t* part_piv, const uint32_t* part_piv2, int32_t slices,
+                                       int32_t nblk, int32_t L, const uint8_t* pivot_state, const uint8_t* pivot2_state,
                                        const uint32_t* start_mask, uint32_t* col, uint32_t* codon,
                                        int32_t count_codons, int32_t nseg, int32_t seg_len);
 __global__ void pileup_atomic_kernel(const uint32_t* packed, int64_t R, int32_t L, int32_t nblk,
@@ -72,6 +73,6 @@ __global__ void coverage_kernel(uint32_t* col, int32_t L);
 
 void pileup_set_smem_attr(int max_smem);
 void pileup_launch(int mode, bool dense, int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a);
-void pileup_exceptions_launch(int pileup_grid, int pileup_threads, cudaStream_t s, const PileupArgs& a);
+void pileup_exceptions_launch(bool dense, int pileup_grid, int pileup_threads, cudaStream_t s, const PileupArgs& a);
 
 }  // namespace ms
