@@ -312,8 +312,7 @@ def main():
     sampler.start()
     import torch
     import torch.distributed as dist
-    from minorseq_b200 import Fuse, Juliet, _lib, encode_rows
-    from minorseq_b200._lib import SynthParams
+    from minorseq_b200 import Fuse, Juliet, _lib, encode_rows, host_rows, synth_device
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -338,11 +337,11 @@ def main():
     nw = int(lib.ms_row_words(L))
 
     def synth(tab, read0, n):
-        out = torch.empty((max(n, 1), nw), dtype=torch.int32, device=dev)
-        sp = SynthParams(tab.cfg.seed, L, tab.nstrains, tab.thr_N, tab.thr_sub, tab.thr_ins20, tab.thr_trunc16)
-        _lib.check(lib.ms_synth_dev(j.hd.h, C.byref(sp), tab.strain_base.ctypes.data_as(C.c_void_p), tab.thr_del.ctypes.data_as(C.c_void_p),
-                                    tab.strain_cum.ctypes.data_as(C.c_void_p), read0, n, C.c_void_p(out.data_ptr())), j.hd.h)
-        return out
+        return synth_device(j.hd, tab, read0, n)          # device tile layout (csrc/rows.cuh)
+
+    def rows_to_host(n):
+        """the first n reads of this rank's batch as plain host rows [n, row_words]"""
+        return host_rows(d_packed[: int(lib.ms_tiled_words(L, n))], n, L)
 
     d_packed = synth(t, lo, Rg)
     torch.cuda.synchronize()
@@ -419,7 +418,7 @@ def main():
     e2e, expand_ms = None, None
     if not args.no_e2e:
         base = t.refseq                 # the sequence the rows are encoded against: the configured / major-strain reference
-        rows_host = d_packed[:Rg].cpu().numpy().view(np.uint32)
+        rows_host = rows_to_host(Rg)
         hdr, ev = encode_rows(rows_host, L, base)
         del rows_host
         th = torch.from_numpy(hdr.view(np.uint8)).pin_memory()
@@ -461,9 +460,7 @@ def main():
                "h2d_bytes_per_read": float(h2d.item()) / c["total_reads"], "planar_row_bytes_per_read": nw * 4}
         # for comparison: the same pass from planar rows in pinned host memory (round 1's e2e path), config T at N=1 only
         if c["name"] == "T" and world == 1:
-            host = torch.empty((Rg, nw), dtype=torch.int32, pin_memory=True)
-            host.copy_(d_packed[:Rg])
-            torch.cuda.synchronize()
+            host = torch.from_numpy(rows_to_host(Rg).view(np.int32)).pin_memory()
             hp_ = host.numpy().view(np.uint32)
             j.run_host(hp_)
             t0 = time.perf_counter()
@@ -540,10 +537,10 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_binding
         oracle = oracle_binding.load()
-        probe = oracle.unpack(d_packed[:2000].cpu().numpy().view(np.uint32), L)
+        probe = oracle.unpack(rows_to_host(min(2000, Rg)), L)
         tp = cpu_pass(oracle, probe, c, refseq, 1)
         sample = args.cpu_sample or int(min(Rg, max(2000, 2000 * 12.0 / max(tp, 1e-3))))
-        st = oracle.unpack(d_packed[:sample].cpu().numpy().view(np.uint32), L, nthreads=os.cpu_count() or 1)   # not timed
+        st = oracle.unpack(rows_to_host(sample), L, nthreads=os.cpu_count() or 1)   # not timed
         ts = cpu_pass(oracle, st, c, refseq, 1)
         cpu = {"value": sample / ts, "unit": UNIT, "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
                "sample": f"first {sample} reads of the same device-generated batch as resident column states, one pass, {ts:.1f} s; "

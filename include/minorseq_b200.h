@@ -24,8 +24,18 @@
  *   32b+j.  (P0,P1,P2) = state bits 0,1,2:
  *       0=A 1=C 2=G 3=T 4='-' deletion 5='N' QV-filtered base 7=not spanned
  *   P3 = an insertion follows this column in this read.  Columns >= L in the
- *   last block are state 7.  Rows are contiguous: read r starts at word
- *   r * ms_row_words(L).
+ *   last block are state 7.
+ * Two arrangements of the same 16-byte blocks:
+ *   plain rows (HOST side: ms_expand_cigar, ms_pack_states, ms_pileup_host, ms_encode_rows): rows are
+ *     contiguous, read r starts at word r * ms_row_words(L);
+ *   tiles (DEVICE side: everything that takes a device pointer to packed reads -- ms_pileup_dev, ms_phase_dev,
+ *     ms_juliet_pass_dev, ms_synth_dev, ms_expand_events_dev): reads are grouped in tiles of 8 consecutive
+ *     reads stored block-major; the 16-byte block b of read 8t+i is the uint4 at index
+ *     (t * nblk + b) * 8 + (i ^ (b & 7)),  nblk = ceil(L/32).  A buffer holds ceil(R/8) whole tiles
+ *     (ms_tiled_words); the slots of reads >= R in the last tile are never interpreted, and a pointer into the
+ *     middle of a buffer must start at a tile (a multiple of 8 reads).  One 128-byte line thus serves one block
+ *     of 8 reads (the phasing gather) and a column segment of a tile is contiguous (the pile-up's bulk copies).
+ *     ms_pileup_host / the event expansion produce tiles themselves; ms_tile_rows(_dev) converts plain rows.
  */
 #ifndef MINORSEQ_B200_H
 #define MINORSEQ_B200_H
@@ -60,6 +70,10 @@ int ms_read_admitted(uint32_t bam_flag);
 /* one byte per column (bits0-2 state, bit3 insertion-follows) -> planar rows. */
 int ms_pack_states(const uint8_t *states, int64_t R, int32_t L, uint32_t *packed);
 int ms_unpack_states(const uint32_t *packed, int64_t R, int32_t L, uint8_t *states);
+/* plain rows <-> device tiles (see the format note above).  ms_tiled_words = u32 words of a tile buffer for R reads. */
+int64_t ms_tiled_words(int32_t L, int64_t R);
+int ms_tile_rows(const uint32_t *rows, int64_t R, int32_t L, uint32_t *tiled /* ms_tiled_words(L,R) */);
+int ms_untile_rows(const uint32_t *tiled, int64_t R, int32_t L, uint32_t *rows);
 /* Replaces juliet/fuse's per-record CIGAR walk (doc/JULIET.md:49-58, doc/FUSE.md:13-15):
  * expands one aligned record into one packed row.  cigar = BAM-encoded ops
  * (len<<4|op); op 'M'(0) is rejected with MS_ERR_FORMAT ("cigar M is forbidden").
@@ -107,12 +121,14 @@ int ms_stage_kernel_ms(ms_handle *h, int stage, double *ms);
 int ms_set_layout(ms_handle *h, int32_t L, const uint32_t *start_mask);
 int ms_set_count_insertions(ms_handle *h, int on);
 int ms_reset_counts(ms_handle *h);
-/* Accumulate R device-resident packed reads into the handle's count tensor.     */
+/* Accumulate R device-resident packed reads (tiles) into the handle's count tensor.     */
 int ms_pileup_dev(ms_handle *h, const uint32_t *d_packed, int64_t R);
-/* Same from host memory (pinned recommended): chunked H2D copies overlapped with
- * the kernel.  If keep_dev != NULL it receives a device pointer to the uploaded
- * rows, owned by the handle and valid until the next ms_pileup_host / ms_destroy,
- * so ms_phase_dev can run without a second upload.                               */
+/* device-resident plain rows -> tiles (d_tiled: ms_tiled_words(L,R) words; needs ms_set_layout) */
+int ms_tile_rows_dev(ms_handle *h, const uint32_t *d_rows, int64_t R, uint32_t *d_tiled);
+/* Same from host memory (plain rows, pinned recommended): chunked H2D copies, permuted into
+ * tiles on the GPU and overlapped with the kernel.  If keep_dev != NULL it receives a device
+ * pointer to the uploaded reads (tiles), owned by the handle and valid until the next
+ * ms_pileup_host / ms_destroy, so ms_phase_dev can run without a second upload.          */
 int ms_pileup_host(ms_handle *h, const uint32_t *h_packed, int64_t R, const uint32_t **keep_dev);
 /* The count tensor [ col: L*8 u32 | codon: L*64 u32 ] in device memory, for the
  * caller's cross-GPU sum (one NCCL all-reduce; integer sums are order independent). */
@@ -152,7 +168,7 @@ int ms_encode_row(const uint32_t *row, int32_t L, const uint32_t *base_planes, m
 int ms_events_seal(ms_read_hdr *hdr, int64_t R, int64_t nevents, const uint8_t *base, int32_t L);
 /* The handle's copy of the base sequence (after ms_set_layout, which forgets it). */
 int ms_set_base(ms_handle *h, const uint8_t *base);
-/* Device-resident event rows -> R planar rows at d_packed (ms_row_words(L) words each).  */
+/* Device-resident event rows -> R packed reads at d_packed (tiles, ms_tiled_words(L,R) words).  */
 int ms_expand_events_dev(ms_handle *h, const ms_read_hdr *d_hdr, const uint16_t *d_events, int64_t R,
                          uint32_t *d_packed);
 /* ms_pileup_host for event rows: chunked H2D of the events, expansion and pile-up behind each chunk.
@@ -198,7 +214,7 @@ typedef struct { uint64_t reported, insufficient, damaged, gaps, heteroduplex, p
  * this handle will phase; allocates the bit matrix and the grouping table.       */
 int ms_phase_begin(ms_handle *h, const int32_t *var_col, const int32_t *var_codon, int32_t V,
                    int64_t max_reads);
-/* Bit-vectors + damage flags for R more device-resident reads, appended.          */
+/* Bit-vectors + damage flags for R more device-resident reads (tiles), appended.          */
 int ms_phase_dev(ms_handle *h, const uint32_t *d_packed, int64_t R);
 /* Distinct patterns of this handle's undamaged reads with their counts (in no particular
  * order; with a communicator attached, the concatenation over all ranks), and the damage
@@ -291,7 +307,7 @@ typedef struct {
     uint32_t thr_N, thr_sub, thr_ins20, thr_trunc16;  /* integer thresholds, see synth.py */
 } ms_synth_params;
 /* strain_base: nstrains*L bytes (0..3); thr_del: L u32; strain_cum: nstrains u32 cumulative
- * mixture thresholds.  Writes R packed rows for reads [read0, read0+R) on the device.  */
+ * mixture thresholds.  Writes R packed reads (tiles, ms_tiled_words(L,R) words) for reads [read0, read0+R) on the device.  */
 int ms_synth_dev(ms_handle *h, const ms_synth_params *p, const uint8_t *strain_base,
                  const uint32_t *thr_del, const uint32_t *strain_cum,
                  int64_t read0, int64_t R, uint32_t *d_packed);

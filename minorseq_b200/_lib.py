@@ -58,6 +58,10 @@ _SIGNATURES = {
     "ms_read_admitted": (C.c_int, [C.c_uint32]),
     "ms_pack_states": (C.c_int, [_P, C.c_int64, C.c_int32, _P]),
     "ms_unpack_states": (C.c_int, [_P, C.c_int64, C.c_int32, _P]),
+    "ms_tiled_words": (C.c_int64, [C.c_int32, C.c_int64]),
+    "ms_tile_rows": (C.c_int, [_P, C.c_int64, C.c_int32, _P]),
+    "ms_untile_rows": (C.c_int, [_P, C.c_int64, C.c_int32, _P]),
+    "ms_tile_rows_dev": (C.c_int, [_P, _P, C.c_int64, _P]),
     "ms_expand_cigar": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_char_p, _P, C.c_int32, C.c_int32, _P, _P, _P, _P,
                                   C.c_int64, _P, _P, C.c_int64, _P]),
     "ms_create": (C.c_int, [C.c_int, C.POINTER(_P)]),

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (CallParams, FuseParams, Gene, PhaseCounters, SynthParams, Variant, check)
-from .synth import start_mask_words
+from .synth import start_mask_words, tile_rows, untile_rows
 
 CODONS = [a + b + c for a in "ACGT" for b in "ACGT" for c in "ACGT"]
 # standard genetic code (NCBI table 1, TCAG order), re-indexed to 16*b0+4*b1+b2 with A<C<G<T.
@@ -439,6 +439,35 @@ class Fuse:
         check(self.lib.ms_fuse(self.hd.h, C.byref(self.params), _ptr(ic), _ptr(io), _ptr(il), nins, _ptr(pool),
                                len(ins_pool), _ptr(seq), cap, C.byref(n)), self.hd.h)
         return seq[: n.value].tobytes().decode()
+
+
+def device_rows(packed: np.ndarray, device=0):
+    """[R, row_words] plain host rows -> int32 torch tensor on the GPU in the device tile layout (csrc/rows.cuh), i.e. what
+    pileup_device / phase_device / run_device take.  ceil(R/8) whole tiles."""
+    import torch
+    packed = np.ascontiguousarray(packed, dtype=np.uint32)
+    if packed.shape[0] == 0:
+        return torch.zeros(max(1, packed.shape[1]) * 8, dtype=torch.int32, device=f"cuda:{device}")
+    return torch.from_numpy(tile_rows(packed).view(np.int32)).to(f"cuda:{device}")
+
+
+def host_rows(d_tiled, R: int, L: int) -> np.ndarray:
+    """device tile tensor -> [R, row_words] plain uint32 rows on the host (tests, fixtures)"""
+    return untile_rows(d_tiled.reshape(-1).cpu().numpy().view(np.uint32), R, L)
+
+
+def synth_device(hd, tables, read0: int, R: int, device=None):
+    """R synthetic reads [read0, read0+R) of `tables` written on the GPU in the device tile layout (ms_synth_dev);
+    returns the int32 torch tensor (ceil(R/8) whole tiles)."""
+    import torch
+    lib = hd.lib
+    L = tables.cfg.L
+    dev = hd.device if device is None else device
+    out = torch.empty(max(8, int(lib.ms_tiled_words(L, max(R, 1)))), dtype=torch.int32, device=f"cuda:{dev}")
+    sp = SynthParams(tables.cfg.seed, L, tables.nstrains, tables.thr_N, tables.thr_sub, tables.thr_ins20, tables.thr_trunc16)
+    check(lib.ms_synth_dev(hd.h, C.byref(sp), tables.strain_base.ctypes.data_as(C.c_void_p), tables.thr_del.ctypes.data_as(C.c_void_p),
+                           tables.strain_cum.ctypes.data_as(C.c_void_p), read0, R, C.c_void_p(out.data_ptr())), hd.h)
+    return out
 
 
 HDR_DTYPE = np.dtype([("ev_off", "<u4"), ("begin", "<u2"), ("end", "<u2")])

@@ -4,10 +4,12 @@
 #include <cstdlib>
 #include "handle.h"
 #include "pileup.cuh"
+#include "rows.cuh"
 
 static std::string g_create_error;
 void ms_events_set_smem_attr(int max_smem);
 void ms_cooc_tc_set_smem_attr();
+int ms_tile_rows_launch(ms_handle* h, const uint32_t* d_rows, int64_t R, uint32_t* d_tiled);
 
 extern "C" {
 
@@ -48,6 +50,12 @@ int ms_create(int device, ms_handle** out) {
         delete h;
         return MS_ERR_CUDA;
     }
+    for (cudaEvent_t& ev : h->ev_stagefree)
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+            g_create_error = cudaGetErrorString(cudaGetLastError());
+            delete h;
+            return MS_ERR_CUDA;
+        }
     for (cudaEvent_t& ev : h->ev_chunk)
         if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
             g_create_error = cudaGetErrorString(cudaGetLastError());
@@ -85,6 +93,8 @@ void ms_destroy(ms_handle* h) {
     h->b_exc_list.release(); h->b_exc_cnt.release();
     h->b_base.release(); h->b_ev_hdr.release(); h->b_ev.release();
     for (cudaEvent_t ev : h->ev_chunk) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : h->ev_stagefree) cudaEventDestroy(ev);
+    h->b_rowstage[0].release(); h->b_rowstage[1].release();
     if (h->call_stage) cudaFreeHost(h->call_stage);
     cudaEventDestroy(h->ev_copy[0]); cudaEventDestroy(h->ev_copy[1]);
     cudaEventDestroy(h->ev_k1[0]); cudaEventDestroy(h->ev_k1[1]);
@@ -181,13 +191,13 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
     if (!h || L < 3) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
     const int32_t nblk = (L + 31) / 32;
-    // CTA shape.  W warps span a row (31 counting lanes per warp -- lane 31 is the codon look-ahead provider -- and 32 in
-    // the last), G row-groups per CTA with W*G <= 12.  A row can also be cut into nseg column segments (CTA c then handles
-    // segment c % nseg of its reads, every segment but the last carrying one look-ahead block of the next).  Whole rows
-    // are the efficient unit -- one bulk copy per 8-read chunk, whole DRAM pages -- and a sweep over nseg at 3, 5, 6.1,
-    // 8 and 9.7 kb (tools/k1_segments.py, profiles/r1_k1_segments_sweep.txt) found segments slower everywhere except where
-    // the unsegmented shape leaves five of the twelve warps idle (W = 7, G = 1: 6.0-7.0 kb, where twelve single-warp
-    // segments are 1.36x faster).  So: segments only there, and when a whole row needs more than 12 warps (L > 11936).
+    // CTA shape.  W warps span a row or a column segment of it (31 counting lanes per warp -- lane 31 is the codon
+    // look-ahead provider -- and 32 in the last), G row-groups per CTA with W*G <= 12.  With nseg > 1 CTA c handles
+    // segment c % nseg of its tiles, every segment but the last carrying one look-ahead block of the next.  In the tile
+    // layout (rows.cuh) a segment of a tile is as contiguous as a whole tile -- one bulk copy per chunk either way -- so
+    // the shape is picked for lane occupancy alone: counting blocks per CTA step out of the 12 x 32 lanes, discounted by
+    // the imbalance when nseg does not divide the CTA count.  3 kb: whole rows (3 warps x 4 groups, 98 %); 9.7 kb: five
+    // segments of 61 blocks (2 x 6, 95 %) instead of one 10-warp row (79 %); 6 kb: two of 96 (4 x 3, 75 %).
     static const int kGroups[13] = {0, 12, 6, 4, 3, 2, 2, 1, 1, 1, 1, 1, 1};
     const int budget = h->max_smem - ms::kPileupSmemHeader - 16;
     const int forced = getenv("MS_K1_NSEG") ? atoi(getenv("MS_K1_NSEG")) : 0;   // tuning knob (tools/k1_segments.py)
@@ -196,26 +206,20 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
         if (nseg > 1 && seg_len * (nseg - 1) >= nblk) return false;        // an empty last segment
         need = seg_len + (nseg > 1 ? 1 : 0);
         W = need <= 32 ? 1 : 1 + (need - 32 + 30) / 31;
-        return W <= 12 && budget / (kGroups[W] * 8 * need * 16) >= 3;    // the ring needs three slots per row-group
+        return W <= 12 && budget / (kGroups[W] * need * 128) >= 3;        // the ring needs three slots per row-group
     };
     int best_nseg = 0, best_W = 0;
     {
-        int W1 = 0, need1 = 0;
-        const bool whole = shape(1, W1, need1);
-        if (forced > 0) {
-            int Wf, nf;
-            if (shape(forced, Wf, nf)) { best_nseg = forced; best_W = Wf; }
-        } else if (whole && !(kGroups[W1] == 1 && W1 <= 7)) {
-            best_nseg = 1; best_W = W1;
-        } else {
-            // W = 7 row: the all-single-warp shape; longer than 12 warps: the fewest (largest) segments that fit
-            for (int nseg = 2; nseg <= 64 && best_nseg == 0; ++nseg) {
-                int Wn, nn;
-                if (!shape(nseg, Wn, nn)) continue;
-                if (whole && Wn != 1) continue;
-                best_nseg = nseg; best_W = Wn;
-            }
-            if (best_nseg == 0 && whole) { best_nseg = 1; best_W = W1; }
+        double best_score = 0.0;
+        for (int nseg = 1; nseg <= 64; ++nseg) {
+            int Wn = 0, nn = 0;
+            if (forced > 0 && nseg != forced) continue;
+            if (!shape(nseg, Wn, nn)) continue;
+            const int ctas = std::max(h->num_sms, nseg);
+            const double balance = static_cast<double>(ctas / nseg) * nseg / ctas;     // segments with one CTA fewer set the pace
+            double score = static_cast<double>(kGroups[Wn]) * nblk / nseg / 384.0 * balance;
+            if (nseg == 1) score *= 1.04;                                               // whole rows: no look-ahead block read twice
+            if (score > best_score) { best_score = score; best_nseg = nseg; best_W = Wn; }
         }
     }
     if (best_nseg == 0) MS_FAIL(h, MS_ERR_ARG, "reference too long for this build's pile-up kernel");
@@ -229,7 +233,7 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
     h->nseg = best_nseg;
     h->seg_len = (nblk + best_nseg - 1) / best_nseg;
     const int row_bytes = (h->seg_len + (best_nseg > 1 ? 1 : 0)) * 16;   // bytes of one read in a ring slot
-    h->stage_bytes = h->groups * 8 * row_bytes;
+    h->stage_bytes = h->groups * 8 * row_bytes;                          // one tile (segment) per row-group
     // Clean non-pivot codons: with one reading frame they are resolved inside K1 from shared memory;
     // with overlapping frames every substituted base makes up to three of them, and it is cheaper
     // to log the flagged 8-read chunks per thread and resolve them afterwards in codon_exception_kernel
@@ -355,29 +359,41 @@ int ms_pileup_host(ms_handle* h, const uint32_t* h_packed, int64_t R, const uint
     if (!h || !h->d_counts || R < 0 || (R > 0 && !h_packed)) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
     const size_t row_bytes = static_cast<size_t>(h->nblk) * 16;
-    const size_t need = std::max<size_t>(16, static_cast<size_t>(R) * row_bytes);
-    if (need > h->upload_cap) {
+    const size_t need = std::max<size_t>(16, static_cast<size_t>(ms::tiles_of(R)) * 8 * row_bytes);   // whole tiles
+    // plain rows go up in chunks on the copy stream into one of two staging buffers; behind each chunk the main stream
+    // permutes it into the tile layout (rows.cuh) and piles it up
+    const int64_t chunk_rows = std::max<int64_t>(1024, ((static_cast<int64_t>(64) << 20) / static_cast<int64_t>(row_bytes)) & ~static_cast<int64_t>(7));
+    const size_t stage_need = static_cast<size_t>(std::min<int64_t>(chunk_rows, std::max<int64_t>(R, 1))) * row_bytes;
+    if (need > h->upload_cap || stage_need > h->b_rowstage[0].cap || stage_need > h->b_rowstage[1].cap) {
         MS_CUDA(h, cudaStreamSynchronize(h->stream));
-        cudaFree(h->d_upload);
-        h->d_upload = nullptr; h->upload_cap = 0;
-        MS_CUDA(h, cudaMalloc(&h->d_upload, need));
-        h->upload_cap = need;
+        MS_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+        if (need > h->upload_cap) {
+            cudaFree(h->d_upload);
+            h->d_upload = nullptr; h->upload_cap = 0;
+            MS_CUDA(h, cudaMalloc(&h->d_upload, need));
+            h->upload_cap = need;
+        }
+        MS_CUDA(h, h->b_rowstage[0].ensure(stage_need));
+        MS_CUDA(h, h->b_rowstage[1].ensure(stage_need));
     }
-    // chunked upload on the copy stream, kernels on the main stream behind an event per chunk
-    const int64_t chunk_rows = std::max<int64_t>(1024, (static_cast<int64_t>(64) << 20) / static_cast<int64_t>(row_bytes));
-    // the copy stream must not start overwriting d_upload before earlier work on the main stream is done
+    // the copy stream must not start overwriting the staging buffers before earlier work on the main stream is done
     MS_CUDA(h, cudaEventRecord(h->ev_copy[1], h->stream));
     MS_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_copy[1], 0));
     int k = 0;
     for (int64_t r0 = 0; r0 < R; r0 += chunk_rows, ++k) {
         const int64_t nr = std::min(chunk_rows, R - r0);
-        uint8_t* dst = reinterpret_cast<uint8_t*>(h->d_upload) + static_cast<size_t>(r0) * row_bytes;
+        uint32_t* stage = h->b_rowstage[k & 1].as<uint32_t>();
+        uint8_t* dst = reinterpret_cast<uint8_t*>(h->d_upload) + static_cast<size_t>(r0) * row_bytes;   // r0 is a multiple of 8
         const uint8_t* src = reinterpret_cast<const uint8_t*>(h_packed) + static_cast<size_t>(r0) * row_bytes;
-        MS_CUDA(h, cudaMemcpyAsync(dst, src, static_cast<size_t>(nr) * row_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        if (k >= 2) MS_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_stagefree[k & 1], 0));   // its previous chunk has been tiled
+        MS_CUDA(h, cudaMemcpyAsync(stage, src, static_cast<size_t>(nr) * row_bytes, cudaMemcpyHostToDevice, h->copy_stream));
         cudaEvent_t ev = h->ev_chunk[k & 15];   // a wait snapshots the record it follows, so the ring can be reused at once
         MS_CUDA(h, cudaEventRecord(ev, h->copy_stream));
         MS_CUDA(h, cudaStreamWaitEvent(h->stream, ev, 0));
-        int rc = ms_pileup_dev(h, reinterpret_cast<const uint32_t*>(dst), nr);
+        int rc = ms_tile_rows_launch(h, stage, nr, reinterpret_cast<uint32_t*>(dst));
+        if (rc != MS_OK) return rc;
+        MS_CUDA(h, cudaEventRecord(h->ev_stagefree[k & 1], h->stream));
+        rc = ms_pileup_dev(h, reinterpret_cast<const uint32_t*>(dst), nr);
         if (rc != MS_OK) return rc;
     }
     if (keep_dev) *keep_dev = h->d_upload;

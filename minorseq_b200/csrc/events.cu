@@ -19,6 +19,7 @@
 #include <cstring>
 #include <vector>
 #include "handle.h"
+#include "rows.cuh"
 
 namespace ms {
 
@@ -93,89 +94,120 @@ __device__ __forceinline__ uint32_t ev_smem_u32(const void* p) { return static_c
 
 constexpr int kExpandMaxWarps = 16;
 
-// One warp per read.  The row is built in the warp's shared-memory slice: base planes masked by the span, then the
-// events are applied 32 at a time -- a warp scan turns the deltas into columns, lanes whose events fall into the same
-// 32-column block (consecutive lanes: the events are sorted) take turns, one read-modify-write per event.  No atomics; the finished row leaves with
-// 16-byte stores, 512 contiguous bytes per warp instruction.
+// One warp per read, eight warps per tile (rows.cuh).  The row is built in the warp's shared-memory slice: base planes
+// masked by the span, then the events are applied 32 at a time -- a warp scan turns the deltas into columns, lanes whose
+// events fall into the same 32-column block (consecutive lanes: the events are sorted) take turns, one read-modify-write
+// per event.  No atomics.  COOP: the eight warps of a tile then write it together, 512 contiguous bytes per warp
+// instruction (rows are kept an odd number of 16-byte words apart, so these reads are bank-conflict free); rows too long
+// for eight of them to fit in shared memory leave with per-warp scattered 16-byte stores instead.
+template <bool COOP>
 __global__ void __launch_bounds__(kExpandMaxWarps * 32) expand_events_kernel(const ms_read_hdr* __restrict__ hdr,
                                                                            const uint16_t* __restrict__ events, int64_t R,
-                                                                           int32_t nblk, const uint2* __restrict__ basepl,
+                                                                           int32_t nblk, int32_t rstride, const uint2* __restrict__ basepl,
                                                                            uint4* __restrict__ out) {
     extern __shared__ __align__(16) uint4 rows_sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpc = blockDim.x >> 5;
-    uint4* row = rows_sm + static_cast<size_t>(warp) * nblk;
-    for (int64_t r = static_cast<int64_t>(blockIdx.x) * wpc + warp; r < R; r += static_cast<int64_t>(gridDim.x) * wpc) {
-        const ms_read_hdr hd = hdr[r];
-        const uint32_t off1 = hdr[r + 1].ev_off;
-        const int32_t begin = hd.begin, end = hd.end;
-        for (int32_t b = lane; b < nblk; b += 32) {
-            const int32_t lo = max(0, begin - 32 * b), hi = min(32, end - 32 * b);
-            uint32_t m = 0u;
-            if (hi > lo) m = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-            const uint2 bp = basepl[b];
-            row[b] = make_uint4((bp.x & m) | ~m, (bp.y & m) | ~m, ~m, 0u);
-        }
-        __syncwarp();
-        const uint32_t n = off1 - hd.ev_off;
-        const uint16_t* ev = events + hd.ev_off;
-        int32_t carry = begin;
-        for (uint32_t i0 = 0; i0 < n; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            const bool have = i < n;
-            const uint32_t e = have ? ev[i] : 0u;
-            int32_t s = static_cast<int32_t>(e >> 4);
+    uint4* row = rows_sm + static_cast<size_t>(warp) * rstride;
+    const int64_t Rpad = COOP ? ((R + 7) >> 3) << 3 : R;     // COOP: whole tiles, every warp of the CTA takes part in the barriers
+    const int64_t step = static_cast<int64_t>(gridDim.x) * wpc;
+    const int64_t iters = (Rpad + step - 1) / step;
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t r = (it * gridDim.x + blockIdx.x) * wpc + warp;
+        if (r < R) {
+            const ms_read_hdr hd = hdr[r];
+            const uint32_t off1 = hdr[r + 1].ev_off;
+            const int32_t begin = hd.begin, end = hd.end;
+            for (int32_t b = lane; b < nblk; b += 32) {
+                const int32_t lo = max(0, begin - 32 * b), hi = min(32, end - 32 * b);
+                uint32_t m = 0u;
+                if (hi > lo) m = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+                const uint2 bp = basepl[b];
+                row[b] = make_uint4((bp.x & m) | ~m, (bp.y & m) | ~m, ~m, 0u);
+            }
+            __syncwarp();
+            const uint32_t n = off1 - hd.ev_off;
+            const uint16_t* ev = events + hd.ev_off;
+            int32_t carry = begin;
+            for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const bool have = i < n;
+                const uint32_t e = have ? ev[i] : 0u;
+                int32_t s = static_cast<int32_t>(e >> 4);
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int32_t t = __shfl_up_sync(0xffffffffu, s, d);
-                if (lane >= d) s += t;
-            }
-            const int32_t c = carry + s;
-            carry = __shfl_sync(0xffffffffu, c, 31);
-            const int32_t blk = c >> 5;
-            const int bit = c & 31;
-            const bool ok = have && blk < nblk;            // a column past the row can only come from a corrupt list
-            uint32_t x = 0u;
-            if (ok) {
-                const uint2 bp = basepl[blk];
-                const uint32_t basenib = (c >= begin && c < end) ? (((bp.x >> bit) & 1u) | (((bp.y >> bit) & 1u) << 1)) : 7u;
-                x = (e & 15u) ^ basenib;
-            }
-            // lanes of one 32-column block are consecutive (the events are sorted): a lane's position inside its block's run comes
-            // from one ballot of the run heads; the lanes then update shared memory in rounds, round k = the k-th event of every
-            // block, so no two lanes of a round touch the same block.  Runs are 1-3 lanes long at CCS error rates.  (MATCH.ANY and
-            // REDUX on per-group masks both serialise over the ~25 distinct groups of a batch and were ~30x slower.)
-            const int32_t key = ok ? blk : -1;
-            const int32_t left = __shfl_up_sync(0xffffffffu, key, 1);
-            const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || key != left);
-            const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-            const int rank = (ok && x) ? lane - start : -1;
-            for (int k = 0; __any_sync(0xffffffffu, rank >= k); ++k) {
-                if (rank == k) {
-                    uint4 v = row[blk];
-                    v.x ^= (x & 1u) << bit; v.y ^= ((x >> 1) & 1u) << bit; v.z ^= ((x >> 2) & 1u) << bit; v.w ^= ((x >> 3) & 1u) << bit;
-                    row[blk] = v;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int32_t t = __shfl_up_sync(0xffffffffu, s, d);
+                    if (lane >= d) s += t;
                 }
-                __syncwarp();
+                const int32_t c = carry + s;
+                carry = __shfl_sync(0xffffffffu, c, 31);
+                const int32_t blk = c >> 5;
+                const int bit = c & 31;
+                const bool ok = have && blk < nblk;            // a column past the row can only come from a corrupt list
+                uint32_t x = 0u;
+                if (ok) {
+                    const uint2 bp = basepl[blk];
+                    const uint32_t basenib = (c >= begin && c < end) ? (((bp.x >> bit) & 1u) | (((bp.y >> bit) & 1u) << 1)) : 7u;
+                    x = (e & 15u) ^ basenib;
+                }
+                // lanes of one 32-column block are consecutive (the events are sorted): a lane's position inside its block's run comes
+                // from one ballot of the run heads; the lanes then update shared memory in rounds, round k = the k-th event of every
+                // block, so no two lanes of a round touch the same block.  Runs are 1-3 lanes long at CCS error rates.  (MATCH.ANY and
+                // REDUX on per-group masks both serialise over the ~25 distinct groups of a batch and were ~30x slower.)
+                const int32_t key = ok ? blk : -1;
+                const int32_t left = __shfl_up_sync(0xffffffffu, key, 1);
+                const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0 || key != left);
+                const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+                const int rank = (ok && x) ? lane - start : -1;
+                for (int k = 0; __any_sync(0xffffffffu, rank >= k); ++k) {
+                    if (rank == k) {
+                        uint4 v = row[blk];
+                        v.x ^= (x & 1u) << bit; v.y ^= ((x >> 1) & 1u) << bit; v.z ^= ((x >> 2) & 1u) << bit; v.w ^= ((x >> 3) & 1u) << bit;
+                        row[blk] = v;
+                    }
+                    __syncwarp();
+                }
             }
         }
-        uint4* dst = out + static_cast<size_t>(r) * nblk;
-        for (int32_t b = lane; b < nblk; b += 32) dst[b] = row[b];
-        __syncwarp();
+        if (COOP) {
+            __syncthreads();
+            // the CTA's tiles are contiguous in the output: slot i of them holds block (i >> 3) % nblk of read pos ^ (block & 7)
+            const int64_t r0 = (it * gridDim.x + blockIdx.x) * wpc;          // first read of this CTA's tiles (a multiple of 8)
+            const int nslots = (wpc >> 3) * nblk * 8;
+            for (int i = threadIdx.x; i < nslots; i += blockDim.x) {
+                const int tb = i >> 3;
+                const int tl = tb / nblk, b = tb - tl * nblk;
+                const int w = tl * 8 + ((i & 7) ^ (b & 7));
+                if (r0 + tl * 8 < Rpad)
+                    out[static_cast<size_t>(r0) * nblk + i] = r0 + w < R ? rows_sm[static_cast<size_t>(w) * rstride + b] : make_uint4(~0u, ~0u, ~0u, 0u);
+            }
+            __syncthreads();
+        } else if (r < R) {
+            for (int32_t b = lane; b < nblk; b += 32) out[tile_slot(r, b, nblk)] = row[b];
+            __syncwarp();
+        }
     }
 }
 
 }  // namespace ms
 
 static int expand_launch(ms_handle* h, const ms_read_hdr* d_hdr, const uint16_t* d_events, int64_t R, uint32_t* d_packed) {
-    const int row_bytes = h->nblk * 16;
-    int wpc = std::min(ms::kExpandMaxWarps, std::max(1, (64 << 10) / row_bytes));
+    const int rstride = h->nblk | 1;                      // uint4 between the rows in shared memory: odd
+    const int row_bytes = rstride * 16;
+    const int smem_cap = std::min(h->max_smem, 100 << 10);
+    const bool coop = 8 * row_bytes <= smem_cap;
+    int wpc = coop ? (16 * row_bytes <= (64 << 10) ? 16 : 8) : std::max(1, std::min(ms::kExpandMaxWarps, smem_cap / row_bytes));
+    if (!coop && row_bytes > smem_cap) MS_FAIL(h, MS_ERR_ARG, "reference too long for the event expansion's shared memory");
     const int64_t want = (R + wpc - 1) / wpc;
     const int ctas_per_sm = std::max(1, 64 / wpc);      // 64 resident warps per SM (40 registers), grid-stride over the reads
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(h->num_sms) * ctas_per_sm)));
     MS_STAGE_BEGIN(h, MS_STAGE_EXPAND);
-    ms::expand_events_kernel<<<grid, wpc * 32, wpc * row_bytes, h->stream>>>(d_hdr, d_events, R, h->nblk, h->b_base.as<uint2>(),
-                                                                             reinterpret_cast<uint4*>(d_packed));
+    if (coop)
+        ms::expand_events_kernel<true><<<grid, wpc * 32, wpc * row_bytes, h->stream>>>(d_hdr, d_events, R, h->nblk, rstride, h->b_base.as<uint2>(),
+                                                                                      reinterpret_cast<uint4*>(d_packed));
+    else
+        ms::expand_events_kernel<false><<<grid, wpc * 32, wpc * row_bytes, h->stream>>>(d_hdr, d_events, R, h->nblk, rstride, h->b_base.as<uint2>(),
+                                                                                       reinterpret_cast<uint4*>(d_packed));
     MS_STAGE_END(h, MS_STAGE_EXPAND);
     h->launches++;
     MS_CUDA(h, cudaGetLastError());
@@ -183,7 +215,8 @@ static int expand_launch(ms_handle* h, const ms_read_hdr* d_hdr, const uint16_t*
 }
 
 void ms_events_set_smem_attr(int max_smem) {
-    cudaFuncSetAttribute(ms::expand_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(max_smem, 100 << 10));
+    cudaFuncSetAttribute(ms::expand_events_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(max_smem, 100 << 10));
+    cudaFuncSetAttribute(ms::expand_events_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(max_smem, 100 << 10));
 }
 
 extern "C" {
@@ -297,7 +330,7 @@ int ms_pileup_events_host(ms_handle* h, const ms_read_hdr* hdr, const uint16_t* 
         MS_FAIL(h, MS_ERR_FORMAT, "event rows were encoded against a different base sequence (or are not sealed)");
     MS_CUDA(h, cudaSetDevice(h->device));
     const size_t row_bytes = static_cast<size_t>(h->nblk) * 16;
-    const size_t need = std::max<size_t>(16, static_cast<size_t>(R) * row_bytes);
+    const size_t need = std::max<size_t>(16, static_cast<size_t>(ms::tiles_of(R)) * 8 * row_bytes);   // whole tiles (rows.cuh)
     const int64_t total_ev = hdr[R].ev_off;
     if (need > h->upload_cap || static_cast<size_t>(R + 1) * sizeof(ms_read_hdr) > h->b_ev_hdr.cap || static_cast<size_t>(total_ev) * 2 + 64 > h->b_ev.cap) {
         MS_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -321,7 +354,7 @@ int ms_pileup_events_host(ms_handle* h, const ms_read_hdr* hdr, const uint16_t* 
     MS_CUDA(h, cudaEventRecord(h->ev_copy[1], h->stream));
     MS_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_copy[1], 0));
     for (int64_t k = 0; k < nchunks; ++k) {
-        const int64_t r0 = R * k / nchunks, r1 = R * (k + 1) / nchunks;
+        const int64_t r0 = (R * k / nchunks) & ~static_cast<int64_t>(7), r1 = k + 1 == nchunks ? R : (R * (k + 1) / nchunks) & ~static_cast<int64_t>(7);   // whole tiles
         if (r1 <= r0) continue;
         const int64_t e0 = hdr[r0].ev_off, e1 = hdr[r1].ev_off;
         const int64_t h0 = r0 + (k > 0 ? 1 : 0);     // entry r0 went up with the previous chunk (as its end marker)

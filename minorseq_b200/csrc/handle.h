@@ -29,6 +29,7 @@ struct ms_handle {
     cudaStream_t own_stream = nullptr, copy_stream = nullptr, stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
     cudaEvent_t ev_chunk[16] = {};              // upload pipeline: one per in-flight chunk, reused round-robin
+    cudaEvent_t ev_stagefree[2] = {};           // ms_pileup_host: staging buffer k has been permuted into tiles
     cudaEvent_t ev_k1[2] = {nullptr, nullptr};  // around the last K1 launch when timing is on
     cudaEvent_t ev_timer[2] = {nullptr, nullptr};  // ms_timer_start / ms_timer_stop
     cudaEvent_t ev_stage[4][2] = {};               // when timing is on: around the last launch of MS_STAGE_* (ms_stage_kernel_ms)
@@ -65,8 +66,9 @@ struct ms_handle {
     bool have_base = false;
 
     // host-upload staging (ms_pileup_host keeps the rows for phasing)
-    uint32_t* d_upload = nullptr;
+    uint32_t* d_upload = nullptr;               // tiles (rows.cuh)
     size_t upload_cap = 0;
+    DevBuf b_rowstage[2];                       // plain rows of one upload chunk, before the permutation into tiles
 
     // call
     void* d_call_buf = nullptr;
@@ -79,6 +81,8 @@ struct ms_handle {
     int32_t V = 0, vwords = 0;
     int64_t phase_cap = 0, phase_n = 0;
     int32_t nblocklist = 0;
+    int32_t phase_nrec = 0;          // variants inside the reference (records of phase_bits_kernel)
+    bool phase_partial_all = false;  // some variant lies outside the reference: every read is partial
     int64_t tab_size = 0, tab_size_max = 0, tab_hint = 0;
     int64_t gcap_hint = 0;       // distinct-pattern capacity the last ordering pass needed
     bool table_valid = false;

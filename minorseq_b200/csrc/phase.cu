@@ -20,169 +20,91 @@
 
 namespace ms {
 
-struct VarDev {
-    int32_t slotA, slotB;  // index into the block list for column col and col+2
-    int32_t shift;         // col & 31
-    int32_t codon;         // 0..63, or -1: variant lies outside the reference (always partial)
-};
+// One record per variant that lies inside the reference, in processing order (ascending first block):
+// x = slot of the first block in the block list (13 bits) | second block is the next slot (1) | first column in its
+// block (5) | plane-0 bits of the three bases (3) | plane-1 bits (3);  y = the variant's index in the caller's list.
+struct VarRec { uint32_t x, y; };
 
-constexpr int kPhaseWarps = 8;
-
-// packed per-variant record of the staged kernel: slot of the first block (13 bits) | second block is the next slot (1)
-// | first column in its block (5) | plane-0 bits of the three bases (3) | plane-1 bits (3) | variant inside the reference (1)
 __host__ __device__ inline uint32_t pack_var(int32_t slotA, int32_t slotB, int32_t shift, int32_t codon) {
-    if (codon < 0) return 0u;
     const uint32_t b0 = (codon >> 4) & 3u, b1 = (codon >> 2) & 3u, b2 = codon & 3u;
     const uint32_t k0 = (b0 & 1u) | ((b1 & 1u) << 1) | ((b2 & 1u) << 2);
     const uint32_t k1 = (b0 >> 1) | ((b1 >> 1) << 1) | ((b2 >> 1) << 2);
     return static_cast<uint32_t>(slotA) | (static_cast<uint32_t>(slotB - slotA) << 13) | (static_cast<uint32_t>(shift) << 14) | (k0 << 19) |
-           (k1 << 22) | (1u << 25);
+           (k1 << 22);
 }
 
-// V > 32: one warp per read.  The touched 32-column blocks are staged in shared memory as three plane arrays (so a
-// lane's three words come from consecutive banks and neighbouring variants broadcast), the variant records sit in
-// shared memory once per CTA, one lane per variant, a ballot per 32 variants; the lane whose index equals the word
-// index keeps the word, so the bit-vector leaves as full 128-byte lines.  LSU-bound: 7 shared-memory wavefronts per 32
-// (read, variant) pairs.
+constexpr int kPhaseWarps = 8;
+constexpr int kPhaseChunk = 10;   // distinct blocks staged per pass (+1: the second block of a codon that straddles the chunk's end)
+
+// Bit-vectors and damage flags, any number of variants.  A lane owns a read, a warp four tiles (rows.cuh): the 32-column
+// blocks the variants touch are staged kPhaseChunk at a time into the warp's shared-memory slice -- per block one
+// 16-byte load per lane, 128 contiguous bytes per tile, every byte of the line used -- and the variants of the chunk
+// are then evaluated from there: all lanes work on the same variant, so the block in registers changes only when the
+// variant list moves on to another block (one LDS.128 per lane and distinct block, not per variant), the three codon
+// columns come out of a funnel shift, and the lane ORs the result into its own word of the bit-vector.  No ballots, no
+// shuffles; the bit-vector (zeroed by the caller) is touched once per 32 variants.  `partial_all`: some variant lies
+// outside the reference, which makes every read partial.
 __global__ void __launch_bounds__(kPhaseWarps * 32) phase_bits_kernel(
     const uint4* __restrict__ packed, int64_t R, int32_t nblk, const int32_t* __restrict__ blocklist, int32_t NB,
-    const VarDev* __restrict__ vars, int32_t V, int32_t vwords, uint32_t* __restrict__ bits, uint8_t* __restrict__ flags,
-    unsigned long long* __restrict__ ctr) {
-    extern __shared__ uint32_t smw[];   // [vwords*32] records | [kPhaseWarps][3][NB] planes
+    const VarRec* __restrict__ recs, int32_t NV, int32_t vwords, int32_t partial_all, uint32_t* __restrict__ bits,
+    uint8_t* __restrict__ flags, unsigned long long* __restrict__ ctr) {
+    __shared__ uint4 stage[kPhaseWarps][kPhaseChunk + 1][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* meta = smw;
-    uint32_t* px = smw + static_cast<size_t>(vwords) * 32 + static_cast<size_t>(warp) * 3 * NB;
-    uint32_t* py = px + NB;
-    uint32_t* pz = py + NB;
-    for (int v = threadIdx.x; v < vwords * 32; v += blockDim.x) {
-        uint32_t m = 0u;
-        bool outside = false;
-        if (v < V) {
-            const VarDev vd = vars[v];
-            m = pack_var(vd.slotA, vd.slotB, vd.shift, vd.codon);
-            outside = vd.codon < 0;
-        }
-        meta[v] = m | (outside ? (1u << 26) : 0u);   // bit 26: variant lies outside the reference (always partial)
-    }
-    __syncthreads();
+    uint4 (*sm)[32] = stage[warp];
+    const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kPhaseWarps;
     unsigned long long c_dam = 0, c_gap = 0, c_het = 0, c_par = 0;
-    for (int64_t r = static_cast<int64_t>(blockIdx.x) * kPhaseWarps + warp; r < R;
-         r += static_cast<int64_t>(gridDim.x) * kPhaseWarps) {
-        const uint4* row = packed + static_cast<size_t>(r) * nblk;
-        for (int i = lane; i < NB; i += 32) {
-            const uint4 q = row[blocklist[i]];
-            px[i] = q.x; py[i] = q.y; pz[i] = q.z;
-        }
-        __syncwarp();
-        uint32_t fg = 0, fh = 0, fp = 0, keep = 0;
-        for (int w = 0; w < vwords; ++w) {
-            const uint32_t m = meta[w * 32 + lane];
-            const uint32_t sa = m & 0x1FFFu, sb = sa + ((m >> 13) & 1u), sh = (m >> 14) & 31u;
-            const uint32_t b0 = __funnelshift_r(px[sa], px[sb], sh) & 7u;
-            const uint32_t b1 = __funnelshift_r(py[sa], py[sb], sh) & 7u;
-            const uint32_t z = __funnelshift_r(pz[sa], pz[sb], sh) & 7u;
-            const bool in = (m >> 25) & 1u;
-            if (in) {
-                fg |= z & ~b0 & ~b1;      // 100
-                fh |= z & b0 & ~b1;       // 101
-                fp |= z & b1;             // 11x
+    for (int64_t base = (static_cast<int64_t>(blockIdx.x) * kPhaseWarps + warp) * 32; base < R; base += nwarps * 32) {
+        const int64_t r = base + lane;
+        const bool live = r < R;
+        const uint4* tile = packed + static_cast<size_t>(r >> 3) * nblk * 8;
+        const uint32_t pos = static_cast<uint32_t>(r & 7);
+        uint32_t fg = 0, fh = 0, fp = partial_all ? 1u : 0u;
+        uint32_t word = 0, widx = 0xffffffffu;
+        uint32_t* myrow = bits + static_cast<size_t>(r) * vwords;
+        int32_t v = 0;
+        for (int32_t c0 = 0; c0 < NB; c0 += kPhaseChunk) {
+            const int32_t nb = min(kPhaseChunk + 1, NB - c0);
+#pragma unroll 8
+            for (int32_t s2 = 0; s2 < nb; ++s2) {
+                const int32_t blk = blocklist[c0 + s2];
+                sm[s2][lane] = live ? tile[blk * 8 + (pos ^ (blk & 7))] : make_uint4(0, 0, 0, 0);
             }
-            fp |= (m >> 26) & 1u;
-            const bool bit = in && (((b0 ^ ((m >> 19) & 7u)) | (b1 ^ ((m >> 22) & 7u)) | z) == 0u);
-            const uint32_t word = __ballot_sync(0xffffffffu, bit);
-            if (lane == (w & 31)) keep = word;
-            if ((w & 31) == 31 || w + 1 == vwords) {
-                if (lane <= (w & 31)) bits[static_cast<size_t>(r) * vwords + (w & ~31) + lane] = keep;
+            __syncwarp();
+            int32_t cur = -1;
+            uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+            for (; v < NV; ++v) {
+                const VarRec rec = recs[v];
+                const int32_t sa = static_cast<int32_t>(rec.x & 0x1FFFu) - c0;
+                if (sa >= kPhaseChunk) break;                   // belongs to the next chunk (the list is in block order)
+                const bool straddle = (rec.x >> 13) & 1u;
+                if (sa != cur) { cur = sa; qa = sm[sa][lane]; }
+                if (straddle) qb = sm[sa + 1][lane];
+                const uint32_t sh = (rec.x >> 14) & 31u;
+                const uint32_t b0 = __funnelshift_r(qa.x, straddle ? qb.x : qa.x, sh) & 7u;
+                const uint32_t b1 = __funnelshift_r(qa.y, straddle ? qb.y : qa.y, sh) & 7u;
+                const uint32_t z = __funnelshift_r(qa.z, straddle ? qb.z : qa.z, sh) & 7u;
+                fg |= z & ~b0 & ~b1;      // 100  deletion
+                fh |= z & b0 & ~b1;       // 101  QV-filtered base
+                fp |= z & b1;             // 11x  not spanned
+                const uint32_t bit = ((b0 ^ ((rec.x >> 19) & 7u)) | (b1 ^ ((rec.x >> 22) & 7u)) | z) == 0u ? 1u : 0u;
+                const uint32_t wi = rec.y >> 5;
+                if (wi != widx) {                               // warp-uniform: all lanes are at the same variant
+                    if (live && widx != 0xffffffffu && word) myrow[widx] |= word;
+                    widx = wi; word = 0;
+                }
+                word |= bit << (rec.y & 31u);
             }
+            __syncwarp();
         }
-        const uint32_t f = (__any_sync(0xffffffffu, fg != 0) ? MS_FLAG_GAP : 0) | (__any_sync(0xffffffffu, fh != 0) ? MS_FLAG_HET : 0) |
-                           (__any_sync(0xffffffffu, fp != 0) ? MS_FLAG_PARTIAL : 0);
-        if (lane == 0) {
+        if (live) {
+            if (widx != 0xffffffffu && word) myrow[widx] |= word;
+            const uint32_t f = (fg ? MS_FLAG_GAP : 0) | (fh ? MS_FLAG_HET : 0) | (fp ? MS_FLAG_PARTIAL : 0);
             flags[r] = static_cast<uint8_t>(f);
             if (f) {
                 ++c_dam;
                 if (f & MS_FLAG_GAP) ++c_gap;
                 if (f & MS_FLAG_HET) ++c_het;
                 if (f & MS_FLAG_PARTIAL) ++c_par;
-            }
-        }
-        __syncwarp();
-    }
-    if (lane == 0 && c_dam) {
-        atomicAdd(ctr + 0, c_dam);
-        atomicAdd(ctr + 1, c_gap);
-        atomicAdd(ctr + 2, c_het);
-        atomicAdd(ctr + 3, c_par);
-    }
-}
-
-// V <= 32: no staging.  LPR lanes per read (power of two >= V), 32/LPR reads per warp pass; each
-// lane gathers the 16-byte block(s) of its own variant straight from global memory, four passes
-// in flight.  Lanes of one read that hit the same block coalesce into one sector.
-template <int LPR>
-__global__ void __launch_bounds__(256) phase_bits_sparse_kernel(const uint4* __restrict__ packed, int64_t R, int32_t nblk,
-                                                                const VarDev* __restrict__ vars, const int32_t* __restrict__ blocklist,
-                                                                int32_t V, uint32_t* __restrict__ bits, uint8_t* __restrict__ flags,
-                                                                unsigned long long* __restrict__ ctr) {
-    constexpr int RPW = 32 / LPR;   // reads per warp pass
-    constexpr int UNR = 4;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane / LPR, vl = lane % LPR;
-    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-    const bool has = vl < V;
-    VarDev vd = {0, 0, 0, -1};
-    int32_t blkA = 0, blkB = 0;
-    if (has) {
-        vd = vars[vl];
-        if (vd.codon >= 0) { blkA = blocklist[vd.slotA]; blkB = blocklist[vd.slotB]; }
-    }
-    const uint32_t submask = (LPR == 32 ? 0xffffffffu : ((1u << LPR) - 1u)) << (sub * LPR);
-    unsigned long long c_dam = 0, c_gap = 0, c_het = 0, c_par = 0;
-    for (int64_t base = warp * RPW * UNR; base < R; base += nwarps * RPW * UNR) {
-        uint4 a[UNR], b[UNR];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const int64_t r = base + u * RPW + sub;
-            a[u] = make_uint4(0, 0, 0, 0);
-            b[u] = a[u];
-            if (has && vd.codon >= 0 && r < R) {
-                const uint4* row = packed + static_cast<size_t>(r) * nblk;
-                a[u] = row[blkA];
-                b[u] = blkB == blkA ? a[u] : row[blkB];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            const int64_t r = base + u * RPW + sub;
-            bool bit = false, gap = false, het = false, par = false;
-            if (has && r < R) {
-                if (vd.codon < 0) par = true;
-                else {
-                    const uint32_t b0 = __funnelshift_r(a[u].x, b[u].x, vd.shift) & 7u;
-                    const uint32_t b1 = __funnelshift_r(a[u].y, b[u].y, vd.shift) & 7u;
-                    const uint32_t z = __funnelshift_r(a[u].z, b[u].z, vd.shift) & 7u;
-                    gap = (z & ~b0 & ~b1) != 0;
-                    het = (z & b0 & ~b1) != 0;
-                    par = (z & b1) != 0;
-                    const uint32_t cod = ((b0 & 1u) << 4) | ((b1 & 1u) << 5) | ((b0 & 2u) << 1) | ((b1 & 2u) << 2) |
-                                         ((b0 & 4u) >> 2) | ((b1 & 4u) >> 1);
-                    bit = (z == 0u) && (cod == static_cast<uint32_t>(vd.codon));
-                }
-            }
-            const uint32_t wb = __ballot_sync(0xffffffffu, bit), wg = __ballot_sync(0xffffffffu, gap);
-            const uint32_t wh = __ballot_sync(0xffffffffu, het), wp = __ballot_sync(0xffffffffu, par);
-            if (vl == 0 && r < R) {
-                const uint32_t f = ((wg & submask) ? MS_FLAG_GAP : 0) | ((wh & submask) ? MS_FLAG_HET : 0) |
-                                   ((wp & submask) ? MS_FLAG_PARTIAL : 0);
-                bits[r] = (wb & submask) >> (sub * LPR);
-                flags[r] = static_cast<uint8_t>(f);
-                if (f) {
-                    ++c_dam;
-                    if (f & MS_FLAG_GAP) ++c_gap;
-                    if (f & MS_FLAG_HET) ++c_het;
-                    if (f & MS_FLAG_PARTIAL) ++c_par;
-                }
             }
         }
     }
@@ -479,16 +401,23 @@ int ms_phase_begin(ms_handle* h, const int32_t* var_col, const int32_t* var_codo
     blocks.erase(std::unique(blocks.begin(), blocks.end()), blocks.end());
     if (blocks.empty()) blocks.push_back(0);
     h->nblocklist = static_cast<int32_t>(blocks.size());
-    std::vector<ms::VarDev> vd(std::max(1, V));
+    // records of the variants inside the reference, in block order (the kernel walks the block list once)
+    std::vector<ms::VarRec> vd;
+    vd.reserve(static_cast<size_t>(std::max(1, V)));
+    h->phase_partial_all = false;
     for (int32_t v = 0; v < V; ++v) {
-        ms::VarDev d;
         if (var_col[v] + 2 < h->L) {
-            d.slotA = static_cast<int32_t>(std::lower_bound(blocks.begin(), blocks.end(), var_col[v] >> 5) - blocks.begin());
-            d.slotB = static_cast<int32_t>(std::lower_bound(blocks.begin(), blocks.end(), (var_col[v] + 2) >> 5) - blocks.begin());
-            d.shift = var_col[v] & 31; d.codon = var_codon[v];
-        } else { d.slotA = d.slotB = 0; d.shift = 0; d.codon = -1; }
-        vd[v] = d;
+            const int32_t sa = static_cast<int32_t>(std::lower_bound(blocks.begin(), blocks.end(), var_col[v] >> 5) - blocks.begin());
+            const int32_t sb = static_cast<int32_t>(std::lower_bound(blocks.begin(), blocks.end(), (var_col[v] + 2) >> 5) - blocks.begin());
+            vd.push_back({ms::pack_var(sa, sb, var_col[v] & 31, var_codon[v]), static_cast<uint32_t>(v)});
+        } else {
+            h->phase_partial_all = true;     // a variant outside the reference: no read spans it
+        }
     }
+    if (blocks.size() > 0x1FFF) MS_FAIL(h, MS_ERR_CAPACITY, "variants touch more than 8191 distinct 32-column blocks");
+    std::stable_sort(vd.begin(), vd.end(), [](const ms::VarRec& a, const ms::VarRec& b) { return (a.x & 0x1FFFu) < (b.x & 0x1FFFu); });
+    h->phase_nrec = static_cast<int32_t>(vd.size());
+    if (vd.empty()) vd.push_back({0u, 0u});
     // The table starts small (distinct patterns are usually a few hundred) and is re-sized by
     // ms_phase_groups when an insert reports overflow; its upper bound is 2x the reads.
     int64_t ts_max = 1024;
@@ -497,11 +426,11 @@ int ms_phase_begin(ms_handle* h, const int32_t* var_col, const int32_t* var_codo
     int64_t ts = std::min<int64_t>(ts_max, std::max<int64_t>(1 << 16, h->tab_hint));   // last pass's grown size is the hint
     h->tab_size = ts;
     // the previous pass may still be reading these buffers on the stream if they have to move
-    const bool grow = vd.size() * sizeof(ms::VarDev) > h->b_var.cap || blocks.size() * 4 > h->b_blocklist.cap ||
+    const bool grow = vd.size() * sizeof(ms::VarRec) > h->b_var.cap || blocks.size() * 4 > h->b_blocklist.cap ||
                       static_cast<size_t>(h->phase_cap) * h->vwords * 4 > h->b_bits.cap || static_cast<size_t>(h->phase_cap) > h->b_flags.cap ||
                       static_cast<size_t>(ts) * 8 > h->b_tab_key.cap || !h->b_ctr.p;
     if (grow) MS_CUDA(h, cudaStreamSynchronize(h->stream));
-    MS_CUDA(h, h->b_var.ensure(vd.size() * sizeof(ms::VarDev)));
+    MS_CUDA(h, h->b_var.ensure(vd.size() * sizeof(ms::VarRec)));
     MS_CUDA(h, h->b_blocklist.ensure(blocks.size() * 4));
     MS_CUDA(h, h->b_bits.ensure(static_cast<size_t>(h->phase_cap) * h->vwords * 4));
     MS_CUDA(h, h->b_flags.ensure(static_cast<size_t>(h->phase_cap)));
@@ -514,7 +443,7 @@ int ms_phase_begin(ms_handle* h, const int32_t* var_col, const int32_t* var_codo
     if (rc != MS_OK) return rc;
     // pageable -> device copies of the small tables go through the pinned stage to stay asynchronous
     uint8_t* st = static_cast<uint8_t*>(h->h_stage);
-    const size_t nb_var = vd.size() * sizeof(ms::VarDev), nb_blk = blocks.size() * 4;
+    const size_t nb_var = vd.size() * sizeof(ms::VarRec), nb_blk = blocks.size() * 4;
     if (nb_var + nb_blk <= h->h_stage_cap) {
         memcpy(st, vd.data(), nb_var);
         memcpy(st + nb_var, blocks.data(), nb_blk);
@@ -538,34 +467,15 @@ int ms_phase_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     uint32_t* bits = h->b_bits.as<uint32_t>() + static_cast<size_t>(h->phase_n) * h->vwords;
     uint8_t* flags = h->b_flags.as<uint8_t>() + h->phase_n;
     const uint4* pk = reinterpret_cast<const uint4*>(d_packed);
-    const ms::VarDev* vars = h->b_var.as<ms::VarDev>();
+    const ms::VarRec* recs = h->b_var.as<ms::VarRec>();
     unsigned long long* ctr = ctr_ptr(h);
+    MS_CUDA(h, cudaMemsetAsync(bits, 0, static_cast<size_t>(R) * h->vwords * 4, h->stream));   // the kernel ORs its words in
     MS_STAGE_BEGIN(h, MS_STAGE_PHASE_BITS);
-    if (h->V <= 32) {
-        int lpr = 1;
-        while (lpr < h->V) lpr <<= 1;
-        const int rpw = 32 / lpr;
-        const int64_t warps_needed = (R + rpw * 4 - 1) / (rpw * 4);
-        const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((warps_needed + 7) / 8, static_cast<int64_t>(h->num_sms) * 8)));
-#define MS_SPARSE(N) ms::phase_bits_sparse_kernel<N><<<grid, 256, 0, h->stream>>>(pk, R, h->nblk, vars, h->b_blocklist.as<int32_t>(), h->V, bits, flags, ctr)
-        switch (lpr) {
-        case 1: MS_SPARSE(1); break;
-        case 2: MS_SPARSE(2); break;
-        case 4: MS_SPARSE(4); break;
-        case 8: MS_SPARSE(8); break;
-        case 16: MS_SPARSE(16); break;
-        default: MS_SPARSE(32); break;
-        }
-#undef MS_SPARSE
-    } else {
-        const size_t smem = (static_cast<size_t>(h->vwords) * 32 + static_cast<size_t>(ms::kPhaseWarps) * 3 * h->nblocklist) * sizeof(uint32_t);
-        if (smem > static_cast<size_t>(h->max_smem)) MS_FAIL(h, MS_ERR_CAPACITY, "too many variants / touched blocks for the phasing kernel's shared memory");
-        if (smem > 48 * 1024)
-            MS_CUDA(h, cudaFuncSetAttribute(ms::phase_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        const int64_t want = (R + ms::kPhaseWarps - 1) / ms::kPhaseWarps;
-        const int grid = static_cast<int>(std::min<int64_t>(want, static_cast<int64_t>(h->num_sms) * 8));
-        ms::phase_bits_kernel<<<grid, ms::kPhaseWarps * 32, smem, h->stream>>>(pk, R, h->nblk, h->b_blocklist.as<int32_t>(), h->nblocklist,
-                                                                              vars, h->V, h->vwords, bits, flags, ctr);
+    {
+        const int64_t want = (R + ms::kPhaseWarps * 32 - 1) / (ms::kPhaseWarps * 32);
+        const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(h->num_sms) * 4)));
+        ms::phase_bits_kernel<<<grid, ms::kPhaseWarps * 32, 0, h->stream>>>(pk, R, h->nblk, h->b_blocklist.as<int32_t>(), h->nblocklist, recs,
+                                                                           h->phase_nrec, h->vwords, h->phase_partial_all ? 1 : 0, bits, flags, ctr);
     }
     MS_STAGE_END(h, MS_STAGE_PHASE_BITS);
     h->launches++;

@@ -1,5 +1,6 @@
 // pileup.cu -- K1 kernels.  See pileup.cuh for the design and reference citations.
 #include "pileup.cuh"
+#include "rows.cuh"
 
 namespace ms {
 
@@ -163,13 +164,13 @@ __device__ __forceinline__ void read_masks(uint32_t addr, const CodonCtx& cx, ui
 
 // Rare path: the reads flagged in pm may carry clean non-pivot codons; re-read them from the slot
 // (still owned by this row-group) and add each such codon to the global 64-bin histogram.
+// addr / naddr: this thread's block and the next one in the slot, swizzle folded in (read i at addr ^ 16 i).
 template <bool DENSE>
-__device__ __forceinline__ void codon_exceptions(uint32_t addr, uint32_t row_bytes, uint32_t pm, const CodonCtx& cx) {
+__device__ __forceinline__ void codon_exceptions(uint32_t addr, uint32_t naddr, uint32_t pm, const CodonCtx& cx) {
     while (pm) {
         const int rd = __ffs(pm) - 1;
         pm &= pm - 1;
-        const uint32_t a = addr + static_cast<uint32_t>(rd) * row_bytes;
-        const uint4 q = lds128(a), n = lds128(a + 16);
+        const uint4 q = lds128(addr ^ (static_cast<uint32_t>(rd) << 4)), n = lds128(naddr ^ (static_cast<uint32_t>(rd) << 4));
         uint32_t np, e;
         codon_masks<DENSE>(q, n, cx, np, e);
         while (e) {
@@ -185,30 +186,29 @@ __device__ __forceinline__ void codon_exceptions(uint32_t addr, uint32_t row_byt
 }
 
 template <int MODE, bool DENSE>
-__device__ __forceinline__ uint32_t block8(uint32_t addr, uint32_t row_bytes, const CodonCtx& cx,
-                                           Vert<Traits<MODE, DENSE>::NM>& v, uint32_t bi) {
+__device__ __forceinline__ uint32_t block8(uint32_t addr, const CodonCtx& cx, Vert<Traits<MODE, DENSE>::NM>& v, uint32_t bi) {
     constexpr int NM = Traits<MODE, DENSE>::NM;
     uint32_t m0[NM], m1[NM], twosA[NM], twosB[NM], foursA[NM], foursB[NM];
     uint32_t pm = 0;
     // reads 0..3
-    read_masks<MODE, DENSE>(addr, cx, m0, pm, 1u);
-    read_masks<MODE, DENSE>(addr + row_bytes, cx, m1, pm, 2u);
+    read_masks<MODE, DENSE>(addr, cx, m0, pm, 1u);   // read i of the tile sits at addr ^ 16 i (rows.cuh)
+    read_masks<MODE, DENSE>(addr ^ 16u, cx, m1, pm, 2u);
 #pragma unroll
     for (int i = 0; i < NM; ++i) csa(twosA[i], v.c[i][0], v.c[i][0], m0[i], m1[i]);
-    read_masks<MODE, DENSE>(addr + 2 * row_bytes, cx, m0, pm, 4u);
-    read_masks<MODE, DENSE>(addr + 3 * row_bytes, cx, m1, pm, 8u);
+    read_masks<MODE, DENSE>(addr ^ 32u, cx, m0, pm, 4u);
+    read_masks<MODE, DENSE>(addr ^ 48u, cx, m1, pm, 8u);
 #pragma unroll
     for (int i = 0; i < NM; ++i) {
         csa(twosB[i], v.c[i][0], v.c[i][0], m0[i], m1[i]);
         csa(foursA[i], v.c[i][1], v.c[i][1], twosA[i], twosB[i]);
     }
     // reads 4..7
-    read_masks<MODE, DENSE>(addr + 4 * row_bytes, cx, m0, pm, 16u);
-    read_masks<MODE, DENSE>(addr + 5 * row_bytes, cx, m1, pm, 32u);
+    read_masks<MODE, DENSE>(addr ^ 64u, cx, m0, pm, 16u);
+    read_masks<MODE, DENSE>(addr ^ 80u, cx, m1, pm, 32u);
 #pragma unroll
     for (int i = 0; i < NM; ++i) csa(twosA[i], v.c[i][0], v.c[i][0], m0[i], m1[i]);
-    read_masks<MODE, DENSE>(addr + 6 * row_bytes, cx, m0, pm, 64u);
-    read_masks<MODE, DENSE>(addr + 7 * row_bytes, cx, m1, pm, 128u);
+    read_masks<MODE, DENSE>(addr ^ 96u, cx, m0, pm, 64u);
+    read_masks<MODE, DENSE>(addr ^ 112u, cx, m1, pm, 128u);
 #pragma unroll
     for (int i = 0; i < NM; ++i) {
         csa(twosB[i], v.c[i][0], v.c[i][0], m0[i], m1[i]);
@@ -255,10 +255,10 @@ struct ExcLog {
 };
 // one entry per 8-read chunk with any flagged read: (first read of the chunk / 8) << 8 | flag byte
 template <bool DENSE>
-__device__ __forceinline__ void log_or_handle(uint32_t pm, uint32_t read0, ExcLog& lg, uint32_t addr, uint32_t row_bytes,
+__device__ __forceinline__ void log_or_handle(uint32_t pm, uint32_t read0, ExcLog& lg, uint32_t addr, uint32_t naddr,
                                               const CodonCtx& cx) {
     if (lg.cnt < lg.cap) lg.list[lg.cnt++] = ((read0 >> 3) << 8) | pm;
-    else codon_exceptions<DENSE>(addr, row_bytes, pm, cx);
+    else codon_exceptions<DENSE>(addr, naddr, pm, cx);
 }
 
 // ---------------------------------------------------------------- flush (cold path)
@@ -391,12 +391,11 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     const int blk0 = SEG ? seg * a.seg_len : 0;
     const int seg_nblk = SEG ? (a.nblk - blk0 < a.seg_len ? a.nblk - blk0 : a.seg_len) : a.nblk;
     const int load_nblk = SEG ? seg_nblk + (blk0 + seg_nblk < a.nblk ? 1 : 0) : a.nblk;
-    const uint32_t row_bytes = static_cast<uint32_t>(load_nblk) * 16u;            // row stride inside a slot
-    const size_t grow_bytes = static_cast<size_t>(a.nblk) * 16u;                  // row stride in global memory
+    const size_t tile_bytes = static_cast<size_t>(a.nblk) * 128u;                 // one tile of 8 reads in global memory (rows.cuh)
     const uint32_t bar0 = smem_u32(smem);          // full barrier of slot (g,s) at bar0 + 8*(g*S+s)
     const uint32_t cnt0 = bar0 + 1024;             // release counter of slot (g,s) at cnt0 + 4*(g*S+s)
     const uint32_t data0 = bar0 + kPileupSmemHeader;  // slot (g,s) at data0 + (g*S+s)*chunk_bytes
-    const uint32_t chunk_bytes = 8u * row_bytes;
+    const uint32_t chunk_bytes = static_cast<uint32_t>(load_nblk) * 128u;         // a slot = this segment's blocks of one tile
     const int64_t Tr = static_cast<int64_t>(G) * 8;  // reads per tile (one 8-read chunk per row-group)
     const int64_t ntiles = (a.R + Tr - 1) / Tr;
 
@@ -421,6 +420,9 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     const bool active = lblk < seg_nblk && (lane < 31 || wig == W - 1);
     if (lblk >= load_nblk) lblk = 0;
     const int blk = blk0 + lblk;                     // block within the reference
+    // offsets of this thread's block and of the next one inside a slot, with the tile swizzle folded in (rows.cuh)
+    const uint32_t blk_off = static_cast<uint32_t>(lblk) * 128u + (static_cast<uint32_t>(blk & 7) << 4);
+    const uint32_t nblk_off = static_cast<uint32_t>(lblk + 1 < load_nblk ? lblk + 1 : lblk) * 128u + (static_cast<uint32_t>((blk + 1) & 7) << 4);
 
     CodonCtx cx;
     cx.codon = a.codon + static_cast<size_t>(blk) * 32 * 64;
@@ -463,18 +465,14 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         if (t >= ntiles) return;
         const int64_t r0 = t * Tr + group * 8;
         if (r0 >= a.R) return;
-        const uint32_t valid = static_cast<uint32_t>((a.R - r0 < 8) ? (a.R - r0) : 8);
         const uint32_t slot = static_cast<uint32_t>(group * S + static_cast<int>(k % S));
         const uint32_t full = bar0 + 8 * slot;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads of the slot before the async write
-        mbar_expect_tx(full, valid * row_bytes);
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.packed) + static_cast<size_t>(r0) * grow_bytes + static_cast<size_t>(blk0) * 16u;
-        if (!SEG) {
-            bulk_g2s(data0 + slot * chunk_bytes, src, valid * row_bytes, full);       // whole rows: one copy per chunk
-        } else {
-            for (uint32_t i = 0; i < valid; ++i)                                      // this segment of every row
-                bulk_g2s(data0 + slot * chunk_bytes + i * row_bytes, src + i * grow_bytes, row_bytes, full);
-        }
+        mbar_expect_tx(full, chunk_bytes);
+        // the blocks [blk0, blk0 + load_nblk) of a tile are contiguous: one copy per chunk, whole rows or a segment
+        // (a buffer holds whole tiles, so the last, partial tile is copied in full as well)
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.packed) + static_cast<size_t>(r0 >> 3) * tile_bytes + static_cast<size_t>(blk0) * 128u;
+        bulk_g2s(data0 + slot * chunk_bytes, src, chunk_bytes, full);
     };
     if (tig == 0)
         for (int k = 0; k < S; ++k) issue_chunk(k);
@@ -502,20 +500,21 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         const int nv = left <= 0 ? 0 : (left > 8 ? 8 : static_cast<int>(left));
         const uint32_t slot = static_cast<uint32_t>(group * S) + stage;
         if (nv > 0) mbar_wait(bar0 + 8 * slot, phase);
-        const uint32_t addr = data0 + slot * chunk_bytes + static_cast<uint32_t>(lblk) * 16u;
+        const uint32_t addr = data0 + slot * chunk_bytes + blk_off;   // read i of the tile at addr ^ 16 i
+        const uint32_t naddr = data0 + slot * chunk_bytes + nblk_off; // same for the next block (rare path only)
         if (nv == 8) {
-            const uint32_t pm = block8<MODE, DENSE>(addr, row_bytes, cx, v, bi);
-            if (T::CODON && pm) log_or_handle<DENSE>(pm, static_cast<uint32_t>(r0), lg, addr, row_bytes, cx);
+            const uint32_t pm = block8<MODE, DENSE>(addr, cx, v, bi);
+            if (T::CODON && pm) log_or_handle<DENSE>(pm, static_cast<uint32_t>(r0), lg, addr, naddr, cx);
             ++bi;
             n += 8;
         } else {
             for (int i = 0; i < nv; ++i) {
                 uint32_t m[NM];
                 uint32_t pm = 0;
-                read_masks<MODE, DENSE>(addr + i * row_bytes, cx, m, pm, 1u);
+                read_masks<MODE, DENSE>(addr ^ (static_cast<uint32_t>(i) << 4), cx, m, pm, 1u);
 #pragma unroll
                 for (int q = 0; q < NM; ++q) ripple(v, q, 0, m[q]);
-                if (T::CODON && pm) log_or_handle<DENSE>(1u << i, static_cast<uint32_t>(r0), lg, addr, row_bytes, cx);
+                if (T::CODON && pm) log_or_handle<DENSE>(1u << i, static_cast<uint32_t>(r0), lg, addr, naddr, cx);
                 ++n;
             }
         }
@@ -607,7 +606,7 @@ void pileup_launch(int mode, bool dense, int grid, int threads, int smem, cudaSt
 
 // ---------------------------------------------------------------- logged exceptions
 // One warp per logged list: every entry is a read whose block may hold clean non-pivot codons.  The
-// exact masks are recomputed from global memory (one 32-byte sector per entry) and each such codon
+// exact masks are recomputed from global memory (the block and its successor of the flagged read) and each such codon
 // goes to the 64-bin histogram with a RED.  ~1.6 % of the (read, block) pairs at CCS error rates.
 template <bool DENSE>
 __global__ void __launch_bounds__(256) codon_exception_kernel(PileupArgs a, int threads_per_cta) {
@@ -653,9 +652,8 @@ __global__ void __launch_bounds__(256) codon_exception_kernel(PileupArgs a, int 
             if (pm) {
                 const int rd = __ffs(pm) - 1;
                 pm &= pm - 1;
-                const uint4* row = rows + (rbase + rd) * a.nblk;
-                q = row[blk];
-                n = blk + 1 < a.nblk ? row[blk + 1] : make_uint4(0, 0, 0xffffffffu, 0);
+                q = rows[tile_slot(static_cast<int64_t>(rbase) + rd, blk, a.nblk)];
+                n = blk + 1 < a.nblk ? rows[tile_slot(static_cast<int64_t>(rbase) + rd, blk + 1, a.nblk)] : make_uint4(0, 0, 0xffffffffu, 0);
                 uint32_t np;
                 codon_masks<DENSE>(q, n, cx, np, e);
             }
@@ -698,7 +696,7 @@ __global__ void pivot_sample_kernel(const uint32_t* packed, int64_t R, int32_t n
     uint4 q = make_uint4(0, 0, 0xffffffffu, 0);  // state 4+: does not vote
     if (tid < ns) {
         const int64_t r = static_cast<int64_t>(tid) * R / ns;
-        q = *reinterpret_cast<const uint4*>(packed + (static_cast<size_t>(r) * nblk + blk) * 4);
+        q = reinterpret_cast<const uint4*>(packed)[tile_slot(r, blk, nblk)];
     }
     for (int j = 0; j < 32; ++j) {
         const uint32_t st = ((q.x >> j) & 1u) | (((q.y >> j) & 1u) << 1) | (((q.z >> j) & 1u) << 2);
@@ -802,9 +800,9 @@ __global__ void pileup_atomic_kernel(const uint32_t* packed, int64_t R, int32_t 
     const uint32_t start = count_codons ? start_mask[blk] : 0u;
     for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < R;
          r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const uint4 q = *reinterpret_cast<const uint4*>(packed + (static_cast<size_t>(r) * nblk + blk) * 4);
+        const uint4 q = reinterpret_cast<const uint4*>(packed)[tile_slot(r, blk, nblk)];
         uint4 n = make_uint4(0, 0, 0xffffffffu, 0);
-        if (blk + 1 < nblk) n = *reinterpret_cast<const uint4*>(packed + (static_cast<size_t>(r) * nblk + blk + 1) * 4);
+        if (blk + 1 < nblk) n = reinterpret_cast<const uint4*>(packed)[tile_slot(r, blk + 1, nblk)];
         for (int j = 0; j < 32; ++j) {
             const uint32_t st = ((q.x >> j) & 1u) | (((q.y >> j) & 1u) << 1) | (((q.z >> j) & 1u) << 2);
             if (st <= 5u) {

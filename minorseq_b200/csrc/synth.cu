@@ -6,6 +6,7 @@
 // function of (seed, read, column) -- see minorseq_b200/synth.py for the numpy twin the
 // tests compare against bit for bit.
 #include "handle.h"
+#include "rows.cuh"
 
 namespace ms {
 
@@ -20,10 +21,14 @@ constexpr uint64_t kK1 = 0x9E3779B97F4A7C15ULL, kK2 = 0xD1B54A32D192ED03ULL;
 __global__ void synth_kernel(ms_synth_params p, const uint8_t* __restrict__ strain_base,
                              const uint32_t* __restrict__ thr_del, const uint32_t* __restrict__ strain_cum,
                              int64_t read0, int64_t R, int32_t nblk, uint4* __restrict__ out) {
+    // one thread per 16-byte slot of the tile layout (rows.cuh): consecutive threads write consecutive slots
     const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (idx >= R * nblk) return;
-    const int64_t rl = idx / nblk;
-    const int32_t blk = static_cast<int32_t>(idx - rl * nblk);
+    if (idx >= ((R + 7) >> 3) * 8 * nblk) return;
+    const int64_t tb = idx >> 3;
+    const int64_t tile = tb / nblk;
+    const int32_t blk = static_cast<int32_t>(tb - tile * nblk);
+    const int64_t rl = tile * 8 + ((idx & 7) ^ (blk & 7));
+    if (rl >= R) { out[idx] = make_uint4(~0u, ~0u, ~0u, 0u); return; }   // padding of the last tile: not spanned
     const uint64_t r = static_cast<uint64_t>(read0 + rl);
     const uint64_t y = mix64(p.seed + r * kK1);
     const uint32_t us = static_cast<uint32_t>(y);
@@ -77,7 +82,7 @@ extern "C" int ms_synth_dev(ms_handle* h, const ms_synth_params* p, const uint8_
     MS_CUDA(h, cudaMemcpyAsync(d_sb, strain_base, static_cast<size_t>(p->nstrains) * p->L, cudaMemcpyHostToDevice, h->stream));
     MS_CUDA(h, cudaMemcpyAsync(d_td, thr_del, static_cast<size_t>(p->L) * 4, cudaMemcpyHostToDevice, h->stream));
     MS_CUDA(h, cudaMemcpyAsync(d_sc, strain_cum, static_cast<size_t>(p->nstrains) * 4, cudaMemcpyHostToDevice, h->stream));
-    const int64_t total = R * nblk;
+    const int64_t total = ms::tiles_of(R) * 8 * nblk;
     ms::synth_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, h->stream>>>(
         *p, d_sb, d_td, d_sc, read0, R, nblk, reinterpret_cast<uint4*>(d_packed));
     h->launches++;

@@ -193,6 +193,32 @@ def unpack_states(packed: np.ndarray, L: int) -> np.ndarray:
     return st.reshape(R, nblk * 32)[:, :L].copy()
 
 
+def tile_rows(packed: np.ndarray) -> np.ndarray:
+    """[R, row_words] plain rows -> the device tile layout (csrc/rows.cuh, numpy twin of ms_tile_rows): a flat uint32
+    array of ceil(R/8) tiles; block b of read 8t+i sits at 16-byte slot (t*nblk + b)*8 + (i ^ (b & 7)); the slots of
+    reads >= R in the last tile hold "not spanned"."""
+    R, rw = packed.shape
+    nblk = rw // 4
+    T = (R + 7) // 8
+    full = np.empty((T * 8, nblk, 4), dtype=np.uint32)
+    full[:R] = packed.reshape(R, nblk, 4)
+    full[R:] = np.array([0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0], dtype=np.uint32)
+    t = full.reshape(T, 8, nblk, 4).transpose(0, 2, 1, 3)             # [T, nblk, 8 reads, 4]
+    src = np.arange(8)[None, :] ^ (np.arange(nblk)[:, None] & 7)        # position p of block b holds read p ^ (b & 7)
+    out = np.take_along_axis(t, src[None, :, :, None], axis=2)
+    return np.ascontiguousarray(out).reshape(-1)
+
+
+def untile_rows(tiled: np.ndarray, R: int, L: int) -> np.ndarray:
+    """inverse of tile_rows: flat tile array -> [R, row_words] plain rows"""
+    nblk = (L + 31) // 32
+    T = (R + 7) // 8
+    t = np.asarray(tiled, dtype=np.uint32).reshape(-1)[: T * nblk * 32].reshape(T, nblk, 8, 4)
+    src = np.arange(8)[None, :] ^ (np.arange(nblk)[:, None] & 7)        # read i of block b sits at position i ^ (b & 7)
+    rows = np.take_along_axis(t, src[None, :, :, None], axis=2).transpose(0, 2, 1, 3)
+    return np.ascontiguousarray(rows).reshape(T * 8, nblk * 4)[:R]
+
+
 def start_mask_words(L: int, genes, region=None) -> np.ndarray:
     """bit j set where a codon of some gene (1-based [begin,end)) starts."""
     nblk = (L + 31) // 32

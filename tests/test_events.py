@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from minorseq_b200 import _lib, decode_events, encode_rows, encode_states
+from minorseq_b200 import _lib, decode_events, encode_rows, encode_states, host_rows, tile_rows
 from minorseq_b200.api import HDR_DTYPE
 from minorseq_b200.synth import SynthConfig, make_tables, pack_states, synth_states
 
@@ -128,12 +128,14 @@ def test_expand_events_equals_packed_rows(L, R):
         j = Juliet(L, [(1, L + 1)], handle=hd)
         lib = j.lib
         dh, de = _dev(hdr, torch), _dev(ev if len(ev) else np.zeros(1, np.uint16), torch)
-        out = torch.zeros((R, j.row_words), dtype=torch.int32, device="cuda")
+        out = torch.zeros(int(lib.ms_tiled_words(L, R)), dtype=torch.int32, device="cuda")
         assert lib.ms_expand_events_dev(hd.h, C.c_void_p(dh.data_ptr()), C.c_void_p(de.data_ptr()), R, C.c_void_p(out.data_ptr())) == -1  # no base yet
         j.set_base(base)
         _lib.check(lib.ms_expand_events_dev(hd.h, C.c_void_p(dh.data_ptr()), C.c_void_p(de.data_ptr()), R, C.c_void_p(out.data_ptr())), hd.h)
         _lib.check(lib.ms_synchronize(hd.h), hd.h)
-        assert np.array_equal(out.cpu().numpy().view(np.uint32), pack_states(st))
+        assert np.array_equal(host_rows(out, R, L), pack_states(st))
+        # the padding of the last tile is "not spanned", so whole tile buffers can be compared as well
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), tile_rows(pack_states(st)))
     finally:
         hd.close()
 

@@ -198,3 +198,28 @@ def test_expand_cigar_randomised_against_python(mslib):
             else: merged.append((l, o))
         rc, st, _ = _expand(mslib, merged, pos, seq, L, qv=qv)
         assert rc == 0 and np.array_equal(st, want), (merged, pos, seq)
+
+
+def test_tile_layout_round_trip_and_definition(mslib):
+    """plain rows <-> device tiles (csrc/rows.cuh): the C helpers, the numpy twins and the formula in the header agree"""
+    from minorseq_b200.synth import tile_rows, untile_rows
+    rng = np.random.default_rng(11)
+    for R, L in [(1, 40), (8, 3000), (13, 100), (77, 9719), (0, 64)]:
+        rw = mslib.ms_row_words(L)
+        nblk = rw // 4
+        rows = rng.integers(0, 2 ** 32, size=(R, rw), dtype=np.uint32)
+        t = tile_rows(rows) if R else np.zeros(0, np.uint32)
+        assert t.size == mslib.ms_tiled_words(L, R) == (R + 7) // 8 * 8 * rw
+        t2 = np.empty_like(t)
+        assert mslib.ms_tile_rows(rows.ctypes.data_as(C.c_void_p), R, L, t2.ctypes.data_as(C.c_void_p)) == 0
+        assert np.array_equal(t, t2)
+        back = np.empty_like(rows)
+        assert mslib.ms_untile_rows(t.ctypes.data_as(C.c_void_p), R, L, back.ctypes.data_as(C.c_void_p)) == 0
+        assert np.array_equal(back, rows)
+        if R:
+            assert np.array_equal(untile_rows(t, R, L), rows)
+            t4 = t.reshape(-1, 4)
+            for r, b in [(0, 0), (R - 1, nblk - 1), (R // 2, nblk // 3)]:
+                assert np.array_equal(t4[((r >> 3) * nblk + b) * 8 + ((r & 7) ^ (b & 7))], rows[r, 4 * b: 4 * b + 4])
+            if R % 8:    # padding slots of the last tile are "not spanned"
+                assert np.array_equal(t4[((R >> 3) * nblk + 0) * 8 + ((R & 7) ^ 0)], np.array([2 ** 32 - 1] * 3 + [0], dtype=np.uint32))

@@ -40,8 +40,8 @@ def test_oracle_reproduces_golden(oracle):
 @pytest.mark.gpu
 def test_gpu_reproduces_golden():
     import torch
-    from minorseq_b200 import Fuse, Juliet
-    d = torch.from_numpy(G["packed"].view(np.int32)).cuda()
+    from minorseq_b200 import Fuse, Juliet, device_rows
+    d = device_rows(G["packed"])
     R = G["packed"].shape[0]
     j = Juliet(L, GENES, refseq=REF, mode_phasing=True)
     j.set_count_insertions(True)

@@ -1,6 +1,6 @@
 """GPU parity at the REAL shapes of BASELINE.json configs[3] and configs[4] (reduced read counts so that the oracle finishes):
 
-* C5: L = 6144, V = 2048 dense variant sites, 64 strains -- K1's DENSE instantiation on twelve column segments, the staged
+* C5: L = 6144, V = 2048 dense variant sites, 64 strains -- K1's DENSE instantiation on column segments,
   phase_bits_kernel with 64-word bit-vectors, ~R distinct patterns through the device merge/order, and the co-occurrence
   matrix through the 36-tile x split-K tcgen05 launch;
 * C4: L = 9719 with the 15-gene / three-frame HXB2-style layout (logged rare path, 10-warp rows), call + phase.
@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip("torch")
 
-from minorseq_b200 import Handle, Juliet, _lib  # noqa: E402
+from minorseq_b200 import Handle, Juliet, _lib, host_rows  # noqa: E402
 from minorseq_b200.synth import SynthConfig, make_tables  # noqa: E402
 from test_gpu_parity import gpu_synth, mask_bytes, variants_equal  # noqa: E402
 
@@ -51,7 +51,7 @@ def test_c5_shape_pileup_phase_cooccurrence(oracle, hd):
     L, R = 6144, 40_000
     t = make_tables(SynthConfig(L=L, seed=20240005, dense_sites=2048, dense_strains=64, n_rate=2e-5, dele=2e-5, trunc=0.0))
     d = gpu_synth(hd, t, 0, R)
-    st = oracle.unpack(d.cpu().numpy().view(np.uint32), L, nthreads=8)
+    st = oracle.unpack(host_rows(d, R, L), L, nthreads=8)
     genes = [(1, L + 1)]
     j = Juliet(L, genes, mode_phasing=True, handle=hd)
     j.pileup_device(d.data_ptr(), R)
@@ -94,7 +94,7 @@ def test_c4_shape_full_genome_call_and_phase(oracle, hd):
     L, R = 9719, 24_000
     t = make_tables(SynthConfig(L=L, seed=20240004))
     d = gpu_synth(hd, t, 0, R)
-    st = oracle.unpack(d.cpu().numpy().view(np.uint32), L, nthreads=8)
+    st = oracle.unpack(host_rows(d, R, L), L, nthreads=8)
     j = Juliet(L, HIV_GENES, mode_phasing=True, min_perc=0.5, handle=hd)
     res = j.run_device(d.data_ptr(), R, want_hap_id=True)
     col, codon = j.get_counts()
@@ -119,7 +119,7 @@ def test_c4_shape_full_genome_call_and_phase(oracle, hd):
     assert np.array_equal(hp.hap_id, g["hap_id"])
     # the same pass from event rows (the e2e entry point) at this length
     from minorseq_b200 import encode_rows
-    hdr, ev = encode_rows(d.cpu().numpy().view(np.uint32), L, t.refseq)
+    hdr, ev = encode_rows(host_rows(d, R, L), L, t.refseq)
     j.set_base(t.refseq)
     res2 = j.run_events_host(hdr, ev, want_hap_id=True)
     col2, codon2 = j.get_counts()

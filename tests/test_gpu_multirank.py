@@ -26,10 +26,8 @@ def _pass(device, read0, nreads, native=False):
     j = Juliet(L, [(1, 3001), (2, 3000)], refseq=t.refseq, device=device, mode_phasing=True)
     if native:
         assert j.hd.attach_comm()
-    d = torch.empty((nreads, j.row_words), dtype=torch.int32, device=f"cuda:{device}")
-    sp = SynthParams(t.cfg.seed, L, t.nstrains, t.thr_N, t.thr_sub, t.thr_ins20, t.thr_trunc16)
-    _lib.check(j.lib.ms_synth_dev(j.hd.h, C.byref(sp), t.strain_base.ctypes.data_as(C.c_void_p), t.thr_del.ctypes.data_as(C.c_void_p),
-                                  t.strain_cum.ctypes.data_as(C.c_void_p), read0, nreads, C.c_void_p(d.data_ptr())), j.hd.h)
+    from minorseq_b200 import synth_device
+    d = synth_device(j.hd, t, read0, nreads)
     res = j.run_device(d.data_ptr(), nreads, want_hap_id=True)
     col, codon = j.get_counts()
     v = [(x.gene, x.col, x.codon, x.count, x.coverage, x.expected, x.ntests, x.pvalue) for x in res.variants]
@@ -93,7 +91,8 @@ def _phase_many(device, lo, hi, native, total=16000):
     j = Juliet(900, [(1, 901)], device=device, mode_phasing=True)
     if native:
         assert j.hd.attach_comm()
-    d = torch.from_numpy(pack_states(st[lo:hi]).view(np.int32)).to(f"cuda:{device}")
+    from minorseq_b200 import device_rows
+    d = device_rows(pack_states(st[lo:hi]), device)
     hap, keys = j.phase_device([V(c, k) for c, k in zip(cols, cods)], d.data_ptr(), hi - lo, cap=6000)
     return dict(patterns=hap.patterns, counts=hap.counts, nreported=hap.nreported, counters=hap.counters, hap_id=hap.hap_id,
                 ndistinct=hap.ndistinct)

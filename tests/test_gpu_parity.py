@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip("torch")
 
-from minorseq_b200 import Fuse, Handle, Juliet, _lib  # noqa: E402
+from minorseq_b200 import Fuse, Handle, Juliet, _lib, device_rows, host_rows, synth_device  # noqa: E402
 from minorseq_b200._lib import SynthParams  # noqa: E402
 from minorseq_b200.synth import (SynthConfig, make_tables, pack_states, read_strains, start_mask_words,  # noqa: E402
                                  synth_states)
@@ -21,7 +21,11 @@ PVAL_RTOL = 1e-9
 
 
 def to_dev(a):
-    return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
+    """plain host rows [R, row_words] -> device tiles (csrc/rows.cuh); anything else goes up as it is"""
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.uint32 and a.ndim == 2:
+        return device_rows(a)
+    return torch.from_numpy(a.view(np.int32)).cuda()
 
 
 def mask_bytes(words, L):
@@ -29,14 +33,7 @@ def mask_bytes(words, L):
 
 
 def gpu_synth(hd, t, read0, R):
-    lib = _lib.load()
-    nw = lib.ms_row_words(t.cfg.L)
-    out = torch.empty((R, nw), dtype=torch.int32, device="cuda")
-    p = SynthParams(t.cfg.seed, t.cfg.L, t.nstrains, t.thr_N, t.thr_sub, t.thr_ins20, t.thr_trunc16)
-    _lib.check(lib.ms_synth_dev(hd.h, C.byref(p), t.strain_base.ctypes.data_as(C.c_void_p),
-                                t.thr_del.ctypes.data_as(C.c_void_p), t.strain_cum.ctypes.data_as(C.c_void_p),
-                                read0, R, C.c_void_p(out.data_ptr())), hd.h)
-    return out
+    return synth_device(hd, t, read0, R)
 
 
 @pytest.fixture(scope="module")
@@ -180,7 +177,7 @@ def test_synth_gpu_equals_numpy(hd):
     for cfg in (SynthConfig(L=3000, seed=20240003), SynthConfig(L=97, seed=5, trunc=0.5),
                 SynthConfig(L=700, seed=6, dense_sites=200, dense_strains=16)):
         t = make_tables(cfg)
-        g = gpu_synth(hd, t, 1000, 600).cpu().numpy().view(np.uint32)
+        g = host_rows(gpu_synth(hd, t, 1000, 600), 600, t.cfg.L)
         assert np.array_equal(g, pack_states(synth_states(t, 1000, 600)))
 
 
@@ -193,7 +190,7 @@ def test_pileup_counter_overflow_flush(oracle, hd):
     j = Juliet(96, [(1, 97), (2, 97)], handle=hd)
     j.pileup_device(d.data_ptr(), R)
     col, codon = j.get_counts()
-    st = oracle.unpack(d.cpu().numpy().view(np.uint32), 96)
+    st = oracle.unpack(host_rows(d, R, 96), 96)
     ocol, ocodon = oracle.pileup(st, mask_bytes(j.start_mask, 96), nthreads=8)
     ocol[:, 6] = 0
     assert np.array_equal(col, ocol) and np.array_equal(codon, ocodon)

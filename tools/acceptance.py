@@ -37,7 +37,7 @@ def _synth(hd, t, R):
     from minorseq_b200 import _lib
     from minorseq_b200._lib import SynthParams
     lib = _lib.load()
-    d = torch.empty((R, lib.ms_row_words(L)), dtype=torch.int32, device="cuda")
+    d = torch.empty(((R + 7) // 8 * 8, lib.ms_row_words(L)), dtype=torch.int32, device="cuda")   # whole tiles (csrc/rows.cuh)
     sp = SynthParams(t.cfg.seed, L, t.nstrains, t.thr_N, t.thr_sub, t.thr_ins20, t.thr_trunc16)
     _lib.check(lib.ms_synth_dev(hd.h, C.byref(sp), t.strain_base.ctypes.data_as(C.c_void_p), t.thr_del.ctypes.data_as(C.c_void_p),
                                 t.strain_cum.ctypes.data_as(C.c_void_p), 0, R, C.c_void_p(d.data_ptr())), hd.h)

@@ -46,7 +46,7 @@ def main():
     j = Juliet(6144, [(1, 6145)], device=local, mode_phasing=True)
     if world > 1:
         assert j.hd.attach_comm()
-    d = torch.empty((R, j.row_words), dtype=torch.int32, device=f"cuda:{local}")
+    d = torch.empty(((R + 7) // 8 * 8, j.row_words), dtype=torch.int32, device=f"cuda:{local}")   # whole tiles (csrc/rows.cuh)
     sp = SynthParams(t.cfg.seed, 6144, t.nstrains, t.thr_N, t.thr_sub, t.thr_ins20, t.thr_trunc16)
     _lib.check(lib.ms_synth_dev(j.hd.h, C.byref(sp), t.strain_base.ctypes.data_as(C.c_void_p), t.thr_del.ctypes.data_as(C.c_void_p),
                                 t.strain_cum.ctypes.data_as(C.c_void_p), lo, R, C.c_void_p(d.data_ptr())), j.hd.h)

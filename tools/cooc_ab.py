@@ -41,7 +41,7 @@ for R, V in cases:
     vc = np.arange(V, dtype=np.int32) * 3
     vk = np.zeros(V, dtype=np.int32)
     _lib.check(lib.ms_phase_begin(hd.h, vc.ctypes.data_as(C.c_void_p), vk.ctypes.data_as(C.c_void_p), V, R), hd.h)
-    rows = torch.zeros((R, lib.ms_row_words(3 * V + 3)), dtype=torch.int32, device="cuda")
+    rows = torch.zeros(((R + 7) // 8 * 8, lib.ms_row_words(3 * V + 3)), dtype=torch.int32, device="cuda")
     _lib.check(lib.ms_phase_dev(hd.h, C.c_void_p(rows.data_ptr()), R), hd.h)      # sizes the buffers, sets phase_n
     pb, pf, pn = C.c_void_p(), C.c_void_p(), C.c_int64()
     _lib.check(lib.ms_phase_device(hd.h, C.byref(pb), C.byref(pf), C.byref(pn)), hd.h)

@@ -19,11 +19,12 @@ lib = _lib.load()
 t = make_tables(SynthConfig(L=L, seed=20240003))
 j = Juliet(L, [(1, L - L % 3 + 1)], refseq=t.refseq, mode_phasing=True, min_perc=0.5)
 nw = j.row_words
-d = torch.empty((R, nw), dtype=torch.int32, device="cuda")
+d = torch.empty(((R + 7) // 8 * 8, nw), dtype=torch.int32, device="cuda")   # whole tiles (csrc/rows.cuh)
 sp = SynthParams(t.cfg.seed, L, t.nstrains, t.thr_N, t.thr_sub, t.thr_ins20, t.thr_trunc16)
 _lib.check(lib.ms_synth_dev(j.hd.h, C.byref(sp), t.strain_base.ctypes.data_as(C.c_void_p), t.thr_del.ctypes.data_as(C.c_void_p),
                             t.strain_cum.ctypes.data_as(C.c_void_p), 0, R, C.c_void_p(d.data_ptr())), j.hd.h)
-rows = d.cpu().numpy().view(np.uint32)
+from minorseq_b200 import host_rows
+rows = host_rows(d, R, L)
 t0 = time.perf_counter()
 hdr, ev = encode_rows(rows, L, t.refseq)
 print(f"host encode: {time.perf_counter() - t0:.2f} s single thread, {len(ev) / R:.1f} events/read, {(hdr.nbytes + ev.nbytes) / R:.1f} B/read")

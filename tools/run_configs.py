@@ -19,7 +19,7 @@ lib = _lib.load()
 
 def synth(hd, t, R):
     nw = lib.ms_row_words(t.cfg.L)
-    d = torch.empty((R, nw), dtype=torch.int32, device="cuda")
+    d = torch.empty(((R + 7) // 8 * 8, nw), dtype=torch.int32, device="cuda")   # whole tiles (csrc/rows.cuh)
     sp = SynthParams(t.cfg.seed, t.cfg.L, t.nstrains, t.thr_N, t.thr_sub, t.thr_ins20, t.thr_trunc16)
     _lib.check(lib.ms_synth_dev(hd.h, C.byref(sp), t.strain_base.ctypes.data_as(C.c_void_p), t.thr_del.ctypes.data_as(C.c_void_p),
                                 t.strain_cum.ctypes.data_as(C.c_void_p), 0, R, C.c_void_p(d.data_ptr())), hd.h)

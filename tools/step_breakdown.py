@@ -9,7 +9,7 @@ from minorseq_b200.synth import SynthConfig, make_tables
 L, R = 3000, int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 t = make_tables(SynthConfig(L=L, seed=20240003))
 j = Juliet(L, [(1, 3001)], refseq=t.refseq, mode_phasing=True)
-d = torch.empty((R, j.row_words), dtype=torch.int32, device="cuda")
+d = torch.empty(((R + 7) // 8 * 8, j.row_words), dtype=torch.int32, device="cuda")   # whole tiles (csrc/rows.cuh)
 sp = SynthParams(t.cfg.seed, L, t.nstrains, t.thr_N, t.thr_sub, t.thr_ins20, t.thr_trunc16)
 _lib.check(j.lib.ms_synth_dev(j.hd.h, C.byref(sp), t.strain_base.ctypes.data_as(C.c_void_p), t.thr_del.ctypes.data_as(C.c_void_p),
                               t.strain_cum.ctypes.data_as(C.c_void_p), 0, R, C.c_void_p(d.data_ptr())), j.hd.h)
