@@ -9,6 +9,7 @@
 static std::string g_create_error;
 void ms_events_set_smem_attr(int max_smem);
 void ms_cooc_tc_set_smem_attr();
+void ms_phase_set_smem_attr();
 int ms_tile_rows_launch(ms_handle* h, const uint32_t* d_rows, int64_t R, uint32_t* d_tiled);
 
 extern "C" {
@@ -66,6 +67,7 @@ int ms_create(int device, ms_handle** out) {
     ms::pileup_set_smem_attr(h->max_smem);
     ms_events_set_smem_attr(h->max_smem);
     ms_cooc_tc_set_smem_attr();
+    ms_phase_set_smem_attr();
     *out = h;
     return MS_OK;
 }
@@ -199,7 +201,7 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
     // the imbalance when nseg does not divide the CTA count.  3 kb: whole rows (3 warps x 4 groups, 98 %); 9.7 kb: five
     // segments of 61 blocks (2 x 6, 95 %) instead of one 10-warp row (79 %); 6 kb: two of 96 (4 x 3, 75 %).
     static const int kGroups[13] = {0, 12, 6, 4, 3, 2, 2, 1, 1, 1, 1, 1, 1};
-    const int budget = h->max_smem - ms::kPileupSmemHeader - 16;
+    const int budget = h->max_smem - ms::kPileupSmemHeaderHi - 16;     // shapes must fit the HI instantiation as well
     const int forced = getenv("MS_K1_NSEG") ? atoi(getenv("MS_K1_NSEG")) : 0;   // tuning knob (tools/k1_segments.py)
     auto shape = [&](int nseg, int& W, int& need) {
         const int seg_len = (nblk + nseg - 1) / nseg;
@@ -242,13 +244,15 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
     if (start_mask)
         for (int32_t j = 0; j + 2 < L; ++j) nstarts += (start_mask[j >> 5] >> (j & 31)) & 1u;
     h->log_mode = start_mask != nullptr && nstarts * 20 > static_cast<int64_t>(L) * 9;   // > 0.45 starts per column
-    const int merge_bytes = (h->groups - 1) * 9 * ms::kPlanes * W * 32 * 4 + 64;  // end-of-kernel group merge reuses the ring (up to 9 masks)
-    h->stages = std::max(3, std::min(8, budget / h->stage_bytes));
+    const int merge_bytes = (h->groups - 1) * 9 * ms::kPlanesAll * W * 32 * 4 + 64;  // end-of-kernel group merge reuses the ring (up to 9 masks)
+    h->stages = std::max(3, std::min(8, (h->max_smem - ms::kPileupSmemHeader - 16) / h->stage_bytes));
+    h->stages_hi = std::max(3, std::min(8, budget / h->stage_bytes));
     h->smem_bytes = ms::kPileupSmemHeader + std::max(h->stages * h->stage_bytes + 16, merge_bytes);
+    h->smem_bytes_hi = ms::kPileupSmemHeaderHi + std::max(h->stages_hi * h->stage_bytes + 16, merge_bytes);
     // DENSE variant (pileup.cu, read_masks): a second bit-sliced codon count per start column; chosen at the first pile-up
     // after this call from the pivot sample's statistics
     h->dense_known = false; h->dense = false;
-    if (h->smem_bytes > h->max_smem) MS_FAIL(h, MS_ERR_ARG, "row too long for the shared-memory ring");
+    if (h->smem_bytes > h->max_smem || h->smem_bytes_hi > h->max_smem) MS_FAIL(h, MS_ERR_ARG, "row too long for the shared-memory ring");
     const size_t ncounts = static_cast<size_t>(L) * 72;
     MS_CUDA(h, cudaMalloc(&h->d_counts, ncounts * 4));
     MS_CUDA(h, cudaMemsetAsync(h->d_counts, 0, ncounts * 4, h->stream));
@@ -323,7 +327,7 @@ int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     a.warps_per_group = h->wpg; a.groups = h->groups;
     a.nseg = h->nseg; a.seg_len = h->seg_len;
     const bool dense = h->count_codons && h->dense;
-    a.stages = h->stages; a.stage_bytes = h->stage_bytes;
+    a.stages = h->stages; a.stages_hi = h->stages_hi; a.stage_bytes = h->stage_bytes;
     a.pivot = h->d_pivot; a.pivot2 = h->d_pivot2; a.start_mask = h->d_start; a.codon = codon;
     a.part_col = h->d_part_col; a.part_piv = h->d_part_piv; a.part_piv2 = h->d_part_piv2;
     const int mode = !h->count_codons ? ms::kModeFuse : (h->count_ins ? ms::kModeBoth : ms::kModeJuliet);
@@ -343,7 +347,10 @@ int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     }
     a.exc_list = h->b_exc_list.as<uint32_t>(); a.exc_cnt = h->b_exc_cnt.as<uint32_t>(); a.exc_cap = exc_cap; a.exc_lists = nlists;
     if (h->timing) MS_CUDA(h, cudaEventRecord(h->ev_k1[0], h->stream));
-    ms::pileup_launch(mode, dense, grid, threads, h->smem_bytes, h->stream, a);
+    // row-groups of more than 2047 reads: the instantiation with two more counter planes in shared memory (pileup.cu)
+    const int64_t steps_max = (ntiles + std::max(1, grid / h->nseg) - 1) / std::max(1, grid / h->nseg);   // tiles of the busiest CTA
+    const bool hi = steps_max * 8 > ms::kMaxReadsPerFlush;
+    ms::pileup_launch(mode, dense, hi, grid, threads, hi ? h->smem_bytes_hi : h->smem_bytes, h->stream, a);
     if (h->timing) { MS_CUDA(h, cudaEventRecord(h->ev_k1[1], h->stream)); h->k1_reads = R; }
     if (log_mode) { ms::pileup_exceptions_launch(dense, grid, threads, h->stream, a); h->launches++; }
     const int64_t nfin = static_cast<int64_t>(h->L) * 9 * 4;

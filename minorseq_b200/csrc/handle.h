@@ -51,7 +51,7 @@ struct ms_handle {
     uint2* d_pivot2 = nullptr;         // [nblk+1] designated base of the DENSE kernel (runner-up of the sample where frequent)
     uint8_t* d_pivot2_state = nullptr;
     uint32_t *d_part_col = nullptr, *d_part_piv = nullptr, *d_part_piv2 = nullptr;
-    int32_t groups = 1, wpg = 1, stages = 2, stage_bytes = 0, smem_bytes = 0;
+    int32_t groups = 1, wpg = 1, stages = 2, stages_hi = 2, stage_bytes = 0, smem_bytes = 0, smem_bytes_hi = 0;
     int32_t nseg = 1, seg_len = 0;   // column segments of K1 (abi_core.cu, ms_set_layout)
     bool have_pivot = false;
     bool log_mode = false;       // K1 logs flagged chunks for codon_exception_kernel (dense start masks)
@@ -81,7 +81,8 @@ struct ms_handle {
     int32_t V = 0, vwords = 0;
     int64_t phase_cap = 0, phase_n = 0;
     int32_t nblocklist = 0;
-    int32_t phase_nrec = 0;          // variants inside the reference (records of phase_bits_kernel)
+    int32_t phase_nrec = 0;          // words of phase_bits_kernel's variant stream
+    bool phase_ordered = true;       // the stream visits the words of the bit-vector one after the other
     bool phase_partial_all = false;  // some variant lies outside the reference: every read is partial
     int64_t tab_size = 0, tab_size_max = 0, tab_hint = 0;
     int64_t gcap_hint = 0;       // distinct-pattern capacity the last ordering pass needed

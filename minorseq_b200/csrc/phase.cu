@@ -20,37 +20,37 @@
 
 namespace ms {
 
-// One record per variant that lies inside the reference, in processing order (ascending first block):
-// x = slot of the first block in the block list (13 bits) | second block is the next slot (1) | first column in its
-// block (5) | plane-0 bits of the three bases (3) | plane-1 bits (3);  y = the variant's index in the caller's list.
-struct VarRec { uint32_t x, y; };
-
-__host__ __device__ inline uint32_t pack_var(int32_t slotA, int32_t slotB, int32_t shift, int32_t codon) {
-    const uint32_t b0 = (codon >> 4) & 3u, b1 = (codon >> 2) & 3u, b2 = codon & 3u;
-    const uint32_t k0 = (b0 & 1u) | ((b1 & 1u) << 1) | ((b2 & 1u) << 2);
-    const uint32_t k1 = (b0 >> 1) | ((b1 >> 1) << 1) | ((b2 >> 1) << 2);
-    return static_cast<uint32_t>(slotA) | (static_cast<uint32_t>(slotB - slotA) << 13) | (static_cast<uint32_t>(shift) << 14) | (k0 << 19) |
-           (k1 << 22);
-}
+// The variant list as a word stream the kernel walks once per read (ms_phase_begin builds it; all lanes read the same
+// word, so these are broadcast loads).  Per touched 32-column block, in block order, one or more LAYERS; a layer is a set of
+// variants starting in that block whose codons agree on every column they share (different codons at the same site, or
+// overlapping genes that disagree, go to further layers):
+//   header, 5 words: [ slot in the block list (13 bits) | variants in this layer (11) << 13 | first layer of its block << 24 ],
+//                    e0, e1  = bit-planes of the expected base per column (layer's codon columns; anything elsewhere),
+//                    en      = the same for columns 32, 33 (a codon that starts at column 30 or 31): e0 in bits 0-1, e1 in bits 2-3,
+//                    cover   = columns of this block that belong to ANY variant's codon (first layer only; damage flags)
+//   then one word per variant: first column in the block (5 bits) | index in the caller's list << 5.
+constexpr uint32_t kHdrFirst = 1u << 24;
 
 constexpr int kPhaseWarps = 8;
-constexpr int kPhaseChunk = 10;   // distinct blocks staged per pass (+1: the second block of a codon that straddles the chunk's end)
+constexpr int kPhaseChunkMax = 16;   // distinct blocks staged per pass (+1: the second block of a codon that straddles the chunk's end)
 
-// Bit-vectors and damage flags, any number of variants.  A lane owns a read, a warp four tiles (rows.cuh): the 32-column
-// blocks the variants touch are staged kPhaseChunk at a time into the warp's shared-memory slice -- per block one
-// 16-byte load per lane, 128 contiguous bytes per tile, every byte of the line used -- and the variants of the chunk
-// are then evaluated from there: all lanes work on the same variant, so the block in registers changes only when the
-// variant list moves on to another block (one LDS.128 per lane and distinct block, not per variant), the three codon
-// columns come out of a funnel shift, and the lane ORs the result into its own word of the bit-vector.  No ballots, no
-// shuffles; the bit-vector (zeroed by the caller) is touched once per 32 variants.  `partial_all`: some variant lies
-// outside the reference, which makes every read partial.
+// Bit-vectors and damage flags, any number of variants, evaluated bit-sliced.  A lane owns a read, a warp four tiles
+// (rows.cuh).  The touched blocks are staged `chunk` at a time into the warp's shared-memory slice -- per block one
+// 16-byte load per lane, 128 contiguous bytes per tile, every byte of the line used, all loads of a chunk in flight
+// together.  Per block and layer the lane then compares its 32 columns with the expected bases at once (2 LOP3 for the
+// mismatch mask, 2 SHF + 1 LOP3 to spread it over the three columns of every possible codon start, exactly K1's pivot
+// trick), and a variant costs one shift to pick its start column's bit and one to drop it into the lane's word of the
+// bit-vector.  Damage (deletion / QV-filtered base / not spanned inside any variant codon) is three masked ORs per block.
+// No ballots, no shuffles.  `ordered`: the stream visits the words of the bit-vector one after the other (the usual,
+// sorted variant list), so a finished word is stored; otherwise it is ORed into the zeroed vector.  `partial_all`: some
+// variant lies outside the reference, which makes every read partial.
 __global__ void __launch_bounds__(kPhaseWarps * 32) phase_bits_kernel(
-    const uint4* __restrict__ packed, int64_t R, int32_t nblk, const int32_t* __restrict__ blocklist, int32_t NB,
-    const VarRec* __restrict__ recs, int32_t NV, int32_t vwords, int32_t partial_all, uint32_t* __restrict__ bits,
-    uint8_t* __restrict__ flags, unsigned long long* __restrict__ ctr) {
-    __shared__ uint4 stage[kPhaseWarps][kPhaseChunk + 1][32];
+    const uint4* __restrict__ packed, int64_t R, int32_t nblk, const int32_t* __restrict__ blocklist, int32_t NB, int32_t chunk,
+    const uint32_t* __restrict__ stream, int32_t nwords, int32_t vwords, int32_t ordered, int32_t partial_all,
+    uint32_t* __restrict__ bits, uint8_t* __restrict__ flags, unsigned long long* __restrict__ ctr) {
+    extern __shared__ __align__(16) uint4 stage_sm[];   // [warp][chunk + 1][32]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint4 (*sm)[32] = stage[warp];
+    uint4* sm = stage_sm + static_cast<size_t>(warp) * (chunk + 1) * 32 + lane;
     const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kPhaseWarps;
     unsigned long long c_dam = 0, c_gap = 0, c_het = 0, c_par = 0;
     for (int64_t base = (static_cast<int64_t>(blockIdx.x) * kPhaseWarps + warp) * 32; base < R; base += nwarps * 32) {
@@ -61,43 +61,60 @@ __global__ void __launch_bounds__(kPhaseWarps * 32) phase_bits_kernel(
         uint32_t fg = 0, fh = 0, fp = partial_all ? 1u : 0u;
         uint32_t word = 0, widx = 0xffffffffu;
         uint32_t* myrow = bits + static_cast<size_t>(r) * vwords;
-        int32_t v = 0;
-        for (int32_t c0 = 0; c0 < NB; c0 += kPhaseChunk) {
-            const int32_t nb = min(kPhaseChunk + 1, NB - c0);
-#pragma unroll 8
+        int32_t p = 0;     // position in the stream
+        for (int32_t c0 = 0; c0 < NB; c0 += chunk) {
+            const int32_t nb = min(chunk + 1, NB - c0);
+            // per-lane 16-byte asynchronous copies global -> shared (LDGSTS): every block of the chunk is in flight at once,
+            // no registers in between
+#pragma unroll 4
             for (int32_t s2 = 0; s2 < nb; ++s2) {
                 const int32_t blk = blocklist[c0 + s2];
-                sm[s2][lane] = live ? tile[blk * 8 + (pos ^ (blk & 7))] : make_uint4(0, 0, 0, 0);
+                const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(sm + s2 * 32));
+                const uint4* src = tile + (blk * 8 + (pos ^ (blk & 7)));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(live ? src : packed), "r"(live ? 16 : 0) : "memory");
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncwarp();
-            int32_t cur = -1;
-            uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
-            for (; v < NV; ++v) {
-                const VarRec rec = recs[v];
-                const int32_t sa = static_cast<int32_t>(rec.x & 0x1FFFu) - c0;
-                if (sa >= kPhaseChunk) break;                   // belongs to the next chunk (the list is in block order)
-                const bool straddle = (rec.x >> 13) & 1u;
-                if (sa != cur) { cur = sa; qa = sm[sa][lane]; }
-                if (straddle) qb = sm[sa + 1][lane];
-                const uint32_t sh = (rec.x >> 14) & 31u;
-                const uint32_t b0 = __funnelshift_r(qa.x, straddle ? qb.x : qa.x, sh) & 7u;
-                const uint32_t b1 = __funnelshift_r(qa.y, straddle ? qb.y : qa.y, sh) & 7u;
-                const uint32_t z = __funnelshift_r(qa.z, straddle ? qb.z : qa.z, sh) & 7u;
-                fg |= z & ~b0 & ~b1;      // 100  deletion
-                fh |= z & b0 & ~b1;       // 101  QV-filtered base
-                fp |= z & b1;             // 11x  not spanned
-                const uint32_t bit = ((b0 ^ ((rec.x >> 19) & 7u)) | (b1 ^ ((rec.x >> 22) & 7u)) | z) == 0u ? 1u : 0u;
-                const uint32_t wi = rec.y >> 5;
-                if (wi != widx) {                               // warp-uniform: all lanes are at the same variant
-                    if (live && widx != 0xffffffffu && word) myrow[widx] |= word;
-                    widx = wi; word = 0;
+            while (p < nwords) {
+                const uint32_t h0 = stream[p];
+                const int32_t sa = static_cast<int32_t>(h0 & 0x1FFFu) - c0;
+                if (sa >= chunk) break;                               // the next chunk's block
+                const uint32_t e0 = stream[p + 1], e1 = stream[p + 2], en = stream[p + 3], cover = stream[p + 4];
+                const int32_t nv = static_cast<int32_t>((h0 >> 13) & 0x7FFu);
+                p += 5;
+                const uint4 q = sm[sa * 32];
+                const uint4 nx = sa + 1 < nb ? sm[(sa + 1) * 32] : make_uint4(0, 0, ~0u, 0);
+                if (h0 & kHdrFirst) {
+                    fg |= q.z & ~q.x & ~q.y & cover;      // 100  deletion
+                    fh |= q.z & q.x & ~q.y & cover;       // 101  QV-filtered base
+                    fp |= q.z & q.y & cover;              // 11x  not spanned
                 }
-                word |= bit << (rec.y & 31u);
+                const uint32_t X = ((q.x ^ e0) | (q.y ^ e1)) | q.z;                       // column is not the clean expected base
+                const uint32_t Xn = ((nx.x ^ en) | (nx.y ^ (en >> 2))) | nx.z;            // columns 32, 33 (bits 0, 1)
+                const uint32_t hit = ~(X | __funnelshift_r(X, Xn, 1) | __funnelshift_r(X, Xn, 2));   // bit c: the codon starting at c matches
+                for (int32_t k = 0; k < nv; ++k) {
+                    const uint32_t w = stream[p + k];
+                    const uint32_t bit = __funnelshift_r(hit, 0u, w) & 1u;                 // shift by the low 5 bits of w: the start column
+                    const uint32_t v = w >> 5;
+                    if ((v >> 5) != widx) {                                                // warp-uniform: all lanes are at the same variant
+                        if (live && widx != 0xffffffffu) {
+                            if (ordered) myrow[widx] = word;
+                            else if (word) myrow[widx] |= word;
+                        }
+                        widx = v >> 5; word = 0;
+                    }
+                    word |= __funnelshift_l(0u, bit, v);                                    // bit << (v & 31)
+                }
+                p += nv;
             }
             __syncwarp();
         }
         if (live) {
-            if (widx != 0xffffffffu && word) myrow[widx] |= word;
+            if (widx != 0xffffffffu) {
+                if (ordered) myrow[widx] = word;
+                else if (word) myrow[widx] |= word;
+            }
             const uint32_t f = (fg ? MS_FLAG_GAP : 0) | (fh ? MS_FLAG_HET : 0) | (fp ? MS_FLAG_PARTIAL : 0);
             flags[r] = static_cast<uint8_t>(f);
             if (f) {
@@ -368,6 +385,12 @@ int phase_groups_copy_out(ms_handle* h, uint32_t* patterns, uint64_t* counts, in
 
 }  // namespace
 
+// opt the bit-vector kernel in to its largest staging area (8 warps x 17 blocks x 512 B), on the current device (ms_create)
+void ms_phase_set_smem_attr() {
+    cudaFuncSetAttribute(ms::phase_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         ms::kPhaseWarps * (ms::kPhaseChunkMax + 1) * 32 * static_cast<int>(sizeof(uint4)));
+}
+
 extern "C" {
 
 void ms_phase_free_internal(ms_handle* h) {
@@ -401,23 +424,69 @@ int ms_phase_begin(ms_handle* h, const int32_t* var_col, const int32_t* var_codo
     blocks.erase(std::unique(blocks.begin(), blocks.end()), blocks.end());
     if (blocks.empty()) blocks.push_back(0);
     h->nblocklist = static_cast<int32_t>(blocks.size());
-    // records of the variants inside the reference, in block order (the kernel walks the block list once)
-    std::vector<ms::VarRec> vd;
-    vd.reserve(static_cast<size_t>(std::max(1, V)));
+    if (blocks.size() > 0x1FFF) MS_FAIL(h, MS_ERR_CAPACITY, "variants touch more than 8191 distinct 32-column blocks");
+    // the word stream of phase_bits_kernel (layout documented there): per touched block its layers, per layer its variants
+    const int32_t NBl = static_cast<int32_t>(blocks.size());
+    std::vector<std::vector<int32_t>> by_block(static_cast<size_t>(NBl));      // variants starting in each listed block, by column
+    std::vector<uint32_t> cover(static_cast<size_t>(NBl), 0u);
     h->phase_partial_all = false;
-    for (int32_t v = 0; v < V; ++v) {
-        if (var_col[v] + 2 < h->L) {
-            const int32_t sa = static_cast<int32_t>(std::lower_bound(blocks.begin(), blocks.end(), var_col[v] >> 5) - blocks.begin());
-            const int32_t sb = static_cast<int32_t>(std::lower_bound(blocks.begin(), blocks.end(), (var_col[v] + 2) >> 5) - blocks.begin());
-            vd.push_back({ms::pack_var(sa, sb, var_col[v] & 31, var_codon[v]), static_cast<uint32_t>(v)});
-        } else {
-            h->phase_partial_all = true;     // a variant outside the reference: no read spans it
+    {
+        std::vector<int32_t> order;
+        for (int32_t v = 0; v < V; ++v) {
+            if (var_col[v] + 2 < h->L) order.push_back(v);
+            else h->phase_partial_all = true;     // a variant outside the reference: no read spans it
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return var_col[a] < var_col[b]; });
+        for (int32_t v : order) {
+            for (int32_t c = var_col[v]; c < var_col[v] + 3; ++c) {
+                const int32_t sl = static_cast<int32_t>(std::lower_bound(blocks.begin(), blocks.end(), c >> 5) - blocks.begin());
+                cover[sl] |= 1u << (c & 31);
+            }
+            by_block[std::lower_bound(blocks.begin(), blocks.end(), var_col[v] >> 5) - blocks.begin()].push_back(v);
         }
     }
-    if (blocks.size() > 0x1FFF) MS_FAIL(h, MS_ERR_CAPACITY, "variants touch more than 8191 distinct 32-column blocks");
-    std::stable_sort(vd.begin(), vd.end(), [](const ms::VarRec& a, const ms::VarRec& b) { return (a.x & 0x1FFFu) < (b.x & 0x1FFFu); });
+    std::vector<uint32_t> vd;
+    bool ordered = true;
+    int64_t last_word = -1;
+    std::vector<char> word_seen(static_cast<size_t>(h->vwords), 0);
+    for (int32_t sl = 0; sl < NBl; ++sl) {
+        // greedy layering: a variant joins the first layer whose expected bases agree with its codon on shared columns
+        struct Layer { int8_t base[34]; std::vector<int32_t> vars; };
+        std::vector<Layer> layers;
+        for (int32_t v : by_block[sl]) {
+            const int32_t c = var_col[v] & 31;
+            const int8_t cod[3] = {static_cast<int8_t>((var_codon[v] >> 4) & 3), static_cast<int8_t>((var_codon[v] >> 2) & 3), static_cast<int8_t>(var_codon[v] & 3)};
+            size_t li = 0;
+            for (; li < layers.size(); ++li) {
+                bool ok = true;
+                for (int k = 0; k < 3; ++k) ok = ok && (layers[li].base[c + k] < 0 || layers[li].base[c + k] == cod[k]);
+                if (ok) break;
+            }
+            if (li == layers.size()) { layers.emplace_back(); memset(layers.back().base, -1, sizeof layers.back().base); }
+            for (int k = 0; k < 3; ++k) layers[li].base[c + k] = cod[k];
+            layers[li].vars.push_back(v);
+        }
+        if (layers.empty()) { layers.emplace_back(); memset(layers.back().base, -1, sizeof layers.back().base); }   // spill-over block: flags only
+        for (size_t li = 0; li < layers.size(); ++li) {
+            const Layer& ly = layers[li];
+            if (ly.vars.size() > 0x7FF) MS_FAIL(h, MS_ERR_CAPACITY, "more than 2047 variants start in one 32-column block");
+            uint32_t e0 = 0, e1 = 0, en = 0;
+            for (int c = 0; c < 32; ++c)
+                if (ly.base[c] > 0) { e0 |= static_cast<uint32_t>(ly.base[c] & 1) << c; e1 |= static_cast<uint32_t>((ly.base[c] >> 1) & 1) << c; }
+            for (int c = 32; c < 34; ++c)
+                if (ly.base[c] > 0) { en |= static_cast<uint32_t>(ly.base[c] & 1) << (c - 32); en |= static_cast<uint32_t>((ly.base[c] >> 1) & 1) << (c - 32 + 2); }
+            vd.push_back(static_cast<uint32_t>(sl) | (static_cast<uint32_t>(ly.vars.size()) << 13) | (li == 0 ? ms::kHdrFirst : 0u));
+            vd.push_back(e0); vd.push_back(e1); vd.push_back(en); vd.push_back(li == 0 ? cover[sl] : 0u);
+            for (int32_t v : ly.vars) {
+                vd.push_back(static_cast<uint32_t>(var_col[v] & 31) | (static_cast<uint32_t>(v) << 5));
+                const int64_t wi = v >> 5;
+                if (wi != last_word) { if (word_seen[wi]) ordered = false; word_seen[wi] = 1; last_word = wi; }
+            }
+        }
+    }
     h->phase_nrec = static_cast<int32_t>(vd.size());
-    if (vd.empty()) vd.push_back({0u, 0u});
+    h->phase_ordered = ordered;
+    if (vd.empty()) vd.push_back(0u);
     // The table starts small (distinct patterns are usually a few hundred) and is re-sized by
     // ms_phase_groups when an insert reports overflow; its upper bound is 2x the reads.
     int64_t ts_max = 1024;
@@ -426,11 +495,11 @@ int ms_phase_begin(ms_handle* h, const int32_t* var_col, const int32_t* var_codo
     int64_t ts = std::min<int64_t>(ts_max, std::max<int64_t>(1 << 16, h->tab_hint));   // last pass's grown size is the hint
     h->tab_size = ts;
     // the previous pass may still be reading these buffers on the stream if they have to move
-    const bool grow = vd.size() * sizeof(ms::VarRec) > h->b_var.cap || blocks.size() * 4 > h->b_blocklist.cap ||
+    const bool grow = vd.size() * 4 > h->b_var.cap || blocks.size() * 4 > h->b_blocklist.cap ||
                       static_cast<size_t>(h->phase_cap) * h->vwords * 4 > h->b_bits.cap || static_cast<size_t>(h->phase_cap) > h->b_flags.cap ||
                       static_cast<size_t>(ts) * 8 > h->b_tab_key.cap || !h->b_ctr.p;
     if (grow) MS_CUDA(h, cudaStreamSynchronize(h->stream));
-    MS_CUDA(h, h->b_var.ensure(vd.size() * sizeof(ms::VarRec)));
+    MS_CUDA(h, h->b_var.ensure(vd.size() * 4));
     MS_CUDA(h, h->b_blocklist.ensure(blocks.size() * 4));
     MS_CUDA(h, h->b_bits.ensure(static_cast<size_t>(h->phase_cap) * h->vwords * 4));
     MS_CUDA(h, h->b_flags.ensure(static_cast<size_t>(h->phase_cap)));
@@ -443,7 +512,7 @@ int ms_phase_begin(ms_handle* h, const int32_t* var_col, const int32_t* var_codo
     if (rc != MS_OK) return rc;
     // pageable -> device copies of the small tables go through the pinned stage to stay asynchronous
     uint8_t* st = static_cast<uint8_t*>(h->h_stage);
-    const size_t nb_var = vd.size() * sizeof(ms::VarRec), nb_blk = blocks.size() * 4;
+    const size_t nb_var = vd.size() * 4, nb_blk = blocks.size() * 4;
     if (nb_var + nb_blk <= h->h_stage_cap) {
         memcpy(st, vd.data(), nb_var);
         memcpy(st + nb_var, blocks.data(), nb_blk);
@@ -467,15 +536,19 @@ int ms_phase_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     uint32_t* bits = h->b_bits.as<uint32_t>() + static_cast<size_t>(h->phase_n) * h->vwords;
     uint8_t* flags = h->b_flags.as<uint8_t>() + h->phase_n;
     const uint4* pk = reinterpret_cast<const uint4*>(d_packed);
-    const ms::VarRec* recs = h->b_var.as<ms::VarRec>();
+    const uint32_t* stream = h->b_var.as<uint32_t>();
     unsigned long long* ctr = ctr_ptr(h);
-    MS_CUDA(h, cudaMemsetAsync(bits, 0, static_cast<size_t>(R) * h->vwords * 4, h->stream));   // the kernel ORs its words in
+    MS_CUDA(h, cudaMemsetAsync(bits, 0, static_cast<size_t>(R) * h->vwords * 4, h->stream));   // words no variant maps to stay zero
     MS_STAGE_BEGIN(h, MS_STAGE_PHASE_BITS);
     {
+        const int chunk = std::min(ms::kPhaseChunkMax, h->nblocklist);
+        const size_t smem = static_cast<size_t>(ms::kPhaseWarps) * (chunk + 1) * 32 * sizeof(uint4);
+        const int per_sm = std::max(1, std::min(6, static_cast<int>((h->max_smem + 1024) / (smem + 1024))));
         const int64_t want = (R + ms::kPhaseWarps * 32 - 1) / (ms::kPhaseWarps * 32);
-        const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(h->num_sms) * 4)));
-        ms::phase_bits_kernel<<<grid, ms::kPhaseWarps * 32, 0, h->stream>>>(pk, R, h->nblk, h->b_blocklist.as<int32_t>(), h->nblocklist, recs,
-                                                                           h->phase_nrec, h->vwords, h->phase_partial_all ? 1 : 0, bits, flags, ctr);
+        const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(h->num_sms) * per_sm)));
+        ms::phase_bits_kernel<<<grid, ms::kPhaseWarps * 32, smem, h->stream>>>(pk, R, h->nblk, h->b_blocklist.as<int32_t>(), h->nblocklist, chunk,
+                                                                              stream, h->phase_nrec, h->vwords, h->phase_ordered ? 1 : 0,
+                                                                              h->phase_partial_all ? 1 : 0, bits, flags, ctr);
     }
     MS_STAGE_END(h, MS_STAGE_PHASE_BITS);
     h->launches++;

@@ -83,8 +83,30 @@ struct Vert {
     uint32_t p3[NM], p4[NM], p5[NM];  // pending carry-save inputs of weight 8, 16 and 32
 };
 
+// Planes kPlanes and kPlanes+1 (weights 2048 and 4096) live in shared memory, one word per thread and mask: a carry out of
+// the register planes reaches them once per 2048 reads of a column, so they cost nothing in the hot loop and lift the
+// capacity of a row-group from 2047 to 8191 reads -- which keeps the barrier-ordered mid-kernel flush out of every
+// workload of ordinary size (it costs G serialised read-modify-write rounds over the CTA's slice).  HI is a template
+// switch: K1 sits at its register limit, and carrying the two extra values cost the 1M x 3 kb kernel 5 %, so launches
+// whose row-groups stay below 2048 reads use the instantiation without it.
+struct HiPlanes {
+    uint32_t base;     // shared-memory address of this thread's word of (plane kPlanes, mask 0)
+    uint32_t stride;   // bytes between consecutive masks (= threads * 4); plane kPlanes+1 follows the NM masks of plane kPlanes
+};
 template <int NM>
-__device__ __forceinline__ void ripple(Vert<NM>& v, int i, int level, uint32_t x) {
+__device__ __forceinline__ void hi_add(const HiPlanes& hp, int i, uint32_t x) {
+    const uint32_t a0 = hp.base + static_cast<uint32_t>(i) * hp.stride;
+    const uint32_t p = lds32(a0);
+    sts32(a0, p ^ x);
+    const uint32_t c = p & x;
+    if (c) {
+        const uint32_t a1 = a0 + static_cast<uint32_t>(NM) * hp.stride;
+        sts32(a1, lds32(a1) ^ c);     // capacity checked by the caller (kMaxReadsPerFlush): no carry out of this one
+    }
+}
+
+template <bool HI, int NM>
+__device__ __forceinline__ void ripple(Vert<NM>& v, const HiPlanes& hp, int i, int level, uint32_t x) {
 #pragma unroll
     for (int k = 0; k < kPlanes; ++k) {
         if (k >= level) {
@@ -92,6 +114,9 @@ __device__ __forceinline__ void ripple(Vert<NM>& v, int i, int level, uint32_t x
             v.c[i][k] ^= x;
             x = t;
         }
+    }
+    if (HI) {
+        if (x) hi_add<NM>(hp, i, x);
     }
 }
 
@@ -185,8 +210,9 @@ __device__ __forceinline__ void codon_exceptions(uint32_t addr, uint32_t naddr, 
     }
 }
 
-template <int MODE, bool DENSE>
-__device__ __forceinline__ uint32_t block8(uint32_t addr, const CodonCtx& cx, Vert<Traits<MODE, DENSE>::NM>& v, uint32_t bi) {
+template <int MODE, bool DENSE, bool HI>
+__device__ __forceinline__ uint32_t block8(uint32_t addr, const CodonCtx& cx, Vert<Traits<MODE, DENSE>::NM>& v, const HiPlanes& hp,
+                                           uint32_t bi) {
     constexpr int NM = Traits<MODE, DENSE>::NM;
     uint32_t m0[NM], m1[NM], twosA[NM], twosB[NM], foursA[NM], foursB[NM];
     uint32_t pm = 0;
@@ -225,7 +251,7 @@ __device__ __forceinline__ uint32_t block8(uint32_t addr, const CodonCtx& cx, Ve
                     csa(x16, v.c[i][3], v.c[i][3], v.p3[i], twosA[i]);
                     csa(x32, v.c[i][4], v.c[i][4], v.p4[i], x16);
                     csa(x64, v.c[i][5], v.c[i][5], v.p5[i], x32);
-                    ripple(v, i, 6, x64);
+                    ripple<HI>(v, hp, i, 6, x64);
                 }
             } else {
 #pragma unroll
@@ -278,10 +304,10 @@ __device__ __forceinline__ void transpose16x2(uint32_t (&a)[16]) {
     }
 }
 
-// planes: this thread's counters (pendings already folded), [NM][kPlanes] in local memory.
+// planes: this thread's counters (pendings already folded), [NM][NP] in local memory (NP = kPlanes, or kPlanesAll with the shared-memory planes).
 // Adds the other groups' planes from shared memory (bit-sliced ripple-carry), transposes to
 // per-column integers and stores / adds them into the CTA's slice.
-template <int MODE, bool DENSE>
+template <int MODE, bool DENSE, int NP>
 __device__ __noinline__ void emit_slice(const uint32_t* planes, uint32_t merge_base, int other_groups, uint32_t group_stride,
                                         uint32_t thread_stride, uint32_t n, uint32_t start, uint32_t* pc, uint32_t* pp, uint32_t* pd,
                                         bool add) {
@@ -292,13 +318,13 @@ __device__ __noinline__ void emit_slice(const uint32_t* planes, uint32_t merge_b
     for (int i = 0; i < NM; ++i) {
         uint32_t acc[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc[k] = k < kPlanes ? planes[i * kPlanes + k] : 0u;
+        for (int k = 0; k < 16; ++k) acc[k] = k < NP ? planes[i * NP + k] : 0u;
         for (int g = 0; g < other_groups; ++g) {
             uint32_t carry = 0;
-            const uint32_t base = merge_base + static_cast<uint32_t>(g) * group_stride + static_cast<uint32_t>(i * kPlanes) * thread_stride;
+            const uint32_t base = merge_base + static_cast<uint32_t>(g) * group_stride + static_cast<uint32_t>(i * NP) * thread_stride;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                const uint32_t b = k < kPlanes ? lds32(base + static_cast<uint32_t>(k) * thread_stride) : 0u;
+                const uint32_t b = k < NP ? lds32(base + static_cast<uint32_t>(k) * thread_stride) : 0u;
                 const uint32_t u = acc[k] ^ b;
                 const uint32_t nc = (acc[k] & b) | (u & carry);
                 acc[k] = u ^ carry;
@@ -351,33 +377,52 @@ __device__ __noinline__ void emit_slice(const uint32_t* planes, uint32_t merge_b
     }
 }
 
-template <int NM>
-__device__ __forceinline__ void fold_pendings(Vert<NM>& v, uint32_t bi) {
+template <bool HI, int NM>
+__device__ __forceinline__ void fold_pendings(Vert<NM>& v, const HiPlanes& hp, uint32_t bi) {
 #pragma unroll
     for (int i = 0; i < NM; ++i) {
-        if (bi & 1u) ripple(v, i, 3, v.p3[i]);
-        if (bi & 2u) ripple(v, i, 4, v.p4[i]);
-        if (bi & 4u) ripple(v, i, 5, v.p5[i]);
+        if (bi & 1u) ripple<HI>(v, hp, i, 3, v.p3[i]);
+        if (bi & 2u) ripple<HI>(v, hp, i, 4, v.p4[i]);
+        if (bi & 4u) ripple<HI>(v, hp, i, 5, v.p5[i]);
     }
 }
 
-template <int NM>
-__device__ __forceinline__ void clear(Vert<NM>& v) {
+template <bool HI, int NM>
+__device__ __forceinline__ void clear(Vert<NM>& v, const HiPlanes& hp) {
 #pragma unroll
     for (int i = 0; i < NM; ++i) {
 #pragma unroll
         for (int k = 0; k < kPlanes; ++k) v.c[i][k] = 0;
         v.p3[i] = v.p4[i] = v.p5[i] = 0;
+        if (HI) {
+            sts32(hp.base + static_cast<uint32_t>(i) * hp.stride, 0u);
+            sts32(hp.base + static_cast<uint32_t>(NM + i) * hp.stride, 0u);
+        }
     }
 }
 
-template <int MODE, bool DENSE, bool SEG>
+// this thread's counters as kPlanesAll planes per mask: registers + the two shared-memory planes
+template <bool HI, int NM>
+__device__ __forceinline__ void gather_planes(const Vert<NM>& v, const HiPlanes& hp, uint32_t* planes) {
+    constexpr int NP = HI ? kPlanesAll : kPlanes;
+#pragma unroll
+    for (int i = 0; i < NM; ++i) {
+#pragma unroll
+        for (int k = 0; k < kPlanes; ++k) planes[i * NP + k] = v.c[i][k];
+        if (HI) {
+            planes[i * NP + kPlanes] = lds32(hp.base + static_cast<uint32_t>(i) * hp.stride);
+            planes[i * NP + kPlanes + 1] = lds32(hp.base + static_cast<uint32_t>(NM + i) * hp.stride);
+        }
+    }
+}
+
+template <int MODE, bool DENSE, bool SEG, bool HI>
 __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     using T = Traits<MODE, DENSE>;
     constexpr int NM = T::NM;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int W = a.warps_per_group, G = a.groups, S = a.stages;
+    const int W = a.warps_per_group, G = a.groups, S = HI ? a.stages_hi : a.stages;
     const int ncw = W * G;  // all warps are consumers; lane 0 of warp 0 also produces
     // Column segments: with nseg > 1 a CTA handles only the blocks [blk0, blk0 + seg_nblk) of its reads (plus one
     // look-ahead block of the next segment), so that row lengths whose warp count per row does not divide 12 still
@@ -394,7 +439,7 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     const size_t tile_bytes = static_cast<size_t>(a.nblk) * 128u;                 // one tile of 8 reads in global memory (rows.cuh)
     const uint32_t bar0 = smem_u32(smem);          // full barrier of slot (g,s) at bar0 + 8*(g*S+s)
     const uint32_t cnt0 = bar0 + 1024;             // release counter of slot (g,s) at cnt0 + 4*(g*S+s)
-    const uint32_t data0 = bar0 + kPileupSmemHeader;  // slot (g,s) at data0 + (g*S+s)*chunk_bytes
+    const uint32_t data0 = bar0 + (HI ? kPileupSmemHeaderHi : kPileupSmemHeader);  // slot (g,s) at data0 + (g*S+s)*chunk_bytes
     const uint32_t chunk_bytes = static_cast<uint32_t>(load_nblk) * 128u;         // a slot = this segment's blocks of one tile
     const int64_t Tr = static_cast<int64_t>(G) * 8;  // reads per tile (one 8-read chunk per row-group)
     const int64_t ntiles = (a.R + Tr - 1) / Tr;
@@ -447,8 +492,15 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     lg.cnt = 0;
     lg.list = a.exc_list + list_id * a.exc_cap;
 
+    // shared-memory planes kPlanes, kPlanes+1 of this thread's counters (in the header area)
+    HiPlanes hp;
+    hp.stride = HI ? static_cast<uint32_t>(blockDim.x) * 4u : 0u;
+    hp.base = HI ? bar0 + kPileupHiOffset + static_cast<uint32_t>(threadIdx.x) * 4u : 0u;
+    constexpr uint32_t kFlushAt = HI ? kMaxReadsPerFlushHi : kMaxReadsPerFlush;
+    constexpr int NP = HI ? kPlanesAll : kPlanes;     // counter planes per mask
+
     Vert<NM> v;
-    clear(v);
+    clear<HI>(v, hp);
     uint32_t bi = 0, n = 0, tiles_since_flush = 0;
     bool mid = false;
     uint32_t* pc = a.part_col + (static_cast<size_t>(blockIdx.x) * a.nblk + blk) * 256;
@@ -480,19 +532,16 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     uint32_t stage = 0, phase = 0;
     int64_t kt = 0;
     for (int64_t t = cta_in_seg; t < ntiles; t += ctas_in_seg, ++kt) {
-        if (8u * (tiles_since_flush + 1u) > static_cast<uint32_t>(kMaxReadsPerFlush)) {
+        if (8u * (tiles_since_flush + 1u) > kFlushAt) {
             // counters would overflow: every group adds its integers into the slice, one group at a time
-            fold_pendings(v, bi);
-            uint32_t planes[NM * kPlanes];
-#pragma unroll
-            for (int i = 0; i < NM; ++i)
-#pragma unroll
-                for (int k = 0; k < kPlanes; ++k) planes[i * kPlanes + k] = v.c[i][k];
+            fold_pendings<HI>(v, hp, bi);
+            uint32_t planes[NM * NP];
+            gather_planes<HI>(v, hp, planes);
             for (int g = 0; g < G; ++g) {
-                if (g == group && active) emit_slice<MODE, DENSE>(planes, 0u, 0, 0u, 0u, n, cx.start, pc, pp, pd, mid || g > 0);
+                if (g == group && active) emit_slice<MODE, DENSE, NP>(planes, 0u, 0, 0u, 0u, n, cx.start, pc, pp, pd, mid || g > 0);
                 consumer_barrier(nct);
             }
-            clear(v);
+            clear<HI>(v, hp);
             bi = 0; n = 0; tiles_since_flush = 0; mid = true;
         }
         const int64_t r0 = t * Tr + group * 8;
@@ -503,7 +552,7 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         const uint32_t addr = data0 + slot * chunk_bytes + blk_off;   // read i of the tile at addr ^ 16 i
         const uint32_t naddr = data0 + slot * chunk_bytes + nblk_off; // same for the next block (rare path only)
         if (nv == 8) {
-            const uint32_t pm = block8<MODE, DENSE>(addr, cx, v, bi);
+            const uint32_t pm = block8<MODE, DENSE, HI>(addr, cx, v, hp, bi);
             if (T::CODON && pm) log_or_handle<DENSE>(pm, static_cast<uint32_t>(r0), lg, addr, naddr, cx);
             ++bi;
             n += 8;
@@ -513,7 +562,7 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
                 uint32_t pm = 0;
                 read_masks<MODE, DENSE>(addr ^ (static_cast<uint32_t>(i) << 4), cx, m, pm, 1u);
 #pragma unroll
-                for (int q = 0; q < NM; ++q) ripple(v, q, 0, m[q]);
+                for (int q = 0; q < NM; ++q) ripple<HI>(v, hp, q, 0, m[q]);
                 if (T::CODON && pm) log_or_handle<DENSE>(1u << i, static_cast<uint32_t>(r0), lg, addr, naddr, cx);
                 ++n;
             }
@@ -537,71 +586,70 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     if (T::CODON) a.exc_cnt[list_id] = lg.cnt;
 
     // ---------------- final merge: groups 1..G-1 hand their planes to group 0 through shared memory
-    fold_pendings(v, bi);
+    fold_pendings<HI>(v, hp, bi);
     // all tiles are consumed and every bulk copy has landed, so the stage ring is free to reuse
     consumer_barrier(nct);
     const uint32_t tg = static_cast<uint32_t>(W) * 32u;           // threads per group
     const uint32_t thread_stride = tg * 4u;                       // bytes between planes
-    const uint32_t group_stride = static_cast<uint32_t>(NM * kPlanes) * thread_stride;
+    const uint32_t group_stride = static_cast<uint32_t>(NM * NP) * thread_stride;
     const uint32_t ncount0 = data0 + static_cast<uint32_t>(G - 1) * group_stride;  // n of groups 1..G-1
     if (group > 0) {
         const uint32_t base = data0 + static_cast<uint32_t>(group - 1) * group_stride + static_cast<uint32_t>(tig) * 4u;
 #pragma unroll
-        for (int i = 0; i < NM; ++i)
+        for (int i = 0; i < NM; ++i) {
 #pragma unroll
-            for (int k = 0; k < kPlanes; ++k) sts32(base + static_cast<uint32_t>(i * kPlanes + k) * thread_stride, v.c[i][k]);
+            for (int k = 0; k < kPlanes; ++k) sts32(base + static_cast<uint32_t>(i * NP + k) * thread_stride, v.c[i][k]);
+            if (HI) {
+                sts32(base + static_cast<uint32_t>(i * NP + kPlanes) * thread_stride, lds32(hp.base + static_cast<uint32_t>(i) * hp.stride));
+                sts32(base + static_cast<uint32_t>(i * NP + kPlanes + 1) * thread_stride, lds32(hp.base + static_cast<uint32_t>(NM + i) * hp.stride));
+            }
+        }
         if (tig == 0) sts32(ncount0 + static_cast<uint32_t>(group - 1) * 4u, n);
     }
     consumer_barrier(nct);
     if (group == 0 && active) {
         uint32_t ntot = n;
         for (int g = 1; g < G; ++g) ntot += lds32(ncount0 + static_cast<uint32_t>(g - 1) * 4u);
-        uint32_t planes[NM * kPlanes];
-#pragma unroll
-        for (int i = 0; i < NM; ++i)
-#pragma unroll
-            for (int k = 0; k < kPlanes; ++k) planes[i * kPlanes + k] = v.c[i][k];
-        emit_slice<MODE, DENSE>(planes, data0 + static_cast<uint32_t>(tig) * 4u, G - 1, group_stride, thread_stride, ntot, cx.start,
-                                pc, pp, pd, mid);
+        uint32_t planes[NM * NP];
+        gather_planes<HI>(v, hp, planes);
+        emit_slice<MODE, DENSE, NP>(planes, data0 + static_cast<uint32_t>(tig) * 4u, G - 1, group_stride, thread_stride, ntot, cx.start,
+                                    pc, pp, pd, mid);
     }
 }
 
-template <int MODE, bool DENSE, bool SEG>
+template <int MODE, bool DENSE, bool SEG, bool HI>
 __global__ void __launch_bounds__(kPileupMaxThreads, 1) pileup_csa_kernel(PileupArgs a) {
-    pileup_body<MODE, DENSE, SEG>(a);
+    pileup_body<MODE, DENSE, SEG, HI>(a);
 }
 
-template <int MODE, bool DENSE, bool SEG>
-static void launch_one(int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a) {
-    pileup_csa_kernel<MODE, DENSE, SEG><<<grid, threads, smem, s>>>(a);
+// launch = false: opt the instantiation in to the large dynamic shared memory on the current device (ms_create)
+template <int MODE, bool DENSE>
+static void launch_or_attr(bool launch, bool seg, bool hi, int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a) {
+#define MS_K1(SEG, HI)                                                                                                          \
+    do {                                                                                                                        \
+        if (launch) pileup_csa_kernel<MODE, DENSE, SEG, HI><<<grid, threads, smem, s>>>(a);                                     \
+        else cudaFuncSetAttribute(pileup_csa_kernel<MODE, DENSE, SEG, HI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);  \
+    } while (0)
+    if (!launch || (!seg && !hi)) MS_K1(false, false);
+    if (!launch || (seg && !hi)) MS_K1(true, false);
+    if (!launch || (!seg && hi)) MS_K1(false, true);
+    if (!launch || (seg && hi)) MS_K1(true, true);
+#undef MS_K1
 }
 
-// opt every instantiation in to the large dynamic shared memory, on the current device (called by ms_create)
-void pileup_set_smem_attr(int max_smem) {
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeFuse, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeFuse, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeJuliet, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeJuliet, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeJuliet, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeJuliet, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeBoth, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeBoth, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeBoth, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    cudaFuncSetAttribute(pileup_csa_kernel<kModeBoth, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+static void dispatch(bool launch, int mode, bool dense, bool seg, bool hi, int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a) {
+    if (!launch || mode == kModeFuse) launch_or_attr<kModeFuse, false>(launch, seg, hi, grid, threads, smem, s, a);
+    if (!launch || (mode == kModeJuliet && !dense)) launch_or_attr<kModeJuliet, false>(launch, seg, hi, grid, threads, smem, s, a);
+    if (!launch || (mode == kModeJuliet && dense)) launch_or_attr<kModeJuliet, true>(launch, seg, hi, grid, threads, smem, s, a);
+    if (!launch || (mode == kModeBoth && !dense)) launch_or_attr<kModeBoth, false>(launch, seg, hi, grid, threads, smem, s, a);
+    if (!launch || (mode == kModeBoth && dense)) launch_or_attr<kModeBoth, true>(launch, seg, hi, grid, threads, smem, s, a);
 }
 
-void pileup_launch(int mode, bool dense, int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a) {
-    const bool seg = a.nseg > 1;
-    if (mode == kModeFuse) {
-        if (seg) launch_one<kModeFuse, false, true>(grid, threads, smem, s, a);
-        else launch_one<kModeFuse, false, false>(grid, threads, smem, s, a);
-    } else if (mode == kModeJuliet) {
-        if (dense) { if (seg) launch_one<kModeJuliet, true, true>(grid, threads, smem, s, a); else launch_one<kModeJuliet, true, false>(grid, threads, smem, s, a); }
-        else { if (seg) launch_one<kModeJuliet, false, true>(grid, threads, smem, s, a); else launch_one<kModeJuliet, false, false>(grid, threads, smem, s, a); }
-    } else {
-        if (dense) { if (seg) launch_one<kModeBoth, true, true>(grid, threads, smem, s, a); else launch_one<kModeBoth, true, false>(grid, threads, smem, s, a); }
-        else { if (seg) launch_one<kModeBoth, false, true>(grid, threads, smem, s, a); else launch_one<kModeBoth, false, false>(grid, threads, smem, s, a); }
-    }
+void pileup_set_smem_attr(int max_smem) { dispatch(false, 0, false, false, false, 0, 0, max_smem, nullptr, PileupArgs()); }
+
+// hi: the instantiation with the two shared-memory counter planes (row-groups of more than kMaxReadsPerFlush reads)
+void pileup_launch(int mode, bool dense, bool hi, int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a) {
+    dispatch(true, mode, dense, a.nseg > 1, hi, grid, threads, smem, s, a);
 }
 
 // ---------------------------------------------------------------- logged exceptions

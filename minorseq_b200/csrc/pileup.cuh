@@ -24,9 +24,16 @@
 
 namespace ms {
 
-constexpr int kPlanes = 11;             // vertical counter depth: up to 2047 reads between flushes
-constexpr int kMaxReadsPerFlush = 2047;
-constexpr int kPileupSmemHeader = 2048;  // mbarriers + release counters in front of the chunk slots
+constexpr int kPlanes = 11;             // vertical counter planes held in registers
+constexpr int kPlanesAll = 13;          // + two planes per mask in shared memory (HI instantiations)
+constexpr int kMaxReadsPerFlush = 2047;     // reads of a row-group between flushes: register planes only ...
+constexpr int kMaxReadsPerFlushHi = 8191;   // ... and with the two shared-memory planes
+// shared memory in front of the chunk slots: mbarriers + release counters (2 KB); HI instantiations add the two upper
+// counter planes (2 planes x up to 9 masks x 384 threads).  The plain kernel keeps the small header: the shared memory it
+// does not claim stays L1, and K1 lost ~5 % at 1M x 3 kb with 27 KB less of it.
+constexpr int kPileupHiOffset = 2048;
+constexpr int kPileupSmemHeader = 2048;
+constexpr int kPileupSmemHeaderHi = 2048 + 2 * 9 * 384 * 4;
 constexpr int kPileupMaxThreads = 384;  // 12 warps = 3 per SM sub-partition -> 168 registers per thread
 
 // which one-bit masks are counted
@@ -42,7 +49,7 @@ struct PileupArgs {
     int32_t warps_per_group;  // W = ceil(nblk/32)
     int32_t groups;           // G row-groups per CTA
     int32_t nseg, seg_len;    // column segments: CTA c handles blocks [seg_len*(c%nseg), +seg_len) of its reads
-    int32_t stages;
+    int32_t stages, stages_hi;   // ring depth of the plain and of the HI instantiation (smaller header / larger header)
     int32_t stage_bytes;      // G*8*row_bytes
     const uint2* pivot;       // [nblk+1] {r0, r1} planes of the pivot base
     const uint2* pivot2;      // [nblk+1] DENSE: planes of the designated base (runner-up of the sample where frequent, else the pivot)
@@ -57,7 +64,7 @@ struct PileupArgs {
     int64_t exc_lists;        // gridDim*blockDim of the pileup launch
 };
 
-template <int MODE, bool DENSE, bool SEG>
+template <int MODE, bool DENSE, bool SEG, bool HI>
 __global__ void pileup_csa_kernel(PileupArgs a);
 
 __global__ void pivot_sample_kernel(const uint32_t* packed, int64_t R, int32_t nblk, int32_t L,
@@ -72,7 +79,7 @@ __global__ void pileup_atomic_kernel(const uint32_t* packed, int64_t R, int32_t 
 __global__ void coverage_kernel(uint32_t* col, int32_t L);
 
 void pileup_set_smem_attr(int max_smem);
-void pileup_launch(int mode, bool dense, int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a);
+void pileup_launch(int mode, bool dense, bool hi, int grid, int threads, int smem, cudaStream_t s, const PileupArgs& a);
 void pileup_exceptions_launch(bool dense, int pileup_grid, int pileup_threads, cudaStream_t s, const PileupArgs& a);
 
 }  // namespace ms
