@@ -83,6 +83,7 @@ int ms_comm_init(ms_handle* h, const char id[128], int rank, int world) {
     if (!api().ok) MS_FAIL(h, MS_ERR_NODEVICE, "libnccl.so.2 could not be loaded");
     MS_CUDA(h, cudaSetDevice(h->device));
     ms_comm_free_internal(h);
+    h->gcap_hint = 0;   // sizes of the phasing exchange: every rank of the new communicator starts from the same value
     if (world == 1) return MS_OK;
     ncclUniqueId u;
     memcpy(&u, id, 128);

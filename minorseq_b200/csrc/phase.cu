@@ -323,6 +323,10 @@ int phase_build_table(ms_handle* h, int attempt) {
     MS_CUDA(h, cudaMemsetAsync(h->b_tab_rep.p, 0x7f, static_cast<size_t>(h->tab_size) * 8, h->stream));
     MS_CUDA(h, cudaMemsetAsync(ctr + 4, 0, 8, h->stream));
     MS_CUDA(h, cudaMemsetAsync(ctr + 6, 0, 8, h->stream));
+    // spare word of the exchanged header: 1 = this build was this rank's last resort (table at its maximum size, or the
+    // fourth hash seed), so that an overflow / a collision reported with it makes EVERY rank give up in the same iteration
+    MS_CUDA(h, cudaMemsetAsync(ctr + 7, 0, 8, h->stream));
+    if (h->tab_size >= h->tab_size_max || attempt >= 3) MS_CUDA(h, cudaMemsetAsync(ctr + 7, 1, 1, h->stream));
     if (R > 0) {
         const int grid = static_cast<int>((R + 255) / 256);
         phase_insert_kernel<<<grid, 256, 0, h->stream>>>(h->b_bits.as<uint32_t>(), h->b_flags.as<uint8_t>(), R, h->vwords,
@@ -601,6 +605,8 @@ int ms_phase_groups(ms_handle* h, uint32_t* patterns, uint64_t* counts, int64_t 
         for (int r = 0; r < world; ++r) {
             uint64_t hc[8];
             memcpy(hc, st + static_cast<size_t>(r) * block, 64);
+            if ((hc[6] != 0 || hc[4] != 0) && (hc[7] & 0xff) != 0)   // rank r cannot recover: every rank sees this header and stops here
+                MS_FAIL(h, MS_ERR_CUDA, hc[6] != 0 ? "haplotype table overflow at maximum size" : "haplotype hash collided under four seeds");
             if (hc[6] != 0) {
                 any_overflow = true;
                 if (r == me) {  // table too small for this rank's distinct patterns: grow and rebuild
@@ -611,7 +617,7 @@ int ms_phase_groups(ms_handle* h, uint32_t* patterns, uint64_t* counts, int64_t 
             } else if (hc[4] != 0) {
                 any_collision = true;
                 if (r == me) {  // a 64-bit hash collision between different patterns here: re-hash with another seed
-                    if (++attempt >= 4) MS_FAIL(h, MS_ERR_CUDA, "haplotype hash collided under four seeds");
+                    ++attempt;
                     h->table_valid = false;
                 }
             } else if (r == me) {
@@ -708,6 +714,8 @@ int ms_phase_assign(ms_handle* h, const uint32_t* ordered_patterns, int64_t H, i
     if (!h || !h->b_bits.p || H < 0 || (H > 0 && !ordered_patterns) || !hap_id) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
     if (!h->table_valid) {
+        // with a communicator the grouping pass is a collective: it must not be entered from here by some ranks only
+        if (h->comm) MS_FAIL(h, MS_ERR_ARG, "ms_phase_assign: call ms_phase_groups (on every rank) first");
         int64_t dummy = 0;
         int rc = ms_phase_groups(h, nullptr, nullptr, 0, &dummy, nullptr);
         if (rc != MS_OK) return rc;

@@ -301,6 +301,8 @@ extern "C" int ms_phase_haplotypes(ms_handle* h, int32_t min_reads, uint32_t* pa
     const int32_t nw = h->vwords;
     const int world = h->comm ? h->world : 1;
     const int me = h->comm ? h->rank : 0;
+    // the size of the exchanged block must be the same on every rank: the hint is reset when a communicator is attached
+    // (ms_comm_init, a collective itself) and from then on only changes by values all ranks compute from the same headers
     int64_t gcap = std::max<int64_t>(4096, h->gcap_hint);
     int attempt = h->table_valid ? h->table_attempt : 0;
     int merge_attempt = 0;
@@ -404,13 +406,15 @@ extern "C" int ms_phase_haplotypes(ms_handle* h, int32_t min_reads, uint32_t* pa
         for (int r = 0; r < world; ++r) {
             uint64_t hc[8];
             memcpy(hc, st + 64 + static_cast<size_t>(r) * 64, 64);
+            if ((hc[6] != 0 || hc[4] != 0) && (hc[7] & 0xff) != 0)   // rank r cannot recover (header's spare word, phase_build_table): every rank stops here
+                MS_FAIL(h, MS_ERR_CUDA, hc[6] != 0 ? "haplotype table overflow at maximum size" : "haplotype hash collided under four seeds");
             if (hc[6] != 0) {
                 any_overflow = true;
                 if (r == me) { rc = ms::phase_grow_table(h); if (rc != MS_OK) return rc; }
             } else if (hc[4] != 0) {
                 any_collision = true;
                 if (r == me) {  // a 64-bit hash collision between different patterns here: re-hash with another seed
-                    if (++attempt >= 4) MS_FAIL(h, MS_ERR_CUDA, "haplotype hash collided under four seeds");
+                    ++attempt;
                     h->table_valid = false;
                 }
             } else if (r == me) {

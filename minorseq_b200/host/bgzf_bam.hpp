@@ -84,7 +84,7 @@ inline const uint8_t* Record::find_tag(const char tag[2]) const {
     const uint8_t* end = p + aux.size();
     while (p + 3 <= end) {
         const size_t vs = detail::aux_value_size(p + 2, end);
-        if (vs == 0) return nullptr;
+        if (vs == 0 || vs > static_cast<size_t>(end - (p + 2))) return nullptr;     // malformed, or a value that runs past the record
         if (p[0] == static_cast<uint8_t>(tag[0]) && p[1] == static_cast<uint8_t>(tag[1])) return p + 2;
         p += 2 + vs;
     }
@@ -298,14 +298,17 @@ inline Bytes inflate_file(const std::string& path, unsigned nthreads) {
         const uint8_t* hd = file.data() + o;
         if (hd[0] != 31 || hd[1] != 139 || hd[2] != 8 || !(hd[3] & 4)) throw Error("not a BGZF block");
         const uint16_t xlen = detail::u16(hd + 10);
+        if (o + 12 + static_cast<size_t>(xlen) > file.size()) throw Error("truncated BGZF header");
         int bsize = -1;
-        for (size_t i = 0; i + 4 <= xlen;) {
+        for (size_t i = 0; i + 4 <= xlen;) {       // the extra subfields lie inside the file (checked above)
             const uint8_t* x = hd + 12 + i;
             const uint16_t slen = detail::u16(x + 2);
-            if (x[0] == 66 && x[1] == 67 && slen == 2) bsize = detail::u16(x + 4);
-            i += 4 + slen;
+            if (x[0] == 66 && x[1] == 67 && slen == 2 && i + 6 <= xlen) bsize = detail::u16(x + 4);
+            i += 4 + static_cast<size_t>(slen);
         }
-        if (bsize < 0 || o + static_cast<size_t>(bsize) + 1 > file.size()) throw Error("bad BGZF block");
+        // a block is header (12 + xlen) + deflate data + CRC32 + ISIZE (8): anything shorter would wrap clen below
+        if (bsize < 0 || o + static_cast<size_t>(bsize) + 1 > file.size() || static_cast<size_t>(bsize) + 1 < 12 + static_cast<size_t>(xlen) + 8)
+            throw Error("bad BGZF block");
         const size_t total = static_cast<size_t>(bsize) + 1, cpos = o + 12 + xlen, clen = total - 12 - xlen - 8;
         const uint32_t crc = detail::u32(file.data() + o + total - 8), isize = detail::u32(file.data() + o + total - 4);
         blks.push_back({cpos, clen, utotal, isize, crc});

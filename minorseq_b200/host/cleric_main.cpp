@@ -76,7 +76,7 @@ int main(int argc, char** argv) {
         std::atomic<int64_t> n_ok{0}, n_unmapped{0}, n_other{0};
         std::atomic<int> bad{0};
         std::string bad_name;
-        auto work = [&](unsigned t) {
+        auto work = [&](unsigned t) { try {
             for (size_t k = recs.size() * t / nt; k < recs.size() * (t + 1) / nt; ++k) {
                 msbam::Record& r = recs[k];
                 msbam::BamReader::parse_record(stream.data() + in.records[k].first, in.records[k].second, r);
@@ -94,7 +94,9 @@ int main(int argc, char** argv) {
                     break;
                 }
             }
-        };
+        } catch (const std::exception& e) {     // a corrupt record: reported after the join, not std::terminate on this thread
+            if (!bad.exchange(3)) bad_name = e.what();
+        } };
         std::vector<std::thread> th;
         for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
         for (auto& x : th) x.join();

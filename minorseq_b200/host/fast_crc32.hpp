@@ -3,6 +3,13 @@
 // 128-bit lanes with PCLMULQDQ (Gopal et al., "Fast CRC Computation for Generic Polynomials Using PCLMULQDQ
 // Instruction", Intel 2009) runs at memory speed.  Selected at run time; anything else goes through zlib, and
 // host_selftest compares the two on random buffers.
+//
+// Third-party provenance: crc32_clmul below -- its folding constants (k1k2, k3k4, k5k0, poly) and the structure of the
+// fold / reduce steps -- follows the well-known SSE4.2 + PCLMULQDQ CRC-32 routine distributed with Chromium's zlib
+// (crc32_simd.c, crc32_sse42_simd_), Copyright 2017 The Chromium Authors, BSD-3-Clause licence
+// (https://chromium.googlesource.com/chromium/src/third_party/zlib, LICENSE file of the Chromium project: redistribution
+// in source and binary form permitted with this notice retained; provided "as is" without warranty; the names of the
+// copyright holders may not be used to endorse derived products).  It is not derived from /root/reference.
 #pragma once
 #include <cstddef>
 #include <cstdint>

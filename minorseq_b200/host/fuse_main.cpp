@@ -19,7 +19,7 @@
 int main(int argc, char** argv) {
     ms_fuse_params prm;
     ms_fuse_params_default(&prm);
-    int device = 0;
+    int device = 0, ngpus = 1;
     mshost::QvFilter qv;
     qv.threshold = 0;  // fuse takes every base
     std::vector<std::string> pos;
@@ -30,27 +30,51 @@ int main(int argc, char** argv) {
             return argv[++i];
         };
         if (a == "-h" || a == "--help") {
-            puts("Usage: fuse [--min-coverage n] [--ins-fraction f] [--ins-distance d] [--device n] <in.bam> <out.fasta>");
+            puts("Usage: fuse [--min-coverage n] [--ins-fraction f] [--ins-distance d] [--device n] [--gpus n] <in.bam> <out.fasta>\n"
+                 "  --gpus n: shard the reads over n GPUs (devices n0..n0+n-1), one NCCL all-reduce of the column counts");
             return 0;
         } else if (a == "--version") { puts("minorseq_b200 fuse 0.1.0 (B200-native restatement; not PacBio fuse)"); return 0; }
         else if (a == "--min-coverage") prm.min_coverage = atoi(need("--min-coverage").c_str());
         else if (a == "--ins-fraction") prm.ins_fraction = atof(need("--ins-fraction").c_str());
         else if (a == "--ins-distance") prm.ins_distance = atoi(need("--ins-distance").c_str());
         else if (a == "--device") device = atoi(need("--device").c_str());
+        else if (a == "--gpus") ngpus = atoi(need("--gpus").c_str());
         else if (!a.empty() && a[0] == '-') mshost::die("unknown option " + a);
         else pos.push_back(a);
     }
     if (pos.size() != 2) { puts("Usage: fuse <in.bam> <out.fasta>"); return 1; }
+    if (ngpus < 1 || ngpus > 64) mshost::die("--gpus expects 1..64");
     try {
-        // the CUDA context comes up (~0.5 s) on this thread while a helper thread inflates and indexes the BAM
-        ms_handle* h = nullptr;
+        // the CUDA contexts come up (~0.5 s, one thread per GPU) while a helper thread inflates and indexes the BAM
+        std::vector<ms_handle*> hs(static_cast<size_t>(ngpus), nullptr);
         mshost::Alignments aln;
         mshost::load_alignments_overlapped(pos[0], qv, false, true, aln, [&] {
-            if (ms_create(device, &h) != MS_OK) mshost::die(ms_last_error(nullptr));   // there is no CPU path
+            char id[128];
+            if (ngpus > 1 && ms_comm_unique_id(id) != MS_OK) mshost::die("NCCL is not available (libnccl.so.2): --gpus needs it");
+            std::vector<std::string> errs(static_cast<size_t>(ngpus));
+            mshost::run_ranks(ngpus, [&](int r) {
+                if (ms_create(device + r, &hs[r]) != MS_OK) { errs[r] = ms_last_error(nullptr); return; }   // there is no CPU path
+                if (ngpus > 1 && ms_comm_init(hs[r], id, r, ngpus) != MS_OK) errs[r] = ms_last_error(hs[r]);
+            });
+            for (const std::string& e : errs)
+                if (!e.empty()) mshost::die(e);
         });
         if (aln.nreads == 0) mshost::die("no primary or supplementary alignments in " + pos[0]);
-        CK(h, ms_set_layout(h, aln.L, nullptr));
-        CK(h, ms_pileup_host(h, aln.rows, aln.nreads, nullptr));
+        // every rank piles up its contiguous range of the reads; the all-reduce leaves the column counts of all reads on rank 0
+        {
+            const int32_t rw = ms_row_words(aln.L);
+            std::vector<std::string> errs(static_cast<size_t>(ngpus));
+            mshost::run_ranks(ngpus, [&](int r) {
+                ms_handle* hr = hs[r];
+                const int64_t r0 = aln.nreads * r / ngpus, r1 = aln.nreads * (r + 1) / ngpus;
+                if (ms_set_layout(hr, aln.L, nullptr) != MS_OK || ms_pileup_host(hr, aln.rows + static_cast<size_t>(r0) * rw, r1 - r0, nullptr) != MS_OK ||
+                    ms_allreduce_counts(hr) != MS_OK || ms_synchronize(hr) != MS_OK)
+                    errs[r] = ms_last_error(hr);
+            });
+            for (const std::string& e : errs)
+                if (!e.empty()) mshost::die("pile-up failed: " + e);
+        }
+        ms_handle* h = hs[0];
         std::string seq(static_cast<size_t>(aln.L) + aln.ins_pool.size() + 16, '\0');
         int64_t len = 0;
         CK(h, ms_fuse(h, &prm, aln.ins_col.data(), aln.ins_off.data(), aln.ins_len.data(), static_cast<int64_t>(aln.ins_col.size()),
@@ -67,7 +91,7 @@ int main(int argc, char** argv) {
         f.close();
         fflush(nullptr);
         if (!getenv("MS_FULL_TEARDOWN")) _exit(0);
-        ms_destroy(h);
+        for (ms_handle* x : hs) ms_destroy(x);
     } catch (const std::exception& e) {
         mshost::die(e.what());
     }

@@ -80,6 +80,16 @@ inline void die(const std::string& m) {
     exit(1);
 }
 
+// f(rank) for rank 0..n-1: on this thread when n == 1, else one thread per rank (one rank per GPU; the ranks meet inside the
+// library's collectives, so they have to run concurrently)
+template <class F>
+inline void run_ranks(int n, F f) {
+    if (n <= 1) { f(0); return; }
+    std::vector<std::thread> th;
+    for (int r = 0; r < n; ++r) th.emplace_back([&f, r] { f(r); });
+    for (std::thread& t : th) t.join();
+}
+
 // One record -> one packed row (+ optional insertion events appended to the caller's vectors).
 inline void expand_record(const msbam::Record& rec, const QvFilter& qv, int32_t L, uint32_t* row, bool want_insertions,
                           std::vector<uint8_t>& mask, std::vector<int32_t>& ic, std::vector<int64_t>& io, std::vector<int32_t>& il,
@@ -96,8 +106,9 @@ inline void expand_record(const msbam::Record& rec, const QvFilter& qv, int32_t 
         if (rc != MS_ERR_CAPACITY) break;
         ic.resize(ic.size() * 2); io.resize(io.size() * 2); il.resize(il.size() * 2); pool.resize(pool.size() * 2);
     }
-    if (rc == MS_ERR_FORMAT) die("record " + rec.name + ": BAM files have to be PacBio-compliant, cigar M is forbidden");
-    if (rc != MS_OK) die("record " + rec.name + ": cannot expand CIGAR");
+    // thrown, not die(): this runs on worker threads (an exit() from there would race the other workers)
+    if (rc == MS_ERR_FORMAT) throw std::runtime_error("record " + rec.name + ": BAM files have to be PacBio-compliant, cigar M is forbidden");
+    if (rc != MS_OK) throw std::runtime_error("record " + rec.name + ": cannot expand CIGAR");
     for (int64_t i = 0; i < ni; ++i) {
         out_col.push_back(ic[i]);
         out_len.push_back(il[i]);
@@ -157,7 +168,8 @@ inline void expand_alignments(const Decoded& d, const QvFilter& qv, bool want_na
     struct Part { std::vector<int32_t> col, len; std::vector<int64_t> off; std::string pool; };
     nt = static_cast<unsigned>(std::min<size_t>(nt, keep.size()));
     std::vector<Part> parts(nt);
-    auto work = [&](unsigned t) {
+    std::vector<std::string> errs(nt);      // a corrupt record throws on its worker: carried to the caller after the join
+    auto work = [&](unsigned t) { try {
         const size_t i0 = keep.size() * t / nt, i1 = keep.size() * (t + 1) / nt;
         msbam::Record rec;
         std::vector<uint8_t> mask;
@@ -170,13 +182,15 @@ inline void expand_alignments(const Decoded& d, const QvFilter& qv, bool want_na
             expand_record(rec, qv, out.L, out.rows + k * rw, want_insertions, mask, ic, io, il, pool, parts[t].col, parts[t].len, parts[t].off, parts[t].pool);
             if (want_names) out.names[k] = rec.name;
         }
-    };
+    } catch (const std::exception& e) { errs[t] = e.what(); } };
     if (nt == 1) work(0);
     else {
         std::vector<std::thread> th;
         for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
         for (auto& x : th) x.join();
     }
+    for (const std::string& e : errs)
+        if (!e.empty()) throw std::runtime_error(e);
     for (const Part& p : parts) {   // read order is preserved: thread t holds a contiguous range
         const int64_t base = static_cast<int64_t>(out.ins_pool.size());
         out.ins_col.insert(out.ins_col.end(), p.col.begin(), p.col.end());

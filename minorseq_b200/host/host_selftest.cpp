@@ -65,6 +65,53 @@ int main(int argc, char** argv) {
             }
         }
         unsetenv("MS_ZLIB_INFLATE");
+        // truncated and corrupted files must end in msbam::Error, never in an out-of-bounds read: cut the file at many
+        // lengths, shrink a block's BSIZE below its header size (would wrap the deflate length), inflate XLEN past the file end
+        {
+            FILE* f = fopen(tmp.c_str(), "rb");
+            REQUIRE(f != nullptr);
+            std::vector<uint8_t> whole;
+            for (int ch; (ch = fgetc(f)) != EOF;) whole.push_back(static_cast<uint8_t>(ch));
+            fclose(f);
+            REQUIRE(whole.size() > 1000);
+            const std::string bad = tmp + ".bad";
+            auto attempt = [&](const std::vector<uint8_t>& bytes) -> int {      // 0 = loaded, 1 = rejected with msbam::Error
+                FILE* g = fopen(bad.c_str(), "wb");
+                if (!g) return -1;
+                if (!bytes.empty()) fwrite(bytes.data(), 1, bytes.size(), g);
+                fclose(g);
+                try {
+                    const msbam::Bytes u = msbam::inflate_file(bad, 2);
+                    const msbam::BamIndexed bx = msbam::index_stream(u);
+                    msbam::Record rec;
+                    for (const auto& rr : bx.records) msbam::BamReader::parse_record(u.data() + rr.first, rr.second, rec);
+                    return 0;
+                } catch (const msbam::Error&) { return 1; } catch (const std::exception&) { return 1; }
+            };
+            for (size_t cut : {size_t(1), size_t(11), size_t(17), size_t(18), size_t(19), size_t(30), whole.size() / 3, whole.size() / 2, whole.size() - 29, whole.size() - 1}) {
+                std::vector<uint8_t> part(whole.begin(), whole.begin() + static_cast<long>(cut));
+                REQUIRE(attempt(part) >= 0);          // either outcome is fine, a crash is not
+            }
+            std::vector<uint8_t> v = whole;
+            v[16] = 5; v[17] = 0;                     // BSIZE = 5: shorter than header + trailer
+            REQUIRE(attempt(v) == 1);
+            v = whole;
+            v[10] = 0xff; v[11] = 0xff;               // XLEN = 65535: subfields would run far past the first block
+            REQUIRE(attempt(v) == 1);
+            v = whole;
+            v.resize(40);                             // header says a full block follows, the file ends
+            REQUIRE(attempt(v) == 1);
+            remove(bad.c_str());
+            // aux fields whose value runs past the record: never found, never read
+            msbam::Record cr;
+            cr.aux = {'d', 'q', 'B', 'C', 0xff, 0xff, 0xff, 0x7f, 1, 2, 3};       // B array claiming 2^31 elements
+            REQUIRE(cr.find_tag("dq") == nullptr && cr.tag_per_base("dq").empty());
+            cr.aux = {'r', 'q', 'f', 0, 0};                                       // float cut short
+            double dummy = 0;
+            REQUIRE(!cr.tag_number("rq", dummy));
+            cr.aux = {'s', 'q', 'Z', 'I', 'I'};                                   // string without its terminator
+            REQUIRE(cr.find_tag("sq") == nullptr);
+        }
         // the parallel whole-file writer (cleric) produces a BAM the sequential reader reads back record for record
         {
             std::vector<msbam::Record> recs;

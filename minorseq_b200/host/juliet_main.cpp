@@ -23,7 +23,9 @@
 
 static void usage() {
     puts("Usage: juliet [options] <in.bam> <out.json|out.html> [<out.html|out.json>]\n"
-         "  -c, --config <HIV|ABL1|file.json>  target configuration (genes, DRMs, referenceSequence)\n"
+         "  -c, --config <HIV|ABL1|file.json>  target configuration (genes, DRMs, referenceSequence); the built-in HIV and ABL1\n"
+         "                                     hold only what the public documentation shows (doc/JULIET.md:138-157 and the\n"
+         "                                     target screenshot), not PacBio's full tables: pass the real config as a file\n"
          "      --region <begin-end>           1-based window to subset the target config\n"
          "      --mode-phasing                 phase variants into haplotypes\n"
          "      --min-perc <p>                 only variants with abundance > p %\n"
@@ -34,7 +36,9 @@ static void usage() {
          "      --alpha <a>                    significance after Bonferroni (default 0.01)\n"
          "      --min-haplotype-reads <n>      reads needed to report a haplotype (default 10)\n"
          "      --qv-threshold <q>             rich-QV base filter, 0 = off (default 20 on dq,iq,sq when present)\n"
-         "      --device <n>                   CUDA device (default 0)\n"
+         "      --device <n>                   first CUDA device (default 0)\n"
+         "      --gpus <n>                     shard the reads over n GPUs (devices n0..n0+n-1) of this machine: contiguous read\n"
+         "                                     ranges, one NCCL all-reduce of the count tensor, same report as with one GPU\n"
          "      --timing-json <file>           write the wall-clock time of every stage as JSON\n"
          "  -h, --help / --version");
 }
@@ -51,7 +55,7 @@ int main(int argc, char** argv) {
     std::string config, region, cmdline, timing_json;
     bool phasing = false, drm_only = false;
     double min_perc = -1, max_perc = -1, sub = 5e-4, del = 3e-3, alpha = 0.01;
-    int min_hap = 10, device = 0;
+    int min_hap = 10, device = 0, ngpus = 1;
     mshost::QvFilter qv;
     std::vector<std::string> pos;
     for (int i = 0; i < argc; ++i) cmdline += (i ? " " : "") + std::string(argv[i]);
@@ -75,11 +79,13 @@ int main(int argc, char** argv) {
         else if (a == "--min-haplotype-reads") min_hap = atoi(need("--min-haplotype-reads").c_str());
         else if (a == "--qv-threshold") qv.threshold = atoi(need("--qv-threshold").c_str());
         else if (a == "--device") device = atoi(need("--device").c_str());
+        else if (a == "--gpus") ngpus = atoi(need("--gpus").c_str());
         else if (a == "--timing-json") timing_json = need("--timing-json");
         else if (!a.empty() && a[0] == '-') mshost::die("unknown option " + a);
         else pos.push_back(a);
     }
     if (pos.size() < 2) { usage(); return 1; }
+    if (ngpus < 1 || ngpus > 64) mshost::die("--gpus expects 1..64");
     std::string out_json, out_html;
     for (size_t i = 1; i < pos.size(); ++i) {
         if (ends_with(pos[i], ".json")) out_json = pos[i];
@@ -106,11 +112,20 @@ int main(int argc, char** argv) {
         mscfg::TargetConfig cfg;
         if (!config.empty()) cfg = mscfg::load(config);
 
-        // the CUDA context comes up (~0.5 s) on this thread while a helper thread inflates and indexes the BAM
-        ms_handle* h = nullptr;
+        // the CUDA contexts come up (~0.5 s each, one thread per GPU) while a helper thread inflates and indexes the BAM;
+        // with --gpus N every GPU gets its own handle and the handles share one NCCL communicator (one rank per thread)
+        std::vector<ms_handle*> hs(static_cast<size_t>(ngpus), nullptr);
         mshost::Alignments aln;
         mshost::load_alignments_overlapped(pos[0], qv, phasing, false, aln, [&] {
-            if (ms_create(device, &h) != MS_OK) mshost::die(ms_last_error(nullptr));   // there is no CPU path
+            char id[128];
+            if (ngpus > 1 && ms_comm_unique_id(id) != MS_OK) mshost::die("NCCL is not available (libnccl.so.2): --gpus needs it");
+            std::vector<std::string> errs(static_cast<size_t>(ngpus));
+            mshost::run_ranks(ngpus, [&](int r) {
+                if (ms_create(device + r, &hs[r]) != MS_OK) { errs[r] = ms_last_error(nullptr); return; }   // there is no CPU path
+                if (ngpus > 1 && ms_comm_init(hs[r], id, r, ngpus) != MS_OK) errs[r] = ms_last_error(hs[r]);
+            });
+            for (const std::string& e : errs)
+                if (!e.empty()) mshost::die(e);
         });
         lap("CUDA context || BAM inflate + CIGAR expansion");
         if (aln.nreads == 0) mshost::die("no primary or supplementary alignments in " + pos[0]);
@@ -134,85 +149,119 @@ int main(int argc, char** argv) {
             for (int s = g.begin - 1; s + 3 <= std::min(g.end - 1, L); s += 3)
                 if (s >= lo && s + 3 <= hi && s >= 0) start[s >> 5] |= 1u << (s & 31);
         }
-
-        CK(h, ms_set_layout(h, L, start.data()));
-        const uint32_t* d_rows = nullptr;
-        CK(h, ms_pileup_host(h, aln.rows, aln.nreads, &d_rows));
-        CK(h, ms_synchronize(h));
-        lap("H2D + pileup");
-
         ms_call_params prm;
         ms_call_params_default(&prm);
         prm.substitution_rate = sub; prm.deletion_rate = del; prm.alpha = alpha;
         prm.min_perc = min_perc; prm.max_perc = max_perc; prm.region_begin = rb; prm.region_end = re;
-        std::vector<ms_variant> mv(4096);
-        int64_t nv = 0;
         const char* ref = cfg.reference_sequence.size() >= static_cast<size_t>(L) ? cfg.reference_sequence.c_str() : nullptr;
-        CK(h, ms_call(h, mg.data(), static_cast<int32_t>(mg.size()), ref, &prm, mv.data(), static_cast<int64_t>(mv.size()), &nv));
-        if (nv > static_cast<int64_t>(mv.size())) {
-            mv.resize(nv);
-            CK(h, ms_call(h, mg.data(), static_cast<int32_t>(mg.size()), ref, &prm, mv.data(), static_cast<int64_t>(mv.size()), &nv));
-        }
-        mv.resize(nv);
+        const int32_t rw = ms_row_words(L);
 
-        // DRM annotation and --drm-only (doc/JULIET.md:104-107,:370)
+        // Every rank piles up its contiguous range of the reads; after the all-reduce the counts, and with them the
+        // variant list, are the same on every rank; phasing merges the ranks' pattern lists on the device and leaves the
+        // per-read haplotype ids in the rank's slice of `hap`.  Rank 0's copy of the replicated results goes into the report.
         std::vector<msreport::VariantRow> rows;
-        for (const ms_variant& v : mv) {
-            msreport::VariantRow r;
-            r.gene = v.gene; r.aa_pos = v.codon_index + 1; r.col = v.col; r.ref_codon = v.ref_codon; r.codon = v.codon;
-            r.count = v.count; r.coverage = v.coverage; r.expected = v.expected; r.ntests = v.ntests; r.pvalue = v.pvalue;
-            const char ra = mscfg::translate(v.ref_codon), va = mscfg::translate(v.codon);
-            for (const mscfg::Drm& d : genes[v.gene].drms)
-                for (const mscfg::DrmPosition& p : d.positions)
-                    if (mscfg::drm_matches(p, r.aa_pos, ra, va)) { r.drugs.push_back(d.name); break; }
-            if (drm_only && r.drugs.empty()) continue;
-            rows.push_back(r);
-        }
-
-        lap("call + DRM annotation");
         std::vector<uint32_t> col(static_cast<size_t>(L) * 8);
-        CK(h, ms_get_counts(h, col.data(), nullptr));
-
         std::vector<msreport::HaplotypeRow> haps;
         unsigned long long counters[6] = {0, 0, 0, 0, 0, 0};
+        std::vector<int32_t> hap(phasing ? aln.nreads : 0);
+        std::vector<std::pair<int, int>> keys;
+        std::vector<uint32_t> pat;
+        std::vector<uint64_t> cnt;
+        int64_t nrep_all = 0;
+        std::vector<std::string> errs(static_cast<size_t>(ngpus));
+#define CKR(call)                                                                                      \
+    do {                                                                                               \
+        if ((call) != MS_OK) { errs[r] = std::string(#call) + " failed: " + ms_last_error(h); return; } \
+    } while (0)
+        mshost::run_ranks(ngpus, [&](int r) {
+            ms_handle* h = hs[r];
+            const int64_t r0 = aln.nreads * r / ngpus, r1 = aln.nreads * (r + 1) / ngpus;
+            CKR(ms_set_layout(h, L, start.data()));
+            const uint32_t* d_rows = nullptr;
+            CKR(ms_pileup_host(h, aln.rows + static_cast<size_t>(r0) * rw, r1 - r0, &d_rows));
+            CKR(ms_allreduce_counts(h));
+            CKR(ms_synchronize(h));
+            if (r == 0) lap(ngpus > 1 ? "H2D + pileup + all-reduce" : "H2D + pileup");
+
+            std::vector<ms_variant> mv(4096);
+            int64_t nv = 0;
+            CKR(ms_call(h, mg.data(), static_cast<int32_t>(mg.size()), ref, &prm, mv.data(), static_cast<int64_t>(mv.size()), &nv));
+            if (nv > static_cast<int64_t>(mv.size())) {
+                mv.resize(nv);
+                CKR(ms_call(h, mg.data(), static_cast<int32_t>(mg.size()), ref, &prm, mv.data(), static_cast<int64_t>(mv.size()), &nv));
+            }
+            mv.resize(nv);
+
+            // DRM annotation and --drm-only (doc/JULIET.md:104-107,:370)
+            std::vector<msreport::VariantRow> my_rows;
+            for (const ms_variant& v : mv) {
+                msreport::VariantRow vr;
+                vr.gene = v.gene; vr.aa_pos = v.codon_index + 1; vr.col = v.col; vr.ref_codon = v.ref_codon; vr.codon = v.codon;
+                vr.count = v.count; vr.coverage = v.coverage; vr.expected = v.expected; vr.ntests = v.ntests; vr.pvalue = v.pvalue;
+                const char ra = mscfg::translate(v.ref_codon), va = mscfg::translate(v.codon);
+                for (const mscfg::Drm& d : genes[v.gene].drms)
+                    for (const mscfg::DrmPosition& p : d.positions)
+                        if (mscfg::drm_matches(p, vr.aa_pos, ra, va)) { vr.drugs.push_back(d.name); break; }
+                if (drm_only && vr.drugs.empty()) continue;
+                my_rows.push_back(vr);
+            }
+            if (r == 0) {
+                lap("call + DRM annotation");
+                CKR(ms_get_counts(h, col.data(), nullptr));
+            }
+            if (phasing) {
+                // one global variant list over all genes (screenshot juliet_hiv-phasing.png: same columns in every table)
+                std::vector<std::pair<int, int>> my_keys;
+                for (const msreport::VariantRow& vr : my_rows) my_keys.emplace_back(vr.col, vr.codon);
+                std::sort(my_keys.begin(), my_keys.end());
+                my_keys.erase(std::unique(my_keys.begin(), my_keys.end()), my_keys.end());
+                const int32_t V = static_cast<int32_t>(my_keys.size());
+                const int32_t nw = std::max(1, (V + 31) / 32);
+                std::vector<int32_t> vc(V), vk(V);
+                for (int32_t i = 0; i < V; ++i) { vc[i] = my_keys[i].first; vk[i] = my_keys[i].second; }
+                CKR(ms_phase_begin(h, vc.data(), vk.data(), V, r1 - r0));
+                CKR(ms_phase_dev(h, d_rows, r1 - r0));
+                // grouping, merge over the ranks, haplotype order and per-read ids in one device-side call; only the reported
+                // haplotypes are read back (every rank takes the same turns through this loop: nrep is a merged result)
+                int64_t H = 0, nrep = 0, cap = 256;
+                std::vector<uint32_t> my_pat;
+                std::vector<uint64_t> my_cnt;
+                ms_phase_counters c2;
+                for (;;) {
+                    my_pat.assign(static_cast<size_t>(cap) * nw, 0u);
+                    my_cnt.assign(cap, 0);
+                    CKR(ms_phase_haplotypes(h, min_hap, my_pat.data(), my_cnt.data(), cap, &H, &nrep, &c2, hap.data() + r0));
+                    if (nrep <= cap) break;
+                    cap = nrep;
+                }
+                if (r == 0) {
+                    counters[0] = c2.reported; counters[1] = c2.insufficient; counters[2] = c2.damaged;
+                    counters[3] = c2.gaps; counters[4] = c2.heteroduplex; counters[5] = c2.partial;
+                    keys.swap(my_keys); pat.swap(my_pat); cnt.swap(my_cnt); nrep_all = nrep;
+                }
+            }
+            if (r == 0) rows.swap(my_rows);
+        });
+#undef CKR
+        for (const std::string& e : errs)
+            if (!e.empty()) mshost::die(e);
+        ms_handle* h = hs[0];
+
         if (phasing) {
-            // one global variant list over all genes (screenshot juliet_hiv-phasing.png: same columns in every table)
-            std::vector<std::pair<int, int>> keys;
-            for (const msreport::VariantRow& r : rows) keys.emplace_back(r.col, r.codon);
-            std::sort(keys.begin(), keys.end());
-            keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
             const int32_t V = static_cast<int32_t>(keys.size());
             const int32_t nw = std::max(1, (V + 31) / 32);
-            std::vector<int32_t> vc(V), vk(V);
-            for (int32_t i = 0; i < V; ++i) { vc[i] = keys[i].first; vk[i] = keys[i].second; }
-            CK(h, ms_phase_begin(h, vc.data(), vk.data(), V, aln.nreads));
-            CK(h, ms_phase_dev(h, d_rows, aln.nreads));
-            // grouping, haplotype order and per-read ids in one device-side call; only the reported haplotypes are read back
-            int64_t H = 0, nrep = 0, cap = 256;
-            std::vector<uint32_t> pat;
-            std::vector<uint64_t> cnt;
-            std::vector<int32_t> hap(aln.nreads);
-            ms_phase_counters c2;
-            for (;;) {
-                pat.assign(static_cast<size_t>(cap) * nw, 0u);
-                cnt.assign(cap, 0);
-                CK(h, ms_phase_haplotypes(h, min_hap, pat.data(), cnt.data(), cap, &H, &nrep, &c2, hap.data()));
-                if (nrep <= cap) break;
-                cap = nrep;
-            }
-            counters[0] = c2.reported; counters[1] = c2.insufficient; counters[2] = c2.damaged;
-            counters[3] = c2.gaps; counters[4] = c2.heteroduplex; counters[5] = c2.partial;
+            const int64_t nrep = nrep_all;
             haps.resize(nrep);
             for (int64_t k = 0; k < nrep; ++k) {
                 char nb[3];
                 ms_haplotype_name(k, nb);
                 haps[k].name = nb;
                 haps[k].reads = cnt[k];
-                haps[k].frequency = c2.reported ? static_cast<double>(cnt[k]) / static_cast<double>(c2.reported) : 0.0;
+                haps[k].frequency = counters[0] ? static_cast<double>(cnt[k]) / static_cast<double>(counters[0]) : 0.0;
                 for (int32_t v = 0; v < V; ++v) {
                     char cb[4];
                     const bool on = (pat[static_cast<size_t>(k) * nw + (v >> 5)] >> (v & 31)) & 1u;
-                    haps[k].codons.push_back(on ? mscfg::codon_string(vk[v], cb) : "");
+                    haps[k].codons.push_back(on ? mscfg::codon_string(keys[v].second, cb) : "");
                 }
             }
             for (int64_t r = 0; r < aln.nreads; ++r)
@@ -268,7 +317,7 @@ int main(int argc, char** argv) {
                 static_cast<long long>(aln.nskipped), rows.size(), phasing ? (", " + std::to_string(haps.size()) + " haplotypes").c_str() : "");
         fflush(nullptr);
         if (!getenv("MS_FULL_TEARDOWN")) _exit(0);   // outputs are written and closed; skip the ~0.2 s CUDA teardown
-        ms_destroy(h);
+        for (ms_handle* x : hs) ms_destroy(x);
     } catch (const std::exception& e) {
         mshost::die(e.what());
     }

@@ -1,6 +1,7 @@
 """C++ host layer (minorseq_b200/host): CPU-only self test, and -- on a GPU -- the juliet / fuse binaries
 run end to end on BAM files written by an independent Python BAM writer, checked against the oracle."""
 import json
+import re
 import os
 import subprocess
 
@@ -132,7 +133,29 @@ def test_juliet_cli_matches_oracle(binaries, oracle, tmp_path, n_via_qv):
             for vc in va["variant_codons"]:
                 assert (vc["known_drm"] == "drugX") == (vp["ref_position"] <= 100)
     html = open(oh).read()
-    assert "Variant Discovery" in html and "Haplotypes %" in html and "geneA" in html
+    # the page is a 1:1 rendering of the JSON (doc/JULIET.md:68-107): four sections in the documented order, the input block's four
+    # fields, the per-gene table header of the screenshots, one haplotype column per reported haplotype with its percentage and
+    # read count, the read-category tooltip (:372-381), one row per variant codon and the -3..+5 context rows (juliet_hiv-context.png)
+    order = [html.index(f"<summary>{t}</summary>") for t in ("Input data", "Target config", "Variant Discovery", "Drug Summaries")]
+    assert order == sorted(order)
+    for field in ("Timestamp:", "Input File:", "Command Line Call:", "Juliet Version:"):
+        assert field in html
+    assert rep["input"]["command_line"] in html and "--mode-phasing" in rep["input"]["command_line"]
+    assert "<th>Codon</th><th>AA</th><th>Pos</th><th>AA</th><th>Codon</th><th>%</th><th>Coverage</th><th>Affected Drugs</th>" in html
+    assert "Sample Variants" in html and "Haplotypes %" in html and "geneA" in html and "geneB" in html and "synthetic_ref" in html
+    for hp in rep["haplotypes"]:
+        assert f'<th title="{hp["reads"]} reads">{hp["percentage"]}</th>' in html
+        assert re.search(rf'<th class="gene" style="color:[^"]+">{hp["name"]}</th>', html)
+    tip = (f'Reported: {cats["reported"]} | Insufficient coverage: {cats["insufficient_coverage"]} | Unsuitable: {cats["unsuitable"]} '
+           f'(gaps {cats["unsuitable_gaps"]}, heteroduplexes {cats["unsuitable_heteroduplex"]}, partial {cats["unsuitable_partial"]})')
+    assert tip in html
+    assert cats["unsuitable_gaps"] == g["counters"]["gaps"] and cats["unsuitable_heteroduplex"] == g["counters"]["heteroduplex"] and cats["unsuitable_partial"] == g["counters"]["partial"]
+    assert html.count('<tr class="var"') == len(got)
+    nctx = sum(len(vp["msa"]) for gg in rep["genes"] for vp in gg["variant_positions"])
+    assert html.count('<tr class="msa m') == nctx + sum(len(gg["variant_positions"]) for gg in rep["genes"])      # + one header row per position
+    assert "drugX" in html and html.count("<b>drugX</b>") == 1                                                 # drug summary entry
+    nhit = sum(sum(vc["haplotype_hit"]) for gg in rep["genes"] for vp in gg["variant_positions"] for va in vp["variant_amino_acids"] for vc in va["variant_codons"])
+    assert html.count('<td class="hap" style="background:') == nhit
     # --drm-only, --region, --min-perc
     res = subprocess.run([os.path.join(binaries, "juliet"), "-c", str(cpath), "--drm-only", "--region", "1-200", "--min-perc", "2", bam, oj], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
@@ -142,6 +165,43 @@ def test_juliet_cli_matches_oracle(binaries, oracle, tmp_path, n_via_qv):
                   for va in vp["variant_amino_acids"] for vc in va["variant_codons"])
     want2 = sorted((v.gene, v.codon_index + 1, "".join("ACGT"[(v.codon >> s) & 3] for s in (4, 2, 0))) for v in ov2 if v.gene == 0 and v.codon_index < 100)
     assert got2 == want2
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+def test_juliet_and_fuse_cli_two_gpus_equal_one(binaries, tmp_path):
+    """`juliet --gpus 2` (reads sharded over two GPUs, one NCCL all-reduce, device-side haplotype merge) writes the same JSON and
+    HTML, byte for byte, as `--gpus 1`; likewise fuse's FASTA.  MS_FIXED_TIMESTAMP pins the only run-dependent field."""
+    if _gpu_count() < 2:
+        pytest.skip("needs two GPUs")
+    cfg = SynthConfig(L=900, seed=78, n_rate=2e-3, trunc=0.05, ins=2e-3)
+    t = make_tables(cfg)
+    st = synth_states(t, 0, 20001)
+    bam = str(tmp_path / "in.bam")
+    _make_bam(bam, t, st)
+    env = dict(os.environ, MS_FIXED_TIMESTAMP="2026-01-01T00:00:00.000Z")
+    outs = {}
+    for n in (1, 2):
+        oj, oh, of = str(tmp_path / f"o{n}.json"), str(tmp_path / f"o{n}.html"), str(tmp_path / f"o{n}.fasta")
+        res = subprocess.run([os.path.join(binaries, "juliet"), "--mode-phasing", "--gpus", str(n), bam, oj, oh], capture_output=True, text=True, env=env)
+        assert res.returncode == 0, res.stderr
+        res = subprocess.run([os.path.join(binaries, "fuse"), "--gpus", str(n), bam, of], capture_output=True, text=True, env=env)
+        assert res.returncode == 0, res.stderr
+        rep = json.load(open(oj))
+        cmd = rep["input"]["command_line"]
+        outs[n] = (open(oj).read().replace(cmd, "CMD"), open(oh).read().replace(cmd, "CMD"), open(of).read())
+        assert len(rep["haplotypes"]) >= 2 and sum(len(g["variant_positions"]) for g in rep["genes"]) >= 3
+    for a, b in zip(outs[1], outs[2]):
+        a2 = a.replace("o1.json", "X").replace("o1.html", "X")
+        b2 = b.replace("o2.json", "X").replace("o2.html", "X")
+        assert a2 == b2
 
 
 @pytest.mark.gpu
