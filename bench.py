@@ -303,6 +303,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout, in front of the one JSON line
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -408,6 +410,7 @@ def main():
         ms = C.c_double()
         return ms.value if lib.ms_stage_kernel_ms(j.hd.h, stage, C.byref(ms)) == 0 else None
     k3_ms, cooc_ms = stage_ms(1), stage_ms(2)
+    allreduce_ms, hapmerge_ms = stage_ms(4), stage_ms(5)     # N > 1: the two exchanges of the pass, device time on this rank
     tm = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -549,6 +552,10 @@ def main():
                 "dtype": "u32 counts / f64 p-values", "data": "synthetic", "config": workload_config(c, world),
                 "clocks": clocks, "e2e": e2e, "host_affinity_cpus": affinity, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
                 "digest": digest}
+        if world > 1:
+            line["exchanges"] = {"count_allreduce_ms": allreduce_ms, "haplotype_allgather_and_merge_ms": hapmerge_ms,
+                                 "note": "device time on rank 0 of the pass's two exchanges (NCCL all-reduce of the count tensor; "
+                                         "all-gather of the compact pattern lists + the replicated merge kernels)"}
         if c["kind"] == "juliet":
             hp = res.haplotypes
             line["result_check"] = {"variants": len(res.variants), "haplotypes_reported": hp.nreported if hp else None, "counters": hp.counters if hp else None}

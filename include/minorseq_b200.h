@@ -109,8 +109,9 @@ int ms_timer_start(ms_handle *h);
 int ms_timer_stop(ms_handle *h, double *ms);
 int ms_pileup_kernel_ms(ms_handle *h, double *ms, int64_t *reads);
 /* Same for the other measured kernels (most recent launch while timing was on; MS_ERR_ARG if none):
- * phase_bits(_sparse)_kernel, the co-occurrence kernel (popcount-AND or tcgen05), expand_events_kernel. */
-enum { MS_STAGE_PHASE_BITS = 1, MS_STAGE_COOCCURRENCE = 2, MS_STAGE_EXPAND = 3 };
+ * phase_bits_kernel, the co-occurrence kernel (popcount-AND or tcgen05), expand_events_kernel, and with a communicator
+ * attached the two exchanges: the count all-reduce, and the haplotype-list all-gather + merge kernels.      */
+enum { MS_STAGE_PHASE_BITS = 1, MS_STAGE_COOCCURRENCE = 2, MS_STAGE_EXPAND = 3, MS_STAGE_ALLREDUCE = 4, MS_STAGE_HAPMERGE = 5 };
 int ms_stage_kernel_ms(ms_handle *h, int stage, double *ms);
 
 /* ---- K1: pileup (juliet "MSA counts", doc/JULIET.md:96-100; fuse doc/FUSE.md:17-20) -- */

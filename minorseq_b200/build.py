@@ -52,7 +52,7 @@ def build_host(force=False):
         out = os.path.join(BIN, name)
         if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in hdrs if os.path.exists(d)):
             continue
-        cmd = ["/usr/bin/g++", "-O3", "-std=c++17", "-Wall", "-o", out, os.path.join(HOST, src), "-lz", "-pthread"]
+        cmd = ["/usr/bin/g++", "-O3", "-std=c++17", "-Wall", "-I/usr/local/cuda/include", "-o", out, os.path.join(HOST, src), "-lz", "-pthread", "-ldl"]
         if name in ("juliet", "fuse", "cleric"):
             cmd += ["-L" + HERE, "-lminorseq_b200", "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath," + HERE]
         res = subprocess.run(cmd, capture_output=True, text=True)

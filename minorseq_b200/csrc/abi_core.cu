@@ -46,7 +46,9 @@ int ms_create(int device, ms_handle** out) {
         cudaEventCreate(&h->ev_timer[0]) != cudaSuccess || cudaEventCreate(&h->ev_timer[1]) != cudaSuccess ||
         cudaEventCreate(&h->ev_stage[1][0]) != cudaSuccess || cudaEventCreate(&h->ev_stage[1][1]) != cudaSuccess ||
         cudaEventCreate(&h->ev_stage[2][0]) != cudaSuccess || cudaEventCreate(&h->ev_stage[2][1]) != cudaSuccess ||
-        cudaEventCreate(&h->ev_stage[3][0]) != cudaSuccess || cudaEventCreate(&h->ev_stage[3][1]) != cudaSuccess) {
+        cudaEventCreate(&h->ev_stage[3][0]) != cudaSuccess || cudaEventCreate(&h->ev_stage[3][1]) != cudaSuccess ||
+        cudaEventCreate(&h->ev_stage[4][0]) != cudaSuccess || cudaEventCreate(&h->ev_stage[4][1]) != cudaSuccess ||
+        cudaEventCreate(&h->ev_stage[5][0]) != cudaSuccess || cudaEventCreate(&h->ev_stage[5][1]) != cudaSuccess) {
         g_create_error = cudaGetErrorString(cudaGetLastError());
         delete h;
         return MS_ERR_CUDA;
@@ -101,7 +103,7 @@ void ms_destroy(ms_handle* h) {
     cudaEventDestroy(h->ev_copy[0]); cudaEventDestroy(h->ev_copy[1]);
     cudaEventDestroy(h->ev_k1[0]); cudaEventDestroy(h->ev_k1[1]);
     cudaEventDestroy(h->ev_timer[0]); cudaEventDestroy(h->ev_timer[1]);
-    for (int s = 1; s < 4; ++s) { cudaEventDestroy(h->ev_stage[s][0]); cudaEventDestroy(h->ev_stage[s][1]); }
+    for (int s = 1; s < 6; ++s) { cudaEventDestroy(h->ev_stage[s][0]); cudaEventDestroy(h->ev_stage[s][1]); }
     cudaStreamDestroy(h->own_stream); cudaStreamDestroy(h->copy_stream);
     delete h;
 }
@@ -168,7 +170,7 @@ int ms_pileup_kernel_ms(ms_handle* h, double* ms, int64_t* reads) {
 }
 
 int ms_stage_kernel_ms(ms_handle* h, int stage, double* ms) {
-    if (!h || !ms || stage < 1 || stage > 3 || !h->timing || !h->stage_seen[stage]) return MS_ERR_ARG;
+    if (!h || !ms || stage < 1 || stage > 5 || !h->timing || !h->stage_seen[stage]) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
     MS_CUDA(h, cudaEventSynchronize(h->ev_stage[stage][1]));
     float f = 0.f;
@@ -289,6 +291,7 @@ int ms_reset_counts(ms_handle* h) {
 }
 
 int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
+    MsRange nvtx_range("K1 pileup");
     if (!h || !h->d_counts || R < 0 || (R > 0 && !d_packed)) return MS_ERR_ARG;
     if (R == 0) return MS_OK;
     MS_CUDA(h, cudaSetDevice(h->device));
@@ -363,6 +366,7 @@ int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
 }
 
 int ms_pileup_host(ms_handle* h, const uint32_t* h_packed, int64_t R, const uint32_t** keep_dev) {
+    MsRange nvtx_range("H2D rows + tile + K1");
     if (!h || !h->d_counts || R < 0 || (R > 0 && !h_packed)) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
     const size_t row_bytes = static_cast<size_t>(h->nblk) * 16;

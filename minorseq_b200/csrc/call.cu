@@ -101,6 +101,7 @@ void ms_call_params_default(ms_call_params* p) {
 
 int ms_call(ms_handle* h, const ms_gene* genes, int32_t ngenes, const char* refseq, const ms_call_params* prm,
             ms_variant* out, int64_t cap, int64_t* n) {
+    MsRange nvtx_range("K2 call");
     if (!h || !h->d_counts || !genes || ngenes < 0 || !prm || !n || (cap > 0 && !out)) return MS_ERR_ARG;
     if (!h->count_codons) MS_FAIL(h, MS_ERR_ARG, "ms_set_layout was called without a codon start mask");
     MS_CUDA(h, cudaSetDevice(h->device));

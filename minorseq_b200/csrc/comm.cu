@@ -96,11 +96,14 @@ int ms_comm_init(ms_handle* h, const char id[128], int rank, int world) {
 int ms_comm_size(const ms_handle* h) { return h ? h->world : 0; }
 
 int ms_allreduce_counts(ms_handle* h) {
+    MsRange nvtx_range("all-reduce counts");
     if (!h || !h->d_counts) return MS_ERR_ARG;
     if (!h->comm) return MS_OK;  // single rank
     MS_CUDA(h, cudaSetDevice(h->device));
+    MS_STAGE_BEGIN(h, MS_STAGE_ALLREDUCE);
     MS_NCCL(h, api().AllReduce(h->d_counts, h->d_counts, static_cast<size_t>(h->L) * 72, ncclUint32, ncclSum,
                                static_cast<ncclComm_t>(h->comm), h->stream));
+    MS_STAGE_END(h, MS_STAGE_ALLREDUCE);
     h->launches++;
     return MS_OK;
 }

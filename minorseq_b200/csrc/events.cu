@@ -313,6 +313,7 @@ int ms_set_base(ms_handle* h, const uint8_t* base) {
 }
 
 int ms_expand_events_dev(ms_handle* h, const ms_read_hdr* d_hdr, const uint16_t* d_events, int64_t R, uint32_t* d_packed) {
+    MsRange nvtx_range("expand events");
     if (!h || !h->d_counts || R < 0 || (R > 0 && (!d_hdr || !d_packed))) return MS_ERR_ARG;
     if (!h->have_base) MS_FAIL(h, MS_ERR_ARG, "ms_set_base has not been called for this layout");
     if (R == 0) return MS_OK;
@@ -324,6 +325,7 @@ int ms_expand_events_dev(ms_handle* h, const ms_read_hdr* d_hdr, const uint16_t*
 // stream; behind each chunk the main stream expands it into the handle's row buffer and piles it up, so that only the
 // last chunk's kernels are not hidden behind the PCIe transfer.
 int ms_pileup_events_host(ms_handle* h, const ms_read_hdr* hdr, const uint16_t* events, int64_t R, const uint32_t** keep_dev) {
+    MsRange nvtx_range("H2D events + expand + K1");
     if (!h || !h->d_counts || R < 0 || !hdr || (R > 0 && !events && hdr[R].ev_off > 0)) return MS_ERR_ARG;
     if (!h->have_base) MS_FAIL(h, MS_ERR_ARG, "ms_set_base has not been called for this layout");
     if ((static_cast<uint32_t>(hdr[R].begin) | (static_cast<uint32_t>(hdr[R].end) << 16)) != h->base_hash)

@@ -103,6 +103,21 @@ __global__ void __launch_bounds__(1024) consensus_kernel(const uint32_t* __restr
 
 }  // namespace ms
 
+namespace {
+// frees every temporary of one ms_fuse call on every way out (errors included)
+struct DevScope {
+    std::vector<void*> ptrs;
+    ~DevScope() { for (void* p : ptrs) cudaFree(p); }
+    template <class T> cudaError_t alloc(T** out, size_t bytes) {
+        void* p = nullptr;
+        const cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e == cudaSuccess) ptrs.push_back(p);
+        *out = static_cast<T*>(p);
+        return e;
+    }
+};
+}  // namespace
+
 extern "C" {
 
 void ms_fuse_params_default(ms_fuse_params* p) {
@@ -112,12 +127,14 @@ void ms_fuse_params_default(ms_fuse_params* p) {
 
 int ms_fuse(ms_handle* h, const ms_fuse_params* prm, const int32_t* ins_col, const int64_t* ins_off, const int32_t* ins_len,
             int64_t nins, const char* ins_pool, int64_t pool_len, char* seq, int64_t cap, int64_t* len) {
+    MsRange nvtx_range("K4 fuse");
     if (!h || !h->d_counts || !prm || !len || nins < 0 || (nins > 0 && (!ins_col || !ins_off || !ins_len || !ins_pool)))
         return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
     const int32_t L = h->L;
     std::vector<long long> acc_off(L, -1);
     std::vector<int32_t> acc_len(L, 0);
+    DevScope tmp;
     int32_t* d_col = nullptr; long long* d_off = nullptr; int32_t* d_len = nullptr; char* d_pool = nullptr;
     size_t extra = 0;
     if (nins > 0) {
@@ -127,10 +144,10 @@ int ms_fuse(ms_handle* h, const ms_fuse_params* prm, const int32_t* ins_col, con
         while (ts < 2 * nins) ts <<= 1;
         unsigned long long* t_key = nullptr; uint32_t* t_cnt = nullptr; long long* t_rep = nullptr;
         ms::InsCand* d_cand = nullptr; unsigned long long* d_n = nullptr;
-        MS_CUDA(h, cudaMalloc(&d_col, nins * 4)); MS_CUDA(h, cudaMalloc(&d_off, nins * 8)); MS_CUDA(h, cudaMalloc(&d_len, nins * 4));
-        MS_CUDA(h, cudaMalloc(&d_pool, std::max<int64_t>(1, pool_len)));
-        MS_CUDA(h, cudaMalloc(&t_key, ts * 8)); MS_CUDA(h, cudaMalloc(&t_cnt, ts * 4)); MS_CUDA(h, cudaMalloc(&t_rep, ts * 8));
-        MS_CUDA(h, cudaMalloc(&d_cand, nins * sizeof(ms::InsCand))); MS_CUDA(h, cudaMalloc(&d_n, 8));
+        MS_CUDA(h, tmp.alloc(&d_col, nins * 4)); MS_CUDA(h, tmp.alloc(&d_off, nins * 8)); MS_CUDA(h, tmp.alloc(&d_len, nins * 4));
+        MS_CUDA(h, tmp.alloc(&d_pool, std::max<int64_t>(1, pool_len)));
+        MS_CUDA(h, tmp.alloc(&t_key, ts * 8)); MS_CUDA(h, tmp.alloc(&t_cnt, ts * 4)); MS_CUDA(h, tmp.alloc(&t_rep, ts * 8));
+        MS_CUDA(h, tmp.alloc(&d_cand, nins * sizeof(ms::InsCand))); MS_CUDA(h, tmp.alloc(&d_n, 8));
         MS_CUDA(h, cudaMemcpyAsync(d_col, ins_col, nins * 4, cudaMemcpyHostToDevice, h->stream));
         MS_CUDA(h, cudaMemcpyAsync(d_off, ins_off, nins * 8, cudaMemcpyHostToDevice, h->stream));
         MS_CUDA(h, cudaMemcpyAsync(d_len, ins_len, nins * 4, cudaMemcpyHostToDevice, h->stream));
@@ -151,7 +168,6 @@ int ms_fuse(ms_handle* h, const ms_fuse_params* prm, const int32_t* ins_col, con
             MS_CUDA(h, cudaMemcpyAsync(cand.data(), d_cand, nc * sizeof(ms::InsCand), cudaMemcpyDeviceToHost, h->stream));
             MS_CUDA(h, cudaStreamSynchronize(h->stream));
         }
-        cudaFree(t_key); cudaFree(t_cnt); cudaFree(t_rep); cudaFree(d_cand); cudaFree(d_n);
         // exactness guard against a 64-bit hash collision: recount the survivors' strings
         for (const ms::InsCand& c : cand) {
             uint32_t exact = 0;
@@ -173,8 +189,8 @@ int ms_fuse(ms_handle* h, const ms_fuse_params* prm, const int32_t* ins_col, con
         }
     }
     long long* d_acc_off = nullptr; int32_t* d_acc_len = nullptr; long long* d_outlen = nullptr;
-    MS_CUDA(h, cudaMalloc(&d_acc_off, static_cast<size_t>(L) * 8)); MS_CUDA(h, cudaMalloc(&d_acc_len, static_cast<size_t>(L) * 4));
-    MS_CUDA(h, cudaMalloc(&d_outlen, 8));
+    MS_CUDA(h, tmp.alloc(&d_acc_off, static_cast<size_t>(L) * 8)); MS_CUDA(h, tmp.alloc(&d_acc_len, static_cast<size_t>(L) * 4));
+    MS_CUDA(h, tmp.alloc(&d_outlen, 8));
     cudaFree(h->d_seq); h->d_seq = nullptr;
     MS_CUDA(h, cudaMalloc(&h->d_seq, static_cast<size_t>(L) + extra + 16));
     MS_CUDA(h, cudaMemcpyAsync(d_acc_off, acc_off.data(), static_cast<size_t>(L) * 8, cudaMemcpyHostToDevice, h->stream));
@@ -186,8 +202,6 @@ int ms_fuse(ms_handle* h, const ms_fuse_params* prm, const int32_t* ins_col, con
     MS_CUDA(h, cudaStreamSynchronize(h->stream));
     if (seq && cap > 0 && n > 0)
         MS_CUDA(h, cudaMemcpy(seq, h->d_seq, static_cast<size_t>(std::min<int64_t>(cap, n)), cudaMemcpyDeviceToHost));
-    cudaFree(d_acc_off); cudaFree(d_acc_len); cudaFree(d_outlen);
-    cudaFree(d_col); cudaFree(d_off); cudaFree(d_len); cudaFree(d_pool);
     MS_CUDA(h, cudaGetLastError());
     *len = n;
     return MS_OK;

@@ -5,6 +5,16 @@
 #include <string>
 #include <vector>
 #include "../../include/minorseq_b200.h"
+#include <nvtx3/nvToolsExt.h>
+
+// NVTX range over a stage of the path (decode / H2D / K1-K4 / exchanges): shows up in Nsight timelines, costs a
+// few nanoseconds when no tool is attached
+struct MsRange {
+    explicit MsRange(const char* name) { nvtxRangePushA(name); }
+    ~MsRange() { nvtxRangePop(); }
+    MsRange(const MsRange&) = delete;
+    MsRange& operator=(const MsRange&) = delete;
+};
 
 // grow-only device buffer: the hot path never pays cudaMalloc/cudaFree twice for the same size
 struct DevBuf {
@@ -32,8 +42,8 @@ struct ms_handle {
     cudaEvent_t ev_stagefree[2] = {};           // ms_pileup_host: staging buffer k has been permuted into tiles
     cudaEvent_t ev_k1[2] = {nullptr, nullptr};  // around the last K1 launch when timing is on
     cudaEvent_t ev_timer[2] = {nullptr, nullptr};  // ms_timer_start / ms_timer_stop
-    cudaEvent_t ev_stage[4][2] = {};               // when timing is on: around the last launch of MS_STAGE_* (ms_stage_kernel_ms)
-    bool stage_seen[4] = {false, false, false, false};
+    cudaEvent_t ev_stage[6][2] = {};               // when timing is on: around the last launch of MS_STAGE_* (ms_stage_kernel_ms)
+    bool stage_seen[6] = {false, false, false, false, false, false};
     bool timing = false;
     int64_t k1_reads = 0;
     std::string err;

@@ -86,6 +86,7 @@ __global__ void nw_init_kernel(int32_t* __restrict__ hrow, int32_t* __restrict__
 
 extern "C" int ms_align_refs(ms_handle* h, const char* a, int32_t la, const char* b, int32_t lb, char* ops, int64_t cap, int64_t* nops,
                              int64_t* score) {
+    MsRange nvtx_range("K5 align references");
     if (!h || la < 0 || lb < 0 || (la > 0 && !a) || (lb > 0 && !b) || !nops || (cap > 0 && !ops)) return MS_ERR_ARG;
     *nops = static_cast<int64_t>(la) + lb;     // upper bound, refined below
     if (cap < static_cast<int64_t>(la) + lb) return MS_ERR_CAPACITY;

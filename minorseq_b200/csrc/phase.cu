@@ -531,6 +531,7 @@ int ms_phase_begin(ms_handle* h, const int32_t* var_col, const int32_t* var_codo
 }
 
 int ms_phase_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
+    MsRange nvtx_range("K3 phase bits");
     if (!h || !h->b_bits.p || R < 0 || (R > 0 && !d_packed)) return MS_ERR_ARG;
     if (h->phase_n + R > h->phase_cap) MS_FAIL(h, MS_ERR_CAPACITY, "more reads than ms_phase_begin(max_reads)");
     if (R == 0) return MS_OK;
@@ -562,6 +563,7 @@ int ms_phase_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
 }
 
 int ms_phase_groups(ms_handle* h, uint32_t* patterns, uint64_t* counts, int64_t cap, int64_t* H, ms_phase_counters* ctr) {
+    MsRange nvtx_range("K3 grouping");
     if (!h || !h->b_bits.p || !H) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
     if (h->groups_valid) return phase_groups_copy_out(h, patterns, counts, cap, H, ctr);   // same pass asked again (bigger cap)
@@ -759,6 +761,7 @@ int ms_set_cooccurrence_variant(ms_handle* h, int32_t variant) {
 }
 
 int ms_cooccurrence(ms_handle* h, int32_t** d_C) {
+    MsRange nvtx_range("K3 co-occurrence");
     if (!h || !h->b_bits.p || !d_C) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
     const int32_t V = h->V, nw = h->vwords;

@@ -296,6 +296,7 @@ int sort_big(ms_handle* h, const uint32_t* cnt, const uint32_t* pat, int32_t nw,
 
 extern "C" int ms_phase_haplotypes(ms_handle* h, int32_t min_reads, uint32_t* patterns, uint64_t* counts, int64_t cap, int64_t* H,
                                    int64_t* nreported, ms_phase_counters* ctr, int32_t* hap_id) {
+    MsRange nvtx_range("K3 haplotypes (merge + order)");
     if (!h || !h->b_bits.p || !H || cap < 0 || (cap > 0 && (!patterns || !counts)) || min_reads < 0) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
     const int32_t nw = h->vwords;
@@ -364,6 +365,7 @@ extern "C" int ms_phase_haplotypes(ms_handle* h, int32_t min_reads, uint32_t* pa
             MS_CUDA(h, h->b_m_cnt.ensure(static_cast<size_t>(bound) * 4));
             MS_CUDA(h, h->b_m_pat.ensure(static_cast<size_t>(bound) * nw * 4));
             // the one exchange of the phasing step: every rank's compact (pattern, count) list and marginals
+            MS_STAGE_BEGIN(h, MS_STAGE_HAPMERGE);
             rc = ms_comm_allgather_bytes(h, blk, h->b_gather.p, block);
             if (rc != MS_OK) return rc;
             MS_CUDA(h, cudaMemsetAsync(h->b_mt_key.p, 0, static_cast<size_t>(tsize) * 8, h->stream));
@@ -380,6 +382,7 @@ extern "C" int ms_phase_haplotypes(ms_handle* h, int32_t min_reads, uint32_t* pa
                                                                                 tsize, o.res, h->b_m_cnt.as<uint32_t>(), h->b_m_pat.as<uint32_t>(),
                                                                                 h->b_mindex.as<uint32_t>());
             h->launches += 3;
+            MS_STAGE_END(h, MS_STAGE_HAPMERGE);
             v_cnt = h->b_m_cnt.as<uint32_t>();
             v_pat = h->b_m_pat.as<uint32_t>();
             Mptr = o.res;

@@ -13,6 +13,16 @@
 #include <vector>
 #include "../../include/minorseq_b200.h"
 #include "bgzf_bam.hpp"
+#if defined(__has_include)
+#if __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>
+#define MSHOST_RANGE(name) mshost::NvtxRange nvtx_range_(name)
+namespace mshost { struct NvtxRange { explicit NvtxRange(const char* n) { nvtxRangePushA(n); } ~NvtxRange() { nvtxRangePop(); } }; }
+#endif
+#endif
+#ifndef MSHOST_RANGE
+#define MSHOST_RANGE(name) do {} while (0)     // built without the CUDA toolkit's headers: no NVTX ranges on the host stages
+#endif
 
 namespace mshost {
 
@@ -128,6 +138,7 @@ struct Decoded {
 };
 
 inline void decode_alignments(const std::string& path, Decoded& d, Alignments& out) {
+    MSHOST_RANGE("BAM inflate + index + admission");
     unsigned nt = std::thread::hardware_concurrency();
     if (const char* e = getenv("MS_HOST_THREADS")) nt = static_cast<unsigned>(atoi(e));
     if (nt < 1) nt = 1;
@@ -155,6 +166,7 @@ inline void decode_alignments(const std::string& path, Decoded& d, Alignments& o
 }
 
 inline void expand_alignments(const Decoded& d, const QvFilter& qv, bool want_names, bool want_insertions, Alignments& out) {
+    MSHOST_RANGE("CIGAR expansion + QV filter");
     const msbam::Bytes& u = d.u;
     const msbam::BamIndexed& bx = d.bx;
     const std::vector<size_t>& keep = d.keep;
