@@ -145,36 +145,40 @@ int ms_set_pileup_variant(ms_handle *h, int variant);
  * What juliet/fuse's per-record CIGAR walk (doc/JULIET.md:49-58, doc/FUSE.md:13-15) hands to the GPU when the
  * caller wants the PCIe link to carry events instead of whole rows: a CCS alignment is "the base sequence, except
  * at a few columns" (X / D / I ops and QV-filtered bases, :256-259).  Per read: its span [begin,end) and a sorted
- * list of 16-bit events, event = delta << 4 | nibble, column = previous event's column (the read's begin for the
- * first) + delta, nibble = state | insertion-follows << 3.  Spanned columns without an event hold the base
- * sequence's base, columns outside the span are "not spanned".  hdr has R+1 entries: the events of read r are
- * events[hdr[r].ev_off .. hdr[r+1].ev_off); hdr[R] is the sentinel written by ms_events_seal (total event count +
- * a hash of the base sequence; rows encoded against another base are rejected with MS_ERR_FORMAT).  Reference
- * length <= 65535.  The GPU rebuilds the planar rows (expand_events_kernel) and K1/K3 run on them unchanged.   */
+ * list of 12-bit events, event = delta << 4 | nibble, column = previous event's column (the read's begin for the
+ * first) + delta (0..255), nibble = state | insertion-follows << 3.  Spanned columns without an event hold the base
+ * sequence's base, columns outside the span are "not spanned"; the encoder restates an unchanged column (a filler)
+ * when two events are more than 255 columns apart.  The events of a read are packed back to back, event k in bits
+ * [12k, 12k+12) of the read's little-endian byte string, which starts on a byte boundary: n events take
+ * ceil(1.5 n) bytes.  hdr has R+1 entries: the byte string of read r is events[hdr[r].ev_off .. hdr[r+1].ev_off);
+ * hdr[R] is the sentinel written by ms_events_seal (total byte count + a hash of the base sequence; rows encoded
+ * against another base are rejected with MS_ERR_FORMAT).  Reference length <= 65535.  The GPU rebuilds the packed
+ * reads (expand_events_kernel) and K1/K3 run on them unchanged.  ~136 B per 3 kb read at CCS error rates
+ * (85 events), against 1504 B for the plain row.                                                              */
 typedef struct { uint32_t ev_off; uint16_t begin, end; } ms_read_hdr;
-/* worst-case number of events of one read (every column differs + fillers) */
+/* worst-case number of event BYTES of one read (every column differs + fillers) */
 int64_t ms_events_bound(int32_t L);
 /* base: L bytes, one base (0..3) per reference column: the configured referenceSequence, or any sequence close to
  * the reads (the encoding is lossless for every base; a close one makes it short).                                */
 int ms_encode_states(const uint8_t *states, int64_t R, int32_t L, const uint8_t *base,
-                     ms_read_hdr *hdr /* R+1 */, uint16_t *events, int64_t cap, int64_t *nevents);
+                     ms_read_hdr *hdr /* R+1 */, uint8_t *events, int64_t cap /* bytes */, int64_t *nbytes);
 int ms_encode_rows(const uint32_t *packed, int64_t R, int32_t L, const uint8_t *base,
-                   ms_read_hdr *hdr /* R+1 */, uint16_t *events, int64_t cap, int64_t *nevents);
+                   ms_read_hdr *hdr /* R+1 */, uint8_t *events, int64_t cap /* bytes */, int64_t *nbytes);
 /* Incremental form for a BAM loop (one ms_expand_cigar row at a time, e.g. per host thread): base_planes from
- * ms_base_planes (2*ceil(L/32) words); appends the row's events at events[*nevents...] and advances *nevents;
- * fills *hdr (ev_off = the old *nevents).  The caller seals the finished array with ms_events_seal.               */
+ * ms_base_planes (2*ceil(L/32) words); appends the row's event bytes at events[*nbytes...] and advances *nbytes;
+ * fills *hdr (ev_off = the old *nbytes).  The caller seals the finished array with ms_events_seal.                */
 int ms_base_planes(const uint8_t *base, int32_t L, uint32_t *planes);
 int ms_encode_row(const uint32_t *row, int32_t L, const uint32_t *base_planes, ms_read_hdr *hdr,
-                  uint16_t *events, int64_t cap, int64_t *nevents);
-int ms_events_seal(ms_read_hdr *hdr, int64_t R, int64_t nevents, const uint8_t *base, int32_t L);
+                  uint8_t *events, int64_t cap /* bytes */, int64_t *nbytes);
+int ms_events_seal(ms_read_hdr *hdr, int64_t R, int64_t nbytes, const uint8_t *base, int32_t L);
 /* The handle's copy of the base sequence (after ms_set_layout, which forgets it). */
 int ms_set_base(ms_handle *h, const uint8_t *base);
 /* Device-resident event rows -> R packed reads at d_packed (tiles, ms_tiled_words(L,R) words).  */
-int ms_expand_events_dev(ms_handle *h, const ms_read_hdr *d_hdr, const uint16_t *d_events, int64_t R,
+int ms_expand_events_dev(ms_handle *h, const ms_read_hdr *d_hdr, const uint8_t *d_events, int64_t R,
                          uint32_t *d_packed);
 /* ms_pileup_host for event rows: chunked H2D of the events, expansion and pile-up behind each chunk.
  * keep_dev as in ms_pileup_host (the expanded rows, for ms_phase_dev).                               */
-int ms_pileup_events_host(ms_handle *h, const ms_read_hdr *hdr, const uint16_t *events, int64_t R,
+int ms_pileup_events_host(ms_handle *h, const ms_read_hdr *hdr, const uint8_t *events, int64_t R,
                           const uint32_t **keep_dev);
 
 /* ---- cross-GPU exchange (one process per GPU) ---------------------------------
@@ -277,8 +281,8 @@ int ms_juliet_pass_host(ms_handle *h, const uint32_t *h_packed, int64_t R, const
                         ms_juliet_result *out);
 
 /* The same pass from event rows in host memory (ms_pileup_events_host in place of ms_pileup_host): what the
- * juliet main and bench.py's e2e call -- the PCIe link carries ~190 B instead of 1504 B per 3 kb read.     */
-int ms_juliet_pass_events_host(ms_handle *h, const ms_read_hdr *hdr, const uint16_t *events, int64_t R,
+ * bench.py's e2e calls -- the PCIe link carries ~136 B instead of 1504 B per 3 kb read.                       */
+int ms_juliet_pass_events_host(ms_handle *h, const ms_read_hdr *hdr, const uint8_t *events, int64_t R,
                                const ms_gene *genes, int32_t ngenes, const char *refseq, const ms_call_params *prm,
                                int32_t phase, int32_t min_hap_reads, ms_juliet_result *out);
 

@@ -487,13 +487,13 @@ def base_array(base, L):
 
 
 def _encode(fn_name, src, R, L, base):
-    """-> (hdr[R+1] structured array, events uint16 array)"""
+    """-> (hdr[R+1] structured array, event bytes: uint8 array of packed 12-bit events)"""
     lib = _lib.load()
     base = base_array(base, L)
-    cap = max(1024, int(R) * 64)
+    cap = max(1024, int(R) * 128)
     while True:
         hdr = np.zeros(R + 1, dtype=HDR_DTYPE)
-        ev = np.empty(cap, dtype=np.uint16)
+        ev = np.empty(cap, dtype=np.uint8)
         n = C.c_int64()
         rc = getattr(lib, fn_name)(_ptr(src), R, L, _ptr(base), _ptr(hdr), _ptr(ev), cap, C.byref(n))
         if rc == -4:
@@ -523,7 +523,12 @@ def decode_events(hdr, events, L, base):
     for r in range(R):
         b, e = int(hdr["begin"][r]), int(hdr["end"][r])
         out[r, b:e] = base[b:e]
-        ev = events[int(hdr["ev_off"][r]): int(hdr["ev_off"][r + 1])].astype(np.int64)
+        raw = np.asarray(events[int(hdr["ev_off"][r]): int(hdr["ev_off"][r + 1])], dtype=np.uint8).astype(np.int64)
+        n = (2 * len(raw)) // 3                                   # ceil(1.5 n) bytes hold n 12-bit events
+        k = np.arange(n)
+        o = (3 * k) >> 1
+        two = raw[o] | (raw[o + 1] << 8)
+        ev = np.where(k & 1, two >> 4, two & 0xFFF)
         cols = b + np.cumsum(ev >> 4)
         out[r, cols] = (ev & 15).astype(np.uint8)
     return out

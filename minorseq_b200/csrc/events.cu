@@ -3,18 +3,18 @@
 // A PacBio CCS alignment is "the reference, except at a few columns" (CIGAR `=` runs with sparse X / D / I ops,
 // /root/reference/doc/JULIET.md:49-58, plus the QV-filtered bases that become N, :256-259).  The planar rows K1 and K3
 // read cost L/2 bytes per read on the PCIe link (1504 B at 3 kb), which is what bounds the end-to-end pass.  Here the
-// host ships, per read, its span and a sorted list of 16-bit events (column delta, new 4-bit column value) against a
-// base sequence both sides hold (~90 events = ~190 B per 3 kb read at CCS error rates), and expand_events_kernel
+// host ships, per read, its span and a sorted list of 12-bit events (column delta, new 4-bit column value) against a
+// base sequence both sides hold (~85 events = ~136 B per 3 kb read at CCS error rates), and expand_events_kernel
 // rebuilds the planar rows in HBM, where the pile-up and the phasing kernels run unchanged.  SURVEY.md rows a2/a3
 // (host CIGAR walk) and 8f-2 ("GPU-side CIGAR expansion is the next real speed-up").
 //
-// Format (include/minorseq_b200.h):  ms_read_hdr hdr[R+1] = {ev_off, begin, end}; the events of read r are
-// events[hdr[r].ev_off .. hdr[r+1].ev_off).  event = delta << 4 | nibble: the column is the previous event's column
-// (the read's `begin` for the first) + delta, nibble = state | insertion-follows << 3 of that column.  Every spanned
-// column without an event holds the base sequence's base; columns outside [begin, end) are "not spanned".  The encoder
-// emits a filler event (a column's unchanged value) when two events are more than 4095 columns apart.  hdr[R] is a
-// sentinel: ev_off = total number of events, begin | end << 16 = a 32-bit hash of the base sequence, so that rows
-// encoded against another base are rejected instead of silently mis-expanded.
+// Format (include/minorseq_b200.h):  ms_read_hdr hdr[R+1] = {ev_off, begin, end}; the byte string of read r is
+// events[hdr[r].ev_off .. hdr[r+1].ev_off), event k in its bits [12k, 12k+12): delta << 4 | nibble, the column is the
+// previous event's column (the read's `begin` for the first) + delta, nibble = state | insertion-follows << 3 of that
+// column.  Every spanned column without an event holds the base sequence's base, columns outside [begin, end) are "not
+// spanned".  The encoder emits a filler event (a column's unchanged value) when two events are more than 255 columns
+// apart.  hdr[R] is a sentinel: ev_off = total number of event bytes, begin | end << 16 = a 32-bit hash of the base
+// sequence, so that rows encoded against another base are rejected instead of silently mis-expanded.
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -54,8 +54,31 @@ static inline uint32_t nibble_at(const uint32_t* row, int32_t c) {
     return ((w[0] >> sh) & 1u) | (((w[1] >> sh) & 1u) << 1) | (((w[2] >> sh) & 1u) << 2) | (((w[3] >> sh) & 1u) << 3);
 }
 
-// one planar row -> span + events.  Returns the number of events written, or -1 when ev_cap is too small.
-static int64_t encode_row(const uint32_t* row, int32_t L, const uint32_t* bpl, uint16_t* ev, int64_t ev_cap, int32_t& begin, int32_t& end) {
+constexpr int32_t kMaxDelta = 255;
+
+// appends 12-bit events to a read's byte string
+struct EventWriter {
+    uint8_t* ev;
+    int64_t cap, o = 0;   // o: bytes completely or partly written
+    bool half = false;    // the low nibble of ev[o-1]... see put(): an odd number of events so far
+    bool put(uint32_t e) {
+        if (!half) {
+            if (o + 2 > cap) return false;
+            ev[o] = static_cast<uint8_t>(e & 0xffu);
+            ev[o + 1] = static_cast<uint8_t>(e >> 8);          // low nibble; the next event fills the high one
+            o += 2; half = true;
+        } else {
+            if (o + 1 > cap) return false;
+            ev[o - 1] = static_cast<uint8_t>(ev[o - 1] | ((e & 0xfu) << 4));
+            ev[o] = static_cast<uint8_t>(e >> 4);
+            o += 1; half = false;
+        }
+        return true;
+    }
+};
+
+// one planar row -> span + event bytes.  Returns the number of bytes written, or -1 when cap is too small.
+static int64_t encode_row(const uint32_t* row, int32_t L, const uint32_t* bpl, uint8_t* ev, int64_t cap, int32_t& begin, int32_t& end) {
     const int32_t nblk = (L + 31) / 32;
     begin = end = 0;
     int32_t first = -1, last = -1;
@@ -68,25 +91,23 @@ static int64_t encode_row(const uint32_t* row, int32_t L, const uint32_t* bpl, u
     }
     if (first < 0) return 0;
     begin = first; end = last + 1;
-    int64_t n = 0;
+    EventWriter w{ev, cap};
     int32_t prev = begin;
     for (int32_t b = begin >> 5; b <= (end - 1) >> 5; ++b) {
-        const uint32_t* w = row + 4 * b;
-        uint32_t diff = ((w[0] ^ bpl[2 * b]) | (w[1] ^ bpl[2 * b + 1]) | w[2] | w[3]) & span_mask(b, begin, end);
+        const uint32_t* q = row + 4 * b;
+        uint32_t diff = ((q[0] ^ bpl[2 * b]) | (q[1] ^ bpl[2 * b + 1]) | q[2] | q[3]) & span_mask(b, begin, end);
         while (diff) {
             const int32_t c = 32 * b + __builtin_ctz(diff);
             diff &= diff - 1;
-            while (c - prev > 4095) {   // filler: restate an unchanged column
-                prev += 4095;
-                if (n >= ev_cap) return -1;
-                ev[n++] = static_cast<uint16_t>((4095u << 4) | nibble_at(row, prev));
+            while (c - prev > kMaxDelta) {   // filler: restate an unchanged column
+                prev += kMaxDelta;
+                if (!w.put((static_cast<uint32_t>(kMaxDelta) << 4) | nibble_at(row, prev))) return -1;
             }
-            if (n >= ev_cap) return -1;
-            ev[n++] = static_cast<uint16_t>((static_cast<uint32_t>(c - prev) << 4) | nibble_at(row, c));
+            if (!w.put((static_cast<uint32_t>(c - prev) << 4) | nibble_at(row, c))) return -1;
             prev = c;
         }
     }
-    return n;
+    return w.o;
 }
 
 // ---------------------------------------------------------------- device side
@@ -102,7 +123,7 @@ constexpr int kExpandMaxWarps = 16;
 // for eight of them to fit in shared memory leave with per-warp scattered 16-byte stores instead.
 template <bool COOP>
 __global__ void __launch_bounds__(kExpandMaxWarps * 32) expand_events_kernel(const ms_read_hdr* __restrict__ hdr,
-                                                                           const uint16_t* __restrict__ events, int64_t R,
+                                                                           const uint8_t* __restrict__ events, int64_t R,
                                                                            int32_t nblk, int32_t rstride, const uint2* __restrict__ basepl,
                                                                            uint4* __restrict__ out) {
     extern __shared__ __align__(16) uint4 rows_sm[];
@@ -126,13 +147,18 @@ __global__ void __launch_bounds__(kExpandMaxWarps * 32) expand_events_kernel(con
                 row[b] = make_uint4((bp.x & m) | ~m, (bp.y & m) | ~m, ~m, 0u);
             }
             __syncwarp();
-            const uint32_t n = off1 - hd.ev_off;
-            const uint16_t* ev = events + hd.ev_off;
+            const uint32_t n = (2u * (off1 - hd.ev_off)) / 3u;        // ceil(1.5 n) bytes hold n 12-bit events
+            const uint8_t* ev = events + hd.ev_off;
             int32_t carry = begin;
             for (uint32_t i0 = 0; i0 < n; i0 += 32) {
                 const uint32_t i = i0 + lane;
                 const bool have = i < n;
-                const uint32_t e = have ? ev[i] : 0u;
+                uint32_t e = 0u;
+                if (have) {                                            // event i sits in bits [12 i, 12 i + 12) of the byte string
+                    const uint32_t o = (3u * i) >> 1;
+                    const uint32_t two = static_cast<uint32_t>(ev[o]) | (static_cast<uint32_t>(ev[o + 1]) << 8);
+                    e = (i & 1u) ? two >> 4 : two & 0xfffu;
+                }
                 int32_t s = static_cast<int32_t>(e >> 4);
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -191,7 +217,7 @@ __global__ void __launch_bounds__(kExpandMaxWarps * 32) expand_events_kernel(con
 
 }  // namespace ms
 
-static int expand_launch(ms_handle* h, const ms_read_hdr* d_hdr, const uint16_t* d_events, int64_t R, uint32_t* d_packed) {
+static int expand_launch(ms_handle* h, const ms_read_hdr* d_hdr, const uint8_t* d_events, int64_t R, uint32_t* d_packed) {
     const int rstride = h->nblk | 1;                      // uint4 between the rows in shared memory: odd
     const int row_bytes = rstride * 16;
     const int smem_cap = std::min(h->max_smem, 100 << 10);
@@ -221,9 +247,9 @@ void ms_events_set_smem_attr(int max_smem) {
 
 extern "C" {
 
-int64_t ms_events_bound(int32_t L) { return L > 0 ? static_cast<int64_t>(L) + L / 4095 + 1 : 0; }
+int64_t ms_events_bound(int32_t L) { return L > 0 ? ((static_cast<int64_t>(L) + L / ms::kMaxDelta + 2) * 3 + 1) / 2 : 0; }
 
-int ms_encode_rows(const uint32_t* packed, int64_t R, int32_t L, const uint8_t* base, ms_read_hdr* hdr, uint16_t* events,
+int ms_encode_rows(const uint32_t* packed, int64_t R, int32_t L, const uint8_t* base, ms_read_hdr* hdr, uint8_t* events,
                    int64_t cap, int64_t* nevents) {
     if (!packed || !base || !hdr || (!events && cap > 0) || R < 0 || L <= 0 || L > 65535 || cap < 0 || !nevents) return MS_ERR_ARG;
     std::vector<uint32_t> bpl;
@@ -244,7 +270,7 @@ int ms_encode_rows(const uint32_t* packed, int64_t R, int32_t L, const uint8_t* 
     return ms_events_seal(hdr, R, n, base, L);
 }
 
-int ms_encode_states(const uint8_t* states, int64_t R, int32_t L, const uint8_t* base, ms_read_hdr* hdr, uint16_t* events,
+int ms_encode_states(const uint8_t* states, int64_t R, int32_t L, const uint8_t* base, ms_read_hdr* hdr, uint8_t* events,
                      int64_t cap, int64_t* nevents) {
     if (!states || !base || !hdr || R < 0 || L <= 0 || L > 65535 || cap < 0 || !nevents) return MS_ERR_ARG;
     std::vector<uint32_t> bpl;
@@ -267,7 +293,7 @@ int ms_encode_states(const uint8_t* states, int64_t R, int32_t L, const uint8_t*
     return ms_events_seal(hdr, R, n, base, L);
 }
 
-int ms_encode_row(const uint32_t* row, int32_t L, const uint32_t* base_planes, ms_read_hdr* hdr, uint16_t* events, int64_t cap,
+int ms_encode_row(const uint32_t* row, int32_t L, const uint32_t* base_planes, ms_read_hdr* hdr, uint8_t* events, int64_t cap,
                   int64_t* nevents) {
     if (!row || !base_planes || !hdr || !nevents || L <= 0 || L > 65535 || *nevents < 0 || cap < *nevents) return MS_ERR_ARG;
     int32_t b, e;
@@ -312,7 +338,7 @@ int ms_set_base(ms_handle* h, const uint8_t* base) {
     return MS_OK;
 }
 
-int ms_expand_events_dev(ms_handle* h, const ms_read_hdr* d_hdr, const uint16_t* d_events, int64_t R, uint32_t* d_packed) {
+int ms_expand_events_dev(ms_handle* h, const ms_read_hdr* d_hdr, const uint8_t* d_events, int64_t R, uint32_t* d_packed) {
     MsRange nvtx_range("expand events");
     if (!h || !h->d_counts || R < 0 || (R > 0 && (!d_hdr || !d_packed))) return MS_ERR_ARG;
     if (!h->have_base) MS_FAIL(h, MS_ERR_ARG, "ms_set_base has not been called for this layout");
@@ -324,7 +350,7 @@ int ms_expand_events_dev(ms_handle* h, const ms_read_hdr* d_hdr, const uint16_t*
 // Event rows from host memory (pinned recommended): the header and event arrays go up in a few chunks on the copy
 // stream; behind each chunk the main stream expands it into the handle's row buffer and piles it up, so that only the
 // last chunk's kernels are not hidden behind the PCIe transfer.
-int ms_pileup_events_host(ms_handle* h, const ms_read_hdr* hdr, const uint16_t* events, int64_t R, const uint32_t** keep_dev) {
+int ms_pileup_events_host(ms_handle* h, const ms_read_hdr* hdr, const uint8_t* events, int64_t R, const uint32_t** keep_dev) {
     MsRange nvtx_range("H2D events + expand + K1");
     if (!h || !h->d_counts || R < 0 || !hdr || (R > 0 && !events && hdr[R].ev_off > 0)) return MS_ERR_ARG;
     if (!h->have_base) MS_FAIL(h, MS_ERR_ARG, "ms_set_base has not been called for this layout");
@@ -334,7 +360,7 @@ int ms_pileup_events_host(ms_handle* h, const ms_read_hdr* hdr, const uint16_t* 
     const size_t row_bytes = static_cast<size_t>(h->nblk) * 16;
     const size_t need = std::max<size_t>(16, static_cast<size_t>(ms::tiles_of(R)) * 8 * row_bytes);   // whole tiles (rows.cuh)
     const int64_t total_ev = hdr[R].ev_off;
-    if (need > h->upload_cap || static_cast<size_t>(R + 1) * sizeof(ms_read_hdr) > h->b_ev_hdr.cap || static_cast<size_t>(total_ev) * 2 + 64 > h->b_ev.cap) {
+    if (need > h->upload_cap || static_cast<size_t>(R + 1) * sizeof(ms_read_hdr) > h->b_ev_hdr.cap || static_cast<size_t>(total_ev) + 64 > h->b_ev.cap) {
         MS_CUDA(h, cudaStreamSynchronize(h->stream));
         if (need > h->upload_cap) {
             cudaFree(h->d_upload);
@@ -343,12 +369,12 @@ int ms_pileup_events_host(ms_handle* h, const ms_read_hdr* hdr, const uint16_t* 
             h->upload_cap = need;
         }
         MS_CUDA(h, h->b_ev_hdr.ensure(static_cast<size_t>(R + 1) * sizeof(ms_read_hdr)));
-        MS_CUDA(h, h->b_ev.ensure(static_cast<size_t>(total_ev) * 2 + 64));
+        MS_CUDA(h, h->b_ev.ensure(static_cast<size_t>(total_ev) + 64));
     }
     ms_read_hdr* d_hdr = h->b_ev_hdr.as<ms_read_hdr>();
-    uint16_t* d_ev = h->b_ev.as<uint16_t>();
+    uint8_t* d_ev = h->b_ev.as<uint8_t>();
     // chunking: ~24 MB of payload per chunk (0.4 ms on the link), at most 16 chunks, at least 64 Ki reads per chunk
-    const double payload = static_cast<double>(total_ev) * 2 + static_cast<double>(R) * 8;
+    const double payload = static_cast<double>(total_ev) + static_cast<double>(R) * 8;
     static const double chunk_mb = getenv("MS_EVENTS_CHUNK_MB") ? atof(getenv("MS_EVENTS_CHUNK_MB")) : 24.0;
     int64_t nchunks = std::max<int64_t>(1, std::min<int64_t>(16, static_cast<int64_t>(payload / (chunk_mb * 1048576.0) + 0.5)));
     nchunks = std::max<int64_t>(1, std::min<int64_t>(nchunks, R / 65536));
@@ -361,7 +387,7 @@ int ms_pileup_events_host(ms_handle* h, const ms_read_hdr* hdr, const uint16_t* 
         const int64_t e0 = hdr[r0].ev_off, e1 = hdr[r1].ev_off;
         const int64_t h0 = r0 + (k > 0 ? 1 : 0);     // entry r0 went up with the previous chunk (as its end marker)
         MS_CUDA(h, cudaMemcpyAsync(d_hdr + h0, hdr + h0, static_cast<size_t>(r1 - h0 + 1) * sizeof(ms_read_hdr), cudaMemcpyHostToDevice, h->copy_stream));
-        if (e1 > e0) MS_CUDA(h, cudaMemcpyAsync(d_ev + e0, events + e0, static_cast<size_t>(e1 - e0) * 2, cudaMemcpyHostToDevice, h->copy_stream));
+        if (e1 > e0) MS_CUDA(h, cudaMemcpyAsync(d_ev + e0, events + e0, static_cast<size_t>(e1 - e0), cudaMemcpyHostToDevice, h->copy_stream));
         cudaEvent_t ev = h->ev_chunk[k & 15];
         MS_CUDA(h, cudaEventRecord(ev, h->copy_stream));
         MS_CUDA(h, cudaStreamWaitEvent(h->stream, ev, 0));

@@ -11,7 +11,7 @@
 
 enum RowSource { kDeviceRows, kHostRows, kHostEvents };
 
-static int juliet_pass(ms_handle* h, const void* src, const uint16_t* events, RowSource from, int64_t R, const ms_gene* genes, int32_t ngenes,
+static int juliet_pass(ms_handle* h, const void* src, const uint8_t* events, RowSource from, int64_t R, const ms_gene* genes, int32_t ngenes,
                        const char* refseq, const ms_call_params* prm, int32_t phase, int32_t min_hap_reads, ms_juliet_result* out) {
     if (!h || !out || !prm || R < 0) return MS_ERR_ARG;
     int rc = ms_reset_counts(h);
@@ -65,7 +65,7 @@ int ms_juliet_pass_host(ms_handle* h, const uint32_t* h_packed, int64_t R, const
     return juliet_pass(h, h_packed, nullptr, kHostRows, R, genes, ngenes, refseq, prm, phase, min_hap_reads, out);
 }
 
-int ms_juliet_pass_events_host(ms_handle* h, const ms_read_hdr* hdr, const uint16_t* events, int64_t R, const ms_gene* genes, int32_t ngenes,
+int ms_juliet_pass_events_host(ms_handle* h, const ms_read_hdr* hdr, const uint8_t* events, int64_t R, const ms_gene* genes, int32_t ngenes,
                                const char* refseq, const ms_call_params* prm, int32_t phase, int32_t min_hap_reads, ms_juliet_result* out) {
     return juliet_pass(h, hdr, events, kHostEvents, R, genes, ngenes, refseq, prm, phase, min_hap_reads, out);
 }

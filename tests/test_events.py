@@ -1,7 +1,7 @@
 """Event rows (csrc/events.cu): the compact host->device form of an aligned read.
 
 CPU part: the host encoders against an independent numpy decoder (minorseq_b200.api.decode_events) on generator reads,
-random states, fillers (> 4095 unchanged columns between two events), unspanned reads, reference skips inside a read.
+random states, fillers (> 255 unchanged columns between two events), unspanned reads, reference skips inside a read.
 GPU part: expand_events_kernel rebuilds exactly the planar rows ms_pack_states / ms_expand_cigar would have produced, and
 the pass from event rows gives the pass from rows (counts, variants, haplotypes, read ids) and the oracle's.
 """
@@ -42,35 +42,36 @@ def test_encode_decode_roundtrip_random(L):
 
 def test_encode_generator_reads_are_compact():
     """CCS-like reads against the major strain: ~85 events (N 2 %, deletions, substitutions, insertion flags) per 3 kb read,
-    i.e. ~180 B instead of the 1504-byte planar row."""
+    i.e. ~136 B (12 bits per event + an 8-byte header) instead of the 1504-byte planar row."""
     t = make_tables(SynthConfig(L=3000, seed=20240003))
     st = synth_states(t, 0, 500)
     hdr, ev = encode_states(st, t.refseq)
     assert np.array_equal(decode_events(hdr, ev, 3000, t.refseq), st)
-    per_read = (2 * len(ev) + 8 * len(hdr)) / 500
-    assert 120 < per_read < 260, per_read
+    per_read = (len(ev) + 8 * len(hdr)) / 500
+    assert 100 < per_read < 170, per_read
     # lossless for ANY base: a wrong base only makes the list longer
     rng = np.random.default_rng(1)
     other = rng.integers(0, 4, size=3000, dtype=np.uint8)
     hdr2, ev2 = encode_states(st[:50], other)
-    assert np.array_equal(decode_events(hdr2, ev2, 3000, other), st[:50]) and len(ev2) > 50 * 2000
+    assert np.array_equal(decode_events(hdr2, ev2, 3000, other), st[:50]) and len(ev2) > 50 * 2000 * 3 // 2
 
 
 def test_encode_fillers_and_edges():
     L = 20000
     base = np.zeros(L, dtype=np.uint8)
     st = np.tile(base, (6, 1))
-    st[0, 19999] = 2                      # one event 19999 columns after begin: four fillers
-    st[1, 4095] = 1                       # exactly the largest delta: no filler
-    st[2, 4096] = 1                       # one more: one filler
+    st[0, 19999] = 2                      # one event 19999 columns after begin: 78 fillers (19999 = 78 * 255 + 109)
+    st[1, 255] = 1                        # exactly the largest delta: no filler
+    st[2, 256] = 1                        # one more: one filler
     st[3, :] = 7                          # spans nothing
     st[4, :100] = 7; st[4, 150:] = 7; st[4, 120:125] = 7     # reference skip (CIGAR N) inside the read
     st[5, 0] = 15; st[5, 1] = 8           # insertion flags on an unspanned-looking and on an unchanged column
     hdr, ev = encode_states(st, base)
-    n = np.diff(hdr["ev_off"].astype(np.int64))
-    assert list(n[:4]) == [5, 1, 2, 0]
+    nbytes = np.diff(hdr["ev_off"].astype(np.int64))
+    n = (2 * nbytes) // 3                 # events per read: ceil(1.5 n) bytes hold n events
+    assert list(n[:4]) == [79, 1, 2, 0] and list(nbytes[:4]) == [119, 2, 3, 0]
     assert (int(hdr["begin"][3]), int(hdr["end"][3])) == (0, 0)
-    assert (int(hdr["begin"][4]), int(hdr["end"][4])) == (100, 150) and n[4] == 5
+    assert (int(hdr["begin"][4]), int(hdr["end"][4])) == (100, 150) and n[4] == 5 and nbytes[4] == 8
     assert np.array_equal(decode_events(hdr, ev, L, base), st)
 
 
@@ -78,15 +79,15 @@ def test_encode_errors(mslib):
     base = np.zeros(100, dtype=np.uint8)
     st = np.full((3, 100), 1, dtype=np.uint8)
     hdr = np.zeros(4, dtype=HDR_DTYPE)
-    ev = np.zeros(10, dtype=np.uint16)
+    ev = np.zeros(10, dtype=np.uint8)
     n = C.c_int64()
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     assert mslib.ms_encode_states(p(st), 3, 100, p(base), p(hdr), p(ev), 10, C.byref(n)) == -4      # MS_ERR_CAPACITY
     assert mslib.ms_encode_states(p(st), 3, 70000, p(base), p(hdr), p(ev), 10, C.byref(n)) == -1    # L > 65535
     st[1, 5] = 6
-    big = np.zeros(400, dtype=np.uint16)
-    assert mslib.ms_encode_states(p(st), 3, 100, p(base), p(hdr), p(big), 400, C.byref(n)) == -5    # reserved state
-    assert mslib.ms_events_bound(3000) == 3001 and mslib.ms_events_bound(20000) == 20005
+    big = np.zeros(600, dtype=np.uint8)
+    assert mslib.ms_encode_states(p(st), 3, 100, p(base), p(hdr), p(big), 600, C.byref(n)) == -5    # reserved state
+    assert mslib.ms_events_bound(3000) >= (3000 + 3000 // 255 + 1) * 3 // 2 + 1 and mslib.ms_events_bound(3000) < 4600
 
 
 def test_encode_row_incremental_matches_batch(mslib):
@@ -99,7 +100,7 @@ def test_encode_row_incremental_matches_batch(mslib):
     planes = np.zeros(2 * ((777 + 31) // 32), dtype=np.uint32)
     assert mslib.ms_base_planes(p(base), 777, p(planes)) == 0
     hdr = np.zeros(41, dtype=HDR_DTYPE)
-    ev = np.zeros(len(want_ev) + 8, dtype=np.uint16)
+    ev = np.zeros(len(want_ev) + 8, dtype=np.uint8)
     n = C.c_int64(0)
     for r in range(40):
         assert mslib.ms_encode_row(p(rows[r]), 777, p(planes), C.c_void_p(hdr.ctypes.data + 8 * r), p(ev), len(ev), C.byref(n)) == 0
@@ -127,7 +128,7 @@ def test_expand_events_equals_packed_rows(L, R):
     try:
         j = Juliet(L, [(1, L + 1)], handle=hd)
         lib = j.lib
-        dh, de = _dev(hdr, torch), _dev(ev if len(ev) else np.zeros(1, np.uint16), torch)
+        dh, de = _dev(hdr, torch), _dev(ev if len(ev) else np.zeros(1, np.uint8), torch)
         out = torch.zeros(int(lib.ms_tiled_words(L, R)), dtype=torch.int32, device="cuda")
         assert lib.ms_expand_events_dev(hd.h, C.c_void_p(dh.data_ptr()), C.c_void_p(de.data_ptr()), R, C.c_void_p(out.data_ptr())) == -1  # no base yet
         j.set_base(base)
