@@ -297,58 +297,60 @@ class Juliet:
         return t[: self._V * self._V].view(self._V, self._V)
 
     # -- the whole pass in one C-ABI call (what bench.py times)
+    @staticmethod
+    def _hap_names(n):
+        """[A-Z][a-z]? in rank order (doc/JULIET.md:198; ms_haplotype_name)"""
+        return [chr(65 + i) if i < 26 else chr(65 + ((i - 26) // 26) % 26) + chr(97 + (i - 26) % 26) for i in range(n)]
+
     def _pass(self, ptr, nreads, host, want_hap_id, events=None):
         from ._lib import JulietResult as _JR
         st = getattr(self, "_pass_state", None)
         if st is None:
             st = self._pass_state = dict(vcap=1024, kcap=1024, pcap=4096)
         while True:
-            if st.get("alloc") != (st["vcap"], st["kcap"], st["pcap"]):
-                st["alloc"] = (st["vcap"], st["kcap"], st["pcap"])
+            sig = (st["vcap"], st["kcap"], st["pcap"], self.mode_phasing, self.min_hap_reads, self.refseq, tuple(self.genes))
+            if st.get("alloc") != sig:          # ctypes buffers and the argument tail are reused from pass to pass
+                st["alloc"] = sig
                 st["var"] = (Variant * st["vcap"])()
                 st["kc"] = np.zeros(st["kcap"], dtype=np.int32)
                 st["kk"] = np.zeros(st["kcap"], dtype=np.int32)
                 st["pat"] = np.zeros(st["pcap"] * ((st["kcap"] + 31) // 32), dtype=np.uint32)
                 st["cnt"] = np.zeros(st["pcap"], dtype=np.uint64)
                 st["genes"] = (Gene * len(self.genes))(*[Gene(b, e) for (b, e) in self.genes])
+                st["ref"] = self.refseq.encode() if self.refseq else None
                 r = st["res"] = _JR()
                 r.variants = st["var"]; r.variants_cap = st["vcap"]
                 r.key_col = st["kc"].ctypes.data_as(C.POINTER(C.c_int32)); r.key_codon = st["kk"].ctypes.data_as(C.POINTER(C.c_int32)); r.keys_cap = st["kcap"]
                 r.patterns = st["pat"].ctypes.data_as(C.POINTER(C.c_uint32)); r.counts = st["cnt"].ctypes.data_as(C.POINTER(C.c_uint64)); r.patterns_cap = st["pcap"]
+                st["tail"] = (st["genes"], len(self.genes), st["ref"], C.byref(self.params), 1 if self.mode_phasing else 0, self.min_hap_reads, C.byref(r))
             r = st["res"]
             hap = np.empty(nreads, dtype=np.int32) if (want_hap_id and self.mode_phasing) else None
             r.hap_id = hap.ctypes.data_as(C.POINTER(C.c_int32)) if hap is not None else None
-            tail = (nreads, st["genes"], len(self.genes), self.refseq.encode() if self.refseq else None,
-                    C.byref(self.params), 1 if self.mode_phasing else 0, self.min_hap_reads, C.byref(r))
             if events is not None:
-                rc = self.lib.ms_juliet_pass_events_host(self.hd.h, C.c_void_p(ptr), _ptr(events), *tail)
+                rc = self.lib.ms_juliet_pass_events_host(self.hd.h, ptr, events.ctypes.data, nreads, *st["tail"])
             else:
                 fn = self.lib.ms_juliet_pass_host if host else self.lib.ms_juliet_pass_dev
-                rc = fn(self.hd.h, C.c_void_p(ptr), *tail)
+                rc = fn(self.hd.h, ptr, nreads, *st["tail"])
             if rc == -4:   # MS_ERR_CAPACITY: grow what was too small and run the pass again
                 st["vcap"] = max(st["vcap"], int(r.nvariants)); st["kcap"] = max(st["kcap"], int(r.nkeys)); st["pcap"] = max(st["pcap"], int(r.nreported))
                 continue
             check(rc, self.hd.h)
             break
-        res = JulietResult(variants=[Variant.from_buffer_copy(st["var"][i]) for i in range(r.nvariants)])
-        res.keys = [(int(st["kc"][i]), int(st["kk"][i])) for i in range(r.nkeys)]
+        nv = int(r.nvariants)
+        res = JulietResult(variants=list((Variant * nv).from_buffer_copy(st["var"])) if nv else [])
+        V = int(r.nkeys)
+        res.keys = list(zip(st["kc"][:V].tolist(), st["kk"][:V].tolist()))
         if self.mode_phasing:
-            V = int(r.nkeys)
             self._V = V
             nw = max(1, (V + 31) // 32)
             H = min(int(r.npatterns), st["pcap"])
             pat = st["pat"][: H * nw].reshape(H, nw).copy()
             cnt = st["cnt"][:H].copy()
-            names = []
-            buf = C.create_string_buffer(3)
-            for i in range(r.nreported):
-                self.lib.ms_haplotype_name(i, buf)
-                names.append(buf.value.decode())
             c = r.counters
             counters = dict(reported=int(c.reported), insufficient=int(c.insufficient), damaged=int(c.damaged), gaps=int(c.gaps),
                             heteroduplex=int(c.heteroduplex), partial=int(c.partial))
-            res.haplotypes = Haplotypes(patterns=pat, counts=cnt, nreported=int(r.nreported), names=names, counters=counters, hap_id=hap,
-                                        ndistinct=int(r.npatterns))
+            res.haplotypes = Haplotypes(patterns=pat, counts=cnt, nreported=int(r.nreported), names=self._hap_names(int(r.nreported)),
+                                        counters=counters, hap_id=hap, ndistinct=int(r.npatterns))
         return res
 
     def run_device(self, d_packed_ptr: int, nreads: int, want_hap_id=False) -> JulietResult:

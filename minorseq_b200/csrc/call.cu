@@ -99,10 +99,14 @@ void ms_call_params_default(ms_call_params* p) {
     p->min_perc = -1.0; p->max_perc = -1.0; p->region_begin = 0; p->region_end = 0;
 }
 
-int ms_call(ms_handle* h, const ms_gene* genes, int32_t ngenes, const char* refseq, const ms_call_params* prm,
-            ms_variant* out, int64_t cap, int64_t* n) {
+}  // extern "C"
+
+// K2 in two halves so that the single-call pass (pass.cu) can keep the GPU busy between them: ms_call_launch enqueues the kernel
+// and tells where its output lives on the device, ms_call_collect downloads, waits, sorts.  ms_call = launch + collect.
+int ms_call_launch(ms_handle* h, const ms_gene* genes, int32_t ngenes, const char* refseq, const ms_call_params* prm,
+                   const ms_variant** d_calls, const unsigned long long** d_ncalls, int64_t* calls_cap) {
     MsRange nvtx_range("K2 call");
-    if (!h || !h->d_counts || !genes || ngenes < 0 || !prm || !n || (cap > 0 && !out)) return MS_ERR_ARG;
+    if (!h || !h->d_counts || !genes || ngenes < 0 || !prm) return MS_ERR_ARG;
     if (!h->count_codons) MS_FAIL(h, MS_ERR_ARG, "ms_set_layout was called without a codon start mask");
     MS_CUDA(h, cudaSetDevice(h->device));
     const int32_t L = h->L;
@@ -131,7 +135,10 @@ int ms_call(ms_handle* h, const ms_gene* genes, int32_t ngenes, const char* refs
         const uint32_t nt = static_cast<uint32_t>(pos.size() - first);
         for (size_t i = first; i < pos.size(); ++i) pos[i].ntests = nt;
     }
-    *n = 0;
+    h->call_npos = pos.size();
+    if (d_calls) *d_calls = nullptr;
+    if (d_ncalls) *d_ncalls = nullptr;
+    if (calls_cap) *calls_cap = 0;
     if (pos.empty()) return MS_OK;
     const size_t npos = pos.size();
     const size_t dev_cap = npos * 63;
@@ -177,7 +184,24 @@ int ms_call(ms_handle* h, const ms_gene* genes, int32_t ngenes, const char* refs
     MS_CUDA(h, cudaGetLastError());
     const size_t quick = std::min(kQuick, dev_cap);
     MS_CUDA(h, cudaMemcpyAsync(h->call_stage, base, 64 + quick * sizeof(ms_variant), cudaMemcpyDeviceToHost, h->stream));
-    MS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (d_calls) *d_calls = d_out;
+    if (d_ncalls) *d_ncalls = d_n;
+    if (calls_cap) *calls_cap = static_cast<int64_t>(dev_cap);
+    return MS_OK;
+}
+
+// waits for the stream (unless the caller already has: `synced`), sorts, hands the variants over
+int ms_call_collect(ms_handle* h, bool synced, ms_variant* out, int64_t cap, int64_t* n) {
+    if (!h || !n || (cap > 0 && !out)) return MS_ERR_ARG;
+    *n = 0;
+    if (h->call_npos == 0) return MS_OK;
+    MS_CUDA(h, cudaSetDevice(h->device));
+    if (!synced) MS_CUDA(h, cudaStreamSynchronize(h->stream));
+    constexpr size_t kQuick = 1024;
+    const size_t dev_cap = h->call_npos * 63;
+    const size_t quick = std::min(kQuick, dev_cap);
+    uint8_t* base = static_cast<uint8_t*>(h->d_call_buf);
+    const ms_variant* d_out = reinterpret_cast<const ms_variant*>(base + 64);
     unsigned long long cnt = 0;
     memcpy(&cnt, h->call_stage, 8);
     std::vector<ms_variant> v(cnt);
@@ -195,6 +219,16 @@ int ms_call(ms_handle* h, const ms_gene* genes, int32_t ngenes, const char* refs
     *n = static_cast<int64_t>(cnt);
     for (int64_t i = 0; i < std::min<int64_t>(cap, static_cast<int64_t>(cnt)); ++i) out[i] = v[i];
     return MS_OK;
+}
+
+extern "C" {
+
+int ms_call(ms_handle* h, const ms_gene* genes, int32_t ngenes, const char* refseq, const ms_call_params* prm,
+            ms_variant* out, int64_t cap, int64_t* n) {
+    if (!n || (cap > 0 && !out)) return MS_ERR_ARG;
+    int rc = ms_call_launch(h, genes, ngenes, refseq, prm, nullptr, nullptr, nullptr);
+    if (rc != MS_OK) return rc;
+    return ms_call_collect(h, false, out, cap, n);
 }
 
 }  // extern "C"

@@ -86,6 +86,7 @@ struct ms_handle {
     void* call_stage = nullptr;   // pinned
     size_t call_stage_cap = 0;
     std::vector<uint8_t> call_pos_cache;
+    size_t call_npos = 0;        // codon positions of the last ms_call_launch (sizes of its device buffers)
 
     // phasing (all buffers grow-only, reused across ms_phase_begin calls)
     int32_t V = 0, vwords = 0;
@@ -98,6 +99,8 @@ struct ms_handle {
     int64_t gcap_hint = 0;       // distinct-pattern capacity the last ordering pass needed
     bool table_valid = false;
     int table_attempt = 0;
+    DevBuf b_plan;   // PhasePlan built on the device by the single-call pass
+    void* plan_stage = nullptr;   // pinned, sizeof(PhasePlan): its download
     DevBuf b_var, b_blocklist, b_bits, b_flags, b_slot, b_tab_key, b_tab_cnt, b_tab_rep, b_ctr, b_groups, b_gather, b_rank, b_hap,
         b_pat, b_cooc, b_bits_t;
     // device-side merge + ordering (phase_order.cu)

@@ -8,8 +8,16 @@
 #include <cstring>
 #include <vector>
 #include "handle.h"
+#include "phase_internal.cuh"
 
 enum RowSource { kDeviceRows, kHostRows, kHostEvents };
+
+int ms_call_launch(ms_handle* h, const ms_gene* genes, int32_t ngenes, const char* refseq, const ms_call_params* prm,
+                   const ms_variant** d_calls, const unsigned long long** d_ncalls, int64_t* calls_cap);
+int ms_call_collect(ms_handle* h, bool synced, ms_variant* out, int64_t cap, int64_t* n);
+int ms_phase_planned_dev(ms_handle* h, const ms_variant* d_calls, const unsigned long long* d_ncalls, int64_t calls_cap,
+                         const uint32_t* d_packed, int64_t R, ms::PhasePlan** d_plan_out);
+void ms_phase_planned_adopt(ms_handle* h, int32_t V);
 
 static int juliet_pass(ms_handle* h, const void* src, const uint8_t* events, RowSource from, int64_t R, const ms_gene* genes, int32_t ngenes,
                        const char* refseq, const ms_call_params* prm, int32_t phase, int32_t min_hap_reads, ms_juliet_result* out) {
@@ -23,11 +31,48 @@ static int juliet_pass(ms_handle* h, const void* src, const uint8_t* events, Row
     if (rc != MS_OK) return rc;
     rc = ms_allreduce_counts(h);
     if (rc != MS_OK) return rc;
-    rc = ms_call(h, genes, ngenes, refseq, prm, out->variants, out->variants_cap, &out->nvariants);
-    if (rc != MS_OK) return rc;
-    out->nkeys = 0; out->npatterns = 0; out->nreported = 0;
+    out->nkeys = 0; out->npatterns = 0; out->nreported = 0; out->nvariants = 0;
     memset(&out->counters, 0, sizeof out->counters);
-    if (!phase) return MS_OK;
+    const ms_variant* d_calls = nullptr;
+    const unsigned long long* d_ncalls = nullptr;
+    int64_t calls_cap = 0;
+    rc = ms_call_launch(h, genes, ngenes, refseq, prm, &d_calls, &d_ncalls, &calls_cap);
+    if (rc != MS_OK) return rc;
+    if (!phase) return ms_call_collect(h, false, out->variants, out->variants_cap, &out->nvariants);
+
+    // Phasing without a host round trip in the middle of the pass: the plan (pooled variant list, touched blocks, the
+    // bit-vector kernel's word stream) is built on the device from K2's output, the bit-vectors, the grouping and the order
+    // follow on the stream, and calls, plan and haplotypes come down together at the end.  The plan covers the usual case
+    // (<= 32 distinct variant codons); when it gives up, or a caller buffer is too small, the host-planned path below runs.
+    static const bool planner_on = getenv("MS_NO_PLANNER") == nullptr;
+    if (planner_on && d_calls && out->patterns_cap > 0 && out->keys_cap >= ms::kPlanMaxKeys) {
+        ms::PhasePlan* d_plan = nullptr;
+        rc = ms_phase_planned_dev(h, d_calls, d_ncalls, calls_cap, d_rows, R, &d_plan);
+        if (rc != MS_OK) return rc;
+        if (!h->plan_stage) MS_CUDA(h, cudaMallocHost(&h->plan_stage, sizeof(ms::PhasePlan)));
+        MS_CUDA(h, cudaMemcpyAsync(h->plan_stage, d_plan, sizeof(ms::PhasePlan), cudaMemcpyDeviceToHost, h->stream));
+        int64_t H = 0, nrep = 0;
+        rc = ms_phase_haplotypes(h, min_hap_reads, out->patterns, out->counts, out->patterns_cap, &H, &nrep, &out->counters, out->hap_id);
+        if (rc != MS_OK) return rc;          // (synchronises the stream: the calls and the plan have arrived as well)
+        ms::PhasePlan plan;
+        memcpy(&plan, h->plan_stage, sizeof plan);
+        rc = ms_call_collect(h, true, out->variants, out->variants_cap, &out->nvariants);
+        if (rc != MS_OK) return rc;
+        if (!plan.fallback) {
+            if (out->nvariants > out->variants_cap) return MS_ERR_CAPACITY;   // the caller re-runs with a larger buffer
+            ms_phase_planned_adopt(h, plan.V);
+            out->nkeys = plan.V;
+            for (int32_t i = 0; i < plan.V; ++i) { out->key_col[i] = plan.key_col[i]; out->key_codon[i] = plan.key_codon[i]; }
+            out->npatterns = H;
+            out->nreported = nrep;
+            if (nrep > out->patterns_cap) return MS_ERR_CAPACITY;
+            return MS_OK;
+        }
+        memset(&out->counters, 0, sizeof out->counters);
+    } else {
+        rc = ms_call_collect(h, false, out->variants, out->variants_cap, &out->nvariants);
+        if (rc != MS_OK) return rc;
+    }
     if (out->nvariants > out->variants_cap) return MS_ERR_CAPACITY;   // the caller re-runs with a larger buffer
     // one pooled, de-duplicated variant list over all genes (screenshot juliet_hiv-phasing.png)
     std::vector<std::pair<int32_t, int32_t>> keys;

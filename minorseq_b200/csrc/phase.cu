@@ -47,8 +47,12 @@ constexpr int kPhaseChunkMax = 16;   // distinct blocks staged per pass (+1: the
 __global__ void __launch_bounds__(kPhaseWarps * 32) phase_bits_kernel(
     const uint4* __restrict__ packed, int64_t R, int32_t nblk, const int32_t* __restrict__ blocklist, int32_t NB, int32_t chunk,
     const uint32_t* __restrict__ stream, int32_t nwords, int32_t vwords, int32_t ordered, int32_t partial_all,
-    uint32_t* __restrict__ bits, uint8_t* __restrict__ flags, unsigned long long* __restrict__ ctr) {
+    uint32_t* __restrict__ bits, uint8_t* __restrict__ flags, unsigned long long* __restrict__ ctr, const PhasePlan* __restrict__ plan) {
     extern __shared__ __align__(16) uint4 stage_sm[];   // [warp][chunk + 1][32]
+    if (plan) {     // the sizes come from the device-built plan (one-word bit-vectors); a plan that gave up leaves everything to the host
+        if (plan->fallback) return;
+        NB = plan->NB; nwords = plan->nwords; partial_all = plan->partial_all; ordered = 1;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint4* sm = stage_sm + static_cast<size_t>(warp) * (chunk + 1) * 32 + lane;
     const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kPhaseWarps;
@@ -138,6 +142,153 @@ __global__ void __launch_bounds__(kPhaseWarps * 32) phase_bits_kernel(
         atomicAdd(ctr + 1, c_gap);
         atomicAdd(ctr + 2, c_het);
         atomicAdd(ctr + 3, c_par);
+    }
+}
+
+// The phasing plan on the device (PhasePlan, phase_internal.cuh): one warp turns K2's calls into the pooled, sorted,
+// de-duplicated (column, codon) list juliet phases over (screenshot juliet_hiv-phasing.png: one variant list for all genes), the
+// list of touched 32-column blocks and the block / layer / variant word stream phase_bits_kernel walks -- the same stream
+// ms_phase_begin builds on the host.  Lanes own calls, then keys, then block slots; sorting is by rank counting (a few dozen
+// items).  A few microseconds, and the pass keeps the GPU busy instead of waiting for a device -> host -> device round trip.
+constexpr int kPlanSlotWords = kPlanMaxLayers * 5 + kPlanMaxKeys;
+
+// first[i] = no earlier entry holds the same value; returns this lane's ranks among the distinct values (entries lane, lane + 32)
+__device__ __forceinline__ void rank_distinct(const int32_t* vals, int n, int lane, int32_t* first, int (&rank)[2]) {
+    for (int e = 0; e < 2; ++e) {
+        const int i = lane + 32 * e;
+        int f = 0;
+        if (i < n && vals[i] != 0x7fffffff) {
+            f = 1;
+            for (int j = 0; j < i; ++j) f &= vals[j] != vals[i];
+        }
+        first[i] = f;
+    }
+    __syncwarp();
+    for (int e = 0; e < 2; ++e) {
+        const int i = lane + 32 * e;
+        int r = 0;
+        if (i < n)
+            for (int j = 0; j < n; ++j) r += (first[j] && vals[j] < vals[i]) ? 1 : 0;
+        rank[e] = r;
+    }
+}
+
+__global__ void __launch_bounds__(32) phase_plan_kernel(const ms_variant* __restrict__ calls, const unsigned long long* __restrict__ ncalls_ptr,
+                                                        int64_t calls_cap, int32_t L, PhasePlan* __restrict__ plan, int32_t* __restrict__ blocklist,
+                                                        uint32_t* __restrict__ stream) {
+    __shared__ int32_t s_key[kPlanMaxCalls], s_first[kPlanMaxCalls];
+    __shared__ int32_t s_kc[kPlanMaxKeys], s_kk[kPlanMaxKeys];
+    __shared__ int32_t s_cand[2 * kPlanMaxKeys], s_blk[kPlanMaxBlocks], s_nw[kPlanMaxBlocks];
+    __shared__ uint32_t s_words[kPlanMaxBlocks][kPlanSlotWords];
+    __shared__ int s_fail;
+    const int lane = threadIdx.x;
+    const unsigned long long n64 = *ncalls_ptr;
+    if (lane == 0) {
+        plan->ncalls = static_cast<int32_t>(n64 > 0x7fffffffULL ? 0x7fffffff : n64);
+        plan->fallback = 1;
+        plan->V = plan->NB = plan->nwords = plan->partial_all = 0;
+        s_fail = 0;
+    }
+    if (n64 > static_cast<unsigned long long>(kPlanMaxCalls) || static_cast<int64_t>(n64) > calls_cap) return;
+    const int n = static_cast<int>(n64);
+    // pooled keys: distinct (column, codon), ascending
+    for (int i = lane; i < kPlanMaxCalls; i += 32) s_key[i] = i < n ? ((calls[i].col << 6) | calls[i].codon) : 0x7fffffff;
+    __syncwarp();
+    int rank[2];
+    rank_distinct(s_key, n, lane, s_first, rank);
+    const int V = __popc(__ballot_sync(0xffffffffu, s_first[lane])) + __popc(__ballot_sync(0xffffffffu, s_first[lane + 32]));
+    if (V > kPlanMaxKeys) return;
+    for (int e = 0; e < 2; ++e) {
+        const int i = lane + 32 * e;
+        if (s_first[i]) { s_kc[rank[e]] = s_key[i] >> 6; s_kk[rank[e]] = s_key[i] & 63; }
+    }
+    __syncwarp();
+    // touched blocks: distinct (col >> 5) and ((col + 2) >> 5) of the keys inside the reference, ascending
+    const bool inside = lane < V && s_kc[lane] + 2 < L;
+    const int partial = __any_sync(0xffffffffu, lane < V && !inside) ? 1 : 0;     // a variant outside the reference: no read spans it
+    s_cand[2 * lane] = inside ? (s_kc[lane] >> 5) : 0x7fffffff;
+    s_cand[2 * lane + 1] = inside ? ((s_kc[lane] + 2) >> 5) : 0x7fffffff;
+    __syncwarp();
+    rank_distinct(s_cand, 2 * kPlanMaxKeys, lane, s_first, rank);
+    int NB = __popc(__ballot_sync(0xffffffffu, s_first[lane])) + __popc(__ballot_sync(0xffffffffu, s_first[lane + 32]));
+    for (int e = 0; e < 2; ++e) {
+        const int i = lane + 32 * e;
+        if (s_first[i]) s_blk[rank[e]] = s_cand[i];
+    }
+    if (NB == 0) { if (lane == 0) s_blk[0] = 0; NB = 1; }
+    __syncwarp();
+    // per block slot: cover mask, greedy layers, the slot's words
+    for (int e = 0; e < 2; ++e) {
+        const int sl = lane + 32 * e;
+        int nwords = 0;
+        if (sl < NB) {
+            const int32_t blk = s_blk[sl];
+            uint32_t cover = 0;
+            int8_t base[kPlanMaxLayers][34];
+            uint8_t lv[kPlanMaxLayers][kPlanMaxKeys];
+            int ln[kPlanMaxLayers];
+            int nl = 0;
+            bool fail = false;
+            for (int v = 0; v < V; ++v) {
+                const int32_t col = s_kc[v];
+                if (col + 2 >= L) continue;
+                for (int c = col; c < col + 3; ++c)
+                    if ((c >> 5) == blk) cover |= 1u << (c & 31);
+                if ((col >> 5) != blk) continue;
+                const int c = col & 31;
+                const int32_t kk = s_kk[v];
+                const int8_t cod[3] = {static_cast<int8_t>((kk >> 4) & 3), static_cast<int8_t>((kk >> 2) & 3), static_cast<int8_t>(kk & 3)};
+                int li = 0;
+                for (; li < nl; ++li) {
+                    bool ok = true;
+                    for (int k = 0; k < 3; ++k) ok = ok && (base[li][c + k] < 0 || base[li][c + k] == cod[k]);
+                    if (ok) break;
+                }
+                if (li == nl) {
+                    if (nl == kPlanMaxLayers) { fail = true; break; }
+                    for (int k = 0; k < 34; ++k) base[nl][k] = -1;
+                    ln[nl] = 0; ++nl;
+                }
+                for (int k = 0; k < 3; ++k) base[li][c + k] = cod[k];
+                lv[li][ln[li]++] = static_cast<uint8_t>(v);
+            }
+            if (fail) s_fail = 1;
+            if (nl == 0) {                                        // spill-over block: damage flags only
+                for (int k = 0; k < 34; ++k) base[0][k] = -1;
+                ln[0] = 0; nl = 1;
+            }
+            if (!fail) {
+                for (int li = 0; li < nl; ++li) {
+                    uint32_t e0 = 0, e1 = 0, en = 0;
+                    for (int c = 0; c < 32; ++c)
+                        if (base[li][c] > 0) { e0 |= static_cast<uint32_t>(base[li][c] & 1) << c; e1 |= static_cast<uint32_t>((base[li][c] >> 1) & 1) << c; }
+                    for (int c = 32; c < 34; ++c)
+                        if (base[li][c] > 0) { en |= static_cast<uint32_t>(base[li][c] & 1) << (c - 32); en |= static_cast<uint32_t>((base[li][c] >> 1) & 1) << (c - 32 + 2); }
+                    s_words[sl][nwords++] = static_cast<uint32_t>(sl) | (static_cast<uint32_t>(ln[li]) << 13) | (li == 0 ? kHdrFirst : 0u);
+                    s_words[sl][nwords++] = e0; s_words[sl][nwords++] = e1; s_words[sl][nwords++] = en; s_words[sl][nwords++] = li == 0 ? cover : 0u;
+                    for (int k = 0; k < ln[li]; ++k) s_words[sl][nwords++] = static_cast<uint32_t>(s_kc[lv[li][k]] & 31) | (static_cast<uint32_t>(lv[li][k]) << 5);
+                }
+            }
+        }
+        s_nw[sl] = nwords;
+    }
+    __syncwarp();
+    if (s_fail) return;
+    int total = 0;
+    for (int e = 0; e < 2; ++e) {
+        const int sl = lane + 32 * e;
+        int off = 0;
+        for (int t = 0; t < sl; ++t) off += s_nw[t];
+        for (int k = 0; k < s_nw[sl]; ++k) stream[off + k] = s_words[sl][k];
+        if (sl < NB) blocklist[sl] = s_blk[sl];
+    }
+    for (int t = 0; t < kPlanMaxBlocks; ++t) total += s_nw[t];
+    if (lane < V) { plan->key_col[lane] = s_kc[lane]; plan->key_codon[lane] = s_kk[lane]; }
+    __syncwarp();
+    if (lane == 0) {
+        plan->V = V; plan->NB = NB; plan->nwords = total; plan->partial_all = partial;
+        __threadfence();
+        plan->fallback = 0;
     }
 }
 
@@ -398,7 +549,7 @@ void ms_phase_set_smem_attr() {
 extern "C" {
 
 void ms_phase_free_internal(ms_handle* h) {
-    DevBuf* all[] = {&h->b_var, &h->b_blocklist, &h->b_bits, &h->b_flags, &h->b_slot, &h->b_tab_key, &h->b_tab_cnt, &h->b_tab_rep,
+    DevBuf* all[] = {&h->b_plan, &h->b_var, &h->b_blocklist, &h->b_bits, &h->b_flags, &h->b_slot, &h->b_tab_key, &h->b_tab_cnt, &h->b_tab_rep,
                      &h->b_ctr, &h->b_groups, &h->b_gather, &h->b_rank, &h->b_hap, &h->b_pat, &h->b_cooc, &h->b_bits_t,
                      &h->b_gslot, &h->b_mt_key, &h->b_mt_cnt, &h->b_mt_rep, &h->b_mslot, &h->b_mindex, &h->b_m_cnt, &h->b_m_pat, &h->b_m_rank,
                      &h->b_ord, &h->b_keys, &h->b_out, &h->b_tc_tiles,
@@ -406,6 +557,8 @@ void ms_phase_free_internal(ms_handle* h) {
     for (DevBuf* b : all) b->release();
     if (h->h_stage) cudaFreeHost(h->h_stage);
     h->h_stage = nullptr; h->h_stage_cap = 0;
+    if (h->plan_stage) cudaFreeHost(h->plan_stage);
+    h->plan_stage = nullptr;
     h->phase_cap = h->phase_n = 0; h->V = 0; h->vwords = 0; h->table_valid = false;
 }
 
@@ -553,7 +706,7 @@ int ms_phase_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
         const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(h->num_sms) * per_sm)));
         ms::phase_bits_kernel<<<grid, ms::kPhaseWarps * 32, smem, h->stream>>>(pk, R, h->nblk, h->b_blocklist.as<int32_t>(), h->nblocklist, chunk,
                                                                               stream, h->phase_nrec, h->vwords, h->phase_ordered ? 1 : 0,
-                                                                              h->phase_partial_all ? 1 : 0, bits, flags, ctr);
+                                                                              h->phase_partial_all ? 1 : 0, bits, flags, ctr, nullptr);
     }
     MS_STAGE_END(h, MS_STAGE_PHASE_BITS);
     h->launches++;
@@ -561,6 +714,73 @@ int ms_phase_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     h->phase_n += R;
     return MS_OK;
 }
+
+}  // extern "C"
+
+// ---- the planned form of ms_phase_begin + ms_phase_dev used by the single-call pass (pass.cu): the variant list is still on
+// the device (d_calls / d_ncalls, K2's output buffers); phase_plan_kernel builds the plan there, phase_bits_kernel reads its
+// sizes from it.  One-word bit-vectors (V <= 32).  The caller reads the plan back with the pass's final download and, if it
+// says `fallback`, runs the host-planned calls after all.
+int ms_phase_planned_dev(ms_handle* h, const ms_variant* d_calls, const unsigned long long* d_ncalls, int64_t calls_cap,
+                         const uint32_t* d_packed, int64_t R, ms::PhasePlan** d_plan_out) {
+    if (!h || h->L <= 0 || R < 0 || !d_calls || !d_ncalls || (R > 0 && !d_packed)) return MS_ERR_ARG;
+    MS_CUDA(h, cudaSetDevice(h->device));
+    h->V = 0;                       // known after the download of the plan (ms_phase_planned_adopt)
+    h->vwords = 1;
+    h->phase_cap = std::max<int64_t>(1, R);
+    h->phase_n = 0;
+    h->table_valid = false;
+    h->groups_valid = false;
+    int64_t ts_max = 1024;
+    while (ts_max < 2 * h->phase_cap) ts_max <<= 1;
+    h->tab_size_max = ts_max;
+    const int64_t ts = std::min<int64_t>(ts_max, std::max<int64_t>(1 << 16, h->tab_hint));
+    h->tab_size = ts;
+    const size_t plan_bytes = sizeof(ms::PhasePlan);
+    const bool grow = static_cast<size_t>(ms::kPlanStreamWords) * 4 > h->b_var.cap || static_cast<size_t>(ms::kPlanMaxBlocks) * 4 > h->b_blocklist.cap ||
+                      static_cast<size_t>(h->phase_cap) * 4 > h->b_bits.cap || static_cast<size_t>(h->phase_cap) > h->b_flags.cap ||
+                      static_cast<size_t>(ts) * 8 > h->b_tab_key.cap || !h->b_ctr.p || plan_bytes > h->b_plan.cap;
+    if (grow) MS_CUDA(h, cudaStreamSynchronize(h->stream));
+    MS_CUDA(h, h->b_var.ensure(static_cast<size_t>(ms::kPlanStreamWords) * 4));
+    MS_CUDA(h, h->b_blocklist.ensure(static_cast<size_t>(ms::kPlanMaxBlocks) * 4));
+    MS_CUDA(h, h->b_bits.ensure(static_cast<size_t>(h->phase_cap) * 4));
+    MS_CUDA(h, h->b_flags.ensure(static_cast<size_t>(h->phase_cap)));
+    MS_CUDA(h, h->b_slot.ensure(static_cast<size_t>(h->phase_cap) * 4));
+    MS_CUDA(h, h->b_tab_key.ensure(static_cast<size_t>(ts) * 8));
+    MS_CUDA(h, h->b_tab_cnt.ensure(static_cast<size_t>(ts) * 4));
+    MS_CUDA(h, h->b_tab_rep.ensure(static_cast<size_t>(ts) * 8));
+    MS_CUDA(h, h->b_ctr.ensure(64));
+    MS_CUDA(h, h->b_plan.ensure(plan_bytes));
+    int rc = ensure_stage(h, 1 << 20);
+    if (rc != MS_OK) return rc;
+    ms::PhasePlan* d_plan = h->b_plan.as<ms::PhasePlan>();
+    MS_CUDA(h, cudaMemsetAsync(h->b_ctr.p, 0, 64, h->stream));
+    ms::phase_plan_kernel<<<1, 32, 0, h->stream>>>(d_calls, d_ncalls, calls_cap, h->L, d_plan, h->b_blocklist.as<int32_t>(), h->b_var.as<uint32_t>());
+    h->launches++;
+    if (R > 0) {
+        MS_CUDA(h, cudaMemsetAsync(h->b_bits.p, 0, static_cast<size_t>(R) * 4, h->stream));
+        MS_STAGE_BEGIN(h, MS_STAGE_PHASE_BITS);
+        const int chunk = ms::kPhaseChunkMax;          // the block count is only known on the device: stage with the largest chunk
+        const size_t smem = static_cast<size_t>(ms::kPhaseWarps) * (chunk + 1) * 32 * sizeof(uint4);
+        const int per_sm = std::max(1, std::min(6, static_cast<int>((h->max_smem + 1024) / (smem + 1024))));
+        const int64_t want = (R + ms::kPhaseWarps * 32 - 1) / (ms::kPhaseWarps * 32);
+        const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(h->num_sms) * per_sm)));
+        ms::phase_bits_kernel<<<grid, ms::kPhaseWarps * 32, smem, h->stream>>>(reinterpret_cast<const uint4*>(d_packed), R, h->nblk, h->b_blocklist.as<int32_t>(),
+                                                                              0, chunk, h->b_var.as<uint32_t>(), 0, 1, 1, 0, h->b_bits.as<uint32_t>(),
+                                                                              h->b_flags.as<uint8_t>(), ctr_ptr(h), d_plan);
+        MS_STAGE_END(h, MS_STAGE_PHASE_BITS);
+        h->launches++;
+    }
+    MS_CUDA(h, cudaGetLastError());
+    h->phase_n = R;
+    if (d_plan_out) *d_plan_out = d_plan;
+    return MS_OK;
+}
+
+// after the plan has been read back: the handle learns the number of keys (ms_cooccurrence, ms_phase_device need it)
+void ms_phase_planned_adopt(ms_handle* h, int32_t V) { h->V = V; }
+
+extern "C" {
 
 int ms_phase_groups(ms_handle* h, uint32_t* patterns, uint64_t* counts, int64_t cap, int64_t* H, ms_phase_counters* ctr) {
     MsRange nvtx_range("K3 grouping");

@@ -30,6 +30,17 @@ inline uint64_t phase_seed(int attempt) { return 0x6d696e6f72736571ULL + 0x9E377
 // ctr layout (u64): [0] damaged [1] gaps [2] heteroduplex [3] partial [4] hash collisions [5] ngroups [6] table overflow [7] spare
 inline unsigned long long* phase_ctr(ms_handle* h) { return h->b_ctr.as<unsigned long long>(); }
 
+// Device-built phasing plan (phase_plan_kernel): the pooled variant list and the word stream of phase_bits_kernel made on the
+// GPU from K2's output, so that the juliet pass needs no host round trip between the codon test and the bit-vectors.
+// Covers the usual case -- at most 32 distinct (column, codon) keys from at most 64 calls; anything else sets `fallback`
+// and the host builds the plan (ms_phase_begin) after all.
+constexpr int kPlanMaxKeys = 32, kPlanMaxCalls = 64, kPlanMaxBlocks = 64, kPlanMaxLayers = 4;
+constexpr int kPlanStreamWords = kPlanMaxBlocks * kPlanMaxLayers * 5 + kPlanMaxKeys;
+struct PhasePlan {
+    int32_t V, NB, nwords, partial_all, fallback, ncalls;
+    int32_t key_col[kPlanMaxKeys], key_codon[kPlanMaxKeys];
+};
+
 int phase_ensure_stage(ms_handle* h, size_t bytes);
 int phase_build_table(ms_handle* h, int attempt);
 // enqueue: distinct patterns of the local table -> g_cnt/g_pat (and the table slot of each in g_slot, may be null); count in ctr[5]

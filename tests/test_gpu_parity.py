@@ -524,3 +524,34 @@ def test_nw_align_equals_oracle(oracle, hd, la):
     lib = _lib.load()
     n = C.c_int64()
     assert lib.ms_align_refs(hd.h, b"ACGT", 4, b"ACG", 3, C.create_string_buffer(3), 3, C.byref(n), None) == -4 and n.value == 7
+
+
+@pytest.mark.parametrize("nminor,frames,nvar,copies,planned", [(3, 1, 5, 1, True), (2, 3, 4, 1, True), (3, 1, 5, 2, True), (7, 3, 5, 1, False),
+                                                               (9, 1, 5, 1, False), (3, 1, 5, 5, False)],
+                         ids=["few-1frame", "few-3frames", "same-gene-twice", "over32keys-3frames", "over32keys-1frame", "over64calls"])
+def test_pass_device_planner_equals_host_planned_phasing(oracle, hd, nminor, frames, nvar, copies, planned):
+    """The single-call pass builds the phasing plan on the device (phase_plan_kernel: pooled keys, touched blocks, block / layer /
+    variant stream) and falls back to the host-built plan beyond 32 keys: same variants, keys, haplotypes, read ids as the staged
+    three-call path, and the oracle's bit-vectors.  Overlapping frames give calls that share columns (several layers per block)
+    and the same codon called in more than one gene (duplicates to pool)."""
+    L, R = 1500, 30_000
+    cfg = SynthConfig(L=L, seed=4100 + nminor, minor_fracs=tuple([0.08] * nminor), variants_per_minor=(nvar, nvar), n_rate=2e-3)
+    t = make_tables(cfg)
+    st = synth_states(t, 0, R)
+    genes = [(f + 1, L + 1) for f in range(frames)] * copies
+    d = to_dev(pack_states(st))
+    j = Juliet(L, genes, refseq=t.refseq, mode_phasing=True, min_perc=1.0, handle=hd)
+    a = j.run_device(d.data_ptr(), R, want_hap_id=True)              # planner (or its fallback)
+    b = j._run_staged(d.data_ptr(), R, True)                         # ms_call + host-built plan + ms_phase_haplotypes
+    key = lambda v: (v.gene, v.col, v.codon, v.count, v.coverage, v.pvalue)
+    assert [key(v) for v in a.variants] == [key(v) for v in b.variants]
+    assert a.keys == b.keys == sorted({(v.col, v.codon) for v in a.variants})
+    assert (len(a.keys) <= 32 and len(a.variants) <= 64) == planned, (len(a.keys), len(a.variants))   # device planner, or its fallback
+    ha, hb = a.haplotypes, b.haplotypes
+    assert ha.ndistinct == hb.ndistinct and ha.nreported == hb.nreported and ha.counters == hb.counters
+    k = min(len(ha.counts), len(hb.counts))
+    assert np.array_equal(ha.counts[:k], hb.counts[:k]) and np.array_equal(ha.patterns[:k], hb.patterns[:k])
+    assert np.array_equal(ha.hap_id, hb.hap_id)
+    obits, oflags = oracle.phase_bits(st, [c for c, _ in a.keys], [k2 for _, k2 in a.keys], nthreads=8)
+    g = oracle.phase_group(obits, oflags, len(a.keys))
+    assert np.array_equal(ha.hap_id, g["hap_id"]) and ha.counters == {kk: int(v) for kk, v in g["counters"].items()}
