@@ -238,14 +238,23 @@ int ms_set_layout(ms_handle* h, int32_t L, const uint32_t* start_mask) {
     h->seg_len = (nblk + best_nseg - 1) / best_nseg;
     const int row_bytes = (h->seg_len + (best_nseg > 1 ? 1 : 0)) * 16;   // bytes of one read in a ring slot
     h->stage_bytes = h->groups * 8 * row_bytes;                          // one tile (segment) per row-group
-    // Clean non-pivot codons: with one reading frame they are resolved inside K1 from shared memory;
-    // with overlapping frames every substituted base makes up to three of them, and it is cheaper
-    // to log the flagged 8-read chunks per thread and resolve them afterwards in codon_exception_kernel
-    // (measured on 1M x 3 kb: 1 frame 0.374 vs 0.345+0.065 ms, 3 frames 0.591 vs 0.421+0.07 ms).
-    int64_t nstarts = 0;
-    if (start_mask)
-        for (int32_t j = 0; j + 2 < L; ++j) nstarts += (start_mask[j >> 5] >> (j & 31)) & 1u;
-    h->log_mode = start_mask != nullptr && nstarts * 20 > static_cast<int64_t>(L) * 9;   // > 0.45 starts per column
+    // Clean non-pivot codons: with one reading frame they are resolved inside K1 from the shared-memory slot; where reading
+    // frames overlap every substituted base makes up to three of them, and it is cheaper to log the flagged 8-read chunks per
+    // thread and resolve them afterwards in codon_exception_kernel (1M x 3 kb: 1 frame K1 0.386 vs 0.351 + 0.09 ms for the
+    // exception kernel; 1M x 9.7 kb with HIV's 15 genes: K1 1.40 vs 1.14 ms and a step of 1.69 vs 1.66 ms; three full-length
+    // frames: 0.59 vs 0.42 + 0.07 ms).  Logged as soon as more than 0.5 % of the columns start codons of overlapping frames
+    // (HIV's genes: 1.6 %).
+    int64_t nstarts = 0, noverlap = 0;
+    if (start_mask) {
+        auto is_start = [&](int32_t j) { return j + 2 < L && ((start_mask[j >> 5] >> (j & 31)) & 1u) != 0; };
+        for (int32_t j = 0; j + 2 < L; ++j) {
+            if (!is_start(j)) continue;
+            ++nstarts;
+            if (is_start(j + 1) || is_start(j + 2)) ++noverlap;
+        }
+    }
+    h->log_mode = start_mask != nullptr && (nstarts * 20 > static_cast<int64_t>(L) * 9 || noverlap * 200 > static_cast<int64_t>(L));
+    if (const char* e = getenv("MS_K1_LOG")) h->log_mode = start_mask != nullptr && atoi(e) != 0;   // tuning knob (A/B runs)
     const int merge_bytes = (h->groups - 1) * 9 * ms::kPlanesAll * W * 32 * 4 + 64;  // end-of-kernel group merge reuses the ring (up to 9 masks)
     h->stages = std::max(3, std::min(8, (h->max_smem - ms::kPileupSmemHeader - 16) / h->stage_bytes));
     h->stages_hi = std::max(3, std::min(8, budget / h->stage_bytes));
@@ -339,16 +348,20 @@ int ms_pileup_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     const int grid = static_cast<int>(std::min<int64_t>(h->num_sms, ntiles * h->nseg));   // >= nseg: every segment has a CTA
     const int threads = h->wpg * h->groups * 32;
     if (R > (1LL << 27)) MS_FAIL(h, MS_ERR_ARG, "more than 2^27 reads in one ms_pileup_dev call: split the batch");
-    const bool log_mode = mode != ms::kModeFuse && h->log_mode;   // decided with the layout (ms_set_layout)
+    // decided with the layout (ms_set_layout); the DENSE instantiation always logs (its exact trigger leaves few entries, and it
+    // has no registers to spare for the in-kernel path: C5 K1 0.56 -> 0.49 ms)
+    static const bool log_forced = getenv("MS_K1_LOG") != nullptr;
+    const bool log_mode = mode != ms::kModeFuse && (h->log_mode || (dense && !log_forced));
     const int64_t groups_per_seg = static_cast<int64_t>(std::max(1, grid / h->nseg)) * h->groups;
     const int64_t reads_per_group = (R + groups_per_seg - 1) / groups_per_seg;
-    const uint32_t exc_cap = log_mode ? static_cast<uint32_t>(std::min<int64_t>(8192, std::max<int64_t>(64, reads_per_group / 8 / 3))) : 0u;
+    // entries = flagged reads (~1.6 % of a thread's reads at CCS error rates, more at variant columns): room for 4 %
+    const uint32_t exc_cap = log_mode ? static_cast<uint32_t>(std::min<int64_t>(8192, std::max<int64_t>(64, reads_per_group / 25))) : 0u;
     const int64_t nlists = static_cast<int64_t>(grid) * threads;
     if (mode != ms::kModeFuse) {
-        MS_CUDA(h, h->b_exc_list.ensure(static_cast<size_t>(nlists) * std::max(1u, exc_cap) * 4));
+        MS_CUDA(h, h->b_exc_list.ensure(static_cast<size_t>(nlists) * std::max(1u, exc_cap) * 16));
         MS_CUDA(h, h->b_exc_cnt.ensure(static_cast<size_t>(nlists) * 4));
     }
-    a.exc_list = h->b_exc_list.as<uint32_t>(); a.exc_cnt = h->b_exc_cnt.as<uint32_t>(); a.exc_cap = exc_cap; a.exc_lists = nlists;
+    a.exc_list = h->b_exc_list.as<uint4>(); a.exc_cnt = h->b_exc_cnt.as<uint32_t>(); a.exc_cap = exc_cap; a.exc_lists = nlists;
     if (h->timing) MS_CUDA(h, cudaEventRecord(h->ev_k1[0], h->stream));
     // row-groups of more than 2047 reads: the instantiation with two more counter planes in shared memory (pileup.cu)
     const int64_t steps_max = (ntiles + std::max(1, grid / h->nseg) - 1) / std::max(1, grid / h->nseg);   // tiles of the busiest CTA

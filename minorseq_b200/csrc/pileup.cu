@@ -275,16 +275,25 @@ __device__ __forceinline__ uint32_t block8(uint32_t addr, const CodonCtx& cx, Ve
 // Flagged reads are logged to this thread's private list in global memory (fire-and-forget stores)
 // and resolved after the kernel by codon_exception_kernel with full parallelism; only when the
 // list is full (dense-variation data) does the thread fall back to the in-kernel rare path.
+// An entry is the flagged read's block itself -- planes P0 P1 P2 and, in the fourth word, the first two columns of the next
+// block (2 bits of each plane) -- so the exception kernel never goes back to the rows: logging by reference made it re-read
+// 256 bytes of row data per flagged read (403 MB at 1M x 3 kb, 85 us; 1.3 GB at 1M x 9.7 kb), the 16-byte entries are 27 MB.
 struct ExcLog {
-    uint32_t* list;
+    uint4* list;
     uint32_t cnt, cap;
 };
-// one entry per 8-read chunk with any flagged read: (first read of the chunk / 8) << 8 | flag byte
 template <bool DENSE>
-__device__ __forceinline__ void log_or_handle(uint32_t pm, uint32_t read0, ExcLog& lg, uint32_t addr, uint32_t naddr,
-                                              const CodonCtx& cx) {
-    if (lg.cnt < lg.cap) lg.list[lg.cnt++] = ((read0 >> 3) << 8) | pm;
-    else codon_exceptions<DENSE>(addr, naddr, pm, cx);
+__device__ __forceinline__ void log_or_handle(uint32_t pm, ExcLog& lg, uint32_t addr, uint32_t naddr, const CodonCtx& cx) {
+    if (lg.cnt + static_cast<uint32_t>(__popc(pm)) <= lg.cap) {
+        while (pm) {
+            const uint32_t rd = static_cast<uint32_t>(__ffs(pm) - 1);
+            pm &= pm - 1;
+            const uint4 q = lds128(addr ^ (rd << 4)), n = lds128(naddr ^ (rd << 4));
+            lg.list[lg.cnt++] = make_uint4(q.x, q.y, q.z, (n.x & 3u) | ((n.y & 3u) << 2) | ((n.z & 3u) << 4));
+        }
+    } else {
+        codon_exceptions<DENSE>(addr, naddr, pm, cx);
+    }
 }
 
 // ---------------------------------------------------------------- flush (cold path)
@@ -490,7 +499,7 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
     ExcLog lg;
     lg.cap = a.exc_cap;
     lg.cnt = 0;
-    lg.list = a.exc_list + list_id * a.exc_cap;
+    lg.list = a.exc_list + list_id * a.exc_cap;   // (exc_cap = 0: no logging, everything in-kernel)
 
     // shared-memory planes kPlanes, kPlanes+1 of this thread's counters (in the header area)
     HiPlanes hp;
@@ -553,7 +562,7 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
         const uint32_t naddr = data0 + slot * chunk_bytes + nblk_off; // same for the next block (rare path only)
         if (nv == 8) {
             const uint32_t pm = block8<MODE, DENSE, HI>(addr, cx, v, hp, bi);
-            if (T::CODON && pm) log_or_handle<DENSE>(pm, static_cast<uint32_t>(r0), lg, addr, naddr, cx);
+            if (T::CODON && pm) log_or_handle<DENSE>(pm, lg, addr, naddr, cx);
             ++bi;
             n += 8;
         } else {
@@ -563,7 +572,7 @@ __device__ __forceinline__ void pileup_body(const PileupArgs& a) {
                 read_masks<MODE, DENSE>(addr ^ (static_cast<uint32_t>(i) << 4), cx, m, pm, 1u);
 #pragma unroll
                 for (int q = 0; q < NM; ++q) ripple<HI>(v, hp, q, 0, m[q]);
-                if (T::CODON && pm) log_or_handle<DENSE>(1u << i, static_cast<uint32_t>(r0), lg, addr, naddr, cx);
+                if (T::CODON && pm) log_or_handle<DENSE>(1u << i, lg, addr, naddr, cx);
                 ++n;
             }
         }
@@ -653,9 +662,9 @@ void pileup_launch(int mode, bool dense, bool hi, int grid, int threads, int sme
 }
 
 // ---------------------------------------------------------------- logged exceptions
-// One warp per logged list: every entry is a read whose block may hold clean non-pivot codons.  The
-// exact masks are recomputed from global memory (the block and its successor of the flagged read) and each such codon
-// goes to the 64-bin histogram with a RED.  ~1.6 % of the (read, block) pairs at CCS error rates.
+// One warp per logged list: every entry is the block of a read that may hold clean non-pivot codons (planes + the two
+// look-ahead columns, see ExcLog).  The exact masks are recomputed from the entry and each such codon goes to the 64-bin
+// histogram with a RED.  ~1.6 % of the (read, block) pairs at CCS error rates.
 template <bool DENSE>
 __global__ void __launch_bounds__(256) codon_exception_kernel(PileupArgs a, int threads_per_cta) {
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -684,41 +693,33 @@ __global__ void __launch_bounds__(256) codon_exception_kernel(PileupArgs a, int 
     cx.start = a.start_mask[blk];
     cx.cols = cx.lookcols = 0;
     cx.codon = a.codon + static_cast<size_t>(blk) * 32 * 64;
-    const uint32_t* list = a.exc_list + static_cast<size_t>(warp) * a.exc_cap;
-    const uint4* rows = reinterpret_cast<const uint4*>(a.packed);
-    // work items = (entry, flagged read); lanes take consecutive entries, then walk their flag bits.
-    // Minor variants make many reads hit the SAME bin, so equal addresses within the warp are merged
-    // (__match_any_sync) and only one lane issues the RED with the group's size.
+    const uint4* list = a.exc_list + static_cast<size_t>(warp) * a.exc_cap;
+    // lanes take consecutive entries.  Minor variants make many reads hit the SAME bin, so equal addresses within the warp
+    // are merged (__match_any_sync) and only one lane issues the RED with the group's size.
     for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
         const uint32_t i = i0 + lane;
-        uint32_t ent = i < cnt ? list[i] : 0u;
-        uint32_t pm = ent & 0xffu;
-        const size_t rbase = static_cast<size_t>(ent >> 8) << 3;
-        while (__any_sync(0xffffffffu, pm != 0)) {
-            uint32_t e = 0;
-            uint4 q = make_uint4(0, 0, 0, 0), n = q;
-            if (pm) {
-                const int rd = __ffs(pm) - 1;
-                pm &= pm - 1;
-                q = rows[tile_slot(static_cast<int64_t>(rbase) + rd, blk, a.nblk)];
-                n = blk + 1 < a.nblk ? rows[tile_slot(static_cast<int64_t>(rbase) + rd, blk + 1, a.nblk)] : make_uint4(0, 0, 0xffffffffu, 0);
-                uint32_t np;
-                codon_masks<DENSE>(q, n, cx, np, e);
+        uint32_t e = 0;
+        uint4 q = make_uint4(0, 0, 0, 0), n = q;
+        if (i < cnt) {
+            const uint4 ent = list[i];
+            q = make_uint4(ent.x, ent.y, ent.z, 0u);
+            n = make_uint4(ent.w & 3u, (ent.w >> 2) & 3u, (ent.w >> 4) & 3u, 0u);     // columns 32, 33: only bits 0, 1 are ever shifted in
+            uint32_t np;
+            codon_masks<DENSE>(q, n, cx, np, e);
+        }
+        while (__any_sync(0xffffffffu, e != 0)) {
+            uint32_t key = 0xffffffffu;
+            if (e) {
+                const int j = __ffs(e) - 1;
+                e &= e - 1;
+                const uint32_t b0 = __funnelshift_r(q.x, n.x, j) & 7u;
+                const uint32_t b1 = __funnelshift_r(q.y, n.y, j) & 7u;
+                const uint32_t cod = ((b0 & 1u) << 4) | ((b1 & 1u) << 5) | ((b0 & 2u) << 1) | ((b1 & 2u) << 2) |
+                                     ((b0 & 4u) >> 2) | ((b1 & 4u) >> 1);
+                key = static_cast<uint32_t>(j) * 64u + cod;
             }
-            while (__any_sync(0xffffffffu, e != 0)) {
-                uint32_t key = 0xffffffffu;
-                if (e) {
-                    const int j = __ffs(e) - 1;
-                    e &= e - 1;
-                    const uint32_t b0 = __funnelshift_r(q.x, n.x, j) & 7u;
-                    const uint32_t b1 = __funnelshift_r(q.y, n.y, j) & 7u;
-                    const uint32_t cod = ((b0 & 1u) << 4) | ((b1 & 1u) << 5) | ((b0 & 2u) << 1) | ((b1 & 2u) << 2) |
-                                         ((b0 & 4u) >> 2) | ((b1 & 4u) >> 1);
-                    key = static_cast<uint32_t>(j) * 64u + cod;
-                }
-                const uint32_t peers = __match_any_sync(0xffffffffu, key);
-                if (key != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(cx.codon + key, static_cast<uint32_t>(__popc(peers)));
-            }
+            const uint32_t peers = __match_any_sync(0xffffffffu, key);
+            if (key != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(cx.codon + key, static_cast<uint32_t>(__popc(peers)));
         }
     }
 }

@@ -58,7 +58,7 @@ struct PileupArgs {
     uint32_t* part_col;       // [gridDim][nblk*32][8]
     uint32_t* part_piv;       // [gridDim][nblk*32]
     uint32_t* part_piv2;      // [gridDim][nblk*32] DENSE: designated-codon counts
-    uint32_t* exc_list;       // [gridDim*blockDim][exc_cap] reads logged for the exact codon pass
+    uint4* exc_list;          // [gridDim*blockDim][exc_cap] blocks of the reads logged for the exact codon pass (ExcLog, pileup.cu)
     uint32_t* exc_cnt;        // [gridDim*blockDim]
     uint32_t exc_cap;
     int64_t exc_lists;        // gridDim*blockDim of the pileup launch
