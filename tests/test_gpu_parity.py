@@ -555,3 +555,38 @@ def test_pass_device_planner_equals_host_planned_phasing(oracle, hd, nminor, fra
     obits, oflags = oracle.phase_bits(st, [c for c, _ in a.keys], [k2 for _, k2 in a.keys], nthreads=8)
     g = oracle.phase_group(obits, oflags, len(a.keys))
     assert np.array_equal(ha.hap_id, g["hap_id"]) and ha.counters == {kk: int(v) for kk, v in g["counters"].items()}
+
+
+def test_phase_bits_unsorted_and_shared_site_variants(oracle, hd):
+    """Variant lists the packed (bit-compress) form of phase_bits_kernel's stream cannot take: shuffled order, several codons
+    at one site (F18: one position may carry several variant codons), overlapping frames, a duplicate entry -- next to the
+    sorted dense list it is made for.  Bits and flags word for word against the oracle."""
+    L, R = 960, 5000
+    cfg = SynthConfig(L=L, seed=77, dense_sites=120, dense_strains=8, n_rate=5e-3, dele=2e-3, trunc=0.05)
+    t = make_tables(cfg)
+    st = synth_states(t, 0, R)
+    d = to_dev(pack_states(st))
+    truth = sorted({(c, k) for (_, c, k) in t.truth})
+    rng = np.random.default_rng(5)
+    extra = [(c, (k + 1) % 64) for (c, k) in truth[::3]] + [(c + 1, 7) for (c, _) in truth[::5] if c + 4 < L] + [truth[0]]
+    for name, keys in (("sorted-dense", truth), ("shuffled", [truth[i] for i in rng.permutation(len(truth))]),
+                       ("shared-sites", sorted(truth + extra)), ("shuffled-shared", [(truth + extra)[i] for i in rng.permutation(len(truth + extra))])):
+        j = Juliet(L, [(1, L + 1)], mode_phasing=True, handle=hd)
+
+        class V:
+            def __init__(self, c, k):
+                self.col, self.codon = c, k
+        cols = np.array([c for c, _ in keys], dtype=np.int32)
+        cods = np.array([k for _, k in keys], dtype=np.int32)
+        _lib.check(j.lib.ms_phase_begin(hd.h, cols.ctypes.data_as(C.c_void_p), cods.ctypes.data_as(C.c_void_p), len(keys), R), hd.h)
+        _lib.check(j.lib.ms_phase_dev(hd.h, C.c_void_p(d.data_ptr()), R), hd.h)
+        from minorseq_b200.api import _as_tensor
+        nw = (len(keys) + 31) // 32
+        pb, pf, pn = C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(j.lib.ms_phase_device(hd.h, C.byref(pb), C.byref(pf), C.byref(pn)), hd.h)
+        _lib.check(j.lib.ms_synchronize(hd.h), hd.h)
+        gbits = _as_tensor(pb.value, (R * nw,), torch.int32, 0).cpu().numpy().view(np.uint32).reshape(R, nw)
+        gflags = _as_tensor(pf.value, (R,), torch.uint8, 0).cpu().numpy()
+        obits, oflags = oracle.phase_bits(st, [int(c) for c in cols], [int(k) for k in cods])
+        assert np.array_equal(gflags, oflags), name
+        assert np.array_equal(gbits, obits), name
