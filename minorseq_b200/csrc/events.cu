@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kExpandMaxWarps * 32) expand_events_kernel(con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpc = blockDim.x >> 5;
     uint4* row = rows_sm + static_cast<size_t>(warp) * rstride;
-    const int64_t Rpad = COOP ? ((R + 7) >> 3) << 3 : R;     // COOP: whole tiles, every warp of the CTA takes part in the barriers
+    const int64_t Rpad = ((R + 7) >> 3) << 3;                // whole tiles (COOP: every warp of the CTA takes part in the barriers)
     const int64_t step = static_cast<int64_t>(gridDim.x) * wpc;
     const int64_t iters = (Rpad + step - 1) / step;
     for (int64_t it = 0; it < iters; ++it) {
@@ -208,8 +208,8 @@ __global__ void __launch_bounds__(kExpandMaxWarps * 32) expand_events_kernel(con
                     out[static_cast<size_t>(r0) * nblk + i] = r0 + w < R ? rows_sm[static_cast<size_t>(w) * rstride + b] : make_uint4(~0u, ~0u, ~0u, 0u);
             }
             __syncthreads();
-        } else if (r < R) {
-            for (int32_t b = lane; b < nblk; b += 32) out[tile_slot(r, b, nblk)] = row[b];
+        } else if (r < Rpad) {     // the padding of the last tile is "not spanned" here as well
+            for (int32_t b = lane; b < nblk; b += 32) out[tile_slot(r, b, nblk)] = r < R ? row[b] : make_uint4(~0u, ~0u, ~0u, 0u);
             __syncwarp();
         }
     }

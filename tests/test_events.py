@@ -117,7 +117,8 @@ def _dev(a, torch):
 
 
 @gpu
-@pytest.mark.parametrize("L,R", [(3, 5), (32, 40), (33, 100), (97, 1000), (3000, 3000), (6144, 300), (9719, 700), (20000, 200)])
+@pytest.mark.parametrize("L,R", [(3, 5), (32, 40), (33, 100), (97, 1000), (3000, 3000), (6144, 300), (9719, 700), (20000, 200), (40000, 61),
+                                 (65535, 20)])   # the last two: rows too long for eight of them in shared memory (per-warp stores)
 def test_expand_events_equals_packed_rows(L, R):
     import torch
     from minorseq_b200 import Handle, Juliet

@@ -590,3 +590,24 @@ def test_phase_bits_unsorted_and_shared_site_variants(oracle, hd):
         obits, oflags = oracle.phase_bits(st, [int(c) for c in cols], [int(k) for k in cods])
         assert np.array_equal(gflags, oflags), name
         assert np.array_equal(gbits, obits), name
+
+
+def test_pileup_mid_kernel_flush_with_shared_memory_planes(hd):
+    """More than 8191 reads per row-group: the instantiation with the two shared-memory counter planes (HI) has to flush in the
+    middle of the kernel.  Checked against the same reads piled up in launches small enough to need neither the planes nor a
+    flush (that path is compared with the oracle in the tests above)."""
+    cfg = SynthConfig(L=96, seed=32, variants_per_minor=(1, 1), minor_fracs=(0.05,))
+    t = make_tables(cfg)
+    R = 148 * 12 * 8191 + 40_003
+    d = gpu_synth(hd, t, 0, R)
+    j = Juliet(96, [(1, 97), (2, 97)], handle=hd)
+    j.pileup_device(d.data_ptr(), R)
+    col1, codon1 = j.get_counts()
+    j.reset()
+    step = 148 * 12 * 2000            # < 2048 reads per row-group: plain instantiation, no flush
+    row_bytes = j.row_words * 4
+    for r0 in range(0, R, step):
+        j.pileup_device(d.data_ptr() + r0 * row_bytes, min(step, R - r0))
+    col2, codon2 = j.get_counts()
+    assert int(col1[:, 7].max()) > 14_000_000 * 0.9
+    assert np.array_equal(col1, col2) and np.array_equal(codon1, codon2)
