@@ -148,7 +148,9 @@ __global__ void __launch_bounds__(kPhaseWarps * 32, 4) phase_bits_kernel(
             __syncwarp();
         }
         if (live) {
-            if (widx != 0xffffffffu) {
+            if (ordered && vwords == 1) {
+                myrow[0] = word;                 // the only word: written whether or not any variant maps to it (no zeroing by the caller)
+            } else if (widx != 0xffffffffu) {
                 if (ordered) myrow[widx] = word;
                 else if (word) myrow[widx] |= word;
             }
@@ -323,6 +325,20 @@ __global__ void __launch_bounds__(32) phase_plan_kernel(const ms_variant* __rest
         __threadfence();
         plan->fallback = 0;
     }
+}
+
+// One launch instead of six memsets in front of every table build: empty keys, zero counts, "no representative yet", and the
+// build's counters (ctr[4] collisions, ctr[6] overflow, ctr[7] "this build is the rank's last resort").
+__global__ void __launch_bounds__(256) phase_clear_kernel(unsigned long long* __restrict__ tab_key, uint32_t* __restrict__ tab_cnt,
+                                                          long long* __restrict__ tab_rep, int64_t tab_size, unsigned long long* __restrict__ ctr,
+                                                          unsigned long long last_resort) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < tab_size; i += stride) {
+        tab_key[i] = 0ULL;
+        tab_cnt[i] = 0u;
+        tab_rep[i] = 0x7f7f7f7f7f7f7f7fLL;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctr[4] = 0ULL; ctr[6] = 0ULL; ctr[7] = last_resort; }
 }
 
 // One thread per read; lanes of a warp that carry the same pattern elect a leader (lowest lane =
@@ -502,15 +518,12 @@ int phase_ensure_stage(ms_handle* h, size_t bytes) {
 int phase_build_table(ms_handle* h, int attempt) {
     const int64_t R = h->phase_n;
     unsigned long long* ctr = phase_ctr(h);
-    MS_CUDA(h, cudaMemsetAsync(h->b_tab_key.p, 0, static_cast<size_t>(h->tab_size) * 8, h->stream));
-    MS_CUDA(h, cudaMemsetAsync(h->b_tab_cnt.p, 0, static_cast<size_t>(h->tab_size) * 4, h->stream));
-    MS_CUDA(h, cudaMemsetAsync(h->b_tab_rep.p, 0x7f, static_cast<size_t>(h->tab_size) * 8, h->stream));
-    MS_CUDA(h, cudaMemsetAsync(ctr + 4, 0, 8, h->stream));
-    MS_CUDA(h, cudaMemsetAsync(ctr + 6, 0, 8, h->stream));
-    // spare word of the exchanged header: 1 = this build was this rank's last resort (table at its maximum size, or the
+    // spare word of the exchanged header (ctr[7]): 1 = this build was this rank's last resort (table at its maximum size, or the
     // fourth hash seed), so that an overflow / a collision reported with it makes EVERY rank give up in the same iteration
-    MS_CUDA(h, cudaMemsetAsync(ctr + 7, 0, 8, h->stream));
-    if (h->tab_size >= h->tab_size_max || attempt >= 3) MS_CUDA(h, cudaMemsetAsync(ctr + 7, 1, 1, h->stream));
+    const unsigned long long last_resort = (h->tab_size >= h->tab_size_max || attempt >= 3) ? 1ULL : 0ULL;
+    phase_clear_kernel<<<static_cast<int>(std::min<int64_t>((h->tab_size + 255) / 256, static_cast<int64_t>(h->num_sms) * 8)), 256, 0, h->stream>>>(
+        h->b_tab_key.as<unsigned long long>(), h->b_tab_cnt.as<uint32_t>(), h->b_tab_rep.as<long long>(), h->tab_size, ctr, last_resort);
+    h->launches++;
     if (R > 0) {
         const int grid = static_cast<int>((R + 255) / 256);
         phase_insert_kernel<<<grid, 256, 0, h->stream>>>(h->b_bits.as<uint32_t>(), h->b_flags.as<uint8_t>(), R, h->vwords,
@@ -751,7 +764,8 @@ int ms_phase_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
     const uint4* pk = reinterpret_cast<const uint4*>(d_packed);
     const uint32_t* stream = h->b_var.as<uint32_t>();
     unsigned long long* ctr = ctr_ptr(h);
-    MS_CUDA(h, cudaMemsetAsync(bits, 0, static_cast<size_t>(R) * h->vwords * 4, h->stream));   // words no variant maps to stay zero
+    if (!(h->phase_ordered && h->vwords == 1))   // one-word ordered vectors are written in full by the kernel
+        MS_CUDA(h, cudaMemsetAsync(bits, 0, static_cast<size_t>(R) * h->vwords * 4, h->stream));   // words no variant maps to stay zero
     MS_STAGE_BEGIN(h, MS_STAGE_PHASE_BITS);
     {
         const int chunk = std::min(ms::kPhaseChunkMax, h->nblocklist);
@@ -813,8 +827,7 @@ int ms_phase_planned_dev(ms_handle* h, const ms_variant* d_calls, const unsigned
     ms::phase_plan_kernel<<<1, 32, 0, h->stream>>>(d_calls, d_ncalls, calls_cap, h->L, d_plan, h->b_blocklist.as<int32_t>(), h->b_var.as<uint32_t>());
     h->launches++;
     if (R > 0) {
-        MS_CUDA(h, cudaMemsetAsync(h->b_bits.p, 0, static_cast<size_t>(R) * 4, h->stream));
-        MS_STAGE_BEGIN(h, MS_STAGE_PHASE_BITS);
+        MS_STAGE_BEGIN(h, MS_STAGE_PHASE_BITS);   // (one-word ordered vectors: no zeroing of the bit matrix needed)
         const int chunk = ms::kPhaseChunkMax;          // the block count is only known on the device: stage with the largest chunk
         const size_t smem = static_cast<size_t>(ms::kPhaseWarps) * (chunk + 1) * 32 * sizeof(uint4);
         const int per_sm = std::max(1, std::min(6, static_cast<int>((h->max_smem + 1024) / (smem + 1024))));
