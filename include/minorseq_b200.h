@@ -67,7 +67,7 @@ int32_t ms_row_words(int32_t L);
 /* Read admission filter (doc/JULIET.md:58 "Reads that are not primary or supplementary
  * alignments, get ignored"): 1 = use the record, 0 = skip (BAM FLAG 0x4 unmapped, 0x100 secondary). */
 int ms_read_admitted(uint32_t bam_flag);
-/* one byte per column (bits0-2 state, bit3 insertion-follows) -> planar rows. */
+/* one byte per column (bits0-2 state, bit3 insertion-follows) -> plain planar rows (host arrangement). */
 int ms_pack_states(const uint8_t *states, int64_t R, int32_t L, uint32_t *packed);
 int ms_unpack_states(const uint32_t *packed, int64_t R, int32_t L, uint8_t *states);
 /* plain rows <-> device tiles (see the format note above).  ms_tiled_words = u32 words of a tile buffer for R reads. */

@@ -5,7 +5,7 @@
 // read cost L/2 bytes per read on the PCIe link (1504 B at 3 kb), which is what bounds the end-to-end pass.  Here the
 // host ships, per read, its span and a sorted list of 12-bit events (column delta, new 4-bit column value) against a
 // base sequence both sides hold (~85 events = ~136 B per 3 kb read at CCS error rates), and expand_events_kernel
-// rebuilds the planar rows in HBM, where the pile-up and the phasing kernels run unchanged.  SURVEY.md rows a2/a3
+// rebuilds the packed reads in HBM (as tiles, rows.cuh), where the pile-up and the phasing kernels run unchanged.  SURVEY.md rows a2/a3
 // (host CIGAR walk) and 8f-2 ("GPU-side CIGAR expansion is the next real speed-up").
 //
 // Format (include/minorseq_b200.h):  ms_read_hdr hdr[R+1] = {ev_off, begin, end}; the byte string of read r is

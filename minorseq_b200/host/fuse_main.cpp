@@ -48,7 +48,7 @@ int main(int argc, char** argv) {
         // the CUDA contexts come up (~0.5 s, one thread per GPU) while a helper thread inflates and indexes the BAM
         std::vector<ms_handle*> hs(static_cast<size_t>(ngpus), nullptr);
         mshost::Alignments aln;
-        mshost::load_alignments_overlapped(pos[0], qv, false, true, aln, [&] {
+        mshost::load_alignments_overlapped(pos[0], qv, false, true, std::string(), aln, [&] {
             char id[128];
             if (ngpus > 1 && ms_comm_unique_id(id) != MS_OK) mshost::die("NCCL is not available (libnccl.so.2): --gpus needs it");
             std::vector<std::string> errs(static_cast<size_t>(ngpus));
@@ -62,14 +62,20 @@ int main(int argc, char** argv) {
         if (aln.nreads == 0) mshost::die("no primary or supplementary alignments in " + pos[0]);
         // every rank piles up its contiguous range of the reads; the all-reduce leaves the column counts of all reads on rank 0
         {
-            const int32_t rw = ms_row_words(aln.L);
             std::vector<std::string> errs(static_cast<size_t>(ngpus));
             mshost::run_ranks(ngpus, [&](int r) {
                 ms_handle* hr = hs[r];
                 const int64_t r0 = aln.nreads * r / ngpus, r1 = aln.nreads * (r + 1) / ngpus;
-                if (ms_set_layout(hr, aln.L, nullptr) != MS_OK || ms_pileup_host(hr, aln.rows + static_cast<size_t>(r0) * rw, r1 - r0, nullptr) != MS_OK ||
-                    ms_allreduce_counts(hr) != MS_OK || ms_synchronize(hr) != MS_OK)
-                    errs[r] = ms_last_error(hr);
+                if (ms_set_layout(hr, aln.L, nullptr) != MS_OK || ms_set_base(hr, aln.base.data()) != MS_OK) { errs[r] = ms_last_error(hr); return; }
+                ms_read_hdr* my_hdr = ngpus > 1 ? nullptr : aln.hdr;      // the reads as event rows (base = majority of a sample of them)
+                const uint8_t* my_ev = aln.events;
+                if (ngpus > 1) {
+                    try { my_ev = mshost::shard_events(aln, r0, r1, &my_hdr); } catch (const std::exception& e) { errs[r] = e.what(); return; }
+                }
+                const bool ok = ms_pileup_events_host(hr, my_hdr, my_ev, r1 - r0, nullptr) == MS_OK && ms_allreduce_counts(hr) == MS_OK &&
+                                ms_synchronize(hr) == MS_OK;
+                if (!ok) errs[r] = ms_last_error(hr);
+                if (ngpus > 1) { ms_synchronize(hr); ms_free_pinned(my_hdr); }
             });
             for (const std::string& e : errs)
                 if (!e.empty()) mshost::die("pile-up failed: " + e);

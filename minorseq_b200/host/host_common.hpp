@@ -75,15 +75,35 @@ struct Alignments {
     int32_t ref_id = -1;
     std::string ref_name;
     int64_t nreads = 0, nskipped = 0;
-    uint32_t* rows = nullptr;          // pinned, nreads * ms_row_words(L)
-    size_t cap_rows = 0;
+    // The reads as EVENT ROWS against `base` (include/minorseq_b200.h, csrc/events.cu): span + 12-bit events per read,
+    // ~136 B instead of a 1504-byte plain row per 3 kb read -- what is kept in pinned memory and goes over the PCIe link;
+    // the GPU expands them into tiles.  `base` is the configured referenceSequence, or the per-column majority of a sample
+    // of the reads (any base is lossless, a close one is short).
+    std::vector<uint8_t> base;         // L entries, 0..3
+    ms_read_hdr* hdr = nullptr;        // pinned, nreads + 1 entries, sealed
+    uint8_t* events = nullptr;         // pinned, ev_bytes
+    int64_t ev_bytes = 0;
     std::vector<std::string> names;
     // insertion events (only when want_insertions)
     std::vector<int32_t> ins_col, ins_len;
     std::vector<int64_t> ins_off;
     std::string ins_pool;
-    ~Alignments() { ms_free_pinned(rows); }
+    ~Alignments() { ms_free_pinned(hdr); ms_free_pinned(events); }
 };
+
+// The reads [r0, r1) of `a` as a sealed event-row array of their own (one rank's shard): `hdr_out` (pinned, r1 - r0 + 1 entries,
+// owned by the caller: ms_free_pinned) with offsets relative to the returned events pointer.
+inline const uint8_t* shard_events(const Alignments& a, int64_t r0, int64_t r1, ms_read_hdr** hdr_out) {
+    const int64_t n = r1 - r0;
+    ms_read_hdr* h = static_cast<ms_read_hdr*>(ms_alloc_pinned(static_cast<size_t>(n + 1) * sizeof(ms_read_hdr)));
+    if (!h) throw std::runtime_error("cannot allocate pinned host memory for a shard's read headers");
+    const uint32_t e0 = a.hdr[r0].ev_off;
+    for (int64_t i = 0; i < n; ++i) { h[i] = a.hdr[r0 + i]; h[i].ev_off -= e0; }
+    const int64_t bytes = static_cast<int64_t>(a.hdr[r1].ev_off) - e0;
+    if (ms_events_seal(h, n, bytes, a.base.data(), a.L) != MS_OK) { ms_free_pinned(h); throw std::runtime_error("cannot seal a shard's event rows"); }
+    *hdr_out = h;
+    return a.events + e0;
+}
 
 inline void die(const std::string& m) {
     fprintf(stderr, "ERROR: %s\n", m.c_str());
@@ -165,44 +185,118 @@ inline void decode_alignments(const std::string& path, Decoded& d, Alignments& o
     out.nreads = static_cast<int64_t>(d.keep.size());
 }
 
-inline void expand_alignments(const Decoded& d, const QvFilter& qv, bool want_names, bool want_insertions, Alignments& out) {
-    MSHOST_RANGE("CIGAR expansion + QV filter");
+// refseq: the target configuration's referenceSequence ("" = none): the base the event rows are encoded against
+inline void expand_alignments(const Decoded& d, const QvFilter& qv, bool want_names, bool want_insertions, const std::string& refseq,
+                              Alignments& out) {
+    MSHOST_RANGE("CIGAR expansion + QV filter + event encoding");
     const msbam::Bytes& u = d.u;
     const msbam::BamIndexed& bx = d.bx;
     const std::vector<size_t>& keep = d.keep;
     unsigned nt = d.nt;
     if (keep.empty()) return;
-    const int32_t rw = ms_row_words(out.L);
-    out.rows = static_cast<uint32_t*>(ms_alloc_pinned(keep.size() * rw * sizeof(uint32_t)));
-    if (!out.rows) throw std::runtime_error("cannot allocate pinned host memory for the packed rows");
-    out.cap_rows = keep.size();
+    const int32_t L = out.L;
+    const int32_t rw = ms_row_words(L);
+    if (L > 65535) throw std::runtime_error("reference longer than 65535 columns: event rows cannot address it");
     if (want_names) out.names.resize(keep.size());
-    struct Part { std::vector<int32_t> col, len; std::vector<int64_t> off; std::string pool; };
+    // ---- the base sequence: the configured reference, else the majority base per column over a sample of the reads
+    out.base.assign(static_cast<size_t>(L), 0);
+    bool have_base = refseq.size() >= static_cast<size_t>(L);
+    for (int32_t c = 0; c < L && have_base; ++c) {
+        switch (refseq[c]) {
+        case 'A': case 'a': out.base[c] = 0; break;
+        case 'C': case 'c': out.base[c] = 1; break;
+        case 'G': case 'g': out.base[c] = 2; break;
+        case 'T': case 't': out.base[c] = 3; break;
+        default: have_base = false;
+        }
+    }
+    if (!have_base) {
+        const size_t ns = std::min<size_t>(keep.size(), 256);
+        std::vector<uint32_t> votes(static_cast<size_t>(L) * 4, 0u), row(static_cast<size_t>(rw));
+        msbam::Record rec;
+        std::vector<uint8_t> mask;
+        std::vector<int32_t> ic(4096), il(4096), oc, ol;
+        std::vector<int64_t> io(4096), oo;
+        std::string pool(1 << 16, '\0'), opool;
+        for (size_t s = 0; s < ns; ++s) {
+            const auto& rr = bx.records[keep[s * keep.size() / ns]];
+            msbam::BamReader::parse_record(u.data() + rr.first, rr.second, rec);
+            expand_record(rec, qv, L, row.data(), false, mask, ic, io, il, pool, oc, ol, oo, opool);
+            for (int32_t c = 0; c < L; ++c) {
+                const uint32_t* q = row.data() + 4 * (c >> 5);
+                const int sh = c & 31;
+                const uint32_t st = ((q[0] >> sh) & 1u) | (((q[1] >> sh) & 1u) << 1) | (((q[2] >> sh) & 1u) << 2);
+                if (st < 4) ++votes[static_cast<size_t>(c) * 4 + st];
+            }
+        }
+        for (int32_t c = 0; c < L; ++c) {
+            uint32_t best = 0;
+            for (uint32_t b = 1; b < 4; ++b)
+                if (votes[static_cast<size_t>(c) * 4 + b] > votes[static_cast<size_t>(c) * 4 + best]) best = b;
+            out.base[c] = static_cast<uint8_t>(best);
+        }
+    }
+    std::vector<uint32_t> planes(2 * static_cast<size_t>((L + 31) / 32));
+    if (ms_base_planes(out.base.data(), L, planes.data()) != MS_OK) throw std::runtime_error("ms_base_planes failed");
+    // ---- every thread expands and encodes its contiguous range of the reads into buffers of its own
+    struct Part {
+        std::vector<int32_t> col, len; std::vector<int64_t> off; std::string pool;
+        std::vector<ms_read_hdr> hdr; std::vector<uint8_t> ev; int64_t nbytes = 0;
+    };
     nt = static_cast<unsigned>(std::min<size_t>(nt, keep.size()));
     std::vector<Part> parts(nt);
     std::vector<std::string> errs(nt);      // a corrupt record throws on its worker: carried to the caller after the join
+    const int64_t bound = ms_events_bound(L);
     auto work = [&](unsigned t) { try {
         const size_t i0 = keep.size() * t / nt, i1 = keep.size() * (t + 1) / nt;
+        Part& P = parts[t];
+        P.hdr.resize(i1 - i0);
+        P.ev.resize(static_cast<size_t>(std::max<int64_t>(bound, static_cast<int64_t>(i1 - i0) * 192)));
         msbam::Record rec;
         std::vector<uint8_t> mask;
+        std::vector<uint32_t> row(static_cast<size_t>(rw));
         std::vector<int32_t> ic(4096), il(4096);
         std::vector<int64_t> io(4096);
         std::string pool(1 << 16, '\0');
         for (size_t k = i0; k < i1; ++k) {
             const auto& rr = bx.records[keep[k]];
             msbam::BamReader::parse_record(u.data() + rr.first, rr.second, rec);
-            expand_record(rec, qv, out.L, out.rows + k * rw, want_insertions, mask, ic, io, il, pool, parts[t].col, parts[t].len, parts[t].off, parts[t].pool);
+            expand_record(rec, qv, L, row.data(), want_insertions, mask, ic, io, il, pool, P.col, P.len, P.off, P.pool);
+            if (static_cast<int64_t>(P.ev.size()) - P.nbytes < bound) P.ev.resize(P.ev.size() * 2 + static_cast<size_t>(bound));
+            if (ms_encode_row(row.data(), L, planes.data(), &P.hdr[k - i0], P.ev.data(), static_cast<int64_t>(P.ev.size()), &P.nbytes) != MS_OK)
+                throw std::runtime_error("record " + rec.name + ": cannot encode the expanded row");
             if (want_names) out.names[k] = rec.name;
         }
     } catch (const std::exception& e) { errs[t] = e.what(); } };
-    if (nt == 1) work(0);
-    else {
+    auto run_all = [&](auto&& f) {
+        if (nt == 1) { f(0u); return; }
         std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(f, t);
         for (auto& x : th) x.join();
-    }
+    };
+    run_all(work);
     for (const std::string& e : errs)
         if (!e.empty()) throw std::runtime_error(e);
+    // ---- one pinned header array and one pinned event array; the threads copy their parts into place
+    std::vector<int64_t> ev0(nt + 1, 0);
+    for (unsigned t = 0; t < nt; ++t) ev0[t + 1] = ev0[t] + parts[t].nbytes;
+    out.ev_bytes = ev0[nt];
+    if (out.ev_bytes > 0xffffffffLL) throw std::runtime_error("more than 4 GB of event rows in one run: split the input");
+    out.hdr = static_cast<ms_read_hdr*>(ms_alloc_pinned((keep.size() + 1) * sizeof(ms_read_hdr)));
+    out.events = static_cast<uint8_t*>(ms_alloc_pinned(static_cast<size_t>(out.ev_bytes) + 64));
+    if (!out.hdr || !out.events) throw std::runtime_error("cannot allocate pinned host memory for the event rows");
+    run_all([&](unsigned t) {
+        const size_t i0 = keep.size() * t / nt;
+        const Part& P = parts[t];
+        for (size_t k = 0; k < P.hdr.size(); ++k) {
+            ms_read_hdr hd = P.hdr[k];
+            hd.ev_off += static_cast<uint32_t>(ev0[t]);
+            out.hdr[i0 + k] = hd;
+        }
+        if (P.nbytes) memcpy(out.events + ev0[t], P.ev.data(), static_cast<size_t>(P.nbytes));
+    });
+    if (ms_events_seal(out.hdr, static_cast<int64_t>(keep.size()), out.ev_bytes, out.base.data(), L) != MS_OK)
+        throw std::runtime_error("ms_events_seal failed");
     for (const Part& p : parts) {   // read order is preserved: thread t holds a contiguous range
         const int64_t base = static_cast<int64_t>(out.ins_pool.size());
         out.ins_col.insert(out.ins_col.end(), p.col.begin(), p.col.end());
@@ -214,21 +308,21 @@ inline void expand_alignments(const Decoded& d, const QvFilter& qv, bool want_na
 
 // decode on a helper thread while the caller brings up the CUDA context, then expand
 template <class CreateFn>
-inline void load_alignments_overlapped(const std::string& path, const QvFilter& qv, bool want_names, bool want_insertions, Alignments& out,
-                                       CreateFn create_context) {
+inline void load_alignments_overlapped(const std::string& path, const QvFilter& qv, bool want_names, bool want_insertions, const std::string& refseq,
+                                       Alignments& out, CreateFn create_context) {
     Decoded d;
     std::string err;
     if (getenv("MS_SERIAL_LOAD")) {   // A/B switch for the overlap (tools/from_bam_timing.py)
         create_context();
         decode_alignments(path, d, out);
-        expand_alignments(d, qv, want_names, want_insertions, out);
+        expand_alignments(d, qv, want_names, want_insertions, refseq, out);
         return;
     }
     std::thread dec([&] { try { decode_alignments(path, d, out); } catch (const std::exception& e) { err = e.what(); } });
     create_context();      // dies with the CUDA error when there is no usable GPU: that message wins
     dec.join();
     if (!err.empty()) throw std::runtime_error(err);
-    expand_alignments(d, qv, want_names, want_insertions, out);
+    expand_alignments(d, qv, want_names, want_insertions, refseq, out);
 }
 
 }  // namespace mshost

@@ -116,7 +116,7 @@ int main(int argc, char** argv) {
         // with --gpus N every GPU gets its own handle and the handles share one NCCL communicator (one rank per thread)
         std::vector<ms_handle*> hs(static_cast<size_t>(ngpus), nullptr);
         mshost::Alignments aln;
-        mshost::load_alignments_overlapped(pos[0], qv, phasing, false, aln, [&] {
+        mshost::load_alignments_overlapped(pos[0], qv, phasing, false, cfg.reference_sequence, aln, [&] {
             char id[128];
             if (ngpus > 1 && ms_comm_unique_id(id) != MS_OK) mshost::die("NCCL is not available (libnccl.so.2): --gpus needs it");
             std::vector<std::string> errs(static_cast<size_t>(ngpus));
@@ -127,7 +127,7 @@ int main(int argc, char** argv) {
             for (const std::string& e : errs)
                 if (!e.empty()) mshost::die(e);
         });
-        lap("CUDA context || BAM inflate + CIGAR expansion");
+        lap("CUDA context || BAM inflate + CIGAR expansion + event encoding");
         if (aln.nreads == 0) mshost::die("no primary or supplementary alignments in " + pos[0]);
         const int32_t L = aln.L;
 
@@ -154,7 +154,6 @@ int main(int argc, char** argv) {
         prm.substitution_rate = sub; prm.deletion_rate = del; prm.alpha = alpha;
         prm.min_perc = min_perc; prm.max_perc = max_perc; prm.region_begin = rb; prm.region_end = re;
         const char* ref = cfg.reference_sequence.size() >= static_cast<size_t>(L) ? cfg.reference_sequence.c_str() : nullptr;
-        const int32_t rw = ms_row_words(L);
 
         // Every rank piles up its contiguous range of the reads; after the all-reduce the counts, and with them the
         // variant list, are the same on every rank; phasing merges the ranks' pattern lists on the device and leaves the
@@ -177,11 +176,21 @@ int main(int argc, char** argv) {
             ms_handle* h = hs[r];
             const int64_t r0 = aln.nreads * r / ngpus, r1 = aln.nreads * (r + 1) / ngpus;
             CKR(ms_set_layout(h, L, start.data()));
+            CKR(ms_set_base(h, aln.base.data()));
+            // this rank's reads as event rows (136 B instead of 1504 B per 3 kb read on the link), expanded into tiles on the GPU
             const uint32_t* d_rows = nullptr;
-            CKR(ms_pileup_host(h, aln.rows + static_cast<size_t>(r0) * rw, r1 - r0, &d_rows));
+            ms_read_hdr* my_hdr = ngpus > 1 ? nullptr : aln.hdr;
+            const uint8_t* my_ev = aln.events;
+            if (ngpus > 1) {
+                try { my_ev = mshost::shard_events(aln, r0, r1, &my_hdr); } catch (const std::exception& e) { errs[r] = e.what(); return; }
+            }
+            const int prc = ms_pileup_events_host(h, my_hdr, my_ev, r1 - r0, &d_rows);
+            if (prc == MS_OK && ngpus > 1) ms_synchronize(h);     // the shard's header copy is ours to free once the upload is done
+            if (ngpus > 1) ms_free_pinned(my_hdr);
+            if (prc != MS_OK) { errs[r] = std::string("ms_pileup_events_host failed: ") + ms_last_error(h); return; }
             CKR(ms_allreduce_counts(h));
             CKR(ms_synchronize(h));
-            if (r == 0) lap(ngpus > 1 ? "H2D + pileup + all-reduce" : "H2D + pileup");
+            if (r == 0) lap(ngpus > 1 ? "H2D events + expand + pileup + all-reduce" : "H2D events + expand + pileup");
 
             std::vector<ms_variant> mv(4096);
             int64_t nv = 0;

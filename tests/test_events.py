@@ -2,7 +2,7 @@
 
 CPU part: the host encoders against an independent numpy decoder (minorseq_b200.api.decode_events) on generator reads,
 random states, fillers (> 255 unchanged columns between two events), unspanned reads, reference skips inside a read.
-GPU part: expand_events_kernel rebuilds exactly the planar rows ms_pack_states / ms_expand_cigar would have produced, and
+GPU part: expand_events_kernel rebuilds exactly the rows ms_pack_states / ms_expand_cigar would have produced (as device tiles), and
 the pass from event rows gives the pass from rows (counts, variants, haplotypes, read ids) and the oracle's.
 """
 import ctypes as C

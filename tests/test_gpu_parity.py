@@ -144,7 +144,7 @@ def test_pileup_dense_high_frequency_variants(oracle, hd):
 
 
 def test_pileup_dense_variants_on_segmented_rows(oracle, hd):
-    """BASELINE configs[4] shape at reduced read count: L = 6144 rows are cut into twelve single-warp column segments AND
+    """BASELINE configs[4] shape at reduced read count: L = 6144 rows are cut into single-warp column segments AND
     the data make K1 pick its DENSE instantiation -- the one combination of the two template switches the other tests
     do not reach.  Also a 3-frame layout on the same rows (logged rare path + segments)."""
     cfg = SynthConfig(L=6144, seed=20240005, dense_sites=2048, dense_strains=64, n_rate=2e-5, dele=2e-5, trunc=0.0)
