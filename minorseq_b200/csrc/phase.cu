@@ -49,7 +49,7 @@ constexpr int kPhaseChunkMax = 16;   // distinct blocks staged per pass (+1: the
 // sorted variant list), so a finished word is stored; otherwise it is ORed into the zeroed vector.  `partial_all`: some
 // variant lies outside the reference, which makes every read partial.
 __global__ void __launch_bounds__(kPhaseWarps * 32, 4) phase_bits_kernel(
-    const uint4* __restrict__ packed, int64_t R, int32_t nblk, const int32_t* __restrict__ blocklist, int32_t NB, int32_t chunk,
+    const uint4* __restrict__ packed, int64_t R, int32_t nblk, const int32_t* __restrict__ blocklist, int32_t NB, int32_t chunk, int32_t dbuf,
     const uint32_t* __restrict__ stream, int32_t nwords, int32_t vwords, int32_t ordered, int32_t partial_all,
     uint32_t* __restrict__ bits, uint8_t* __restrict__ flags, unsigned long long* __restrict__ ctr, const PhasePlan* __restrict__ plan) {
     extern __shared__ __align__(16) uint4 stage_sm[];   // [warp][chunk + 1][32]
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kPhaseWarps * 32, 4) phase_bits_kernel(
         NB = plan->NB; nwords = plan->nwords; partial_all = plan->partial_all; ordered = 1;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint4* sm = stage_sm + static_cast<size_t>(warp) * (chunk + 1) * 32 + lane;
+    uint4* sm = stage_sm + static_cast<size_t>(warp) * (dbuf ? 2 : 1) * (chunk + 1) * 32 + lane;
     const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kPhaseWarps;
     unsigned long long c_dam = 0, c_gap = 0, c_het = 0, c_par = 0;
     for (int64_t base = (static_cast<int64_t>(blockIdx.x) * kPhaseWarps + warp) * 32; base < R; base += nwarps * 32) {
@@ -70,19 +70,37 @@ __global__ void __launch_bounds__(kPhaseWarps * 32, 4) phase_bits_kernel(
         uint32_t word = 0, widx = 0xffffffffu;
         uint32_t* myrow = bits + static_cast<size_t>(r) * vwords;
         int32_t p = 0;     // position in the stream
-        for (int32_t c0 = 0; c0 < NB; c0 += chunk) {
-            const int32_t nb = min(chunk + 1, NB - c0);
-            // per-lane 16-byte asynchronous copies global -> shared (LDGSTS): every block of the chunk is in flight at once,
-            // no registers in between
+        // per-lane 16-byte asynchronous copies global -> shared (LDGSTS): every block of a chunk is in flight at once, no
+        // registers in between.  A list of more than one chunk (dbuf) alternates between two buffers: chunk c + 1 is on its way
+        // while chunk c is evaluated.
+        auto stage_chunk = [&](int32_t c0s, uint4* buf) {
+            const int32_t nbs = min(chunk + 1, NB - c0s);
 #pragma unroll 4
-            for (int32_t s2 = 0; s2 < nb; ++s2) {
-                const int32_t blk = blocklist[c0 + s2];
-                const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(sm + s2 * 32));
+            for (int32_t s2 = 0; s2 < nbs; ++s2) {
+                const int32_t blk = blocklist[c0s + s2];
+                const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(buf + s2 * 32));
                 const uint4* src = tile + (blk * 8 + (pos ^ (blk & 7)));
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(live ? src : packed), "r"(live ? 16 : 0) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        };
+        uint4* const sm0 = sm;
+        uint4* const sm1 = sm + (dbuf ? (chunk + 1) * 32 : 0);
+        stage_chunk(0, sm0);
+        int32_t ci = 0;
+        for (int32_t c0 = 0; c0 < NB; c0 += chunk, ++ci) {
+            const int32_t nb = min(chunk + 1, NB - c0);
+            uint4* const sm = (ci & 1) ? sm1 : sm0;
+            if (c0 + chunk < NB) {
+                if (dbuf) {
+                    stage_chunk(c0 + chunk, (ci & 1) ? sm0 : sm1);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");     // everything but the chunk just issued has landed
+                } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                }
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
             __syncwarp();
             while (p < nwords) {
                 const uint32_t h0 = stream[p];
@@ -146,6 +164,7 @@ __global__ void __launch_bounds__(kPhaseWarps * 32, 4) phase_bits_kernel(
                 p += nv;
             }
             __syncwarp();
+            if (!dbuf && c0 + chunk < NB) stage_chunk(c0 + chunk, sm0);       // one buffer: the next chunk goes up after this one is done
         }
         if (live) {
             if (ordered && vwords == 1) {
@@ -589,7 +608,10 @@ int phase_groups_copy_out(ms_handle* h, uint32_t* patterns, uint64_t* counts, in
 // opt the bit-vector kernel in to its largest staging area (8 warps x 17 blocks x 512 B), on the current device (ms_create)
 void ms_phase_set_smem_attr() {
     cudaFuncSetAttribute(ms::phase_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         ms::kPhaseWarps * (ms::kPhaseChunkMax + 1) * 32 * static_cast<int>(sizeof(uint4)));
+                         ms::kPhaseWarps * 2 * (ms::kPhaseChunkMax / 2 + 1) * 32 * static_cast<int>(sizeof(uint4)) >
+                                 ms::kPhaseWarps * (ms::kPhaseChunkMax + 1) * 32 * static_cast<int>(sizeof(uint4))
+                             ? ms::kPhaseWarps * 2 * (ms::kPhaseChunkMax / 2 + 1) * 32 * static_cast<int>(sizeof(uint4))
+                             : ms::kPhaseWarps * (ms::kPhaseChunkMax + 1) * 32 * static_cast<int>(sizeof(uint4)));
 }
 
 extern "C" {
@@ -768,12 +790,14 @@ int ms_phase_dev(ms_handle* h, const uint32_t* d_packed, int64_t R) {
         MS_CUDA(h, cudaMemsetAsync(bits, 0, static_cast<size_t>(R) * h->vwords * 4, h->stream));   // words no variant maps to stay zero
     MS_STAGE_BEGIN(h, MS_STAGE_PHASE_BITS);
     {
-        const int chunk = std::min(ms::kPhaseChunkMax, h->nblocklist);
-        const size_t smem = static_cast<size_t>(ms::kPhaseWarps) * (chunk + 1) * 32 * sizeof(uint4);
+        // up to 16 touched blocks: one chunk, all of it in flight at once; longer lists: chunks of 8, double-buffered
+        const bool dbuf = h->nblocklist > ms::kPhaseChunkMax;
+        const int chunk = dbuf ? ms::kPhaseChunkMax / 2 : std::min(ms::kPhaseChunkMax, h->nblocklist);
+        const size_t smem = static_cast<size_t>(ms::kPhaseWarps) * (dbuf ? 2 : 1) * (chunk + 1) * 32 * sizeof(uint4);
         const int per_sm = std::max(1, std::min(6, static_cast<int>((h->max_smem + 1024) / (smem + 1024))));
         const int64_t want = (R + ms::kPhaseWarps * 32 - 1) / (ms::kPhaseWarps * 32);
         const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(h->num_sms) * per_sm)));
-        ms::phase_bits_kernel<<<grid, ms::kPhaseWarps * 32, smem, h->stream>>>(pk, R, h->nblk, h->b_blocklist.as<int32_t>(), h->nblocklist, chunk,
+        ms::phase_bits_kernel<<<grid, ms::kPhaseWarps * 32, smem, h->stream>>>(pk, R, h->nblk, h->b_blocklist.as<int32_t>(), h->nblocklist, chunk, dbuf ? 1 : 0,
                                                                               stream, h->phase_nrec, h->vwords, h->phase_ordered ? 1 : 0,
                                                                               h->phase_partial_all ? 1 : 0, bits, flags, ctr, nullptr);
     }
@@ -834,7 +858,7 @@ int ms_phase_planned_dev(ms_handle* h, const ms_variant* d_calls, const unsigned
         const int64_t want = (R + ms::kPhaseWarps * 32 - 1) / (ms::kPhaseWarps * 32);
         const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(h->num_sms) * per_sm)));
         ms::phase_bits_kernel<<<grid, ms::kPhaseWarps * 32, smem, h->stream>>>(reinterpret_cast<const uint4*>(d_packed), R, h->nblk, h->b_blocklist.as<int32_t>(),
-                                                                              0, chunk, h->b_var.as<uint32_t>(), 0, 1, 1, 0, h->b_bits.as<uint32_t>(),
+                                                                              0, chunk, 0, h->b_var.as<uint32_t>(), 0, 1, 1, 0, h->b_bits.as<uint32_t>(),
                                                                               h->b_flags.as<uint8_t>(), ctr_ptr(h), d_plan);
         MS_STAGE_END(h, MS_STAGE_PHASE_BITS);
         h->launches++;
