@@ -457,9 +457,22 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
         expand_ms = stage_ms(3)
+        upload_ms, pass_ms = stage_ms(6), stage_ms(7)
+        # the link's share: one plain pinned -> device copy of the same bytes, timed alone (box to box the PCIe rate differs by 30 %)
+        dh_, de_ = torch.empty_like(th, device=dev), torch.empty_like(te, device=dev)
+        for _ in range(2):
+            dh_.copy_(th, non_blocking=True); de_.copy_(te, non_blocking=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            dh_.copy_(th, non_blocking=True); de_.copy_(te, non_blocking=True)
+        torch.cuda.synchronize()
+        copy_ms = (time.perf_counter() - t0) / 5 * 1e3
+        del dh_, de_
         e2e = {"value": c["total_reads"] / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d.item()),
                "d2h_bytes_per_step": int(world * d2h), "ms_per_step": float(dt.item()) * 1e3, "steps": esteps,
-               "host_format": "event rows (ms_read_hdr + packed 12-bit events against the reference sequence), expanded to packed reads on the GPU",
+               "upload_ms": upload_ms, "pass_device_ms": pass_ms, "plain_h2d_copy_ms": copy_ms, "plain_h2d_copy_gbs": (hdr.nbytes + ev.nbytes) / copy_ms / 1e6,
+               "host_format": "event rows (ms_read_hdr + per-read event lists against the reference sequence: 1 byte per QV-filtered base, 12 bits per other event), expanded to packed reads on the GPU",
                "h2d_bytes_per_read": float(h2d.item()) / c["total_reads"], "planar_row_bytes_per_read": nw * 4}
         # for comparison: the same pass from planar rows in pinned host memory (round 1's e2e path), config T at N=1 only
         if c["name"] == "T" and world == 1:

@@ -110,8 +110,11 @@ int ms_timer_stop(ms_handle *h, double *ms);
 int ms_pileup_kernel_ms(ms_handle *h, double *ms, int64_t *reads);
 /* Same for the other measured kernels (most recent launch while timing was on; MS_ERR_ARG if none):
  * phase_bits_kernel, the co-occurrence kernel (popcount-AND or tcgen05), expand_events_kernel, and with a communicator
- * attached the two exchanges: the count all-reduce, and the haplotype-list all-gather + merge kernels.      */
-enum { MS_STAGE_PHASE_BITS = 1, MS_STAGE_COOCCURRENCE = 2, MS_STAGE_EXPAND = 3, MS_STAGE_ALLREDUCE = 4, MS_STAGE_HAPMERGE = 5 };
+ * attached the two exchanges: the count all-reduce, and the haplotype-list all-gather + merge kernels.  Two spans of
+ * the host-buffer pass (ms_juliet_pass_events_host) as well: MS_STAGE_UPLOAD = first to last host->device copy on the
+ * copy stream, MS_STAGE_PASS = start of the pass to the arrival of its last result on the main stream.             */
+enum { MS_STAGE_PHASE_BITS = 1, MS_STAGE_COOCCURRENCE = 2, MS_STAGE_EXPAND = 3, MS_STAGE_ALLREDUCE = 4, MS_STAGE_HAPMERGE = 5,
+       MS_STAGE_UPLOAD = 6, MS_STAGE_PASS = 7 };
 int ms_stage_kernel_ms(ms_handle *h, int stage, double *ms);
 
 /* ---- K1: pileup (juliet "MSA counts", doc/JULIET.md:96-100; fuse doc/FUSE.md:17-20) -- */
@@ -144,19 +147,21 @@ int ms_set_pileup_variant(ms_handle *h, int variant);
 /* ---- event rows: the compact host->device form of an aligned read ------------------------------
  * What juliet/fuse's per-record CIGAR walk (doc/JULIET.md:49-58, doc/FUSE.md:13-15) hands to the GPU when the
  * caller wants the PCIe link to carry events instead of whole rows: a CCS alignment is "the base sequence, except
- * at a few columns" (X / D / I ops and QV-filtered bases, :256-259).  Per read: its span [begin,end) and a sorted
- * list of 12-bit events, event = delta << 4 | nibble, column = previous event's column (the read's begin for the
- * first) + delta (0..255), nibble = state | insertion-follows << 3.  Spanned columns without an event hold the base
- * sequence's base, columns outside the span are "not spanned"; the encoder restates an unchanged column (a filler)
- * when two events are more than 255 columns apart.  The events of a read are packed back to back, event k in bits
- * [12k, 12k+12) of the read's little-endian byte string, which starts on a byte boundary: n events take
- * ceil(1.5 n) bytes.  hdr has R+1 entries: the byte string of read r is events[hdr[r].ev_off .. hdr[r+1].ev_off);
- * hdr[R] is the sentinel written by ms_events_seal (total byte count + a hash of the base sequence; rows encoded
- * against another base are rejected with MS_ERR_FORMAT).  Reference length <= 65535.  The GPU rebuilds the packed
- * reads (expand_events_kernel) and K1/K3 run on them unchanged.  ~136 B per 3 kb read at CCS error rates
- * (85 events), against 1504 B for the plain row.                                                              */
+ * at a few columns" (X / D / I ops and QV-filtered bases, :256-259).  Per read: its span [begin,end) and a byte string
+ *   [nN: u16 little-endian] [N list: nN bytes] [rest list: 12-bit entries, entry k in bits [12k, 12k+12) of the rest]
+ * (no bytes at all when the read equals the base on its whole span).  Both lists walk the columns from `begin`: an
+ * entry's column = the previous entry's column + its delta.  N list, for the QV-filtered bases (two thirds of the
+ * events of CCS data): one byte per entry, 0..254 = this column is 'N', 255 = move on by 255 columns.  Rest list:
+ * entry = delta << 4 | nibble, delta 0..254 = this column holds nibble = state | insertion-follows << 3, delta 255 =
+ * move on by 255 columns; n entries take ceil(1.5 n) bytes.  Spanned columns without an entry hold the base
+ * sequence's base, columns outside the span are "not spanned"; no column appears twice.  hdr has R+1 entries: the
+ * byte string of read r is events[hdr[r].ev_off .. hdr[r+1].ev_off); hdr[R] is the sentinel written by
+ * ms_events_seal (total byte count + a hash of the base sequence; rows encoded against another base are rejected
+ * with MS_ERR_FORMAT).  Reference length <= 65535.  The GPU rebuilds the packed reads (expand_events_kernel) and
+ * K1/K3 run on them unchanged.  ~112 B per 3 kb read at CCS error rates (85 events, 60 of them 'N'), against
+ * 1504 B for the plain row.                                                                                     */
 typedef struct { uint32_t ev_off; uint16_t begin, end; } ms_read_hdr;
-/* worst-case number of event BYTES of one read (every column differs + fillers) */
+/* worst-case number of event BYTES of one read (every column in the rest list + skips + the count) */
 int64_t ms_events_bound(int32_t L);
 /* base: L bytes, one base (0..3) per reference column: the configured referenceSequence, or any sequence close to
  * the reads (the encoding is lossless for every base; a close one makes it short).                                */
@@ -281,7 +286,7 @@ int ms_juliet_pass_host(ms_handle *h, const uint32_t *h_packed, int64_t R, const
                         ms_juliet_result *out);
 
 /* The same pass from event rows in host memory (ms_pileup_events_host in place of ms_pileup_host): what the
- * bench.py's e2e calls -- the PCIe link carries ~136 B instead of 1504 B per 3 kb read.                       */
+ * bench.py's e2e calls -- the PCIe link carries ~112 B instead of 1504 B per 3 kb read.                       */
 int ms_juliet_pass_events_host(ms_handle *h, const ms_read_hdr *hdr, const uint8_t *events, int64_t R,
                                const ms_gene *genes, int32_t ngenes, const char *refseq, const ms_call_params *prm,
                                int32_t phase, int32_t min_hap_reads, ms_juliet_result *out);

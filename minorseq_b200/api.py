@@ -489,7 +489,7 @@ def base_array(base, L):
 
 
 def _encode(fn_name, src, R, L, base):
-    """-> (hdr[R+1] structured array, event bytes: uint8 array of packed 12-bit events)"""
+    """-> (hdr[R+1] structured array, event bytes: uint8 array, per read [nN u16][N list][12-bit rest list], include/minorseq_b200.h)"""
     lib = _lib.load()
     base = base_array(base, L)
     cap = max(1024, int(R) * 128)
@@ -526,13 +526,20 @@ def decode_events(hdr, events, L, base):
         b, e = int(hdr["begin"][r]), int(hdr["end"][r])
         out[r, b:e] = base[b:e]
         raw = np.asarray(events[int(hdr["ev_off"][r]): int(hdr["ev_off"][r + 1])], dtype=np.uint8).astype(np.int64)
-        n = (2 * len(raw)) // 3                                   # ceil(1.5 n) bytes hold n 12-bit events
+        if len(raw) < 2:
+            continue                                              # no bytes: the read is the base on its whole span
+        nN = int(raw[0] | (raw[1] << 8))
+        d = raw[2: 2 + nN]                                        # N list: one byte per entry, 255 = move on by 255 columns
+        out[r, (b + np.cumsum(d))[d != 255]] = 5
+        rest = raw[2 + nN:]
+        n = (2 * len(rest)) // 3                                  # ceil(1.5 n) bytes hold n 12-bit entries
         k = np.arange(n)
         o = (3 * k) >> 1
-        two = raw[o] | (raw[o + 1] << 8)
+        two = rest[o] | (rest[np.minimum(o + 1, len(rest) - 1)] << 8) if n else np.zeros(0, dtype=np.int64)
         ev = np.where(k & 1, two >> 4, two & 0xFFF)
         cols = b + np.cumsum(ev >> 4)
-        out[r, cols] = (ev & 15).astype(np.uint8)
+        keep = (ev >> 4) != 255
+        out[r, cols[keep]] = (ev[keep] & 15).astype(np.uint8)
     return out
 
 

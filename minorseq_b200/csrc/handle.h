@@ -42,8 +42,9 @@ struct ms_handle {
     cudaEvent_t ev_stagefree[2] = {};           // ms_pileup_host: staging buffer k has been permuted into tiles
     cudaEvent_t ev_k1[2] = {nullptr, nullptr};  // around the last K1 launch when timing is on
     cudaEvent_t ev_timer[2] = {nullptr, nullptr};  // ms_timer_start / ms_timer_stop
-    cudaEvent_t ev_stage[6][2] = {};               // when timing is on: around the last launch of MS_STAGE_* (ms_stage_kernel_ms)
-    bool stage_seen[6] = {false, false, false, false, false, false};
+    int expand_ctas = 0, expand_ctas_nblk = -1;   // expand_events_kernel: resident CTAs per SM for row length nblk
+    cudaEvent_t ev_stage[8][2] = {};               // when timing is on: around the last launch of MS_STAGE_* (ms_stage_kernel_ms)
+    bool stage_seen[8] = {false, false, false, false, false, false, false, false};
     bool timing = false;
     int64_t k1_reads = 0;
     std::string err;

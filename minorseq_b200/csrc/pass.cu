@@ -19,9 +19,21 @@ int ms_phase_planned_dev(ms_handle* h, const ms_variant* d_calls, const unsigned
                          const uint32_t* d_packed, int64_t R, ms::PhasePlan** d_plan_out);
 void ms_phase_planned_adopt(ms_handle* h, int32_t V);
 
+static int juliet_pass_body(ms_handle* h, const void* src, const uint8_t* events, RowSource from, int64_t R, const ms_gene* genes, int32_t ngenes,
+                            const char* refseq, const ms_call_params* prm, int32_t phase, int32_t min_hap_reads, ms_juliet_result* out);
+
 static int juliet_pass(ms_handle* h, const void* src, const uint8_t* events, RowSource from, int64_t R, const ms_gene* genes, int32_t ngenes,
                        const char* refseq, const ms_call_params* prm, int32_t phase, int32_t min_hap_reads, ms_juliet_result* out) {
     if (!h || !out || !prm || R < 0) return MS_ERR_ARG;
+    MS_CUDA(h, cudaSetDevice(h->device));
+    MS_STAGE_BEGIN(h, MS_STAGE_PASS);
+    int rc = juliet_pass_body(h, src, events, from, R, genes, ngenes, refseq, prm, phase, min_hap_reads, out);
+    MS_STAGE_END(h, MS_STAGE_PASS);       // (the body has waited for its last result: this is when it arrived)
+    return rc;
+}
+
+static int juliet_pass_body(ms_handle* h, const void* src, const uint8_t* events, RowSource from, int64_t R, const ms_gene* genes, int32_t ngenes,
+                            const char* refseq, const ms_call_params* prm, int32_t phase, int32_t min_hap_reads, ms_juliet_result* out) {
     int rc = ms_reset_counts(h);
     if (rc != MS_OK) return rc;
     const uint32_t* d_rows = static_cast<const uint32_t*>(src);

@@ -75,8 +75,8 @@ struct Alignments {
     int32_t ref_id = -1;
     std::string ref_name;
     int64_t nreads = 0, nskipped = 0;
-    // The reads as EVENT ROWS against `base` (include/minorseq_b200.h, csrc/events.cu): span + 12-bit events per read,
-    // ~136 B instead of a 1504-byte plain row per 3 kb read -- what is kept in pinned memory and goes over the PCIe link;
+    // The reads as EVENT ROWS against `base` (include/minorseq_b200.h, csrc/events.cu): span + event lists per read,
+    // ~112 B instead of a 1504-byte plain row per 3 kb read -- what is kept in pinned memory and goes over the PCIe link;
     // the GPU expands them into tiles.  `base` is the configured referenceSequence, or the per-column majority of a sample
     // of the reads (any base is lossless, a close one is short).
     std::vector<uint8_t> base;         // L entries, 0..3

@@ -177,7 +177,7 @@ int main(int argc, char** argv) {
             const int64_t r0 = aln.nreads * r / ngpus, r1 = aln.nreads * (r + 1) / ngpus;
             CKR(ms_set_layout(h, L, start.data()));
             CKR(ms_set_base(h, aln.base.data()));
-            // this rank's reads as event rows (136 B instead of 1504 B per 3 kb read on the link), expanded into tiles on the GPU
+            // this rank's reads as event rows (~112 B instead of 1504 B per 3 kb read on the link), expanded into tiles on the GPU
             const uint32_t* d_rows = nullptr;
             ms_read_hdr* my_hdr = ngpus > 1 ? nullptr : aln.hdr;
             const uint8_t* my_ev = aln.events;

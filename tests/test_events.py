@@ -1,7 +1,7 @@
 """Event rows (csrc/events.cu): the compact host->device form of an aligned read.
 
 CPU part: the host encoders against an independent numpy decoder (minorseq_b200.api.decode_events) on generator reads,
-random states, fillers (> 255 unchanged columns between two events), unspanned reads, reference skips inside a read.
+random states, skips (> 254 unchanged columns between two entries of a list), unspanned reads, reference skips inside a read.
 GPU part: expand_events_kernel rebuilds exactly the rows ms_pack_states / ms_expand_cigar would have produced (as device tiles), and
 the pass from event rows gives the pass from rows (counts, variants, haplotypes, read ids) and the oracle's.
 """
@@ -42,13 +42,14 @@ def test_encode_decode_roundtrip_random(L):
 
 def test_encode_generator_reads_are_compact():
     """CCS-like reads against the major strain: ~85 events (N 2 %, deletions, substitutions, insertion flags) per 3 kb read,
-    i.e. ~136 B (12 bits per event + an 8-byte header) instead of the 1504-byte planar row."""
+    i.e. ~112 B (one byte per QV-filtered base, 12 bits per other event, a 2-byte count and an 8-byte header) instead of the
+    1504-byte planar row."""
     t = make_tables(SynthConfig(L=3000, seed=20240003))
     st = synth_states(t, 0, 500)
     hdr, ev = encode_states(st, t.refseq)
     assert np.array_equal(decode_events(hdr, ev, 3000, t.refseq), st)
     per_read = (len(ev) + 8 * len(hdr)) / 500
-    assert 100 < per_read < 170, per_read
+    assert 90 < per_read < 130, per_read
     # lossless for ANY base: a wrong base only makes the list longer
     rng = np.random.default_rng(1)
     other = rng.integers(0, 4, size=3000, dtype=np.uint8)
@@ -56,22 +57,42 @@ def test_encode_generator_reads_are_compact():
     assert np.array_equal(decode_events(hdr2, ev2, 3000, other), st[:50]) and len(ev2) > 50 * 2000 * 3 // 2
 
 
-def test_encode_fillers_and_edges():
+def test_encode_skips_and_edges():
     L = 20000
     base = np.zeros(L, dtype=np.uint8)
-    st = np.tile(base, (6, 1))
-    st[0, 19999] = 2                      # one event 19999 columns after begin: 78 fillers (19999 = 78 * 255 + 109)
-    st[1, 255] = 1                        # exactly the largest delta: no filler
-    st[2, 256] = 1                        # one more: one filler
+    st = np.tile(base, (8, 1))
+    st[0, 19999] = 2                      # one event 19999 columns after begin: 78 skips (19999 = 78 * 255 + 109)
+    st[1, 254] = 1                        # exactly the largest delta: no skip
+    st[2, 255] = 1                        # one more: one skip, then delta 0
     st[3, :] = 7                          # spans nothing
     st[4, :100] = 7; st[4, 150:] = 7; st[4, 120:125] = 7     # reference skip (CIGAR N) inside the read
     st[5, 0] = 15; st[5, 1] = 8           # insertion flags on an unspanned-looking and on an unchanged column
+    st[6, 600] = 5                        # one N 600 columns after begin: 2 skips + 1 entry in the byte list, no rest list
+    st[7, 0] = 5; st[7, 1] = 13; st[7, 2] = 5; st[7, 700] = 5; st[7, 701] = 1   # both lists, N with insertion flag goes to the rest list
     hdr, ev = encode_states(st, base)
     nbytes = np.diff(hdr["ev_off"].astype(np.int64))
-    n = (2 * nbytes) // 3                 # events per read: ceil(1.5 n) bytes hold n events
-    assert list(n[:4]) == [79, 1, 2, 0] and list(nbytes[:4]) == [119, 2, 3, 0]
+    off = hdr["ev_off"].astype(np.int64)
+    nN = np.array([int(ev[o]) | (int(ev[o + 1]) << 8) if n >= 2 else 0 for o, n in zip(off[:-1], nbytes)])
+    nrest = np.where(nbytes >= 2, (2 * (nbytes - 2 - nN)) // 3, 0)      # ceil(1.5 n) bytes hold n 12-bit entries
+    assert list(nN) == [0, 0, 0, 0, 0, 0, 3, 5] and list(nrest) == [79, 1, 2, 0, 5, 2, 0, 4]
+    assert list(nbytes) == [121, 4, 5, 0, 10, 5, 5, 13]
     assert (int(hdr["begin"][3]), int(hdr["end"][3])) == (0, 0)
-    assert (int(hdr["begin"][4]), int(hdr["end"][4])) == (100, 150) and n[4] == 5 and nbytes[4] == 8
+    assert (int(hdr["begin"][4]), int(hdr["end"][4])) == (100, 150)
+    assert np.array_equal(decode_events(hdr, ev, L, base), st)
+    # a read that equals the base on its span costs no bytes at all
+    st2 = np.tile(base, (2, 1)); st2[1, :50] = 7
+    hdr2, ev2 = encode_states(st2, base)
+    assert len(ev2) == 0 and (int(hdr2["begin"][1]), int(hdr2["end"][1])) == (50, L)
+    assert np.array_equal(decode_events(hdr2, ev2, L, base), st2)
+
+
+def test_encode_all_n_read():
+    """The longest N list: every column of a 65,535-column read is 'N' (the u16 count still holds)."""
+    L = 65535
+    base = np.zeros(L, dtype=np.uint8)
+    st = np.full((1, L), 5, dtype=np.uint8)
+    hdr, ev = encode_states(st, base)
+    assert len(ev) == 2 + L and (int(ev[0]) | (int(ev[1]) << 8)) == L
     assert np.array_equal(decode_events(hdr, ev, L, base), st)
 
 
@@ -87,7 +108,7 @@ def test_encode_errors(mslib):
     st[1, 5] = 6
     big = np.zeros(600, dtype=np.uint8)
     assert mslib.ms_encode_states(p(st), 3, 100, p(base), p(hdr), p(big), 600, C.byref(n)) == -5    # reserved state
-    assert mslib.ms_events_bound(3000) >= (3000 + 3000 // 255 + 1) * 3 // 2 + 1 and mslib.ms_events_bound(3000) < 4600
+    assert mslib.ms_events_bound(3000) >= 2 + (3000 + 3000 // 255 + 1) * 3 // 2 + 1 and mslib.ms_events_bound(3000) < 4600
 
 
 def test_encode_row_incremental_matches_batch(mslib):
