@@ -294,7 +294,8 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_events_kernel(const 
                 row[b] = v;
             }
             __syncwarp();
-            const uint32_t nbytes = h0.off1 - h0.off0;
+            // (a header whose offsets run backwards or past the array can only be corrupt: the read keeps the base on its span)
+            const uint32_t nbytes = (h0.off1 >= h0.off0 && events + h0.off1 <= ev_end) ? h0.off1 - h0.off0 : 0u;
             if (nbytes >= 2u) {
                 const uint8_t* ev = events + h0.off0;
                 const uint32_t mis = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(ev) & 15u);

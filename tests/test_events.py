@@ -164,6 +164,45 @@ def test_expand_events_equals_packed_rows(L, R):
 
 
 @gpu
+def test_expand_corrupt_event_rows_stay_in_bounds():
+    """Garbage event bytes and headers (counts past the string, columns past the row, offsets running backwards or past the array):
+    the kernel completes, writes only its own tiles, and the untouched reads of the batch still expand exactly."""
+    import torch
+    from minorseq_b200 import Handle, Juliet
+    L, R = 3000, 4096
+    rng = np.random.default_rng(99)
+    base, st = _random_states(rng, R, L, 0.03)
+    hdr, ev = encode_states(st, base)
+    hdr, ev = hdr.copy(), ev.copy()
+    bad = rng.choice(R, size=600, replace=False)
+    off = hdr["ev_off"].astype(np.int64)
+    for r in bad[:400]:                                   # random bytes inside the read's own string
+        ev[off[r]: off[r + 1]] = rng.integers(0, 256, size=int(off[r + 1] - off[r]), dtype=np.uint8)
+    good = np.ones(R, dtype=bool)
+    good[bad] = False
+    for r in bad[400:500]:                                # offsets running backwards / past the array (neighbours see them as well)
+        hdr["ev_off"][r] = rng.choice([0, 0xFFFFFFFF, len(ev) + 12345, int(off[r]) + 100000])
+        good[max(0, r - 1)] = False
+    for r in bad[500:]:                                   # spans past the reference
+        hdr["begin"][r], hdr["end"][r] = rng.integers(0, 65536, size=2)
+    hd = Handle(0)
+    try:
+        j = Juliet(L, [(1, L + 1)], handle=hd)
+        j.set_base(base)
+        lib = j.lib
+        dh, de = _dev(hdr, torch), _dev(ev, torch)
+        nwords = int(lib.ms_tiled_words(L, R))
+        out = torch.full((nwords + 4096,), 0x5A5A5A5A, dtype=torch.int32, device="cuda")      # guard words behind the tiles
+        _lib.check(lib.ms_expand_events_dev(hd.h, C.c_void_p(dh.data_ptr()), C.c_void_p(de.data_ptr()), R, C.c_void_p(out.data_ptr())), hd.h)
+        _lib.check(lib.ms_synchronize(hd.h), hd.h)
+        assert bool((out[nwords:] == 0x5A5A5A5A).all())
+        rows = host_rows(out[:nwords], R, L)
+        assert np.array_equal(rows[good], pack_states(st)[good])
+    finally:
+        hd.close()
+
+
+@gpu
 def test_pass_from_event_rows_equals_pass_from_rows_and_oracle(oracle):
     """juliet --mode-phasing through ms_juliet_pass_events_host: same counts, variants, haplotypes and read ids as the pass from
     planar rows, and the oracle's counts.  Small chunk size so that the chunked upload pipeline has several chunks."""
