@@ -102,6 +102,7 @@ void ms_destroy(ms_handle* h) {
     for (cudaEvent_t ev : h->ev_stagefree) cudaEventDestroy(ev);
     h->b_rowstage[0].release(); h->b_rowstage[1].release();
     if (h->call_stage) cudaFreeHost(h->call_stage);
+    if (h->counts_stage) cudaFreeHost(h->counts_stage);
     cudaEventDestroy(h->ev_copy[0]); cudaEventDestroy(h->ev_copy[1]);
     cudaEventDestroy(h->ev_k1[0]); cudaEventDestroy(h->ev_k1[1]);
     cudaEventDestroy(h->ev_timer[0]); cudaEventDestroy(h->ev_timer[1]);
@@ -437,9 +438,21 @@ int ms_get_counts(ms_handle* h, uint32_t* col, uint32_t* codon) {
     if (!h || !h->d_counts) return MS_ERR_ARG;
     MS_CUDA(h, cudaSetDevice(h->device));
     const size_t L = h->L;
-    if (col) MS_CUDA(h, cudaMemcpyAsync(col, h->d_counts, L * 8 * 4, cudaMemcpyDeviceToHost, h->stream));
-    if (codon) MS_CUDA(h, cudaMemcpyAsync(codon, h->d_counts + L * 8, L * 64 * 4, cudaMemcpyDeviceToHost, h->stream));
-    MS_CUDA(h, cudaStreamSynchronize(h->stream));
+    // one device->host copy into pinned memory, then plain memcpys: a copy straight into a pageable destination is staged by the
+    // driver in small pieces and takes several times as long
+    if (h->counts_stage_words < L * 72) {
+        if (h->counts_stage) cudaFreeHost(h->counts_stage);
+        h->counts_stage = nullptr; h->counts_stage_words = 0;
+        MS_CUDA(h, cudaMallocHost(&h->counts_stage, L * 72 * 4));
+        h->counts_stage_words = L * 72;
+    }
+    const size_t first = col ? 0 : L * 8, last = codon ? L * 72 : L * 8;
+    if (last > first) {
+        MS_CUDA(h, cudaMemcpyAsync(h->counts_stage + first, h->d_counts + first, (last - first) * 4, cudaMemcpyDeviceToHost, h->stream));
+        MS_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (col) memcpy(col, h->counts_stage, L * 8 * 4);
+        if (codon) memcpy(codon, h->counts_stage + L * 8, L * 64 * 4);
+    }
     return MS_OK;
 }
 

@@ -102,6 +102,7 @@ struct ms_handle {
     int table_attempt = 0;
     DevBuf b_plan;   // PhasePlan built on the device by the single-call pass
     void* plan_stage = nullptr;   // pinned, sizeof(PhasePlan): its download
+    uint32_t* counts_stage = nullptr; size_t counts_stage_words = 0;   // pinned: ms_get_counts goes through it (pageable destinations are slow)
     DevBuf b_var, b_blocklist, b_bits, b_flags, b_slot, b_tab_key, b_tab_cnt, b_tab_rep, b_ctr, b_groups, b_gather, b_rank, b_hap,
         b_pat, b_cooc, b_bits_t;
     // device-side merge + ordering (phase_order.cu)
