@@ -96,6 +96,52 @@ def test_encode_all_n_read():
     assert np.array_equal(decode_events(hdr, ev, L, base), st)
 
 
+@pytest.mark.parametrize("L", [1, 2, 254, 255, 256, 511, 3000, 65535])
+def test_events_bound_holds_for_worst_rows(mslib, L):
+    """ms_events_bound(L) covers the longest strings: every column in the rest list, every column an N, one event per 255 columns
+    (a skip before each), alternating lists."""
+    base = np.zeros(L, dtype=np.uint8)
+    rows = []
+    rows.append(np.full(L, 1, dtype=np.uint8))                       # every column a substitution
+    rows.append(np.full(L, 13, dtype=np.uint8))                      # ... with insertion flags
+    rows.append(np.full(L, 5, dtype=np.uint8))                       # every column N
+    alt = np.full(L, 5, dtype=np.uint8); alt[::2] = 2; rows.append(alt)
+    sparse = base.copy(); sparse[254::255] = 3; rows.append(sparse)  # one event after every skip-sized gap
+    sparse2 = base.copy(); sparse2[255::256] = 5; rows.append(sparse2)
+    st = np.stack(rows)
+    hdr, ev = encode_states(st, base)
+    nbytes = np.diff(hdr["ev_off"].astype(np.int64))
+    assert nbytes.max() <= mslib.ms_events_bound(L), (nbytes, mslib.ms_events_bound(L))
+    assert np.array_equal(decode_events(hdr, ev, L, base), st)
+
+
+def test_encode_decode_roundtrip_hypothesis():
+    """Arbitrary short rows over every legal nibble (6 and 14 are reserved), arbitrary base: encode -> decode is the identity and
+    rows and states encoders agree."""
+    from hypothesis import given, settings, strategies as hs
+    legal = [0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 12, 13, 15]
+
+    @settings(max_examples=150, deadline=None)
+    @given(hs.integers(1, 700).flatmap(lambda L: hs.tuples(
+        hs.lists(hs.sampled_from(legal), min_size=L, max_size=L),
+        hs.lists(hs.integers(0, 3), min_size=L, max_size=L),
+        hs.integers(0, L), hs.integers(0, L))))
+    def check(args):
+        nib, base, a, b = args
+        L = len(nib)
+        st = np.array([nib], dtype=np.uint8)
+        lo, hi = min(a, b), max(a, b)
+        st[0, :lo] = 7
+        st[0, hi:] = 7
+        base = np.array(base, dtype=np.uint8)
+        hdr, ev = encode_states(st, base)
+        assert np.array_equal(decode_events(hdr, ev, L, base), st)
+        hdr2, ev2 = encode_rows(pack_states(st), L, base)
+        assert np.array_equal(hdr2, hdr) and np.array_equal(ev2, ev)
+
+    check()
+
+
 def test_encode_errors(mslib):
     base = np.zeros(100, dtype=np.uint8)
     st = np.full((3, 100), 1, dtype=np.uint8)
