@@ -206,9 +206,9 @@ __device__ __forceinline__ void ev_xor_if(uint32_t x, uint32_t bits, uint32_t ad
 
 // One list of a read, 32 entries at a time: a warp scan turns the deltas into columns, every lane XORs its column's difference
 // from the base into the four plane words of the row (shared-memory reductions: XOR commutes, and two lanes hit the same word
-// only when two events share a 32-column block).  NLIST: one byte per entry, nibble 5; else 12 bits per entry.  SMEM: the
-// list is read from the staged window (shared memory), else from global memory (lists longer than the window).
-template <bool NLIST, bool SMEM>
+// only when two events share a 32-column block).  NLIST: one byte per entry, nibble 5; else 12 bits per entry.  `src` is a
+// generic pointer: the staged window in shared memory, or global memory for strings longer than the window.
+template <bool NLIST>
 __device__ __forceinline__ void ev_apply_list(const uint8_t* __restrict__ src, uint32_t n, int32_t begin, int32_t end, int32_t nblk,
                                               const uint2* __restrict__ base_sm, uint32_t row_addr, int lane) {
     int32_t carry = begin;
@@ -243,7 +243,6 @@ __device__ __forceinline__ void ev_apply_list(const uint8_t* __restrict__ src, u
             if (!NLIST) ev_xor_if(x, 8u, w + 12u, v);
         }
     }
-    (void)SMEM;
 }
 
 // One warp per read, eight warps = one tile (rows.cuh) per CTA and iteration; persistent CTAs stride over the tiles.
@@ -304,13 +303,8 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_events_kernel(const 
                 uint32_t nN = static_cast<uint32_t>(str[0]) | (static_cast<uint32_t>(str[1]) << 8);
                 nN = min(nN, nbytes - 2u);                                   // a corrupt count cannot run past the string
                 const uint32_t nrest = (2u * (nbytes - 2u - nN)) / 3u;      // ceil(1.5 n) bytes hold n 12-bit entries
-                if (staged) {
-                    ev_apply_list<true, true>(str + 2, nN, begin, end, nblk, base_sm, row_addr, lane);
-                    ev_apply_list<false, true>(str + 2 + nN, nrest, begin, end, nblk, base_sm, row_addr, lane);
-                } else {
-                    ev_apply_list<true, false>(str + 2, nN, begin, end, nblk, base_sm, row_addr, lane);
-                    ev_apply_list<false, false>(str + 2 + nN, nrest, begin, end, nblk, base_sm, row_addr, lane);
-                }
+                ev_apply_list<true>(str + 2, nN, begin, end, nblk, base_sm, row_addr, lane);
+                ev_apply_list<false>(str + 2 + nN, nrest, begin, end, nblk, base_sm, row_addr, lane);
             }
             __syncwarp();
         }
