@@ -545,6 +545,7 @@ int ms_pileup_events_host(ms_handle* h, const ms_read_hdr* hdr, const uint8_t* e
         const int64_t r0 = bounds[k], r1 = bounds[k + 1];
         if (r1 <= r0) continue;
         const int64_t e0 = hdr[r0].ev_off, e1 = hdr[r1].ev_off;
+        if (e1 < e0 || e1 > total_ev) MS_FAIL(h, MS_ERR_FORMAT, "event rows: header offsets are not ascending");
         const int64_t h0 = r0 + (k > 0 ? 1 : 0);     // entry r0 went up with the previous chunk (as its end marker)
         MS_CUDA(h, cudaMemcpyAsync(d_hdr + h0, hdr + h0, static_cast<size_t>(r1 - h0 + 1) * sizeof(ms_read_hdr), cudaMemcpyHostToDevice, h->copy_stream));
         if (e1 > e0) MS_CUDA(h, cudaMemcpyAsync(d_ev + e0, events + e0, static_cast<size_t>(e1 - e0), cudaMemcpyHostToDevice, h->copy_stream));

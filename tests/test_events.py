@@ -285,6 +285,11 @@ def test_pass_from_event_rows_equals_pass_from_rows_and_oracle(oracle):
         hdr2, ev2 = encode_rows(packed[:100], 3000, other)
         with pytest.raises(_lib.MsError, match="different base"):
             j.run_events_host(hdr2, ev2)
+        # offsets that do not ascend from chunk boundary to chunk boundary are refused before anything is copied
+        hdr3 = hdr.copy()
+        hdr3["ev_off"][0] = len(ev) + 5
+        with pytest.raises(_lib.MsError, match="not ascending"):
+            j.run_events_host(hdr3, ev)
         # zero reads
         hdr0, ev0 = encode_rows(packed[:0], 3000, t.refseq)
         z = j.run_events_host(hdr0, ev0)
