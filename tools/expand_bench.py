@@ -27,7 +27,7 @@ from minorseq_b200 import host_rows
 rows = host_rows(d, R, L)
 t0 = time.perf_counter()
 hdr, ev = encode_rows(rows, L, t.refseq)
-print(f"host encode: {time.perf_counter() - t0:.2f} s single thread, {len(ev) / 1.5 / R:.1f} events/read, {(hdr.nbytes + ev.nbytes) / R:.1f} B/read")
+print(f"host encode: {time.perf_counter() - t0:.2f} s single thread, {len(ev) / R:.1f} event bytes + 8 header bytes = {(hdr.nbytes + ev.nbytes) / R:.1f} B/read")
 j.set_base(t.refseq)
 dh = torch.from_numpy(hdr.view(np.uint8)).cuda()
 de = torch.from_numpy(ev).cuda()
