@@ -30,6 +30,7 @@ struct RefSeq { std::string name; int32_t length = 0; };
 
 struct Record {
     int32_t ref_id = -1, pos = -1;
+    int32_t next_ref_id = -1, next_pos = -1, tlen = 0;   // mate fields, carried through unchanged
     uint8_t mapq = 0;
     uint16_t flag = 0;
     std::string name;
@@ -243,6 +244,7 @@ public:
         const uint16_t ncig = detail::u16(p + 12);
         r.flag = detail::u16(p + 14);
         const uint32_t lseq = detail::u32(p + 16);
+        r.next_ref_id = detail::i32(p + 20); r.next_pos = detail::i32(p + 24); r.tlen = detail::i32(p + 28);
         size_t o = 32;
         if (o + l_name + 4ull * ncig + (lseq + 1) / 2 + lseq > bs) throw Error("corrupt BAM record");
         r.name.assign(reinterpret_cast<const char*>(p + o), l_name ? l_name - 1 : 0);
@@ -386,6 +388,25 @@ inline BamIndexed index_stream(const Bytes& u) {
 }
 
 // ------------------------------------------------------------------ BAM writer (fixtures, mixdata)
+// removes every aux field whose two-letter tag is in `tags` (tags of a record that describe its OLD alignment: NM, MD);
+// a malformed aux block is left as it is
+inline void strip_tags(std::vector<uint8_t>& aux, std::initializer_list<const char*> tags) {
+    std::vector<uint8_t> out;
+    out.reserve(aux.size());
+    const uint8_t* p = aux.data();
+    const uint8_t* end = p + aux.size();
+    while (p + 3 <= end) {
+        const size_t vs = detail::aux_value_size(p + 2, end);
+        if (vs == 0 || p + 2 + vs > end) return;
+        bool drop = false;
+        for (const char* t : tags) drop = drop || (p[0] == static_cast<uint8_t>(t[0]) && p[1] == static_cast<uint8_t>(t[1]));
+        if (!drop) out.insert(out.end(), p, p + 2 + vs);
+        p += 2 + vs;
+    }
+    if (p != end) return;
+    aux.swap(out);
+}
+
 class BamWriter {
 public:
     BamWriter(const std::string& path, const std::string& header_text, const std::vector<RefSeq>& refs) : f_(fopen(path.c_str(), "wb")) {
@@ -394,28 +415,45 @@ public:
         encode_header(header_text, refs, h);
         append(h.data(), h.size());
     }
-    ~BamWriter() { close(); }
     void write(const Record& r) {
         std::vector<uint8_t> b;
         encode(r, b);
         append(b.data(), b.size());
     }
+    // UCSC binning scheme of the SAM specification (section 5.3): the bin of the zero-based half-open interval [beg, end)
+    static uint16_t reg2bin(int64_t beg, int64_t end) {
+        --end;
+        if (beg >> 14 == end >> 14) return static_cast<uint16_t>(((1 << 15) - 1) / 7 + (beg >> 14));
+        if (beg >> 17 == end >> 17) return static_cast<uint16_t>(((1 << 12) - 1) / 7 + (beg >> 17));
+        if (beg >> 20 == end >> 20) return static_cast<uint16_t>(((1 << 9) - 1) / 7 + (beg >> 20));
+        if (beg >> 23 == end >> 23) return static_cast<uint16_t>(((1 << 6) - 1) / 7 + (beg >> 23));
+        if (beg >> 26 == end >> 26) return static_cast<uint16_t>(((1 << 3) - 1) / 7 + (beg >> 26));
+        return 0;
+    }
     // one alignment record in BAM's binary layout, appended to b
     static void encode(const Record& r, std::vector<uint8_t>& b) {
+        if (r.name.size() > 254) throw Error("read name longer than 254 characters: " + r.name.substr(0, 40) + "...");
+        if (r.cigar.size() > 0xffff) throw Error("more than 65535 CIGAR operations in " + r.name + " (the CG-tag form is not written)");
         const size_t at = b.size();
         const uint32_t lseq = static_cast<uint32_t>(r.seq.size());
+        int64_t reflen = 0;                     // reference bases the alignment covers: M D N = X
+        for (uint32_t c : r.cigar) {
+            const uint32_t op = c & 15u;
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) reflen += c >> 4;
+        }
         detail::put32(b, 0);  // block size, patched below
         detail::put32(b, static_cast<uint32_t>(r.ref_id));
         detail::put32(b, static_cast<uint32_t>(r.pos));
         b.push_back(static_cast<uint8_t>(r.name.size() + 1));
         b.push_back(r.mapq);
-        detail::put16(b, 4680);  // bin: unused by this reader
+        // unplaced records: reg2bin(-1, 0) = 4680 (SAM specification, section 4.2.1); no reference bases: one position
+        detail::put16(b, r.pos < 0 ? 4680 : reg2bin(r.pos, static_cast<int64_t>(r.pos) + std::max<int64_t>(1, reflen)));
         detail::put16(b, static_cast<uint16_t>(r.cigar.size()));
         detail::put16(b, r.flag);
         detail::put32(b, lseq);
-        detail::put32(b, static_cast<uint32_t>(-1));
-        detail::put32(b, static_cast<uint32_t>(-1));
-        detail::put32(b, 0);
+        detail::put32(b, static_cast<uint32_t>(r.next_ref_id));
+        detail::put32(b, static_cast<uint32_t>(r.next_pos));
+        detail::put32(b, static_cast<uint32_t>(r.tlen));
         b.insert(b.end(), r.name.begin(), r.name.end());
         b.push_back(0);
         for (uint32_t c : r.cigar) detail::put32(b, c);
@@ -464,13 +502,22 @@ public:
         detail::put32(out, static_cast<uint32_t>(crc32(crc32(0L, Z_NULL, 0), p, static_cast<uInt>(n))));
         detail::put32(out, static_cast<uint32_t>(n));
     }
+    ~BamWriter() { try { close(); } catch (...) {} }   // call close() yourself to see a write error
     void close() {
         if (!f_) return;
-        flush_block();
-        static const uint8_t eof[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        fwrite(eof, 1, 28, f_);
-        fclose(f_);
+        FILE* f = f_;
         f_ = nullptr;
+        bool ok = true;
+        if (!pend_.empty()) {
+            std::vector<uint8_t> out;
+            bgzf_member(pend_.data(), pend_.size(), out);
+            ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+            pend_.clear();
+        }
+        static const uint8_t eof[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        ok = ok && fwrite(eof, 1, 28, f) == 28;
+        ok = (fclose(f) == 0) && ok;
+        if (!ok) throw Error("write error on the BAM output (disk full?)");
     }
     static void aux_string(std::vector<uint8_t>& aux, const char tag[2], const std::string& s) {
         aux.push_back(tag[0]); aux.push_back(tag[1]); aux.push_back('Z');
@@ -495,7 +542,7 @@ private:
         if (pend_.empty()) return;
         std::vector<uint8_t> out;
         bgzf_member(pend_.data(), pend_.size(), out);
-        fwrite(out.data(), 1, out.size(), f_);
+        if (fwrite(out.data(), 1, out.size(), f_) != out.size()) throw Error("write error on the BAM output (disk full?)");
         pend_.clear();
     }
     FILE* f_;
@@ -508,14 +555,19 @@ inline void write_bam_parallel(const std::string& path, const std::string& heade
                                const std::vector<const Record*>& recs, unsigned nthreads) {
     nthreads = std::max(1u, nthreads);
     std::vector<std::vector<uint8_t>> part(nthreads);
+    std::vector<std::string> errs(nthreads);        // an exception must not leave a worker thread: carried to the caller
     {
         std::vector<std::thread> th;
         for (unsigned t = 0; t < nthreads; ++t)
             th.emplace_back([&, t] {
-                for (size_t k = recs.size() * t / nthreads; k < recs.size() * (t + 1) / nthreads; ++k) BamWriter::encode(*recs[k], part[t]);
+                try {
+                    for (size_t k = recs.size() * t / nthreads; k < recs.size() * (t + 1) / nthreads; ++k) BamWriter::encode(*recs[k], part[t]);
+                } catch (const std::exception& e) { errs[t] = e.what(); }
             });
         for (auto& x : th) x.join();
     }
+    for (const std::string& e : errs)
+        if (!e.empty()) throw Error(e);
     std::vector<uint8_t> u;
     BamWriter::encode_header(header_text, refs, u);
     size_t total = u.size();
@@ -528,17 +580,23 @@ inline void write_bam_parallel(const std::string& path, const std::string& heade
         std::vector<std::thread> th;
         for (unsigned t = 0; t < nthreads; ++t)
             th.emplace_back([&, t] {
-                for (size_t b = nblocks * t / nthreads; b < nblocks * (t + 1) / nthreads; ++b)
-                    BamWriter::bgzf_member(u.data() + b * 0xff00, std::min<size_t>(0xff00, u.size() - b * 0xff00), z[t]);
+                try {
+                    for (size_t b = nblocks * t / nthreads; b < nblocks * (t + 1) / nthreads; ++b)
+                        BamWriter::bgzf_member(u.data() + b * 0xff00, std::min<size_t>(0xff00, u.size() - b * 0xff00), z[t]);
+                } catch (const std::exception& e) { errs[t] = e.what(); }
             });
         for (auto& x : th) x.join();
     }
+    for (const std::string& e : errs)
+        if (!e.empty()) throw Error(e);
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) throw Error("cannot create " + path);
-    for (auto& p : z) fwrite(p.data(), 1, p.size(), f);
+    bool ok = true;
+    for (auto& p : z) ok = ok && fwrite(p.data(), 1, p.size(), f) == p.size();
     static const uint8_t eof[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    fwrite(eof, 1, 28, f);
-    fclose(f);
+    ok = ok && fwrite(eof, 1, 28, f) == 28;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) throw Error("write error on " + path + " (disk full?)");
 }
 
 }  // namespace msbam

@@ -83,9 +83,15 @@ int main(int argc, char** argv) {
                 if (r.ref_id < 0 || (r.flag & 0x4)) continue;                     // unmapped records pass through
                 if (r.ref_id != ref_id) { ++n_other; r.ref_id = -2; continue; }   // aligned to something else: dropped
                 switch (mscleric::project_read(path, B.seq, r)) {
-                case mscleric::Projected::Ok: r.ref_id = 0; ++n_ok; break;
+                case mscleric::Projected::Ok:
+                    r.ref_id = 0; ++n_ok;
+                    msbam::strip_tags(r.aux, {"NM", "MD"});                      // they describe the alignment to the old reference
+                    if (r.next_ref_id >= 0) { r.next_ref_id = -1; r.next_pos = -1; r.tlen = 0; }   // a mate's old coordinates mean nothing here
+                    break;
                 case mscleric::Projected::Unmapped:
-                    r.ref_id = -1; r.pos = -1; r.cigar.clear(); r.flag |= 0x4; r.mapq = 0; ++n_unmapped; break;
+                    r.ref_id = -1; r.pos = -1; r.cigar.clear(); r.flag |= 0x4; r.mapq = 0; ++n_unmapped;
+                    msbam::strip_tags(r.aux, {"NM", "MD"});
+                    break;
                 case mscleric::Projected::Unsupported:
                     if (!bad.exchange(1)) bad_name = r.name + ": CIGAR ops other than = X I D S H are not supported (cigar M is forbidden)";
                     break;
@@ -102,7 +108,8 @@ int main(int argc, char** argv) {
         for (auto& x : th) x.join();
         if (bad) mshost::die(bad_name);
 
-        // header: every @SQ line gives way to the target reference; everything else is kept
+        // header: every @SQ line gives way to the target reference; a sort order survives only when no record lost its place
+        // (the projection is monotone in POS, but a record that became unmapped now sits between placed ones); the rest is kept
         std::string text;
         {
             std::istringstream hs(in.text);
@@ -112,6 +119,13 @@ int main(int argc, char** argv) {
                 if (line.compare(0, 3, "@SQ") == 0) {
                     if (!sq_done) text += "@SQ\tSN:" + B.name + "\tLN:" + std::to_string(B.seq.size()) + "\n";
                     sq_done = true;
+                } else if (line.compare(0, 3, "@HD") == 0 && n_unmapped.load() > 0) {
+                    const size_t so = line.find("\tSO:");
+                    if (so != std::string::npos) {
+                        const size_t e = line.find('\t', so + 1);
+                        line = line.substr(0, so) + "\tSO:unknown" + (e == std::string::npos ? "" : line.substr(e));
+                    }
+                    text += line + "\n";
                 } else if (!line.empty()) text += line + "\n";
             }
             if (!sq_done) text += "@SQ\tSN:" + B.name + "\tLN:" + std::to_string(B.seq.size()) + "\n";

@@ -18,6 +18,71 @@
 
 int main(int argc, char** argv) {
     const std::string tmp = argc > 1 ? argv[1] : "/tmp/ms_selftest.bam";
+    {   // ---- BAM writer: bin, mate fields, limits of the fixed-width fields, aux tag removal
+        REQUIRE(msbam::BamWriter::reg2bin(0, 1) == 4681 && msbam::BamWriter::reg2bin(0, 1 << 14) == 4681);
+        REQUIRE(msbam::BamWriter::reg2bin(0, (1 << 14) + 1) == 585 && msbam::BamWriter::reg2bin(1 << 14, (1 << 14) + 10) == 4682);
+        REQUIRE(msbam::BamWriter::reg2bin(0, 1 << 29) == 0 && msbam::BamWriter::reg2bin((1 << 26) - 1, (1 << 26) + 1) == 0);
+        msbam::Record r;
+        r.ref_id = 0; r.pos = 16380; r.flag = 0x1 | 0x40; r.mapq = 7; r.name = "pair/1";
+        r.next_ref_id = 0; r.next_pos = 20000; r.tlen = 3700;
+        r.cigar = {(5u << 4) | 4u, (10u << 4) | 7u, (3u << 4) | 2u, (2u << 4) | 1u, (7u << 4) | 8u};      // 5S 10= 3D 2I 7X: 20 reference bases
+        r.seq = std::string(24, 'A');
+        std::vector<uint8_t> b;
+        msbam::BamWriter::encode(r, b);
+        msbam::Record back;
+        msbam::BamReader::parse_record(b.data() + 4, static_cast<uint32_t>(b.size() - 4), back);
+        REQUIRE(back.next_ref_id == 0 && back.next_pos == 20000 && back.tlen == 3700 && back.mapq == 7 && back.flag == (0x1 | 0x40));
+        REQUIRE((b[4 + 10] | (b[4 + 11] << 8)) == 585);        // [16380, 16400) crosses a 16 kb boundary: a 128 kb bin
+        r.pos = 100;
+        b.clear();
+        msbam::BamWriter::encode(r, b);
+        REQUIRE((b[4 + 10] | (b[4 + 11] << 8)) == 4681);
+        msbam::Record unplaced;
+        unplaced.name = "u"; unplaced.flag = 4; unplaced.seq = "ACGT";
+        b.clear();
+        msbam::BamWriter::encode(unplaced, b);
+        REQUIRE((b[4 + 10] | (b[4 + 11] << 8)) == 4680);
+        bool threw = false;
+        msbam::Record longname = r;
+        longname.name.assign(255, 'x');
+        try { b.clear(); msbam::BamWriter::encode(longname, b); } catch (const msbam::Error&) { threw = true; }
+        REQUIRE(threw);
+        longname.name.assign(254, 'x');
+        b.clear();
+        msbam::BamWriter::encode(longname, b);
+        msbam::BamReader::parse_record(b.data() + 4, static_cast<uint32_t>(b.size() - 4), back);
+        REQUIRE(back.name.size() == 254);
+        threw = false;
+        msbam::Record manyops = r;
+        manyops.cigar.assign(65536, (1u << 4) | 7u);
+        manyops.seq.assign(65536, 'C');
+        try { b.clear(); msbam::BamWriter::encode(manyops, b); } catch (const msbam::Error&) { threw = true; }
+        REQUIRE(threw);
+        // the parallel whole-file writer reports the same error to its caller instead of terminating on a worker thread
+        threw = false;
+        try { msbam::write_bam_parallel(tmp, "@HD\tVN:1.5\n", {{"ref", 1000}}, {&r, &manyops, &r}, 3); } catch (const msbam::Error&) { threw = true; }
+        REQUIRE(threw);
+        threw = false;
+        try { msbam::write_bam_parallel("/nonexistent-dir/x.bam", "@HD\tVN:1.5\n", {{"ref", 1000}}, {&r}, 2); } catch (const msbam::Error&) { threw = true; }
+        REQUIRE(threw);
+        std::vector<uint8_t> aux;
+        msbam::BamWriter::aux_string(aux, "MD", "10A5");
+        msbam::BamWriter::aux_float(aux, "rq", 0.5f);
+        aux.insert(aux.end(), {'N', 'M', 'C', 3});
+        msbam::BamWriter::aux_string(aux, "sq", "III");
+        aux.insert(aux.end(), {'z', 'b', 'B', 's', 2, 0, 0, 0, 1, 0, 2, 0});
+        std::vector<uint8_t> want;
+        msbam::BamWriter::aux_float(want, "rq", 0.5f);
+        msbam::BamWriter::aux_string(want, "sq", "III");
+        want.insert(want.end(), {'z', 'b', 'B', 's', 2, 0, 0, 0, 1, 0, 2, 0});
+        msbam::strip_tags(aux, {"NM", "MD"});
+        REQUIRE(aux == want);
+        std::vector<uint8_t> broken = want;
+        broken.pop_back();                          // a cut 'B' array: left alone
+        const std::vector<uint8_t> before = broken;
+        msbam::strip_tags(broken, {"rq"});
+        REQUIRE(broken == before);
+    }
     {   // ---- BAM round trip over several BGZF blocks
         msbam::BamWriter w(tmp, "@HD\tVN:1.5\tSO:coordinate\n@SQ\tSN:ref\tLN:1000\n", {{"ref", 1000}});
         for (int i = 0; i < 3000; ++i) {

@@ -32,8 +32,17 @@ def aux_z(tag, s):
     return tag.encode() + b"Z" + s.encode() + b"\x00"
 
 
-def write_bam(path, refname, reflen, records):
-    text = f"@HD\tVN:1.5\tSO:unknown\n@SQ\tSN:{refname}\tLN:{reflen}\n".encode()
+def reg2bin(beg, end):
+    """SAM specification section 5.3"""
+    end -= 1
+    for shift, base in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+        if beg >> shift == end >> shift:
+            return base + (beg >> shift)
+    return 0
+
+
+def write_bam(path, refname, reflen, records, sort_order="unknown"):
+    text = f"@HD\tVN:1.5\tSO:{sort_order}\n@SQ\tSN:{refname}\tLN:{reflen}\n".encode()
     stream = b"BAM\x01" + struct.pack("<I", len(text)) + text + struct.pack("<I", 1)
     stream += struct.pack("<I", len(refname) + 1) + refname.encode() + b"\x00" + struct.pack("<I", reflen)
     stream += b"".join(records)
@@ -92,7 +101,7 @@ def states_to_record(name, st, ref, insertions=None, flag=0, n_via_qv=False):
 
 def read_bam(path):
     """Independent minimal BAM reader (BGZF = multi-member gzip): returns (header text, [(name, length)], records) with
-    records as dicts(name, flag, ref_id, pos, mapq, cigar [(len, op)], seq)."""
+    records as dicts(name, flag, ref_id, pos, mapq, cigar [(len, op)], seq, bin, aux bytes)."""
     import gzip
     raw = gzip.decompress(open(path, "rb").read())
     assert raw[:4] == b"BAM\x01"
@@ -115,6 +124,7 @@ def read_bam(path):
         name = raw[p:p + lname - 1].decode(); p += lname
         cig = [((v >> 4), ops[v & 15]) for v in struct.unpack_from("<%dI" % ncig, raw, p)]; p += 4 * ncig
         sq = "".join(dec[(raw[p + i // 2] >> (0 if i & 1 else 4)) & 15] for i in range(lseq))
-        recs.append(dict(name=name, flag=flag, ref_id=ref_id, pos=pos, mapq=mapq, cigar=cig, seq=sq))
+        p += (lseq + 1) // 2 + lseq
+        recs.append(dict(name=name, flag=flag, ref_id=ref_id, pos=pos, mapq=mapq, cigar=cig, seq=sq, bin=_bin, aux=bytes(raw[p:o + bs])))
         o += bs
     return text, refs, recs

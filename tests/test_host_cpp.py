@@ -285,10 +285,11 @@ def test_cleric_cli_matches_oracle(binaries, oracle, tmp_path, combined):
             if merged and merged[-1][1] == o: merged[-1] = (merged[-1][0] + l, o)
             else: merged.append((l, o))
         seq = "".join(seq)
-        recs.append(bam_util.record(f"read/{r}/ccs", 0 if r % 7 else 2048, pos, merged, seq))
+        aux = bam_util.aux_z("MD", "10A5") + b"NMC\x03" + bam_util.aux_z("sq", "I" * len(seq)) if r % 3 == 0 else bam_util.aux_z("sq", "I" * len(seq))
+        recs.append(bam_util.record(f"read/{r}/ccs", 0 if r % 7 else 2048, pos, merged, seq, aux=aux))
         meta.append((pos, merged, seq))
     recs.append(bam_util.record("unmapped/1/ccs", 4, -1, [], "ACGT", ref_id=-1))
-    bam_util.write_bam(str(tmp_path / "in.bam"), "orig", len(a), recs)
+    bam_util.write_bam(str(tmp_path / "in.bam"), "orig", len(a), recs, sort_order="coordinate" if combined else "unknown")
     (tmp_path / "a.fa").write_text(">orig some description\n" + "\n".join(a[i:i + 60] for i in range(0, len(a), 60)) + "\n")
     (tmp_path / "b.fa").write_text(">target\n" + b.lower() + "\n")
     if combined:
@@ -307,7 +308,13 @@ def test_cleric_cli_matches_oracle(binaries, oracle, tmp_path, combined):
         want = oracle.project_read(ops, b, pos, cig, seq)
         assert want is not None
         assert (g["pos"], g["cigar"], g["seq"], g["ref_id"]) == (want[0], want[1], seq, 0), g["name"]
-    assert got[-1]["flag"] & 4 and got[-1]["ref_id"] == -1 and got[0]["flag"] == 2048
+        # tags that describe the alignment to the old reference are gone, the QV track stays; the bin is the new interval's
+        assert g["aux"] == bam_util.aux_z("sq", "I" * len(seq)), g["name"]
+        reflen = sum(l for l, o in want[1] if o in "=XDNM")
+        assert g["bin"] == bam_util.reg2bin(want[0], want[0] + max(1, reflen)), g["name"]
+    assert got[-1]["flag"] & 4 and got[-1]["ref_id"] == -1 and got[0]["flag"] == 2048 and got[-1]["bin"] == 4680
+    # no record lost its place here, so a sort order in the header survives
+    assert ("SO:coordinate" in text) == bool(combined)
     # the BAM's reference must be one of the two sequences (doc/CLERIC.md:16-17); cigar M is refused (:14-15)
     (tmp_path / "x.fa").write_text(">other\nACGT\n")
     bad = subprocess.run([os.path.join(binaries, "cleric"), str(tmp_path / "in.bam"), str(tmp_path / "x.fa"), str(tmp_path / "b.fa"), str(tmp_path / "o2.bam")],
