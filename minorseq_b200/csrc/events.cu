@@ -3,11 +3,11 @@
 // A PacBio CCS alignment is "the reference, except at a few columns" (CIGAR `=` runs with sparse X / D / I ops,
 // /root/reference/doc/JULIET.md:49-58, plus the QV-filtered bases that become N, :256-259).  The planar rows K1 and K3
 // read cost L/2 bytes per read on the PCIe link (1504 B at 3 kb), which is what bounds the end-to-end pass.  Here the
-// host ships, per read, its span and two sorted event lists (one byte per QV-filtered base, 12 bits -- column delta + new 4-bit
-// column value -- per other event) against a base sequence both sides hold (~85 events = ~112 B per 3 kb read at CCS error
-// rates), and expand_events_kernel
-// rebuilds the packed reads in HBM (as tiles, rows.cuh), where the pile-up and the phasing kernels run unchanged.  SURVEY.md rows a2/a3
-// (host CIGAR walk) and 8f-2 ("GPU-side CIGAR expansion is the next real speed-up").
+// host ships, per read, its span and two sorted event lists (one byte per QV-filtered base, 12 bits -- column delta + new
+// 4-bit column value -- per other event) against a base sequence both sides hold (~85 events = ~113 B per 3 kb read at
+// CCS error rates), and expand_events_kernel rebuilds the packed reads in HBM (as tiles, rows.cuh), where the pile-up and
+// the phasing kernels run unchanged.  SURVEY.md rows a2/a3 (host CIGAR walk) and 8f-2 ("GPU-side CIGAR expansion is the
+// next real speed-up").
 //
 // Format (include/minorseq_b200.h):  ms_read_hdr hdr[R+1] = {ev_off, begin, end}; the byte string of read r is
 // events[hdr[r].ev_off .. hdr[r+1].ev_off): empty when the read equals the base on its whole span, else
