@@ -7,6 +7,8 @@ sys.path.insert(0, ROOT)
 from minorseq_b200.synth import SynthConfig, make_tables, pack_states, synth_states
 BIN = os.path.join(ROOT, "minorseq_b200", "bin")
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+REPS = int(sys.argv[2]) if len(sys.argv) > 2 else 5            # runs per variant (min and median are reported)
+VARIANTS = (("", {}),) if len(sys.argv) > 3 and sys.argv[3] == "overlap-only" else (("", {}), ("_serial_load", {"MS_SERIAL_LOAD": "1"}))
 t = make_tables(SynthConfig(L=3000, seed=20240003))
 d = tempfile.mkdtemp()
 packed = pack_states(synth_states(t, 0, R))
@@ -18,10 +20,10 @@ json.dump(cfg, open(os.path.join(d, "cfg.json"), "w"))
 out = {"reads": R, "bam_bytes": os.path.getsize(os.path.join(d, "in.bam"))}
 for name, cmd in (("juliet", [os.path.join(BIN, "juliet"), "-c", os.path.join(d, "cfg.json"), "--mode-phasing", "--min-perc", "0.5", os.path.join(d, "in.bam"), os.path.join(d, "o.json")]),
                   ("fuse", [os.path.join(BIN, "fuse"), os.path.join(d, "in.bam"), os.path.join(d, "o.fasta")])):
-    for tag, extra in (("", {}), ("_serial_load", {"MS_SERIAL_LOAD": "1"})):   # context/decode overlap vs serial, same box
+    for tag, extra in VARIANTS:   # context/decode overlap vs serial, same box
         ts = []
-        for _ in range(5):
+        for _ in range(REPS):
             t0 = time.perf_counter(); subprocess.check_call(cmd, env=dict(os.environ, MS_TIMING="1", **extra)); ts.append(time.perf_counter() - t0)
-        out[name + tag + "_s"] = min(ts); out[name + tag + "_median_s"] = sorted(ts)[2]
+        out[name + tag + "_s"] = min(ts); out[name + tag + "_median_s"] = sorted(ts)[len(ts) // 2]
     out[name + "_reads_per_s"] = R / out[name + "_s"]
 print(json.dumps(out))
