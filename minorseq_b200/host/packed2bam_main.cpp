@@ -20,6 +20,7 @@ int main(int argc, char** argv) {
     if (static_cast<int>(ref.size()) < L) { fputs("reference shorter than L\n", stderr); return 1; }
     FILE* f = fopen(argv[1], "rb");
     if (!f) { fputs("cannot open packed file\n", stderr); return 1; }
+    try {
     msbam::BamWriter w(argv[5], "@HD\tVN:1.5\tSO:unknown\n@SQ\tSN:synthetic_ref\tLN:" + std::to_string(L) + "\n", {{"synthetic_ref", L}});
     std::vector<uint32_t> row(4 * nblk);
     static const char B[] = "ACGT";
@@ -54,5 +55,9 @@ int main(int argc, char** argv) {
     }
     w.close();
     fclose(f);
+    } catch (const std::exception& e) {     // cannot create / write error on the output
+        fprintf(stderr, "packed2bam: %s\n", e.what());
+        return 1;
+    }
     return 0;
 }
